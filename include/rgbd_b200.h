@@ -1,0 +1,137 @@
+/* rgbd_b200 -- C ABI of the B200-native DGGM / E-DSAM depth-guidance hot path.
+ *
+ * This is the drop-in boundary: a plain-C shared library (librgbd_b200.so) with raw device pointers,
+ * sizes and a CUDA stream -- no torch types.  The reference is pure Python (PyTorch nn.Modules in
+ * mask2former/utils/custom_model.py, "CM"; numpy/OpenCV in mask2former/utils/data_process.py, "DP"), so the
+ * reference-side binding a maintainer adds is a ctypes stub; the Python mirror in
+ * rgb-d-instance-segmentation_b200/ is exactly such a binding.
+ *
+ * Conventions: every entry point enqueues work on `stream` and returns immediately (no synchronisation, no
+ * allocation: the caller supplies outputs and workspaces); return 0 on success, non-zero on error with the
+ * text available from rgbd_last_error().  All pointers are DEVICE pointers unless named `*_host`.  Tensors
+ * are contiguous unless a stride argument says otherwise; strides are in ELEMENTS.
+ */
+#ifndef RGBD_B200_H
+#define RGBD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rgbd_stream_t; /* cudaStream_t */
+
+#define RGBD_ABI_VERSION 1
+#define RGBD_HIST_BINS 512 /* CM:701 `bins=512` */
+
+#define RGBD_DTYPE_F32 0
+#define RGBD_DTYPE_BF16 1
+#define RGBD_DTYPE_U8 2
+
+/* status flags written per image by rgbd_depth_decompose */
+#define RGBD_DECOMP_RANGE_NOT_FINITE 1 /* numpy would raise "range ... is not finite" (all-NaN or inf depth) */
+
+int rgbd_abi_version(void);
+const char* rgbd_last_error(void);
+
+/* ---- DGGM -------------------------------------------------------------------------------------------------
+ * rgbd_dggm_fwd replaces DepthGradientInjectionResidual.forward (CM:1204-1269) for all scales in one launch:
+ *   out_i = color_i + ReLU(W_i . (bilinear_down(grad) * nearest_down(mask)) + b_i)
+ * and, if `branch1` is non-NULL, the v0.4.0 branch sum `cp1_i + cp2_i` (CM:354-355): out_i = branch1_i + (...).
+ * color/out/branch1: n_scales pointers to (B, C[i], Hs[i], Ws[i]) fp32; weight[i]: (C[i], D); bias[i]: (C[i]);
+ * grad: (B, D, H, W) with batch stride; mask: (B, 1, H, W) with batch stride.  The pointer ARRAYS are host
+ * arrays.  The None-gradient passthrough (CM:1263-1265) is the caller's branch. */
+int rgbd_dggm_fwd(int n_scales, const float* const* color_host, const float* const* branch1_host, float* const* out_host,
+                  const int* C_host, const int* Hs_host, const int* Ws_host, const float* const* weight_host,
+                  const float* const* bias_host, const float* grad, long long grad_batch_stride, const float* mask,
+                  long long mask_batch_stride, int B, int D, int H, int W, rgbd_stream_t stream);
+
+/* Parameter gradients of the same module (autograd of CM:1251): dW_i = sum 1[pre>0] dOut (x) gated_i,
+ * db_i = sum 1[pre>0] dOut.  Colour features are detached (CM:332-333) and the gradient map is data, so no
+ * other gradient exists.  dweight/dbias are overwritten. */
+int rgbd_dggm_bwd_params(int n_scales, const float* const* dout_host, const int* C_host, const int* Hs_host,
+                         const int* Ws_host, const float* const* weight_host, const float* const* bias_host,
+                         float* const* dweight_host, float* const* dbias_host, const float* grad,
+                         long long grad_batch_stride, const float* mask, long long mask_batch_stride, int B, int D, int H,
+                         int W, rgbd_stream_t stream);
+
+/* rgbd_gradient_features replaces calculate_gradient_features (DP:1247-1305) as called by map_10channel_case2
+ * (mask2former/utils/dataloader.py:412-421): Sobel 3x3 (reflect-101), magnitude, invalid-depth zeroing,
+ * valid mask, min-max normalisation.  depth: (B,H,W) f32 or u8; norm_out receives n_rep identical channels
+ * (channel stride H*W); vmask_out one channel.  Bit-exact with the reference for uint8-valued depth. */
+size_t rgbd_gradient_features_workspace_bytes(int B);
+int rgbd_gradient_features(const void* depth, int depth_dtype, long long depth_batch_stride, float* norm_out,
+                           long long norm_batch_stride, int n_rep, float* vmask_out, long long vmask_batch_stride, int B,
+                           int H, int W, float invalid_value, void* workspace, rgbd_stream_t stream);
+
+/* ---- E-DSAM: depth decomposition ------------------------------------------------------------------------------
+ * rgbd_depth_decompose replaces, for a whole batch and without host round trips, to_grayscale (CM:466-480) and
+ * DSAModule._calculate_depth_histogram / _select_depth_distribution_modes / _define_depth_interval_windows /
+ * _generate_depth_region_masks (CM:701-798) plus the adaptive_max_pool2d of every region mask (CM:687).
+ * Input: depth3 (B,3,H,W) with batch/channel strides (gray written to gray_out) OR gray_in (B,H,W); ratio (B).
+ * Outputs (optional ones may be NULL): hist_out int64 (B,512); edges_out f32 (B,513); n_modes_out (B);
+ * peak_bins_out (B,3); centres_out (B,3); windows_out (B,3,2); status_out (B); codes_out uint8 (B,H,W) REQUIRED:
+ * bit t = region mask t in the reference's list order (modes by (height, centre) descending, then the remaining
+ * region at index n_modes; all zero when no mode survives, CM:676-678); pooled_out_host[l] uint8
+ * (B, level_h[l], level_w[l]) = the codes OR-pooled over adaptive_max_pool2d's windows. */
+size_t rgbd_depth_decompose_workspace_bytes(int B);
+int rgbd_depth_decompose(const float* depth3, long long depth_batch_stride, long long depth_channel_stride,
+                         const float* gray_in, const float* ratio, int B, int H, int W, int num_modes, float* gray_out,
+                         long long* hist_out, float* edges_out, int* n_modes_out, int* peak_bins_out, float* centres_out,
+                         float* windows_out, int* status_out, uint8_t* codes_out, int n_levels, const int* level_h_host,
+                         const int* level_w_host, uint8_t* const* pooled_out_host, void* workspace, rgbd_stream_t stream);
+
+/* ---- E-DSAM: tensor-core building blocks ------------------------------------------------------------------------
+ * rgbd_dsam_pack builds the masked, K-concatenated bf16 operand of a DSAM stage (CM:683-696) from NCHW fp32
+ * features and the pooled region codes: out[img][seg][parity][y2][x2][C_pad] (parity_split=1, 3x3 stride 2) or
+ * out[img][seg][y][x][C_pad] (parity_split=0, 1x1).  Segments < masked_segs are multiplied by bit(code, seg);
+ * the others are plain copies.  The caller zero-initialises `out` once (padding stays zero). */
+int rgbd_dsam_pack(const float* feat, const uint8_t* codes, void* out_bf16, int B, int C, int C_pad, int H, int W, int n_seg,
+                   int masked_segs, int parity_split, rgbd_stream_t stream);
+
+/* Row-im2col of the 3-channel depth image for the predictor's multi-scale stem (CM:1458-1460):
+ * out[img][H+6][W][64] bf16, channel (j*8+dx)*4+c = depth[img][c][r-3+j][x+dx-3]. */
+int rgbd_ratio_stem_pack(const float* depth3, long long batch_stride, long long channel_stride, void* out_bf16, int B,
+                         int H, int W, rgbd_stream_t stream);
+
+/* Implicit-GEMM convolution on tcgen05/TMEM (see csrc/conv_gemm.cu).  A: bf16 channels-last tensor viewed as
+ * (a_planes, a_y, a_x, a_c); each of the n_slices K blocks reads kb_elems channels at the tile's base coordinate
+ * plus slices[j] = (c0, dx, dy, dplane) (out-of-range reads are zero).  W: bf16 (n_pad, n_slices*kb_elems).
+ * Output tile = bx*by (=128) pixels of one image x block_n channels.  y = act(acc*scale[n] + shift[variant][n]);
+ * epi_mode 0: bf16 (n_img, out_h, out_w, n_pad) store, optionally multiplied by `gate` (same layout);
+ * epi_mode 1: fp32 (n_img, n, out_h, out_w) store, optionally + residual (same layout);
+ * epi_mode 2: sums over the cells of a cells_y x cells_x grid into pool (n_img, cells, n_pad) (caller zeroes). */
+typedef struct rgbd_conv_gemm_desc {
+    const void* a; /* bf16 */
+    int a_c, a_x, a_y, a_planes;
+    int plane_per_img;
+    const void* w; /* bf16 */
+    const int* slices; /* device, n_slices x 4 */
+    int n_slices, kb_elems;
+    int n_img, out_h, out_w, bx, by;
+    int n, n_pad, block_n;
+    int tile_order; /* 0: x fastest, 1: y fastest */
+    int epi_mode, act; /* act: 0 none, 1 relu, 2 sigmoid */
+    const float* scale;   /* (n_pad) or NULL */
+    const float* shift;   /* (n_variants, n_pad) */
+    const int* variant;   /* (n_img) or NULL */
+    const void* gate;     /* bf16 or NULL */
+    void* out;
+    const float* residual;
+    float* pool;
+    int cells_y, cells_x;
+} rgbd_conv_gemm_desc;
+int rgbd_conv_gemm(const rgbd_conv_gemm_desc* desc_host, rgbd_stream_t stream);
+
+/* Tail of EnhancedDepthImageRatioPredictor.forward (CM:1473-1485): pooled sums -> conv3x3 256->512 + folded BN +
+ * ReLU -> GAP -> MLP -> 0.01 + 0.49*sigmoid.  conv_w (512,256,3,3) fp32; fc_w_host/fc_b_host: 4 layers. */
+int rgbd_ratio_tail(const float* pool_sums, int pool_stride, int cell_pixels, const float* conv_w, const float* conv_scale,
+                    const float* conv_shift, const float* const* fc_w_host, const float* const* fc_b_host, float out_min,
+                    float out_max, float* gap_ws, float* ratio_out, int B, rgbd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGBD_B200_H */

@@ -1,0 +1,101 @@
+"""ctypes binding of the C ABI in include/rgbd_b200.h (csrc/librgbd_b200.so).
+
+There is no fallback: if the library is missing or fails to load, every op raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librgbd_b200.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_int_p = C.POINTER(C.c_int)
+c_void_pp = C.POINTER(C.c_void_p)
+
+
+class ConvGemmDesc(C.Structure):
+    """Mirror of ``rgbd_conv_gemm_desc``."""
+    _fields_ = [
+        ("a", C.c_void_p), ("a_c", C.c_int), ("a_x", C.c_int), ("a_y", C.c_int), ("a_planes", C.c_int),
+        ("plane_per_img", C.c_int),
+        ("w", C.c_void_p), ("slices", C.c_void_p), ("n_slices", C.c_int), ("kb_elems", C.c_int),
+        ("n_img", C.c_int), ("out_h", C.c_int), ("out_w", C.c_int), ("bx", C.c_int), ("by", C.c_int),
+        ("n", C.c_int), ("n_pad", C.c_int), ("block_n", C.c_int),
+        ("tile_order", C.c_int), ("epi_mode", C.c_int), ("act", C.c_int),
+        ("scale", C.c_void_p), ("shift", C.c_void_p), ("variant", C.c_void_p), ("gate", C.c_void_p),
+        ("out", C.c_void_p), ("residual", C.c_void_p), ("pool", C.c_void_p),
+        ("cells_y", C.c_int), ("cells_x", C.c_int),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/rgbd_b200.h declares
+SIGNATURES = {
+    "rgbd_abi_version": (C.c_int, []),
+    "rgbd_last_error": (C.c_char_p, []),
+    "rgbd_dggm_fwd": (C.c_int, [C.c_int, c_void_pp, c_void_pp, c_void_pp, c_int_p, c_int_p, c_int_p, c_void_pp, c_void_pp,
+                                C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p]),
+    "rgbd_dggm_bwd_params": (C.c_int, [C.c_int, c_void_pp, c_int_p, c_int_p, c_int_p, c_void_pp, c_void_pp, c_void_pp,
+                                       c_void_pp, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_void_p]),
+    "rgbd_gradient_features_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "rgbd_gradient_features": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p,
+                                         C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "rgbd_depth_decompose_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "rgbd_depth_decompose": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_int_p, c_int_p,
+                                       c_void_pp, C.c_void_p, C.c_void_p]),
+    "rgbd_dsam_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_void_p]),
+    "rgbd_ratio_stem_pack": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p]),
+    "rgbd_conv_gemm": (C.c_int, [C.POINTER(ConvGemmDesc), C.c_void_p]),
+    "rgbd_ratio_tail": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_void_pp, c_void_pp,
+                                  C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class RgbdB200Error(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load librgbd_b200.so (built by ``build.py`` / ``__graft_entry__.build()``).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RgbdB200Error(
+            f"{LIB_PATH} is missing: build it with `python rgb-d-instance-segmentation_b200/build.py` "
+            "(rgbd_b200 has no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rgbd_abi_version() != 1:
+        raise RgbdB200Error(f"ABI version mismatch: library reports {lib.rgbd_abi_version()}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().rgbd_last_error().decode("utf-8", "replace")
+        raise RgbdB200Error(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr_array(ptrs) -> "C.Array":
+    arr = (C.c_void_p * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+def int_array(vals) -> "C.Array":
+    return (C.c_int * len(vals))(*[int(v) for v in vals])

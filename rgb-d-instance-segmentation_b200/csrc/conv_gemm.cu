@@ -1,0 +1,441 @@
+// K3/K4 core: implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// One persistent, warp-specialised kernel serves every dense contraction on the E-DSAM path:
+//   * DSAModule.forward (reference mask2former/utils/custom_model.py:683-696): the five 3x3 stride-2
+//     convolutions of a stage are ONE GEMM with K = 45*C_in over the K-concatenated operand
+//     [p0*F | p1*F | p2*F | p3*F | F];
+//   * EnhancedDepthImageRatioPredictor.forward (CM:1458-1473): the multi-scale 3x3/5x5/7x7 stem (as one
+//     7x7 conv over a row-im2col tensor), the 1x1 fusion / attention convs and the 3x3 128->256 conv.
+//
+// A operand: a bf16 channels-last activation tensor addressed as a 4-D TMA tensor (c, x, y, plane).
+// A "K slice" is 64 (or 32) channels of one filter tap: (c0, dx, dy, dplane) offsets added to the tile's
+// base coordinate; out-of-bounds rows are zero-filled by TMA (= conv zero padding).  B operand: packed
+// bf16 weights [N][K] (K-major), K ordered like the slice table.  D: fp32 accumulators in TMEM,
+// 128 pixels x BLOCK_N channels, double buffered so the epilogue of tile i overlaps the MMAs of i+1.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (TMEM -> registers -> fused scale/shift/activation -> global).
+// Epilogues: (0) bf16 channels-last store with optional gating multiply, (1) fp32 NCHW store with
+// optional residual add, (2) adaptive-average-pool accumulation (the 256-channel map of the ratio
+// predictor is never written: CM:1412-1416 BN/ReLU/AdaptiveAvgPool2d(4) are fused here).
+#include "common.cuh"
+#include "rgbd_b200.h"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kMaxStages = 8;
+constexpr int kMaxSlices = 1024;
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+
+struct KParams {
+    int n_img, tiles_x, tiles_y, BX, BY, out_w, out_h;
+    int n_slices, kb_bytes, stages;
+    int N, N_pad, BLOCK_N, n_tiles_n;
+    int plane_per_img, tile_order;
+    const int4* slices;
+    int epi_mode, act;
+    const float* scale;
+    const float* shift;
+    const int* variant;
+    const __nv_bfloat16* gate;
+    void* out;
+    const float* residual;
+    float* pool;
+    int cells_y, cells_x;
+    int total_tiles;
+};
+
+struct SmemCtl {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
+__device__ __forceinline__ void decode_tile(const KParams& p, int t, int& img, int& ty, int& tx, int& nt) {
+    nt = t % p.n_tiles_n;
+    int mt = t / p.n_tiles_n;
+    if (p.tile_order == 0) {
+        tx = mt % p.tiles_x; mt /= p.tiles_x;
+        ty = mt % p.tiles_y;
+        img = mt / p.tiles_y;
+    } else {
+        ty = mt % p.tiles_y; mt /= p.tiles_y;
+        tx = mt % p.tiles_x;
+        img = mt / p.tiles_x;
+    }
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == 1) return fmaxf(x, 0.f);
+    if (act == 2) return 1.0f / (1.0f + __expf(-x));
+    return x;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ KParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = kBlockM * p.kb_bytes;
+    const int b_bytes = p.BLOCK_N * p.kb_bytes;
+    const int stage_bytes = a_bytes + b_bytes;             // multiples of 1024 by construction
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + (size_t)p.stages * stage_bytes);
+    int4* s_slices = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(ctl) + sizeof(SmemCtl));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < p.n_slices; i += blockDim.x) s_slices[i] = p.slices[i];
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_a);
+        tc::prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            tc::mbar_init(&ctl->full[s], 1);
+            tc::mbar_init(&ctl->empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&ctl->tmem_full[s], 1);
+            tc::mbar_init(&ctl->tmem_empty[s], 128);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(&ctl->tmem_base, kTmemCols);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    // contiguous tile range per CTA (keeps pooled partial sums in registers across tiles)
+    const int per = p.total_tiles / gridDim.x, rem = p.total_tiles % gridDim.x;
+    const int t_begin = blockIdx.x * per + min((int)blockIdx.x, rem);
+    const int t_end = t_begin + per + ((int)blockIdx.x < rem ? 1 : 0);
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            int img, ty, tx, nt;
+            decode_tile(p, t, img, ty, tx, nt);
+            const int x0 = tx * p.BX, y0 = ty * p.BY, pl0 = img * p.plane_per_img;
+            for (int j = 0; j < p.n_slices; ++j) {
+                tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                uint8_t* sb = sa + a_bytes;
+                tc::mbar_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
+                const int4 sl = s_slices[j];
+                tc::tma_load_4d(sa, &tmap_a, &ctl->full[stage], sl.x, x0 + sl.y, y0 + sl.z, pl0 + sl.w);
+                tc::tma_load_2d(sb, &tmap_b, &ctl->full[stage], j * (p.kb_bytes >> 1), nt * p.BLOCK_N);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = tc::make_idesc_bf16(kBlockM, p.BLOCK_N);
+        const int k_per_block = p.kb_bytes >> 5;           // UMMA_K = 16 bf16 = 32 bytes
+        int stage = 0;
+        uint32_t phase = 0;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
+            tc::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BLOCK_N);
+            for (int j = 0; j < p.n_slices; ++j) {
+                tc::mbar_wait(&ctl->full[stage], phase);
+                tc::tc_fence_after();
+                const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t sb = sa + a_bytes;
+                const uint64_t adesc = tc::make_kmajor_desc(sa, p.kb_bytes);
+                const uint64_t bdesc = tc::make_kmajor_desc(sb, p.kb_bytes);
+                for (int k = 0; k < k_per_block; ++k)
+                    tc::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (j | k) != 0);
+                tc::umma_commit(&ctl->empty[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            tc::umma_commit(&ctl->tmem_full[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int q = warp - 4;                    // TMEM lane quarter
+        const int row = q * 32 + lane;
+        const int lx = row % p.BX, ly = row / p.BX;
+        const int n_chunks = p.BLOCK_N >> 5;
+        int as = 0;
+        uint32_t aphase = 0;
+        // pooled-mode running sums (lane L owns column 32*k + L of the current N tile)
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        int cur_key = -1, cur_nt = 0;
+        const int cell_h = p.cells_y ? p.out_h / p.cells_y : 1, cell_w = p.cells_x ? p.out_w / p.cells_x : 1;
+        const int ncells = p.cells_y * p.cells_x;
+
+        for (int t = t_begin; t < t_end; ++t) {
+            int img, ty, tx, nt;
+            decode_tile(p, t, img, ty, tx, nt);
+            const int ox = tx * p.BX + lx, oy = ty * p.BY + ly;
+            const bool valid = ox < p.out_w && oy < p.out_h;
+            const float* shift = p.shift + (size_t)(p.variant ? p.variant[img] : 0) * p.N_pad;
+            tc::mbar_wait(&ctl->tmem_full[as], aphase);
+            tc::tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BLOCK_N);
+
+            int key = -1;
+            bool uniform = false;
+            if (p.epi_mode == 2) {
+                key = valid ? img * ncells + (oy / cell_h) * p.cells_x + (ox / cell_w) : -1;
+                const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                const int leader_key = vm ? __shfl_sync(0xffffffffu, key, __ffs(vm) - 1) : -1;
+                uniform = __all_sync(0xffffffffu, !valid || key == leader_key);
+                if (uniform && vm && (leader_key != cur_key || nt != cur_nt)) {
+                    if (cur_key >= 0) {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            if (kk < n_chunks) {
+                                atomicAdd(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
+                                acc[kk] = 0.f;
+                            }
+                        }
+                    }
+                    cur_key = leader_key;
+                    cur_nt = nt;
+                }
+                if (!vm) uniform = false;   // nothing to add; skip below
+            }
+
+#pragma unroll 1
+            for (int k = 0; k < n_chunks; ++k) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(taddr0 + (uint32_t)(k * 32), v);
+                tc::tmem_ld_wait();
+                const int n0 = nt * p.BLOCK_N + k * 32;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    const float sc = p.scale ? __ldg(p.scale + n0 + j) : 1.0f;
+                    x = fmaf(x, sc, __ldg(shift + n0 + j));
+                    f[j] = apply_act(x, p.act);
+                }
+                if (p.epi_mode == 0) {
+                    if (valid) {
+                        const size_t off = ((size_t)(img * p.out_h + oy) * p.out_w + ox) * p.N_pad + n0;
+                        if (p.gate) {
+                            const uint4* gp = reinterpret_cast<const uint4*>(p.gate + off);
+#pragma unroll
+                            for (int g4 = 0; g4 < 4; ++g4) {
+                                uint4 gv = __ldg(gp + g4);
+                                const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float2 gf = __bfloat1622float2(g2[e]);
+                                    f[g4 * 8 + e * 2] *= gf.x;
+                                    f[g4 * 8 + e * 2 + 1] *= gf.y;
+                                }
+                            }
+                        }
+                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            uint4 o;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[g4 * 8 + 0], f[g4 * 8 + 1]);
+                            __nv_bfloat162 h1 = __floats2bfloat162_rn(f[g4 * 8 + 2], f[g4 * 8 + 3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g4 * 8 + 4], f[g4 * 8 + 5]);
+                            __nv_bfloat162 h3 = __floats2bfloat162_rn(f[g4 * 8 + 6], f[g4 * 8 + 7]);
+                            o.x = *reinterpret_cast<uint32_t*>(&h0);
+                            o.y = *reinterpret_cast<uint32_t*>(&h1);
+                            o.z = *reinterpret_cast<uint32_t*>(&h2);
+                            o.w = *reinterpret_cast<uint32_t*>(&h3);
+                            op[g4] = o;
+                        }
+                    }
+                } else if (p.epi_mode == 1) {
+                    if (valid) {
+                        const size_t plane = (size_t)p.out_h * p.out_w;
+                        const size_t base = (size_t)img * p.N * plane + (size_t)oy * p.out_w + ox;
+                        float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = n0 + j;
+                            if (n < p.N) {
+                                float r = f[j];
+                                if (p.residual) r += __ldg(p.residual + base + (size_t)n * plane);
+                                o[base + (size_t)n * plane] = r;
+                            }
+                        }
+                    }
+                } else {
+                    if (uniform) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = valid ? f[j] : 0.f;
+#pragma unroll
+                        for (int s = 16; s >= 1; s >>= 1) {
+                            const bool upper = (lane & s) != 0;
+#pragma unroll
+                            for (int i = 0; i < s; ++i) {
+                                const float send = upper ? f[i] : f[i + s];
+                                const float keep = upper ? f[i + s] : f[i];
+                                f[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                            }
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk)
+                            if (kk == k) acc[kk] += f[0];
+                    } else if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) atomicAdd(p.pool + (size_t)key * p.N_pad + n0 + j, f[j]);
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(&ctl->tmem_empty[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+        if (p.epi_mode == 2 && cur_key >= 0) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+                if (kk < n_chunks)
+                    atomicAdd(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+}  // namespace
+
+extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(d, "conv_gemm: null descriptor");
+    RGBD_CHECK_ARG(d->a && d->w && d->slices, "conv_gemm: null operand pointer");
+    RGBD_CHECK_ARG(d->kb_elems == 64 || d->kb_elems == 32, "conv_gemm: kb_elems must be 64 or 32 (got %d)", d->kb_elems);
+    RGBD_CHECK_ARG(d->a_c % 8 == 0 && d->a_c >= d->kb_elems, "conv_gemm: A channel count %d must be a multiple of 8 and >= kb", d->a_c);
+    RGBD_CHECK_ARG(d->bx >= 1 && d->by >= 1 && d->bx * d->by == kBlockM && d->bx <= 256 && d->by <= 256,
+                   "conv_gemm: box %dx%d must cover exactly %d pixels", d->bx, d->by, kBlockM);
+    RGBD_CHECK_ARG(d->n_slices >= 1 && d->n_slices <= kMaxSlices, "conv_gemm: n_slices %d out of range", d->n_slices);
+    RGBD_CHECK_ARG(d->n_pad % 32 == 0 && d->block_n % 32 == 0 && d->block_n >= 32 && d->block_n <= 256 &&
+                       d->n_pad % d->block_n == 0 && d->n <= d->n_pad && d->n >= 1,
+                   "conv_gemm: bad N tiling (N=%d N_pad=%d BLOCK_N=%d)", d->n, d->n_pad, d->block_n);
+    RGBD_CHECK_ARG(d->epi_mode >= 0 && d->epi_mode <= 2, "conv_gemm: bad epilogue mode %d", d->epi_mode);
+    RGBD_CHECK_ARG(d->shift, "conv_gemm: shift table is required");
+    RGBD_CHECK_ARG(d->n_img >= 1 && d->out_w >= 1 && d->out_h >= 1, "conv_gemm: bad output geometry");
+    if (d->epi_mode == 2) {
+        RGBD_CHECK_ARG(d->pool && d->cells_x >= 1 && d->cells_y >= 1, "conv_gemm: pool epilogue needs pool buffer and cells");
+        RGBD_CHECK_ARG(d->out_w % d->cells_x == 0 && d->out_h % d->cells_y == 0,
+                       "conv_gemm: fused average pooling needs H,W divisible by the %dx%d cell grid (got %dx%d)",
+                       d->cells_y, d->cells_x, d->out_h, d->out_w);
+    } else {
+        RGBD_CHECK_ARG(d->out, "conv_gemm: null output");
+    }
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) {
+        rgbd_set_error("conv_gemm: cuTensorMapEncodeTiled is not available from the driver");
+        return RGBD_ERR_CUDA;
+    }
+    const int kb_bytes = d->kb_elems * 2;
+    const CUtensorMapSwizzle swz = kb_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+
+    CUtensorMap tmap_a, tmap_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)d->a_c, (cuuint64_t)d->a_x, (cuuint64_t)d->a_y, (cuuint64_t)d->a_planes};
+        cuuint64_t strides[3] = {(cuuint64_t)d->a_c * 2, (cuuint64_t)d->a_c * 2 * d->a_x,
+                                 (cuuint64_t)d->a_c * 2 * d->a_x * d->a_y};
+        cuuint32_t box[4] = {(cuuint32_t)d->kb_elems, (cuuint32_t)d->bx, (cuuint32_t)d->by, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->a), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            rgbd_set_error("conv_gemm: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+            return RGBD_ERR_CUDA;
+        }
+    }
+    const long long k_total = (long long)d->n_slices * d->kb_elems;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->n_pad};
+        cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+        cuuint32_t box[2] = {(cuuint32_t)d->kb_elems, (cuuint32_t)d->block_n};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            rgbd_set_error("conv_gemm: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+            return RGBD_ERR_CUDA;
+        }
+    }
+
+    KParams p;
+    p.n_img = d->n_img;
+    p.BX = d->bx; p.BY = d->by;
+    p.out_w = d->out_w; p.out_h = d->out_h;
+    p.tiles_x = ceil_div(d->out_w, d->bx);
+    p.tiles_y = ceil_div(d->out_h, d->by);
+    p.n_slices = d->n_slices;
+    p.kb_bytes = kb_bytes;
+    p.N = d->n; p.N_pad = d->n_pad; p.BLOCK_N = d->block_n; p.n_tiles_n = d->n_pad / d->block_n;
+    p.plane_per_img = d->plane_per_img;
+    p.tile_order = d->tile_order;
+    p.slices = reinterpret_cast<const int4*>(d->slices);
+    p.epi_mode = d->epi_mode; p.act = d->act;
+    p.scale = d->scale; p.shift = d->shift; p.variant = d->variant;
+    p.gate = reinterpret_cast<const __nv_bfloat16*>(d->gate);
+    p.out = d->out; p.residual = d->residual; p.pool = d->pool;
+    p.cells_y = d->cells_y; p.cells_x = d->cells_x;
+    const long long total = (long long)p.n_img * p.tiles_x * p.tiles_y * p.n_tiles_n;
+    RGBD_CHECK_ARG(total < (1ll << 31), "conv_gemm: too many tiles");
+    p.total_tiles = (int)total;
+
+    static int num_sms = 0;
+    static int max_smem = 0;
+    if (!num_sms) {
+        int dev = 0;
+        RGBD_CHECK_CUDA(cudaGetDevice(&dev));
+        RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    }
+    const int stage_bytes = kBlockM * kb_bytes + p.BLOCK_N * kb_bytes;
+    const int fixed = 1024 + (int)sizeof(SmemCtl) + p.n_slices * 16 + 64;
+    int stages = (max_smem - fixed) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    RGBD_CHECK_ARG(stages >= 2, "conv_gemm: not enough shared memory for 2 stages");
+    p.stages = stages;
+    // always take (almost) the whole SM so exactly one CTA (and its 512 TMEM columns) is resident
+    int smem_bytes = fixed + stages * stage_bytes;
+    if (smem_bytes < 160 * 1024) smem_bytes = 160 * 1024;
+    const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+    conv_gemm_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmap_a, tmap_b, p);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}

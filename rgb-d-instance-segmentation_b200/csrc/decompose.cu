@@ -1,0 +1,364 @@
+// K2: E-DSAM depth decomposition on device, bit-exact with the reference's host numpy/scipy path
+// (mask2former/utils/custom_model.py):
+//   to_grayscale                         CM:466-480   ((0.299f*r + 0.587f*g) + 0.114f*b, no FMA)
+//   _calculate_depth_histogram           CM:701-718   np.histogram(bins=512, range=(nanmin,nanmax))
+//   _select_depth_distribution_modes     CM:720-752   scipy find_peaks(prominence=0.01*max) + top-3
+//   _define_depth_interval_windows       CM:754-772   float32 window arithmetic (NumPy-2 promotion)
+//   _generate_depth_region_masks         CM:774-798   inclusive interval masks + complement of union
+//   adaptive_max_pool2d of each mask     CM:687       to every feature resolution that needs it
+// The reference does this per image per DSAM stage on the host (3 D2H copies, 12 H2D copies and
+// 6 stream syncs per image per forward); here one batch-wide, sync-free sequence of small kernels
+// produces, for every image, a 4-bit region code per pixel (bit t = region mask t in the
+// reference's list order) at full resolution and max-pooled to each requested resolution.
+// Compiled with -fmad=false: every float op is a single IEEE-rounded operation.
+#include "common.cuh"
+#include "rgbd_b200.h"
+
+namespace {
+
+constexpr int kBins = RGBD_HIST_BINS;   // 512
+
+struct ImgState {
+    uint32_t min_enc, max_enc;      // order-preserving encodings of nanmin / nanmax
+    uint32_t n_finite, has_inf;
+    float first, last, step, denom; // histogram range after the first==last widening
+    int step_zero;                  // numpy's denormal special case (gh-5437)
+    int n_modes;                    // surviving modes (0..3)
+    int status;                     // RGBD_DECOMP_* flags
+    int pad;
+    float lo[3], hi[3];             // interval windows in mode order
+    float centre[3];
+    int peak_bin[3];
+};
+
+__global__ void decomp_init_kernel(ImgState* st, unsigned long long* hist, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) {
+        ImgState z = {};
+        z.min_enc = 0xffffffffu;
+        z.max_enc = 0u;
+        st[i] = z;
+    }
+    if (i < B * kBins) hist[i] = 0ull;
+}
+
+// gray + per-image nanmin/nanmax
+__global__ void __launch_bounds__(256) decomp_gray_kernel(const float* __restrict__ depth3, long long bs, long long cs,
+                                                          float* __restrict__ gray, ImgState* __restrict__ st, int HW) {
+    const int b = blockIdx.y;
+    const float* r = depth3 + (long long)b * bs;
+    const float* g = r + cs;
+    const float* bl = g + cs;
+    float* out = gray + (long long)b * HW;
+    uint32_t lmin = 0xffffffffu, lmax = 0u, nfin = 0u, ninf = 0u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        float v = (0.299f * r[i] + 0.587f * g[i]) + 0.114f * bl[i];
+        out[i] = v;
+        if (!isnan(v)) {
+            uint32_t e = f32_to_ordered(v);
+            lmin = min(lmin, e);
+            lmax = max(lmax, e);
+            nfin++;
+            if (isinf(v)) ninf = 1u;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        nfin += __shfl_xor_sync(0xffffffffu, nfin, o);
+        ninf |= __shfl_xor_sync(0xffffffffu, ninf, o);
+    }
+    if ((threadIdx.x & 31) == 0 && nfin) {
+        atomicMin(&st[b].min_enc, lmin);
+        atomicMax(&st[b].max_enc, lmax);
+        atomicAdd(&st[b].n_finite, nfin);
+        if (ninf) atomicOr(&st[b].has_inf, 1u);
+    }
+}
+
+// gray supplied by the caller (DSAModule.forward API): only the min/max reduction
+__global__ void __launch_bounds__(256) decomp_minmax_kernel(const float* __restrict__ gray, ImgState* __restrict__ st, int HW) {
+    const int b = blockIdx.y;
+    const float* in = gray + (long long)b * HW;
+    uint32_t lmin = 0xffffffffu, lmax = 0u, nfin = 0u, ninf = 0u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        float v = in[i];
+        if (!isnan(v)) {
+            uint32_t e = f32_to_ordered(v);
+            lmin = min(lmin, e);
+            lmax = max(lmax, e);
+            nfin++;
+            if (isinf(v)) ninf = 1u;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        nfin += __shfl_xor_sync(0xffffffffu, nfin, o);
+        ninf |= __shfl_xor_sync(0xffffffffu, ninf, o);
+    }
+    if ((threadIdx.x & 31) == 0 && nfin) {
+        atomicMin(&st[b].min_enc, lmin);
+        atomicMax(&st[b].max_enc, lmax);
+        atomicAdd(&st[b].n_finite, nfin);
+        if (ninf) atomicOr(&st[b].has_inf, 1u);
+    }
+}
+
+__global__ void decomp_range_kernel(ImgState* st, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    ImgState& s = st[b];
+    if (s.n_finite == 0 || s.has_inf) {   // numpy raises "range ... is not finite"
+        s.status |= RGBD_DECOMP_RANGE_NOT_FINITE;
+        s.first = 0.f; s.last = 1.f;
+    } else {
+        s.first = ordered_to_f32(s.min_enc);
+        s.last = ordered_to_f32(s.max_enc);
+        if (s.first == s.last) {            // _get_outer_edges: expand empty range
+            s.first = s.first - 0.5f;
+            s.last = s.last + 0.5f;
+        }
+    }
+    s.denom = s.last - s.first;
+    s.step = s.denom / (float)kBins;       // linspace: step = delta / div
+    s.step_zero = (s.step == 0.0f);
+}
+
+// np.linspace(first, last, 513, dtype=float32)[i]
+__device__ __forceinline__ float bin_edge(const ImgState& s, int i) {
+    if (i == kBins) return s.last;
+    float y = s.step_zero ? ((float)i / (float)kBins) * s.denom : (float)i * s.step;
+    return y + s.first;
+}
+
+__global__ void __launch_bounds__(256) decomp_hist_kernel(const float* __restrict__ gray, const ImgState* __restrict__ st,
+                                                          unsigned long long* __restrict__ hist, int HW) {
+    __shared__ unsigned int h[kBins];
+    __shared__ float edges[kBins + 1];
+    const int b = blockIdx.y;
+    const ImgState s = st[b];
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x) h[i] = 0u;
+    for (int i = threadIdx.x; i <= kBins; i += blockDim.x) edges[i] = bin_edge(s, i);
+    __syncthreads();
+    if (s.status & RGBD_DECOMP_RANGE_NOT_FINITE) return;
+    const float* in = gray + (long long)b * HW;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        float x = in[i];
+        if (x >= s.first && x <= s.last) {          // drops NaN
+            float f = ((x - s.first) / s.denom) * (float)kBins;
+            int idx = (int)f;                        // astype(intp): truncation
+            if (idx == kBins) idx -= 1;
+            if (x < edges[idx]) idx -= 1;
+            if (x >= edges[idx + 1] && idx != kBins - 1) idx += 1;
+            atomicAdd(&h[idx], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x)
+        if (h[i]) atomicAdd(&hist[(long long)b * kBins + i], (unsigned long long)h[i]);
+}
+
+// One CTA (512 threads, one per bin) per image: scipy _local_maxima_1d + _peak_prominences(wlen=None),
+// keep prominence >= 0.01*max (float64), order by (height, centre) descending, first 3; then windows.
+__global__ void __launch_bounds__(kBins) decomp_modes_kernel(const unsigned long long* __restrict__ hist,
+                                                             ImgState* __restrict__ st, const float* __restrict__ ratio,
+                                                             int num_modes) {
+    __shared__ long long h[kBins];
+    __shared__ long long cand_h[kBins / 2];
+    __shared__ int cand_bin[kBins / 2];
+    __shared__ int n_cand;
+    __shared__ long long hmax_s[kBins / 32];
+    const int b = blockIdx.x;
+    const int i = threadIdx.x;
+    ImgState& s = st[b];
+    h[i] = (long long)hist[(long long)b * kBins + i];
+    if (i == 0) n_cand = 0;
+    __syncthreads();
+    // block max
+    long long m = h[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        long long other = __shfl_xor_sync(0xffffffffu, m, o);
+        m = other > m ? other : m;
+    }
+    if ((i & 31) == 0) hmax_s[i >> 5] = m;
+    __syncthreads();
+    long long hmax = 0;
+    for (int k = 0; k < kBins / 32; ++k) hmax = hmax_s[k] > hmax ? hmax_s[k] : hmax;
+    const double pmin = 0.01 * (double)hmax;
+
+    // every rising edge starts at most one plateau -> independent per thread
+    const int n = kBins, i_max = n - 1;
+    if (i >= 1 && i < i_max && h[i - 1] < h[i]) {
+        int ahead = i + 1;
+        while (ahead < i_max && h[ahead] == h[i]) ++ahead;
+        if (h[ahead] < h[i]) {
+            int peak = (i + ahead - 1) / 2;
+            long long hp = h[peak];
+            int k = peak;
+            long long lmin = hp;
+            while (k >= 0 && h[k] <= hp) { if (h[k] < lmin) lmin = h[k]; --k; }
+            k = peak;
+            long long rmin = hp;
+            while (k <= i_max && h[k] <= hp) { if (h[k] < rmin) rmin = h[k]; ++k; }
+            long long prom = hp - (lmin > rmin ? lmin : rmin);
+            if (pmin <= (double)prom) {
+                int slot = atomicAdd(&n_cand, 1);
+                cand_h[slot] = hp;
+                cand_bin[slot] = peak;
+            }
+        }
+    }
+    __syncthreads();
+    if (i == 0) {
+        const int nc = n_cand;
+        int nm = 0;
+        if (!(s.status & RGBD_DECOMP_RANGE_NOT_FINITE)) {
+            // selection by (height desc, centre desc); centres are non-decreasing in the bin index,
+            // so (height, bin) descending gives the same centres in the same order
+            for (int pick = 0; pick < num_modes && pick < nc; ++pick) {
+                int best = -1;
+                for (int c = 0; c < nc; ++c) {
+                    if (cand_bin[c] < 0) continue;
+                    if (best < 0 || cand_h[c] > cand_h[best] ||
+                        (cand_h[c] == cand_h[best] && cand_bin[c] > cand_bin[best]))
+                        best = c;
+                }
+                int pb = cand_bin[best];
+                cand_bin[best] = -1;
+                float e0 = bin_edge(s, pb), e1 = bin_edge(s, pb + 1);
+                float centre = e0 + (e1 - e0) / 2.0f;
+                float hw = (centre * ratio[b]) / 2.0f;
+                float lo = centre - hw;
+                lo = lo > 0.0f ? lo : 0.0f;          // python max(0, x)
+                s.peak_bin[nm] = pb;
+                s.centre[nm] = centre;
+                s.lo[nm] = lo;
+                s.hi[nm] = centre + hw;
+                ++nm;
+            }
+        }
+        s.n_modes = nm;
+        for (int k = nm; k < 3; ++k) { s.peak_bin[k] = -1; s.centre[k] = 0.f; s.lo[k] = 0.f; s.hi[k] = 0.f; }
+    }
+}
+
+// 4-bit region code per pixel: bit t (t<m) = lo_t <= g <= hi_t ; bit m = none of them; m==0 -> 0
+__global__ void __launch_bounds__(256) decomp_codes_kernel(const float* __restrict__ gray, const ImgState* __restrict__ st,
+                                                           uint8_t* __restrict__ codes, int HW) {
+    const int b = blockIdx.y;
+    const ImgState s = st[b];
+    const float* in = gray + (long long)b * HW;
+    uint8_t* out = codes + (long long)b * HW;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        float g = in[i];
+        unsigned c = 0;
+        for (int t = 0; t < s.n_modes; ++t)
+            if (g >= s.lo[t] && g <= s.hi[t]) c |= 1u << t;
+        if (s.n_modes > 0 && c == 0) c = 1u << s.n_modes;
+        out[i] = (uint8_t)c;
+    }
+}
+
+// adaptive_max_pool2d of each region mask == bitwise OR of the codes over the window
+// [floor(i*H/h), ceil((i+1)*H/h)) x [floor(j*W/w), ceil((j+1)*W/w))
+__global__ void __launch_bounds__(256) decomp_pool_kernel(const uint8_t* __restrict__ codes, uint8_t* __restrict__ pooled,
+                                                          int H, int W, int h, int w) {
+    const int b = blockIdx.y;
+    const uint8_t* in = codes + (long long)b * H * W;
+    uint8_t* out = pooled + (long long)b * h * w;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < h * w; o += gridDim.x * blockDim.x) {
+        int i = o / w, j = o - i * w;
+        int y0 = (int)(((long long)i * H) / h), y1 = (int)((((long long)i + 1) * H + h - 1) / h);
+        int x0 = (int)(((long long)j * W) / w), x1 = (int)((((long long)j + 1) * W + w - 1) / w);
+        unsigned c = 0;
+        for (int y = y0; y < y1; ++y)
+            for (int x = x0; x < x1; ++x) c |= in[(long long)y * W + x];
+        out[o] = (uint8_t)c;
+    }
+}
+
+__global__ void decomp_export_kernel(const ImgState* __restrict__ st, int B, int* n_modes, int* peak_bins, float* centres,
+                                     float* windows, float* edges_first_last, int* status) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const ImgState& s = st[b];
+    if (n_modes) n_modes[b] = s.n_modes;
+    if (status) status[b] = s.status;
+    for (int k = 0; k < 3; ++k) {
+        if (peak_bins) peak_bins[b * 3 + k] = s.peak_bin[k];
+        if (centres) centres[b * 3 + k] = s.centre[k];
+        if (windows) { windows[(b * 3 + k) * 2] = s.lo[k]; windows[(b * 3 + k) * 2 + 1] = s.hi[k]; }
+    }
+    if (edges_first_last) { edges_first_last[b * 2] = s.first; edges_first_last[b * 2 + 1] = s.last; }
+}
+
+__global__ void decomp_edges_kernel(const ImgState* __restrict__ st, float* __restrict__ edges) {
+    const int b = blockIdx.x;
+    const ImgState s = st[b];
+    for (int i = threadIdx.x; i <= kBins; i += blockDim.x) edges[(long long)b * (kBins + 1) + i] = bin_edge(s, i);
+}
+
+}  // namespace
+
+extern "C" size_t rgbd_depth_decompose_workspace_bytes(int B) {
+    if (B < 0) B = 0;
+    return (size_t)B * (sizeof(ImgState) + sizeof(unsigned long long) * kBins) + 256;
+}
+
+extern "C" int rgbd_depth_decompose(const float* depth3, long long depth_batch_stride, long long depth_channel_stride,
+                                    const float* gray_in, const float* ratio, int B, int H, int W, int num_modes,
+                                    float* gray_out, long long* hist_out, float* edges_out, int* n_modes_out,
+                                    int* peak_bins_out, float* centres_out, float* windows_out, int* status_out,
+                                    uint8_t* codes_out, int n_levels, const int* level_h, const int* level_w,
+                                    uint8_t* const* pooled_out, void* workspace, rgbd_stream_t stream) {
+    RGBD_CHECK_ARG((depth3 != nullptr) != (gray_in != nullptr), "depth_decompose: pass exactly one of depth3 / gray_in");
+    RGBD_CHECK_ARG(ratio && workspace && codes_out, "depth_decompose: null ratio / workspace / codes_out");
+    RGBD_CHECK_ARG(depth3 == nullptr || gray_out != nullptr, "depth_decompose: gray_out is required with depth3");
+    RGBD_CHECK_ARG(B >= 1 && H >= 1 && W >= 1, "depth_decompose: bad geometry");
+    RGBD_CHECK_ARG(num_modes >= 1 && num_modes <= 3, "depth_decompose: num_modes must be in [1,3]");
+    RGBD_CHECK_ARG(n_levels >= 0 && n_levels <= 8, "depth_decompose: n_levels out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int HW = H * W;
+    uintptr_t wp = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+    unsigned long long* hist = (unsigned long long*)wp;
+    ImgState* st = (ImgState*)(hist + (size_t)B * kBins);
+    decomp_init_kernel<<<ceil_div(B * kBins, 256), 256, 0, s>>>(st, hist, B);
+    RGBD_CHECK_LAUNCH();
+    dim3 grid(min(ceil_div(HW, 256 * 4), 296), B);
+    const float* gray = gray_in;
+    if (depth3) {
+        decomp_gray_kernel<<<grid, 256, 0, s>>>(depth3, depth_batch_stride, depth_channel_stride, gray_out, st, HW);
+        gray = gray_out;
+    } else {
+        decomp_minmax_kernel<<<grid, 256, 0, s>>>(gray_in, st, HW);
+    }
+    RGBD_CHECK_LAUNCH();
+    decomp_range_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B);
+    RGBD_CHECK_LAUNCH();
+    decomp_hist_kernel<<<grid, 256, 0, s>>>(gray, st, hist, HW);
+    RGBD_CHECK_LAUNCH();
+    decomp_modes_kernel<<<B, kBins, 0, s>>>(hist, st, ratio, num_modes);
+    RGBD_CHECK_LAUNCH();
+    decomp_codes_kernel<<<grid, 256, 0, s>>>(gray, st, codes_out, HW);
+    RGBD_CHECK_LAUNCH();
+    for (int l = 0; l < n_levels; ++l) {
+        RGBD_CHECK_ARG(level_h[l] >= 1 && level_w[l] >= 1 && pooled_out[l], "depth_decompose: bad level %d", l);
+        dim3 g(min(ceil_div(level_h[l] * level_w[l], 256), 296), B);
+        decomp_pool_kernel<<<g, 256, 0, s>>>(codes_out, pooled_out[l], H, W, level_h[l], level_w[l]);
+        RGBD_CHECK_LAUNCH();
+    }
+    decomp_export_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B, n_modes_out, peak_bins_out, centres_out, windows_out,
+                                                         nullptr, status_out);
+    RGBD_CHECK_LAUNCH();
+    if (hist_out)
+        RGBD_CHECK_CUDA(cudaMemcpyAsync(hist_out, hist, sizeof(long long) * (size_t)B * kBins, cudaMemcpyDeviceToDevice, s));
+    if (edges_out) {
+        decomp_edges_kernel<<<B, 256, 0, s>>>(st, edges_out);
+        RGBD_CHECK_LAUNCH();
+    }
+    return RGBD_OK;
+}

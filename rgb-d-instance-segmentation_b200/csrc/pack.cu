@@ -1,0 +1,115 @@
+// Operand packing for the tensor-core kernels (conv_gemm.cu).
+//
+// dsam_pack: NCHW fp32 features + pooled 4-bit region codes -> the K-concatenated, masked, bf16
+//   channels-last operand of a DSAM stage (reference mask2former/utils/custom_model.py:683-696:
+//   `masked_features = rgb_features * resized_mask` for each region, plus the unmasked copy for
+//   rgb_projection).  For the stride-2 variant the pixels are split into 4 parity planes so every
+//   3x3 stride-2 tap becomes a dense, stride-1 TMA box:
+//       out[img][seg][py*2+px][y>>1][x>>1][c] = bf16(F[img][c][y][x] * bit(code, seg))   seg < n_seg-1
+//       out[img][n_seg-1][...]                = bf16(F)                                   (projection copy)
+// ratio_stem_pack: depth (B,3,H,W) -> row-im2col tensor R[img][H+6][W][64] with
+//       R[img][r][x][(j*8+dx)*4+c] = depth[img][c][r-3+j][x+dx-3]   (0 outside, 0 for dx==7 or c==3)
+//   so the 3x3/5x5/7x7 stem convs (CM:1458-1460) are one GEMM of 4 K-slices of 64 (taps dy = 2t+j).
+#include "common.cuh"
+#include "rgbd_b200.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256) dsam_pack_kernel(const float* __restrict__ feat, const uint8_t* __restrict__ codes,
+                                                        __nv_bfloat16* __restrict__ out, int C, int Cp, int H, int W,
+                                                        int n_seg, int masked_segs, int split) {
+    __shared__ float tile[64][33];
+    const int img = blockIdx.z;
+    const int y = blockIdx.y;
+    const int x0 = (blockIdx.x % ((W + 31) / 32)) * 32;
+    const int c0 = (blockIdx.x / ((W + 31) / 32)) * 64;
+    const int tx = threadIdx.x & 31, tyy = threadIdx.x >> 5;   // 32 x 8
+    const size_t plane = (size_t)H * W;
+    for (int c = tyy; c < 64; c += 8) {
+        const int cc = c0 + c, x = x0 + tx;
+        tile[c][tx] = (cc < C && x < W) ? feat[((size_t)img * C + cc) * plane + (size_t)y * W + x] : 0.f;
+    }
+    __syncthreads();
+    const int H2 = split ? (H + 1) / 2 : H, W2 = split ? (W + 1) / 2 : W;
+    const int n_par = split ? 4 : 1;
+    for (int px = tyy; px < 32; px += 8) {
+        const int x = x0 + px;
+        if (x >= W) continue;
+        const unsigned code = codes[(size_t)img * plane + (size_t)y * W + x];
+        const int par = split ? ((y & 1) * 2 + (x & 1)) : 0;
+        const int yy = split ? (y >> 1) : y, xx = split ? (x >> 1) : x;
+        const int c = c0 + tx * 2;
+        if (c >= Cp) continue;
+        const float v0 = tile[tx * 2][px], v1 = tile[tx * 2 + 1][px];
+        for (int s = 0; s < n_seg; ++s) {
+            const bool keep = s >= masked_segs || ((code >> s) & 1u);
+            __nv_bfloat162 h = keep ? __floats2bfloat162_rn(v0, v1) : __floats2bfloat162_rn(0.f, 0.f);
+            const size_t pl = ((size_t)img * n_seg + s) * n_par + par;
+            const size_t off = ((pl * H2 + yy) * W2 + xx) * Cp + c;
+            *reinterpret_cast<__nv_bfloat162*>(out + off) = h;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) ratio_stem_pack_kernel(const float* __restrict__ depth, long long bs, long long cs,
+                                                              __nv_bfloat16* __restrict__ out, int H, int W) {
+    const int img = blockIdx.z;
+    const int r = blockIdx.y;                                 // 0 .. H+5
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const float* d = depth + (size_t)img * bs;
+    uint4* o = reinterpret_cast<uint4*>(out + (((size_t)img * (H + 6) + r) * W + x) * 64);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int y = r - 3 + j;
+        const bool yok = y >= 0 && y < H;
+#pragma unroll
+        for (int dxp = 0; dxp < 4; ++dxp) {                   // two taps (8 bf16 = 16 bytes) per store
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int dx = dxp * 2 + e;
+                const int xs = x + dx - 3;
+                const bool ok = yok && dx < 7 && xs >= 0 && xs < W;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[e * 4 + c] = ok ? __ldg(d + c * cs + (size_t)y * W + xs) : 0.f;
+                v[e * 4 + 3] = 0.f;
+            }
+            uint4 w;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+            w.x = *reinterpret_cast<uint32_t*>(&h0);
+            w.y = *reinterpret_cast<uint32_t*>(&h1);
+            w.z = *reinterpret_cast<uint32_t*>(&h2);
+            w.w = *reinterpret_cast<uint32_t*>(&h3);
+            o[j * 4 + dxp] = w;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int rgbd_dsam_pack(const float* feat, const uint8_t* codes, void* out_bf16, int B, int C, int C_pad, int H, int W,
+                              int n_seg, int masked_segs, int parity_split, rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(feat && codes && out_bf16, "dsam_pack: null pointer");
+    RGBD_CHECK_ARG(B >= 1 && C >= 1 && H >= 1 && W >= 1, "dsam_pack: bad geometry");
+    RGBD_CHECK_ARG(C_pad >= C && C_pad % 32 == 0, "dsam_pack: C_pad %d must be a multiple of 32 and >= C", C_pad);
+    RGBD_CHECK_ARG(n_seg >= 1 && n_seg <= 8 && masked_segs >= 0 && masked_segs <= n_seg && masked_segs <= 4,
+                   "dsam_pack: bad segment counts");
+    dim3 grid(ceil_div(W, 32) * ceil_div(C_pad, 64), H, B);
+    dsam_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feat, codes, (__nv_bfloat16*)out_bf16, C, C_pad, H, W, n_seg,
+                                                            masked_segs, parity_split ? 1 : 0);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_ratio_stem_pack(const float* depth3, long long batch_stride, long long channel_stride, void* out_bf16,
+                                    int B, int H, int W, rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(depth3 && out_bf16, "ratio_stem_pack: null pointer");
+    RGBD_CHECK_ARG(B >= 1 && H >= 1 && W >= 1, "ratio_stem_pack: bad geometry");
+    dim3 grid(ceil_div(W, 128), H + 6, B);
+    ratio_stem_pack_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(depth3, batch_stride, channel_stride,
+                                                                   (__nv_bfloat16*)out_bf16, H, W);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}

@@ -1,0 +1,109 @@
+// K4 tail: the small end of EnhancedDepthImageRatioPredictor.forward (reference
+// mask2former/utils/custom_model.py:1473-1485) after the fused 3x3 conv + BN + ReLU + AdaptiveAvgPool2d(4):
+//   pooled sums / cell size -> Conv3x3(256->512, pad 1) on the 4x4 map -> BN (folded) -> ReLU -> global
+//   average pool -> Linear 512->128->64->32->1 with ReLU (Dropout is identity in eval) ->
+//   ratio = 0.01 + 0.49 * sigmoid(raw).
+// 19 MFLOP per image: fp32 CUDA cores, two launches (conv split over 8 channel groups per image so
+// B*8 CTAs run; then one CTA per image for the MLP).
+#include "common.cuh"
+#include "rgbd_b200.h"
+
+namespace {
+
+constexpr int kCin = 256, kCout = 512, kGroup = 64;
+
+__global__ void __launch_bounds__(256) ratio_tail_conv_kernel(const float* __restrict__ pool, int pool_stride,
+                                                              float inv_cell, const float* __restrict__ w,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, float* __restrict__ gap) {
+    __shared__ float x[kCin][6][6];
+    const int b = blockIdx.x, g = blockIdx.y;
+    for (int i = threadIdx.x; i < kCin * 36; i += blockDim.x) {
+        const int ic = i / 36, r = (i % 36) / 6, c = i % 6;
+        float v = 0.f;
+        if (r >= 1 && r <= 4 && c >= 1 && c <= 4)
+            v = pool[((size_t)b * 16 + (r - 1) * 4 + (c - 1)) * pool_stride + ic] * inv_cell;
+        x[ic][r][c] = v;
+    }
+    __syncthreads();
+    const int oc = g * kGroup + (threadIdx.x >> 2);
+    const int oy = threadIdx.x & 3;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* wr = w + (size_t)oc * kCin * 9;
+    for (int ic = 0; ic < kCin; ++ic) {
+        float wk[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wk[k] = __ldg(wr + ic * 9 + k);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            float row[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) row[c] = x[ic][oy + ky][c];
+#pragma unroll
+            for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) acc[ox] = fmaf(wk[ky * 3 + kx], row[ox + kx], acc[ox]);
+        }
+    }
+    const float sc = scale[oc], sh = shift[oc];
+    float s = 0.f;
+#pragma unroll
+    for (int ox = 0; ox < 4; ++ox) s += fmaxf(fmaf(acc[ox], sc, sh), 0.f);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (oy == 0) gap[(size_t)b * kCout + oc] = s * (1.0f / 16.0f);
+}
+
+__device__ __forceinline__ void fc_layer(const float* __restrict__ w, const float* __restrict__ bias, const float* in,
+                                         float* out, int n_in, int n_out, bool relu) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int o = warp; o < n_out; o += nw) {
+        float s = 0.f;
+        for (int i = lane; i < n_in; i += 32) s = fmaf(__ldg(w + (size_t)o * n_in + i), in[i], s);
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+        if (lane == 0) {
+            s += bias[o];
+            out[o] = relu ? fmaxf(s, 0.f) : s;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) ratio_tail_mlp_kernel(const float* __restrict__ gap, const float* w0, const float* b0,
+                                                             const float* w1, const float* b1, const float* w2,
+                                                             const float* b2, const float* w3, const float* b3,
+                                                             float out_min, float out_span, float* __restrict__ ratio) {
+    __shared__ float a[kCout], h0[128], h1[64], h2[32], raw[1];
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < kCout; i += blockDim.x) a[i] = gap[(size_t)b * kCout + i];
+    __syncthreads();
+    fc_layer(w0, b0, a, h0, 512, 128, true);
+    fc_layer(w1, b1, h0, h1, 128, 64, true);
+    fc_layer(w2, b2, h1, h2, 64, 32, true);
+    fc_layer(w3, b3, h2, raw, 32, 1, false);
+    if (threadIdx.x == 0) {
+        const float sg = 1.0f / (1.0f + expf(-raw[0]));
+        ratio[b] = __fadd_rn(out_min, __fmul_rn(out_span, sg));
+    }
+}
+
+}  // namespace
+
+extern "C" int rgbd_ratio_tail(const float* pool_sums, int pool_stride, int cell_pixels, const float* conv_w,
+                               const float* conv_scale, const float* conv_shift, const float* const* fc_w,
+                               const float* const* fc_b, float out_min, float out_max, float* gap_ws, float* ratio_out,
+                               int B, rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(pool_sums && conv_w && conv_scale && conv_shift && fc_w && fc_b && gap_ws && ratio_out,
+                   "ratio_tail: null pointer");
+    RGBD_CHECK_ARG(B >= 1 && cell_pixels >= 1 && pool_stride >= kCin, "ratio_tail: bad geometry");
+    for (int i = 0; i < 4; ++i) RGBD_CHECK_ARG(fc_w[i] && fc_b[i], "ratio_tail: null fc layer %d", i);
+    cudaStream_t s = (cudaStream_t)stream;
+    ratio_tail_conv_kernel<<<dim3(B, kCout / kGroup), 256, 0, s>>>(pool_sums, pool_stride, 1.0f / (float)cell_pixels, conv_w,
+                                                                   conv_scale, conv_shift, gap_ws);
+    RGBD_CHECK_LAUNCH();
+    ratio_tail_mlp_kernel<<<B, 128, 0, s>>>(gap_ws, fc_w[0], fc_b[0], fc_w[1], fc_b[1], fc_w[2], fc_b[2], fc_w[3], fc_b[3],
+                                            out_min, out_max - out_min, ratio_out);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}

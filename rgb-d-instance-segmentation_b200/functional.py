@@ -1,0 +1,294 @@
+"""Torch-facing wrappers over the C ABI (include/rgbd_b200.h).  PyTorch is plumbing here: device
+memory, the current CUDA stream and shape checks.  Every function requires CUDA tensors and raises
+otherwise -- there is no CPU or eager fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvGemmDesc, RgbdB200Error, check, int_array, ptr_array
+
+HIST_BINS = 512
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, name: str, dtype=None, contiguous: bool = True) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RgbdB200Error(f"{name} must be a CUDA tensor (rgbd_b200 has no CPU fallback); got device {t.device}")
+    if dtype is not None and t.dtype != dtype:
+        raise RgbdB200Error(f"{name} must be {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise RgbdB200Error(f"{name} must be contiguous")
+    return t
+
+
+def _plane_strided(t: torch.Tensor, name: str) -> Tuple[int, int]:
+    """(batch stride, channel stride) of a (B,C,H,W) view whose (H,W) planes are dense (e.g. pixel_values[:,6:9])."""
+    B, Cc, H, W = t.shape
+    if t.stride(3) != 1 or t.stride(2) != W or (Cc > 1 and t.stride(1) != H * W):
+        raise RgbdB200Error(f"{name}: channel planes must be dense (strides {t.stride()})")
+    return t.stride(0), H * W
+
+
+# ------------------------------------------------------------------------------------------------
+# DGGM
+# ------------------------------------------------------------------------------------------------
+def dggm_forward(feats: Sequence[torch.Tensor], grad: torch.Tensor, mask: torch.Tensor,
+                 weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+                 branch1: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+    """K1.  out_i = feats_i + ReLU(conv1x1_i(bilinear(grad) * nearest(mask))) [+ branch1_i]."""
+    lib = _lib.load()
+    n = len(feats)
+    _req(grad, "processed_depth_gradient_map", torch.float32, contiguous=False)
+    _req(mask, "gradient_mask", torch.float32, contiguous=False)
+    B, D, H, W = grad.shape
+    if mask.shape != (B, 1, H, W):
+        raise RgbdB200Error(f"gradient_mask must be {(B, 1, H, W)}, got {tuple(mask.shape)}")
+    gbs, _ = _plane_strided(grad, "processed_depth_gradient_map")
+    mbs, _ = _plane_strided(mask, "gradient_mask")
+    outs = []
+    ws, bs = [], []
+    for i, f in enumerate(feats):
+        _req(f, f"color_feature_maps[{i}]", torch.float32)
+        if f.shape[0] != B:
+            raise RgbdB200Error("batch size mismatch between features and gradient map")
+        w = _req(weights[i].reshape(weights[i].shape[0], -1), f"weight[{i}]", torch.float32)
+        b = _req(biases[i], f"bias[{i}]", torch.float32)
+        if w.shape != (f.shape[1], D) or b.shape != (f.shape[1],):
+            raise RgbdB200Error(f"scale {i}: weight {tuple(w.shape)} / bias {tuple(b.shape)} do not match C={f.shape[1]}, D={D}")
+        ws.append(w)
+        bs.append(b)
+        outs.append(torch.empty_like(f))
+        if branch1 is not None:
+            _req(branch1[i], f"branch1[{i}]", torch.float32)
+            if branch1[i].shape != f.shape:
+                raise RgbdB200Error("branch1 shape mismatch")
+    rc = lib.rgbd_dggm_fwd(
+        n, ptr_array([f.data_ptr() for f in feats]),
+        ptr_array([t.data_ptr() for t in branch1]) if branch1 is not None else None,
+        ptr_array([o.data_ptr() for o in outs]),
+        int_array([f.shape[1] for f in feats]), int_array([f.shape[2] for f in feats]),
+        int_array([f.shape[3] for f in feats]),
+        ptr_array([w.data_ptr() for w in ws]), ptr_array([b.data_ptr() for b in bs]),
+        grad.data_ptr(), gbs, mask.data_ptr(), mbs, B, D, H, W, _stream())
+    check(rc, "rgbd_dggm_fwd")
+    return outs
+
+
+def dggm_backward_params(douts: Sequence[torch.Tensor], grad: torch.Tensor, mask: torch.Tensor,
+                         weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]
+                         ) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+    """K1b.  (dW_i, db_i) of the 1x1 enhancement convs."""
+    lib = _lib.load()
+    B, D, H, W = grad.shape
+    gbs, _ = _plane_strided(_req(grad, "grad", torch.float32, False), "grad")
+    mbs, _ = _plane_strided(_req(mask, "mask", torch.float32, False), "mask")
+    douts = [_req(d.contiguous(), f"dout[{i}]", torch.float32) for i, d in enumerate(douts)]
+    ws = [_req(w.reshape(w.shape[0], -1), "weight", torch.float32) for w in weights]
+    bs = [_req(b, "bias", torch.float32) for b in biases]
+    dws = [torch.empty_like(w) for w in ws]
+    dbs = [torch.empty_like(b) for b in bs]
+    rc = lib.rgbd_dggm_bwd_params(
+        len(douts), ptr_array([d.data_ptr() for d in douts]), int_array([d.shape[1] for d in douts]),
+        int_array([d.shape[2] for d in douts]), int_array([d.shape[3] for d in douts]),
+        ptr_array([w.data_ptr() for w in ws]), ptr_array([b.data_ptr() for b in bs]),
+        ptr_array([w.data_ptr() for w in dws]), ptr_array([b.data_ptr() for b in dbs]),
+        grad.data_ptr(), gbs, mask.data_ptr(), mbs, B, D, H, W, _stream())
+    check(rc, "rgbd_dggm_bwd_params")
+    return [dw.reshape(weights[i].shape) for i, dw in enumerate(dws)], dbs
+
+
+def gradient_features(depth: torch.Tensor, n_rep: int = 3, invalid_value: float = 0.0,
+                      norm_out: Optional[torch.Tensor] = None, vmask_out: Optional[torch.Tensor] = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K0.  depth (B,H,W) float32 or uint8 -> (norm (B,n_rep,H,W), vmask (B,1,H,W)); the outputs may be views
+    into a (B,10,H,W) pixel_values tensor (channels 6:9 and 9:10)."""
+    lib = _lib.load()
+    _req(depth, "depth")
+    if depth.dtype == torch.float32:
+        dt = 0
+    elif depth.dtype == torch.uint8:
+        dt = 2
+    else:
+        raise RgbdB200Error(f"depth must be float32 or uint8, got {depth.dtype}")
+    if depth.dim() != 3:
+        raise RgbdB200Error("depth must be (B,H,W)")
+    B, H, W = depth.shape
+    if norm_out is None:
+        norm_out = torch.empty(B, n_rep, H, W, device=depth.device, dtype=torch.float32)
+    if vmask_out is None:
+        vmask_out = torch.empty(B, 1, H, W, device=depth.device, dtype=torch.float32)
+    _req(norm_out, "norm_out", torch.float32, False)
+    _req(vmask_out, "vmask_out", torch.float32, False)
+    if norm_out.shape != (B, n_rep, H, W) or vmask_out.shape != (B, 1, H, W):
+        raise RgbdB200Error("gradient_features: bad output shapes")
+    nbs, _ = _plane_strided(norm_out, "norm_out")
+    vbs, _ = _plane_strided(vmask_out, "vmask_out")
+    ws = torch.empty(max(int(lib.rgbd_gradient_features_workspace_bytes(B)), 16), device=depth.device, dtype=torch.uint8)
+    rc = lib.rgbd_gradient_features(depth.data_ptr(), dt, H * W, norm_out.data_ptr(), nbs, n_rep, vmask_out.data_ptr(),
+                                    vbs, B, H, W, float(invalid_value), ws.data_ptr(), _stream())
+    check(rc, "rgbd_gradient_features")
+    return norm_out, vmask_out
+
+
+# ------------------------------------------------------------------------------------------------
+# E-DSAM depth decomposition
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Decomposition:
+    gray: torch.Tensor                 # (B,H,W) f32
+    codes: torch.Tensor                # (B,H,W) u8, bit t = region mask t
+    pooled: List[torch.Tensor]         # per level (B,h,w) u8
+    n_modes: torch.Tensor              # (B) i32
+    centres: torch.Tensor              # (B,3) f32
+    windows: torch.Tensor              # (B,3,2) f32
+    peak_bins: torch.Tensor            # (B,3) i32
+    status: torch.Tensor               # (B) i32
+    hist: Optional[torch.Tensor] = None    # (B,512) i64
+    edges: Optional[torch.Tensor] = None   # (B,513) f32
+
+
+def depth_decompose(ratio: torch.Tensor, levels: Sequence[Tuple[int, int]], depth3: Optional[torch.Tensor] = None,
+                    gray: Optional[torch.Tensor] = None, num_modes: int = 3, debug: bool = False) -> Decomposition:
+    """K2.  Exactly one of depth3 (B,3,H,W) / gray (B,H,W).  ratio (B) float32."""
+    lib = _lib.load()
+    if (depth3 is None) == (gray is None):
+        raise RgbdB200Error("pass exactly one of depth3 / gray")
+    _req(ratio, "ratio", torch.float32)
+    if depth3 is not None:
+        _req(depth3, "depth", torch.float32, False)
+        B, c3, H, W = depth3.shape
+        if c3 != 3:
+            raise RgbdB200Error("depth must have 3 channels")
+        dbs, dcs = _plane_strided(depth3, "depth")
+        dev = depth3.device
+        gray_out = torch.empty(B, H, W, device=dev, dtype=torch.float32)
+        d3p, gip = depth3.data_ptr(), None
+    else:
+        _req(gray, "gray", torch.float32)
+        B, H, W = gray.shape
+        dev = gray.device
+        gray_out = gray
+        dbs = dcs = 0
+        d3p, gip = None, gray.data_ptr()
+    if ratio.numel() != B:
+        raise RgbdB200Error(f"ratio must have {B} elements")
+    i32 = dict(device=dev, dtype=torch.int32)
+    codes = torch.empty(B, H, W, device=dev, dtype=torch.uint8)
+    pooled = [torch.empty(B, h, w, device=dev, dtype=torch.uint8) for h, w in levels]
+    n_modes = torch.empty(B, **i32)
+    peak_bins = torch.empty(B, 3, **i32)
+    status = torch.empty(B, **i32)
+    centres = torch.empty(B, 3, device=dev, dtype=torch.float32)
+    windows = torch.empty(B, 3, 2, device=dev, dtype=torch.float32)
+    hist = torch.empty(B, HIST_BINS, device=dev, dtype=torch.int64) if debug else None
+    edges = torch.empty(B, HIST_BINS + 1, device=dev, dtype=torch.float32) if debug else None
+    ws = torch.empty(int(lib.rgbd_depth_decompose_workspace_bytes(B)), device=dev, dtype=torch.uint8)
+    rc = lib.rgbd_depth_decompose(
+        d3p, dbs, dcs, gip, ratio.data_ptr(), B, H, W, num_modes,
+        gray_out.data_ptr() if depth3 is not None else None,
+        hist.data_ptr() if debug else None, edges.data_ptr() if debug else None,
+        n_modes.data_ptr(), peak_bins.data_ptr(), centres.data_ptr(), windows.data_ptr(), status.data_ptr(),
+        codes.data_ptr(), len(levels), int_array([h for h, _ in levels]), int_array([w for _, w in levels]),
+        ptr_array([p.data_ptr() for p in pooled]), ws.data_ptr(), _stream())
+    check(rc, "rgbd_depth_decompose")
+    return Decomposition(gray_out, codes, pooled, n_modes, centres, windows, peak_bins, status, hist, edges)
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core building blocks
+# ------------------------------------------------------------------------------------------------
+def pick_block_n(n_pad: int) -> int:
+    if n_pad <= 256:
+        return n_pad
+    for bn in range(256, 31, -32):
+        if n_pad % bn == 0:
+            return bn
+    return 32
+
+
+def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img: int, w: torch.Tensor,
+              slices: torch.Tensor, kb: int, n_img: int, out_hw: Tuple[int, int], box: Tuple[int, int], n: int,
+              shift: torch.Tensor, *, scale: Optional[torch.Tensor] = None, variant: Optional[torch.Tensor] = None,
+              act: int = 0, epi_mode: int = 0, gate: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              residual: Optional[torch.Tensor] = None, pool: Optional[torch.Tensor] = None,
+              cells: Tuple[int, int] = (0, 0), tile_order: int = 0, block_n: Optional[int] = None) -> None:
+    """Launch the tcgen05 implicit-GEMM kernel.  a_dims = (planes, y, x, c) of the bf16 channels-last operand."""
+    lib = _lib.load()
+    _req(a, "a", torch.bfloat16)
+    _req(w, "w", torch.bfloat16)
+    _req(slices, "slices", torch.int32)
+    _req(shift, "shift", torch.float32)
+    n_pad = w.shape[0]
+    planes, ay, ax, ac = a_dims
+    if a.numel() != planes * ay * ax * ac:
+        raise RgbdB200Error("conv_gemm: operand size does not match a_dims")
+    n_slices = slices.shape[0]
+    if w.shape[1] != n_slices * kb:
+        raise RgbdB200Error(f"conv_gemm: weight K {w.shape[1]} != n_slices*kb {n_slices * kb}")
+    if shift.shape[-1] != n_pad or (scale is not None and scale.numel() != n_pad):
+        raise RgbdB200Error("conv_gemm: scale/shift must have n_pad entries")
+    d = ConvGemmDesc()
+    d.a = a.data_ptr(); d.a_c = ac; d.a_x = ax; d.a_y = ay; d.a_planes = planes
+    d.plane_per_img = plane_per_img
+    d.w = w.data_ptr(); d.slices = slices.data_ptr(); d.n_slices = n_slices; d.kb_elems = kb
+    d.n_img = n_img; d.out_h, d.out_w = out_hw; d.bx, d.by = box
+    d.n = n; d.n_pad = n_pad; d.block_n = block_n or pick_block_n(n_pad)
+    d.tile_order = tile_order; d.epi_mode = epi_mode; d.act = act
+    d.scale = _req(scale, "scale", torch.float32).data_ptr() if scale is not None else None
+    d.shift = shift.data_ptr()
+    d.variant = _req(variant, "variant", torch.int32).data_ptr() if variant is not None else None
+    d.gate = _req(gate, "gate", torch.bfloat16).data_ptr() if gate is not None else None
+    d.out = out.data_ptr() if out is not None else None
+    d.residual = _req(residual, "residual", torch.float32).data_ptr() if residual is not None else None
+    d.pool = _req(pool, "pool", torch.float32).data_ptr() if pool is not None else None
+    d.cells_y, d.cells_x = cells
+    check(lib.rgbd_conv_gemm(C.byref(d), _stream()), "rgbd_conv_gemm")
+
+
+def dsam_pack(feat: torch.Tensor, codes: torch.Tensor, out: torch.Tensor, c_pad: int, n_seg: int, masked_segs: int,
+              parity_split: bool) -> None:
+    lib = _lib.load()
+    _req(feat, "feat", torch.float32)
+    _req(codes, "codes", torch.uint8)
+    _req(out, "packed", torch.bfloat16)
+    B, Cc, H, W = feat.shape
+    if codes.shape != (B, H, W):
+        raise RgbdB200Error(f"codes must be {(B, H, W)}, got {tuple(codes.shape)}")
+    check(lib.rgbd_dsam_pack(feat.data_ptr(), codes.data_ptr(), out.data_ptr(), B, Cc, c_pad, H, W, n_seg, masked_segs,
+                             1 if parity_split else 0, _stream()), "rgbd_dsam_pack")
+
+
+def ratio_stem_pack(depth3: torch.Tensor, out: torch.Tensor) -> None:
+    lib = _lib.load()
+    _req(depth3, "depth", torch.float32, False)
+    _req(out, "stem operand", torch.bfloat16)
+    B, c3, H, W = depth3.shape
+    bs, cs = _plane_strided(depth3, "depth")
+    check(lib.rgbd_ratio_stem_pack(depth3.data_ptr(), bs, cs, out.data_ptr(), B, H, W, _stream()), "rgbd_ratio_stem_pack")
+
+
+def ratio_tail(pool: torch.Tensor, cell_pixels: int, conv_w: torch.Tensor, conv_scale: torch.Tensor,
+               conv_shift: torch.Tensor, fc_w: Sequence[torch.Tensor], fc_b: Sequence[torch.Tensor],
+               out_min: float, out_max: float) -> torch.Tensor:
+    lib = _lib.load()
+    _req(pool, "pool", torch.float32)
+    B = pool.shape[0]
+    gap = torch.empty(B, 512, device=pool.device, dtype=torch.float32)
+    ratio = torch.empty(B, 1, device=pool.device, dtype=torch.float32)
+    for t in (conv_w, conv_scale, conv_shift, *fc_w, *fc_b):
+        _req(t, "ratio tail parameter", torch.float32)
+    check(lib.rgbd_ratio_tail(pool.data_ptr(), pool.shape[-1], cell_pixels, conv_w.data_ptr(), conv_scale.data_ptr(),
+                              conv_shift.data_ptr(), ptr_array([t.data_ptr() for t in fc_w]),
+                              ptr_array([t.data_ptr() for t in fc_b]), out_min, out_max, gap.data_ptr(),
+                              ratio.data_ptr(), B, _stream()), "rgbd_ratio_tail")
+    return ratio

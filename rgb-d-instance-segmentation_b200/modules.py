@@ -1,0 +1,434 @@
+"""Drop-in ``nn.Module`` mirrors of the reference's depth-guidance modules
+(mask2former/utils/custom_model.py, "CM").  Constructor / forward signatures, attribute names and
+``state_dict`` keys are the reference's, so checkpoints move both ways; the arithmetic runs in the
+sm_100a kernels behind include/rgbd_b200.h.  No CPU path exists: CPU tensors raise.
+
+* ``DepthGradientInjectionResidual``      CM:1169-1269  (DGGM, kernel K1 / K1b)
+* ``DSAModule``                           CM:622-799    (E-DSAM core, kernels K2 + K3)
+* ``EnhancedDepthImageRatioPredictor``    CM:1363-1487  (E-DSAM window-ratio predictor, kernel K4)
+* ``DepthGuidance``                       CM:324-355    (the v0.4.0 wiring as one batched, sync-free call)
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import functional as Fn
+from ._lib import RgbdB200Error
+
+
+def _round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def _best_box(out_h: int, out_w: int) -> Tuple[int, int]:
+    """(bx, by) with bx*by == 128 covering an out_h x out_w image with the least padding."""
+    best, best_eff = (128, 1), -1.0
+    for bx in (128, 64, 32, 16, 8, 4, 2, 1):
+        by = 128 // bx
+        cover = (-(-out_w // bx) * bx) * (-(-out_h // by) * by)
+        eff = out_h * out_w / cover
+        if eff > best_eff + 1e-9:
+            best, best_eff = (bx, by), eff
+    return best
+
+
+class _Versioned:
+    """Re-pack derived tensors only when a source parameter changed (torch bumps ``_version`` on in-place
+    updates such as optimizer steps / load_state_dict)."""
+
+    def __init__(self):
+        self._key = None
+
+    def stale(self, tensors: Sequence[torch.Tensor]) -> bool:
+        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+        if key != self._key:
+            self._key = key
+            return True
+        return False
+
+
+# =====================================================================================================
+# DGGM
+# =====================================================================================================
+class _DggmFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, grad_map, mask, n, *args):
+        feats, weights, biases = args[:n], args[n:2 * n], args[2 * n:3 * n]
+        outs = Fn.dggm_forward([f.contiguous() for f in feats], grad_map, mask, weights, biases)
+        ctx.n = n
+        ctx.save_for_backward(grad_map, mask, *weights, *biases)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        grad_map, mask = saved[0], saved[1]
+        weights, biases = saved[2:2 + n], saved[2 + n:2 + 2 * n]
+        dws, dbs = Fn.dggm_backward_params(douts, grad_map, mask, weights, biases)
+        # d(out)/d(color) is the identity; the gradient map and mask are data
+        return (None, None, None, *douts, *dws, *dbs)
+
+
+class DepthGradientInjectionResidual(nn.Module):
+    """CM:1169-1269.  Injects the gated depth-gradient map into every colour feature scale:
+    ``fused_i = color_i + ReLU(Conv1x1_i(bilinear(grad) * nearest(mask)))``."""
+
+    def __init__(self, color_channels: List[int], depth_gradient_channels: int):
+        super().__init__()
+        self.color_channels = color_channels
+        self.depth_gradient_channels = depth_gradient_channels
+        self.num_scales = len(color_channels)
+        self.depth_enhancement_layers = nn.ModuleList()
+        for channels in color_channels:
+            self.depth_enhancement_layers.append(
+                nn.Sequential(nn.Conv2d(depth_gradient_channels, channels, kernel_size=1), nn.ReLU(inplace=True)))
+
+    def _params(self):
+        ws = [l[0].weight for l in self.depth_enhancement_layers]
+        bs = [l[0].bias for l in self.depth_enhancement_layers]
+        return ws, bs
+
+    def forward(self, color_feature_maps: List[torch.Tensor], processed_depth_gradient_map: Optional[torch.Tensor],
+                gradient_mask: Optional[torch.Tensor]) -> List[torch.Tensor]:
+        assert len(color_feature_maps) == self.num_scales, \
+            f"Expected {self.num_scales} color feature maps, but got {len(color_feature_maps)}"
+        if processed_depth_gradient_map is None or gradient_mask is None:
+            return list(color_feature_maps)                                   # CM:1263-1265
+        assert processed_depth_gradient_map.shape[1] == self.depth_gradient_channels
+        assert gradient_mask.shape[1] == 1
+        ws, bs = self._params()
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (*ws, *bs, *color_feature_maps))
+        if needs_grad:
+            return list(_DggmFunction.apply(processed_depth_gradient_map, gradient_mask, self.num_scales,
+                                            *color_feature_maps, *ws, *bs))
+        return Fn.dggm_forward([f.contiguous() for f in color_feature_maps], processed_depth_gradient_map,
+                               gradient_mask, [w.detach() for w in ws], [b.detach() for b in bs])
+
+    def forward_fused_sum(self, color_feature_maps, branch1, processed_depth_gradient_map, gradient_mask):
+        """``branch1_i + (color_i + enh_i)`` in one pass (the v0.4.0 branch sum, CM:354-355). Inference only."""
+        ws, bs = self._params()
+        return Fn.dggm_forward(color_feature_maps, processed_depth_gradient_map, gradient_mask,
+                               [w.detach() for w in ws], [b.detach() for b in bs], branch1=branch1)
+
+
+# =====================================================================================================
+# E-DSAM core
+# =====================================================================================================
+class DSAModule(nn.Module):
+    """CM:622-799.  Depth-sensitive attention: depth histogram modes -> depth-interval region masks ->
+    sum_t Conv_t(mask_t * F) + projection(F).  ``in != out``: 3x3 stride-2 convs + bias-free 3x3 stride-2
+    ``rgb_projection``; ``in == out``: 1x1 convs + identity residual."""
+
+    def __init__(self, in_channels, out_channels, num_depth_regions=3):
+        super().__init__()
+        if not 1 <= num_depth_regions <= 3:
+            raise ValueError("rgbd_b200 supports 1..3 depth regions (4-bit region codes)")
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.num_depth_regions = num_depth_regions
+        if in_channels != out_channels:
+            self.conv_layers = nn.ModuleList([
+                nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=2, padding=1)
+                for _ in range(num_depth_regions + 1)])
+            self.rgb_projection = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=2, padding=1, bias=False)
+        else:
+            self.conv_layers = nn.ModuleList([
+                nn.Conv2d(in_channels, out_channels, kernel_size=1) for _ in range(num_depth_regions + 1)])
+        self._ver = _Versioned()
+        self._packed: Dict[str, torch.Tensor] = {}
+        self._ws: Dict[tuple, torch.Tensor] = {}
+
+    # ---- operand packing -------------------------------------------------------------------------
+    @property
+    def _proj(self) -> bool:
+        return self.in_channels != self.out_channels
+
+    def _geometry(self):
+        c_pad = _round_up(self.in_channels, 32)
+        kb = 64 if c_pad % 64 == 0 else 32
+        n_pad = _round_up(self.out_channels, 32)
+        n_seg = self.num_depth_regions + 1 + (1 if self._proj else 0)
+        return c_pad, kb, n_pad, n_seg
+
+    def _refresh(self):
+        srcs = [p for p in self.parameters()]
+        if not self._ver.stale(srcs) and self._packed:
+            return self._packed
+        dev = srcs[0].device
+        c_in, c_out, R = self.in_channels, self.out_channels, self.num_depth_regions
+        c_pad, kb, n_pad, n_seg = self._geometry()
+        taps = 9 if self._proj else 1
+        k = 3 if self._proj else 1
+        with torch.no_grad():
+            w = torch.zeros(n_pad, n_seg, taps, c_pad, device=dev, dtype=torch.float32)
+            for t in range(R + 1):
+                w[:c_out, t, :, :c_in] = self.conv_layers[t].weight.reshape(c_out, c_in, k * k).permute(0, 2, 1)
+            if self._proj:
+                w[:c_out, R + 1, :, :c_in] = self.rgb_projection.weight.reshape(c_out, c_in, 9).permute(0, 2, 1)
+            w_cat = w.reshape(n_pad, n_seg * taps * c_pad).to(torch.bfloat16).contiguous()
+            # bias table: variant v = sum of the first v conv biases (CM:683-691: only used regions add a bias)
+            bias = torch.zeros(R + 2, n_pad, device=dev, dtype=torch.float32)
+            run = torch.zeros(c_out, device=dev, dtype=torch.float32)
+            for v in range(1, R + 2):
+                run = run + self.conv_layers[v - 1].bias.float()
+                bias[v, :c_out] = run
+        n_par = 4 if self._proj else 1
+        sl = []
+        for seg in range(n_seg):
+            for tap in range(taps):
+                dy, dx = (tap // 3, tap % 3) if self._proj else (1, 1)
+                if self._proj:
+                    # input row 2*oy + dy - 1: dy=0 -> odd plane, row oy-1; dy=1 -> even plane, row oy; dy=2 -> odd, oy
+                    py, yo = (1, -1) if dy == 0 else ((0, 0) if dy == 1 else (1, 0))
+                    px, xo = (1, -1) if dx == 0 else ((0, 0) if dx == 1 else (1, 0))
+                    par = py * 2 + px
+                else:
+                    par, yo, xo = 0, 0, 0
+                for cb in range(c_pad // kb):
+                    sl.append((cb * kb, xo, yo, seg * n_par + par))
+        slices = torch.tensor(sl, device=dev, dtype=torch.int32).contiguous()
+        self._packed = {"w": w_cat, "bias": bias, "slices": slices}
+        return self._packed
+
+    def _workspace(self, B, H, W, dev):
+        c_pad, kb, n_pad, n_seg = self._geometry()
+        key = (B, H, W, str(dev))
+        if key not in self._ws:
+            if self._proj:
+                shape = (B, n_seg, 4, (H + 1) // 2, (W + 1) // 2, c_pad)
+            else:
+                shape = (B, n_seg, 1, H, W, c_pad)
+            self._ws = {key: torch.zeros(shape, device=dev, dtype=torch.bfloat16)}   # keep one shape alive
+        return self._ws[key]
+
+    def stage_forward(self, rgb_features: torch.Tensor, codes: torch.Tensor, n_modes: torch.Tensor,
+                      residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Batched tensor-core path: features (B,C_in,H,W) fp32, pooled region codes (B,H,W) uint8 and the
+        per-image mode count -> sum_t conv_t(F*p_t) + projection(F) [+ residual]  (fp32, bf16 operands)."""
+        pk = self._refresh()
+        x = Fn._req(rgb_features.contiguous(), "rgb_features", torch.float32)
+        B, Cc, H, W = x.shape
+        assert Cc == self.in_channels, f"Expected {self.in_channels} channels, got {Cc}"
+        c_pad, kb, n_pad, n_seg = self._geometry()
+        R = self.num_depth_regions
+        packed = self._workspace(B, H, W, x.device)
+        Fn.dsam_pack(x, codes, packed, c_pad, n_seg, R + 1, self._proj)
+        if self._proj:
+            Ho, Wo = (H + 1) // 2, (W + 1) // 2
+            a_dims = (B * n_seg * 4, Ho, Wo, c_pad)
+            ppi = n_seg * 4
+        else:
+            Ho, Wo = H, W
+            a_dims = (B * n_seg, H, W, c_pad)
+            ppi = n_seg
+            residual = x if residual is None else residual + x
+        out = torch.empty(B, self.out_channels, Ho, Wo, device=x.device, dtype=torch.float32)
+        # no surviving mode -> R+1 all-zero masks, every conv still adds its bias (CM:676-678)
+        variant = torch.where(n_modes == 0, torch.full_like(n_modes, R + 1), n_modes + 1).to(torch.int32).contiguous()
+        Fn.conv_gemm(packed, a_dims, ppi, pk["w"], pk["slices"], kb, B, (Ho, Wo), _best_box(Ho, Wo), self.out_channels,
+                     pk["bias"], variant=variant, epi_mode=1, out=out,
+                     residual=residual.contiguous() if residual is not None else None)
+        return out
+
+    def forward(self, rgb_features, depth_map, window_size_ratio=0.1):
+        """Reference signature (CM:647): one single-channel depth map shared by the batch of features."""
+        if isinstance(depth_map, np.ndarray):
+            depth_map = torch.from_numpy(np.ascontiguousarray(depth_map.squeeze(), dtype=np.float32))
+        elif not isinstance(depth_map, torch.Tensor):
+            raise TypeError("Depth map must be torch.Tensor or numpy.ndarray")
+        gray = depth_map.detach().squeeze().to(device=rgb_features.device, dtype=torch.float32)
+        if gray.dim() != 2:
+            raise RgbdB200Error(f"depth_map must squeeze to (H,W), got {tuple(depth_map.shape)}")
+        gray = gray.contiguous()[None]
+        B, _, H, W = rgb_features.shape
+        ratio = torch.tensor([float(window_size_ratio)], device=rgb_features.device, dtype=torch.float32)
+        dec = Fn.depth_decompose(ratio, [(H, W)], gray=gray, num_modes=self.num_depth_regions)
+        codes = dec.pooled[0].expand(B, H, W).contiguous()
+        return self.stage_forward(rgb_features, codes, dec.n_modes.expand(B).contiguous())
+
+    # ---- reference helper API (CM:701-798), computed by the device kernel --------------------------
+    def _calculate_depth_histogram(self, depth_map, bins=512, value_range=None):
+        if bins != 512 or value_range is not None:
+            raise RgbdB200Error("the device histogram is fixed to bins=512 over (nanmin, nanmax) (CM:701-718)")
+        g = torch.as_tensor(np.ascontiguousarray(depth_map, dtype=np.float32)).reshape(1, 1, -1).cuda()
+        dec = Fn.depth_decompose(torch.tensor([0.1], device=g.device), [], gray=g, debug=True)
+        return dec.hist[0].cpu().numpy(), dec.edges[0].cpu().numpy()
+
+
+# =====================================================================================================
+# E-DSAM ratio predictor
+# =====================================================================================================
+def _fold_bn(conv_bias: torch.Tensor, bn: nn.BatchNorm2d) -> Tuple[torch.Tensor, torch.Tensor]:
+    scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+    shift = bn.bias.float() + (conv_bias.float() - bn.running_mean.float()) * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+class EnhancedDepthImageRatioPredictor(nn.Module):
+    """CM:1363-1487: (B,3,H,W) depth -> (B,1) window_size_ratio in [0.01, 0.5].  BatchNorm is folded
+    (eval semantics, running statistics); the module receives no gradient in the v0.4.0 model (its output
+    is consumed through ``.item()``, CM:339), so only the forward exists."""
+
+    def __init__(self, input_channels: int = 3):
+        super().__init__()
+        if input_channels != 3:
+            raise ValueError("rgbd_b200's fused stem is built for 3-channel depth images")
+        self.input_channels = input_channels
+        self.scale1_conv = nn.Sequential(nn.Conv2d(input_channels, 64, kernel_size=3, padding=1), nn.BatchNorm2d(64), nn.ReLU(inplace=True))
+        self.scale2_conv = nn.Sequential(nn.Conv2d(input_channels, 64, kernel_size=5, padding=2), nn.BatchNorm2d(64), nn.ReLU(inplace=True))
+        self.scale3_conv = nn.Sequential(nn.Conv2d(input_channels, 64, kernel_size=7, padding=3), nn.BatchNorm2d(64), nn.ReLU(inplace=True))
+        self.feature_fusion = nn.Sequential(nn.Conv2d(192, 128, kernel_size=1), nn.BatchNorm2d(128), nn.ReLU(inplace=True))
+        self.attention = nn.Sequential(nn.Conv2d(128, 64, kernel_size=1), nn.ReLU(inplace=True),
+                                       nn.Conv2d(64, 128, kernel_size=1), nn.Sigmoid())
+        self.feature_extractor = nn.Sequential(
+            nn.Conv2d(128, 256, kernel_size=3, padding=1), nn.BatchNorm2d(256), nn.ReLU(inplace=True),
+            nn.AdaptiveAvgPool2d(4),
+            nn.Conv2d(256, 512, kernel_size=3, padding=1), nn.BatchNorm2d(512), nn.ReLU(inplace=True))
+        self.global_avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc_layers = nn.Sequential(
+            nn.Linear(512, 128), nn.ReLU(inplace=True), nn.Dropout(0.3),
+            nn.Linear(128, 64), nn.ReLU(inplace=True), nn.Dropout(0.2),
+            nn.Linear(64, 32), nn.ReLU(inplace=True), nn.Linear(32, 1))
+        self.output_min = 0.01
+        self.output_max = 0.5
+        self.sigmoid = nn.Sigmoid()
+        self._ver = _Versioned()
+        self._packed: Dict[str, torch.Tensor] = {}
+        self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+
+    def _refresh(self):
+        srcs = list(self.parameters()) + list(self.buffers())
+        if not self._ver.stale(srcs) and self._packed:
+            return self._packed
+        dev = srcs[0].device
+        bf = torch.bfloat16
+        with torch.no_grad():
+            # stem: three convs embedded in one 7x7 frame; K = 4 slices x [(j, dx8, c4)], tap dy = 2t + j
+            w1 = torch.zeros(192, 4, 2, 8, 4, device=dev, dtype=torch.float32)
+            sc1, sh1 = [], []
+            for idx, (seq, k) in enumerate(((self.scale1_conv, 3), (self.scale2_conv, 5), (self.scale3_conv, 7))):
+                o = (7 - k) // 2
+                wk = seq[0].weight.float()                       # (64, 3, k, k)
+                full = torch.zeros(64, 3, 8, 8, device=dev)
+                full[:, :, o:o + k, o:o + k] = wk
+                # (n, c, dy, dx) -> (n, t, j, dx, c)
+                w1[idx * 64:(idx + 1) * 64, :, :, :, :3] = full.reshape(64, 3, 4, 2, 8).permute(0, 2, 3, 4, 1)
+                s, h = _fold_bn(seq[0].bias, seq[1])
+                sc1.append(s)
+                sh1.append(h)
+            pk = {"w1": w1.reshape(192, 256).to(bf).contiguous(), "sc1": torch.cat(sc1), "sh1": torch.cat(sh1)}
+            pk["w2"] = self.feature_fusion[0].weight.float().reshape(128, 192).to(bf).contiguous()
+            pk["sc2"], pk["sh2"] = _fold_bn(self.feature_fusion[0].bias, self.feature_fusion[1])
+            pk["w3"] = self.attention[0].weight.float().reshape(64, 128).to(bf).contiguous()
+            pk["sh3"] = self.attention[0].bias.detach().float().contiguous()
+            pk["w4"] = self.attention[2].weight.float().reshape(128, 64).to(bf).contiguous()
+            pk["sh4"] = self.attention[2].bias.detach().float().contiguous()
+            c5 = self.feature_extractor[0]
+            pk["w5"] = c5.weight.float().permute(0, 2, 3, 1).reshape(256, 9 * 128).to(bf).contiguous()   # K = (tap, c)
+            pk["sc5"], pk["sh5"] = _fold_bn(c5.bias, self.feature_extractor[1])
+            c6 = self.feature_extractor[4]
+            pk["w6"] = c6.weight.detach().float().contiguous()
+            pk["sc6"], pk["sh6"] = _fold_bn(c6.bias, self.feature_extractor[5])
+            for j, li in enumerate((0, 3, 6, 8)):
+                pk[f"fw{j}"] = self.fc_layers[li].weight.detach().float().contiguous()
+                pk[f"fb{j}"] = self.fc_layers[li].bias.detach().float().contiguous()
+
+            def sl(entries):
+                return torch.tensor(entries, device=dev, dtype=torch.int32).contiguous()
+            pk["sl1"] = sl([(0, 0, 2 * t, 0) for t in range(4)])
+            pk["sl2"] = sl([(64 * cb, 0, 0, 0) for cb in range(3)])
+            pk["sl3"] = sl([(64 * cb, 0, 0, 0) for cb in range(2)])
+            pk["sl4"] = sl([(0, 0, 0, 0)])
+            pk["sl5"] = sl([(64 * cb, dx - 1, dy - 1, 0) for dy in range(3) for dx in range(3) for cb in range(2)])
+        self._packed = pk
+        return pk
+
+    def _workspace(self, B, H, W, dev):
+        key = (B, H, W, str(dev))
+        if key not in self._ws:
+            bf = dict(device=dev, dtype=torch.bfloat16)
+            self._ws = {key: {
+                "stem": torch.empty(B, H + 6, W, 64, **bf),
+                "x1": torch.empty(B, H, W, 192, **bf),
+                "x2": torch.empty(B, H, W, 128, **bf),
+                "x3": torch.empty(B, H, W, 64, **bf),
+                "x4": torch.empty(B, H, W, 128, **bf),
+                "pool": torch.empty(B, 16, 256, device=dev, dtype=torch.float32),
+            }}
+        return self._ws[key]
+
+    def forward(self, depth_image: torch.Tensor) -> torch.Tensor:
+        assert depth_image.dim() == 4, f"Expected 4D tensor, got {depth_image.dim()}D"
+        assert depth_image.shape[1] == self.input_channels, \
+            f"Expected {self.input_channels} channels, got {depth_image.shape[1]}"
+        B, _, H, W = depth_image.shape
+        if H % 4 or W % 4:
+            raise RgbdB200Error("the fused AdaptiveAvgPool2d(4) epilogue needs H and W divisible by 4")
+        pk = self._refresh()
+        ws = self._workspace(B, H, W, depth_image.device)
+        d = depth_image.detach()
+        if d.dtype != torch.float32:
+            d = d.float()
+        box = _best_box(H, W)
+        Fn.ratio_stem_pack(d, ws["stem"])
+        # multi-scale stem (CM:1458-1463) + BN + ReLU -> 192 channels
+        Fn.conv_gemm(ws["stem"], (B, H + 6, W, 64), 1, pk["w1"], pk["sl1"], 64, B, (H, W), box, 192, pk["sh1"],
+                     scale=pk["sc1"], act=1, out=ws["x1"])
+        # feature_fusion (CM:1466)
+        Fn.conv_gemm(ws["x1"], (B, H, W, 192), 1, pk["w2"], pk["sl2"], 64, B, (H, W), box, 128, pk["sh2"],
+                     scale=pk["sc2"], act=1, out=ws["x2"])
+        # attention (CM:1469-1470): sigmoid(conv(relu(conv(f)))) * f
+        Fn.conv_gemm(ws["x2"], (B, H, W, 128), 1, pk["w3"], pk["sl3"], 64, B, (H, W), box, 64, pk["sh3"], act=1,
+                     out=ws["x3"])
+        Fn.conv_gemm(ws["x3"], (B, H, W, 64), 1, pk["w4"], pk["sl4"], 64, B, (H, W), box, 128, pk["sh4"], act=2,
+                     gate=ws["x2"], out=ws["x4"])
+        # feature_extractor[0:4] (CM:1412-1416): conv3x3 + BN + ReLU + AdaptiveAvgPool2d(4), pooled in the epilogue
+        ws["pool"].zero_()
+        Fn.conv_gemm(ws["x4"], (B, H, W, 128), 1, pk["w5"], pk["sl5"], 64, B, (H, W), box, 256, pk["sh5"],
+                     scale=pk["sc5"], act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), tile_order=1)
+        return Fn.ratio_tail(ws["pool"], (H // 4) * (W // 4), pk["w6"], pk["sc6"], pk["sh6"],
+                             [pk[f"fw{j}"] for j in range(4)], [pk[f"fb{j}"] for j in range(4)],
+                             self.output_min, self.output_max)
+
+
+# =====================================================================================================
+# v0.4.0 wiring
+# =====================================================================================================
+class DepthGuidance(nn.Module):
+    """The hot path between the encoder and the pixel decoder of the v0.4.0 model (CM:324-355), batched and
+    free of host synchronisation: ratio predictor -> device-side depth decomposition -> 3 cascaded DSAM
+    stages -> DGGM injection fused with the branch sum.  Child names match the reference's pixel-level
+    module (``ratio_predictor, dsam0, dsam1, dsam2, depth_gradient_injection``)."""
+
+    def __init__(self, color_channels: Sequence[int] = (96, 192, 384, 768)):
+        super().__init__()
+        c = list(color_channels)
+        assert len(c) == 4
+        self.ratio_predictor = EnhancedDepthImageRatioPredictor(3)
+        self.dsam0 = DSAModule(in_channels=c[0], out_channels=c[1], num_depth_regions=3)
+        self.dsam1 = DSAModule(in_channels=c[1], out_channels=c[2], num_depth_regions=3)
+        self.dsam2 = DSAModule(in_channels=c[2], out_channels=c[3], num_depth_regions=3)
+        self.depth_gradient_injection = DepthGradientInjectionResidual(c, 3)
+
+    def forward(self, pixel_values: torch.Tensor, color_feature_map: Sequence[torch.Tensor],
+                ratios: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+        depth = pixel_values[:, 3:6]
+        gradient_depth = pixel_values[:, 6:9]
+        gradient_mask = pixel_values[:, 9:10]
+        feats = [f.detach().contiguous() for f in color_feature_map]          # CM:332-333 (detach; no clone needed)
+        if ratios is None:
+            ratios = self.ratio_predictor(depth)                                # CM:336
+        levels = [tuple(f.shape[2:]) for f in feats[:3]]
+        dec = Fn.depth_decompose(ratios.reshape(-1).contiguous(), levels, depth3=depth)
+        cp1 = [feats[0]]
+        x = feats[0]
+        for k, dsam in enumerate((self.dsam0, self.dsam1, self.dsam2)):        # CM:339-352
+            x = dsam.stage_forward(x, dec.pooled[k], dec.n_modes, residual=feats[k + 1])
+            cp1.append(x)
+        # CM:354-355: cp2 = DGGM(feats); out = cp1 + cp2, fused into the DGGM kernel
+        return self.depth_gradient_injection.forward_fused_sum(feats, cp1, gradient_depth, gradient_mask)

@@ -1,0 +1,320 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): integer / boolean / index artefacts bit-exact; floating point within
+1e-4 relative where the kernel computes in fp32 (DGGM, gradient features) and within 1e-2 relative where
+the tensor-core path uses bf16 operands (DSAM convs, ratio predictor)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import rgbd_b200  # noqa: F401
+from rgbd_b200 import synthetic
+from oracle import hotpath as O
+from oracle import weights as OW
+from oracle.make_golden import decompose_cases
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1e-2
+FP32_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def fn():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rgbd_b200 import functional
+    return functional
+
+
+@pytest.fixture(scope="module")
+def mods(fn):
+    from rgbd_b200 import modules
+    return modules
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a = a.double().cpu()
+    b = b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a = a.double().cpu()
+    b = b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+# ---------------------------------------------------------------------------------------------------
+# K0 gradient features: bit-exact
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["nyu", "uniform", "constant", "two_valued", "all_invalid"])
+@pytest.mark.parametrize("hw", [(60, 84), (480, 640), (33, 31)])
+def test_gradient_features_bit_exact(fn, kind, hw):
+    ds = [synthetic.synth_rgbd_u8(40 + j, hw[0], hw[1], kind)[1] for j in range(3)]
+    d = torch.from_numpy(np.stack(ds)).cuda()
+    for inp in (d, d.float()):
+        norm, vm = fn.gradient_features(inp)
+        for j in range(3):
+            rn, _, _, rv = O.gradient_features(ds[j])
+            np.testing.assert_array_equal(vm[j, 0].cpu().numpy(), rv)
+            for r in range(3):
+                np.testing.assert_array_equal(norm[j, r].cpu().numpy(), rn)
+
+
+def test_gradient_features_into_pixel_values_view(fn):
+    ds = [synthetic.synth_rgbd_u8(3 + j, 64, 96, "nyu")[1] for j in range(2)]
+    pv = torch.zeros(2, 10, 64, 96, device="cuda")
+    fn.gradient_features(torch.from_numpy(np.stack(ds)).cuda(), norm_out=pv[:, 6:9], vmask_out=pv[:, 9:10])
+    for j in range(2):
+        rn, _, _, rv = O.gradient_features(ds[j])
+        np.testing.assert_array_equal(pv[j, 8].cpu().numpy(), rn)
+        np.testing.assert_array_equal(pv[j, 9].cpu().numpy(), rv)
+    assert float(pv[:, :6].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2 depth decomposition: bit-exact histogram / modes / windows / masks / pooled masks
+# ---------------------------------------------------------------------------------------------------
+def _check_decomposition(fn, grays, ratios, levels):
+    """grays: list of (H,W) float32 arrays of one shape."""
+    g = torch.from_numpy(np.stack(grays)).cuda()
+    r = torch.tensor(ratios, dtype=torch.float32).cuda()
+    dec = fn.depth_decompose(r, levels, gray=g, debug=True)
+    H, W = grays[0].shape
+    for b, (gray, ratio) in enumerate(zip(grays, ratios)):
+        ref = O.depth_decompose(gray, ratio)
+        np.testing.assert_array_equal(dec.hist[b].cpu().numpy(), ref["hist"], err_msg=f"hist img {b}")
+        np.testing.assert_array_equal(dec.edges[b].cpu().numpy(), ref["edges"], err_msg=f"edges img {b}")
+        m = len(ref["centres"])
+        assert int(dec.n_modes[b]) == m
+        np.testing.assert_array_equal(dec.peak_bins[b, :m].cpu().numpy(), np.array(ref["peak_bins"], dtype=np.int32))
+        np.testing.assert_array_equal(dec.centres[b, :m].cpu().numpy(), np.array(ref["centres"], dtype=np.float32))
+        wins = np.array(ref["windows"], dtype=np.float32).reshape(-1, 2)
+        np.testing.assert_array_equal(dec.windows[b, :m].cpu().numpy(), wins)
+        codes = dec.codes[b].cpu().numpy()
+        ref_codes = np.zeros((H, W), dtype=np.uint8)
+        if m > 0:
+            for t, mk in enumerate(ref["masks"]):
+                ref_codes |= (mk.astype(np.uint8) << t)
+        np.testing.assert_array_equal(codes, ref_codes, err_msg=f"codes img {b}")
+        for lvl, (h, w) in enumerate(levels):
+            ref_p = np.zeros((h, w), dtype=np.uint8)
+            if m > 0:
+                for t, mk in enumerate(ref["masks"]):
+                    ref_p |= (O.adaptive_max_pool_mask(mk, (h, w)).astype(np.uint8) << t)
+            np.testing.assert_array_equal(dec.pooled[lvl][b].cpu().numpy(), ref_p, err_msg=f"pooled L{lvl} img {b}")
+
+
+def test_decompose_edge_cases_bit_exact(fn):
+    for name, gray, ratio in decompose_cases(synthetic):
+        H, W = gray.shape
+        levels = [(H // 4, W // 4), (H // 8, W // 8), (max(H // 16, 1), max(W // 16, 1)), (7, 5)]
+        _check_decomposition(fn, [gray], [ratio], levels)
+
+
+def test_decompose_full_size_batch_bit_exact(fn):
+    grays, ratios = [], []
+    for j, kind in enumerate(["nyu", "nyu", "nyu", "uniform", "constant", "two_valued"]):
+        _, d = synthetic.synth_rgbd_u8(100 + j, 480, 640, kind)
+        grays.append(O.to_grayscale(synthetic.normalise_u8(np.repeat(d[:, :, None], 3, axis=2))))
+        ratios.append([0.013, 0.21, 0.5, 0.1, 0.3, 0.07][j])
+    _check_decomposition(fn, grays, ratios, [(120, 160), (60, 80), (30, 40)])
+
+
+def test_gray_from_depth3_bit_exact(fn):
+    rs = np.random.RandomState(11)
+    d3 = (rs.randn(2, 3, 40, 56) * 1.3).astype(np.float32)
+    pv = torch.zeros(2, 10, 40, 56, device="cuda")
+    pv[:, 3:6] = torch.from_numpy(d3).cuda()
+    dec = fn.depth_decompose(torch.tensor([0.1, 0.2], device="cuda"), [(10, 14)], depth3=pv[:, 3:6])
+    for b in range(2):
+        np.testing.assert_array_equal(dec.gray[b].cpu().numpy(), O.to_grayscale(d3[b]))
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1 DGGM forward / K1b parameter gradients
+# ---------------------------------------------------------------------------------------------------
+def _dggm_case(chans, hw, sizes, B, seed):
+    rs = np.random.RandomState(seed)
+    feats = [torch.from_numpy(rs.randn(B, c, h, w).astype(np.float32)) for c, (h, w) in zip(chans, sizes)]
+    grad = torch.from_numpy(rs.rand(B, 3, *hw).astype(np.float32))
+    mask = torch.from_numpy((rs.rand(B, 1, *hw) < 0.6).astype(np.float32))
+    return feats, grad, mask
+
+
+@pytest.mark.parametrize("chans,hw,sizes,B", [
+    ([4, 8, 12, 16], (64, 96), [(16, 24), (8, 12), (4, 6), (2, 3)], 2),
+    ([4, 8, 12, 16], (50, 70), [(13, 18), (7, 9), (4, 5), (2, 3)], 2),
+    ([96, 192, 384, 768], (480, 640), [(120, 160), (60, 80), (30, 40), (15, 20)], 2),
+    ([128, 256, 512, 1024], (96, 128), [(24, 32), (12, 16), (6, 8), (3, 4)], 1),
+])
+def test_dggm_forward(mods, chans, hw, sizes, B):
+    feats, grad, mask = _dggm_case(chans, hw, sizes, B, 9)
+    w = OW.dggm_weights(chans, 3, seed=300)
+    m = mods.DepthGradientInjectionResidual(chans, 3)
+    m.load_state_dict(w)
+    m.cuda().eval()
+    ref = O.dggm_forward(w, feats, grad, mask)
+    pv = torch.zeros(B, 10, *hw, device="cuda")       # exercise the strided pixel_values views
+    pv[:, 6:9] = grad.cuda()
+    pv[:, 9:10] = mask.cuda()
+    with torch.no_grad():
+        out = m([f.cuda() for f in feats], pv[:, 6:9], pv[:, 9:10])
+        fused = m.forward_fused_sum([f.cuda() for f in feats], [(2 * f).cuda() for f in feats], pv[:, 6:9], pv[:, 9:10])
+    for i in range(4):
+        assert rel_err(out[i], ref[i]) < FP32_TOL
+        assert rel_err(fused[i], 2 * feats[i] + ref[i]) < FP32_TOL
+    # None -> passthrough, wrong scale count -> AssertionError (CM:1218-1219, 1263-1265)
+    same = m([f.cuda() for f in feats], None, pv[:, 9:10])
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(same, feats))
+    with pytest.raises(AssertionError):
+        m([feats[0].cuda()], pv[:, 6:9], pv[:, 9:10])
+
+
+def test_dggm_param_gradients(mods):
+    chans, hw, sizes = [8, 16, 24, 32], (64, 96), [(16, 24), (8, 12), (4, 6), (2, 3)]
+    feats, grad, mask = _dggm_case(chans, hw, sizes, 2, 21)
+    w = OW.dggm_weights(chans, 3, seed=301)
+    m = mods.DepthGradientInjectionResidual(chans, 3)
+    m.load_state_dict(w)
+    m.cuda().train()
+    rs = np.random.RandomState(5)
+    douts = [torch.from_numpy(rs.randn(*f.shape).astype(np.float32)) for f in feats]
+    out = m([f.cuda() for f in feats], grad.cuda(), mask.cuda())
+    loss = sum((o * d.cuda()).sum() for o, d in zip(out, douts))
+    loss.backward()
+    # oracle gradients by torch autograd on the CPU restatement
+    wr = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    ref = O.dggm_forward(wr, feats, grad, mask)
+    sum((o * d).sum() for o, d in zip(ref, douts)).backward()
+    for i in range(4):
+        gw = m.depth_enhancement_layers[i][0].weight.grad
+        gb = m.depth_enhancement_layers[i][0].bias.grad
+        assert rel_err(gw, wr[f"depth_enhancement_layers.{i}.0.weight"].grad) < 1e-3
+        assert rel_err(gb, wr[f"depth_enhancement_layers.{i}.0.bias"].grad) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------
+# tensor-core implicit GEMM (tcgen05) against a float64 reference of the same bf16 operands
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kb,c,n,hw", [(64, 128, 64, (4, 128)), (64, 64, 256, (8, 64)), (32, 96, 192, (16, 24)),
+                                       (64, 192, 32, (5, 50))])
+def test_conv_gemm_1x1(fn, kb, c, n, hw):
+    rs = np.random.RandomState(1)
+    B, (H, W) = 2, hw
+    a = torch.from_numpy(rs.randn(B, H, W, c).astype(np.float32)).cuda().to(torch.bfloat16)
+    w = torch.from_numpy((rs.randn(n, c) / np.sqrt(c)).astype(np.float32)).cuda().to(torch.bfloat16)
+    shift = torch.from_numpy(rs.randn(n).astype(np.float32)).cuda()
+    scale = torch.from_numpy(rs.uniform(0.5, 1.5, n).astype(np.float32)).cuda()
+    slices = torch.tensor([(kb * i, 0, 0, 0) for i in range(c // kb)], dtype=torch.int32).cuda()
+    from rgbd_b200.modules import _best_box
+    out = torch.zeros(B, H, W, n, device="cuda", dtype=torch.bfloat16)
+    fn.conv_gemm(a, (B, H, W, c), 1, w, slices, kb, B, (H, W), _best_box(H, W), n, shift, scale=scale, act=1, out=out)
+    ref = torch.relu((a.double() @ w.double().T) * scale.double() + shift.double())
+    assert rel_err(out.double(), ref) < 8e-3            # one bf16 rounding of the output
+    out32 = torch.zeros(B, n, H, W, device="cuda")
+    res = torch.from_numpy(rs.randn(B, n, H, W).astype(np.float32)).cuda()
+    fn.conv_gemm(a, (B, H, W, c), 1, w, slices, kb, B, (H, W), _best_box(H, W), n, shift, epi_mode=1, out=out32,
+                 residual=res)
+    ref32 = (a.double() @ w.double().T + shift.double()).permute(0, 3, 1, 2) + res.double()
+    assert rel_err(out32, ref32) < 1e-4
+
+
+def test_conv_gemm_3x3_pool(fn):
+    rs = np.random.RandomState(2)
+    B, H, W, c, n = 2, 16, 64, 128, 256
+    a = torch.from_numpy(rs.randn(B, H, W, c).astype(np.float32)).cuda().to(torch.bfloat16)
+    wt = torch.from_numpy((rs.randn(n, c, 3, 3) / np.sqrt(9 * c)).astype(np.float32)).cuda().to(torch.bfloat16)
+    w = wt.permute(0, 2, 3, 1).reshape(n, 9 * c).contiguous()
+    shift = torch.from_numpy(rs.randn(n).astype(np.float32) * 0.1).cuda()
+    slices = torch.tensor([(64 * cb, dx - 1, dy - 1, 0) for dy in range(3) for dx in range(3) for cb in range(c // 64)],
+                          dtype=torch.int32).cuda()
+    pool = torch.zeros(B, 16, n, device="cuda")
+    from rgbd_b200.modules import _best_box
+    fn.conv_gemm(a, (B, H, W, c), 1, w, slices, 64, B, (H, W), _best_box(H, W), n, shift, act=1, epi_mode=2, pool=pool,
+                 cells=(4, 4), tile_order=1)
+    y = torch.relu(torch.nn.functional.conv2d(a.double().permute(0, 3, 1, 2), wt.double(), shift.double(), padding=1))
+    ref = torch.nn.functional.adaptive_avg_pool2d(y, 4) * (H // 4) * (W // 4)       # sums per cell
+    ref = ref.permute(0, 2, 3, 1).reshape(B, 16, n)
+    assert rel_err(pool, ref) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------
+# E-DSAM: DSAModule / ratio predictor / v0.4.0 wiring
+# ---------------------------------------------------------------------------------------------------
+def _gray_for(j, kind, dhw):
+    _, d = synthetic.synth_rgbd_u8(20 + j, dhw[0], dhw[1], kind)
+    return O.to_grayscale(synthetic.normalise_u8(np.repeat(d[:, :, None], 3, axis=2)))
+
+
+@pytest.mark.parametrize("ci,co,hw,dhw", [(8, 16, (24, 32), (96, 128)), (8, 8, (24, 32), (96, 128)),
+                                          (8, 24, (15, 20), (60, 80)), (96, 192, (30, 40), (120, 160)),
+                                          (64, 64, (12, 20), (48, 80))])
+def test_dsam_module(mods, ci, co, hw, dhw):
+    w = OW.dsam_weights(ci, co, seed=100 + ci + co)
+    m = mods.DSAModule(ci, co, 3)
+    m.load_state_dict(w)
+    m.cuda().eval()
+    feat = torch.from_numpy(np.random.RandomState(5).randn(2, ci, *hw).astype(np.float32))
+    for j, kind in enumerate(["nyu", "constant", "two_valued"]):
+        gray = _gray_for(j, kind, dhw)
+        with torch.no_grad():
+            y = m(feat.cuda(), torch.from_numpy(gray)[None].cuda(), 0.3)
+            y_np = m(feat.cuda(), gray, 0.3)                      # ndarray depth input (exp6_dsam.py:57-60)
+        ref = torch.cat([O.dsam_forward(w, feat[b:b + 1], gray, 0.3) for b in range(2)])
+        assert y.shape == ref.shape
+        assert rel_err(y, ref) < BF16_TOL, (kind, rel_err(y, ref))
+        assert rel_l2(y, ref) < BF16_TOL
+        assert torch.equal(y, y_np)
+    with pytest.raises(TypeError):
+        m(feat.cuda(), [[0.0]], 0.3)
+
+
+@pytest.mark.parametrize("hw", [(48, 64), (96, 160)])
+def test_ratio_predictor(mods, hw):
+    w = OW.ratio_weights(seed=500)
+    m = mods.EnhancedDepthImageRatioPredictor(3)
+    m.load_state_dict(w)
+    m.cuda().eval()
+    frames = []
+    for j in range(3):
+        _, d = synthetic.synth_rgbd_u8(60 + j, hw[0], hw[1], "nyu")
+        frames.append(synthetic.normalise_u8(np.repeat(d[:, :, None], 3, axis=2)))
+    x = torch.from_numpy(np.stack(frames))
+    ref = O.ratio_predictor_forward(w, x)
+    with torch.no_grad():
+        r = m(x.cuda())
+    assert r.shape == (3, 1)
+    assert ((r >= 0.01) & (r <= 0.5)).all()
+    assert float(((r.cpu() - ref).abs() / ref.abs()).max()) < BF16_TOL
+    with pytest.raises(AssertionError):
+        m(x.cuda()[:, :2])
+
+
+def test_depth_guidance_wiring(mods, golden_dir):
+    g = np.load(os.path.join(golden_dir, "wiring.npz"))
+    w = OW.guidance_weights(seed=700)
+    m = mods.DepthGuidance((96, 192, 384, 768))
+    missing = m.load_state_dict(w, strict=True)
+    m.cuda().eval()
+    pvs = []
+    for j in range(2):
+        rgb, d = synthetic.synth_rgbd_u8(80 + j, 64, 96, "nyu")
+        pvs.append(synthetic.assemble_pixel_values(rgb, d, O.gradient_features))
+    pv = torch.from_numpy(np.stack(pvs)).cuda()
+    feats = [torch.from_numpy(g[f"feat{i}"]).cuda() for i in range(4)]
+    ref_ratio = torch.from_numpy(g["ratios"])
+    with torch.no_grad():
+        ratio = m.ratio_predictor(pv[:, 3:6])
+        fused_given = m(pv, feats, ratios=ref_ratio.cuda())      # stage (i)/(iii): oracle-supplied ratio
+        fused_own = m(pv, feats)                                  # end to end with our bf16 ratio
+    assert float(((ratio.cpu() - ref_ratio).abs() / ref_ratio).max()) < BF16_TOL
+    for i in range(4):
+        ref = torch.from_numpy(g[f"fused{i}"])
+        assert rel_err(fused_given[i], ref) < BF16_TOL, (i, rel_err(fused_given[i], ref))
+        assert rel_l2(fused_given[i], ref) < BF16_TOL
+        # with our own ratio a few boundary pixels of the region masks may flip
+        assert rel_l2(fused_own[i], ref) < 3 * BF16_TOL

