@@ -14,6 +14,14 @@ from ._lib import ConvGemmDesc, RgbdB200Error, check, int_array, ptr_array
 
 HIST_BINS = 512
 
+# kernels launched through this module since it was last reset (bench.py's `gpu_launches`)
+LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -81,6 +89,7 @@ def dggm_forward(feats: Sequence[torch.Tensor], grad: torch.Tensor, mask: torch.
         ptr_array([w.data_ptr() for w in ws]), ptr_array([b.data_ptr() for b in bs]),
         grad.data_ptr(), gbs, mask.data_ptr(), mbs, B, D, H, W, _stream())
     check(rc, "rgbd_dggm_fwd")
+    _count(1)
     return outs
 
 
@@ -104,6 +113,7 @@ def dggm_backward_params(douts: Sequence[torch.Tensor], grad: torch.Tensor, mask
         ptr_array([w.data_ptr() for w in dws]), ptr_array([b.data_ptr() for b in dbs]),
         grad.data_ptr(), gbs, mask.data_ptr(), mbs, B, D, H, W, _stream())
     check(rc, "rgbd_dggm_bwd_params")
+    _count(1)
     return [dw.reshape(weights[i].shape) for i, dw in enumerate(dws)], dbs
 
 
@@ -137,6 +147,7 @@ def gradient_features(depth: torch.Tensor, n_rep: int = 3, invalid_value: float 
     rc = lib.rgbd_gradient_features(depth.data_ptr(), dt, H * W, norm_out.data_ptr(), nbs, n_rep, vmask_out.data_ptr(),
                                     vbs, B, H, W, float(invalid_value), ws.data_ptr(), _stream())
     check(rc, "rgbd_gradient_features")
+    _count(3)
     return norm_out, vmask_out
 
 
@@ -201,6 +212,7 @@ def depth_decompose(ratio: torch.Tensor, levels: Sequence[Tuple[int, int]], dept
         codes.data_ptr(), len(levels), int_array([h for h, _ in levels]), int_array([w for _, w in levels]),
         ptr_array([p.data_ptr() for p in pooled]), ws.data_ptr(), _stream())
     check(rc, "rgbd_depth_decompose")
+    _count(7 + len(levels) + (1 if debug else 0))
     return Decomposition(gray_out, codes, pooled, n_modes, centres, windows, peak_bins, status, hist, edges)
 
 
@@ -253,6 +265,7 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
     d.pool = _req(pool, "pool", torch.float32).data_ptr() if pool is not None else None
     d.cells_y, d.cells_x = cells
     check(lib.rgbd_conv_gemm(C.byref(d), _stream()), "rgbd_conv_gemm")
+    _count(1)
 
 
 def dsam_pack(feat: torch.Tensor, codes: torch.Tensor, out: torch.Tensor, c_pad: int, n_seg: int, masked_segs: int,
@@ -266,6 +279,7 @@ def dsam_pack(feat: torch.Tensor, codes: torch.Tensor, out: torch.Tensor, c_pad:
         raise RgbdB200Error(f"codes must be {(B, H, W)}, got {tuple(codes.shape)}")
     check(lib.rgbd_dsam_pack(feat.data_ptr(), codes.data_ptr(), out.data_ptr(), B, Cc, c_pad, H, W, n_seg, masked_segs,
                              1 if parity_split else 0, _stream()), "rgbd_dsam_pack")
+    _count(1)
 
 
 def ratio_stem_pack(depth3: torch.Tensor, out: torch.Tensor) -> None:
@@ -275,6 +289,7 @@ def ratio_stem_pack(depth3: torch.Tensor, out: torch.Tensor) -> None:
     B, c3, H, W = depth3.shape
     bs, cs = _plane_strided(depth3, "depth")
     check(lib.rgbd_ratio_stem_pack(depth3.data_ptr(), bs, cs, out.data_ptr(), B, H, W, _stream()), "rgbd_ratio_stem_pack")
+    _count(1)
 
 
 def ratio_tail(pool: torch.Tensor, cell_pixels: int, conv_w: torch.Tensor, conv_scale: torch.Tensor,
@@ -291,4 +306,5 @@ def ratio_tail(pool: torch.Tensor, cell_pixels: int, conv_w: torch.Tensor, conv_
                               conv_shift.data_ptr(), ptr_array([t.data_ptr() for t in fc_w]),
                               ptr_array([t.data_ptr() for t in fc_b]), out_min, out_max, gap.data_ptr(),
                               ratio.data_ptr(), B, _stream()), "rgbd_ratio_tail")
+    _count(2)
     return ratio

