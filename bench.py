@@ -331,14 +331,14 @@ class PerKernel:
             def cascade(gemm_only=False):
                 x = feats[0]
                 for k, d in enumerate((m.dsam0, m.dsam1, m.dsam2)):
-                    x = d.stage_forward(x, dec.pooled[k], dec.n_modes, residual=feats[k + 1])
+                    x = d.stage_forward(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1])
             out["dsam_cascade_total"] = self._time(cascade)
             # GEMM-only time of the three stages (operands already packed by the cascade above)
             def gemms():
                 x = feats[0]
                 for k, d in enumerate((m.dsam0, m.dsam1, m.dsam2)):
                     d._gemm_only = True
-                    x = d.stage_forward(x, dec.pooled[k], dec.n_modes, residual=feats[k + 1])
+                    x = d.stage_forward(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1])
                     d._gemm_only = False
             out["dsam_gemm"] = self._time(gemms)
             cp1 = [f.clone() for f in feats]

@@ -72,7 +72,9 @@ int rgbd_gradient_features(const void* depth, int depth_dtype, long long depth_b
  * _generate_depth_region_masks (CM:701-798) plus the adaptive_max_pool2d of every region mask (CM:687).
  * Input: depth3 (B,3,H,W) with batch/channel strides (gray written to gray_out) OR gray_in (B,H,W); ratio (B).
  * Outputs (optional ones may be NULL): hist_out int64 (B,512); edges_out f32 (B,513); n_modes_out (B);
- * peak_bins_out (B,3); centres_out (B,3); windows_out (B,3,2); status_out (B); codes_out uint8 (B,H,W) REQUIRED:
+ * peak_bins_out (B,3); centres_out (B,3); windows_out (B,3,2); status_out (B); bias_variant_out (B) = how many
+ * conv biases the reference adds for the image (n_modes+1, or num_modes+1 when no mode survives, CM:676-691);
+ * codes_out uint8 (B,H,W) REQUIRED:
  * bit t = region mask t in the reference's list order (modes by (height, centre) descending, then the remaining
  * region at index n_modes; all zero when no mode survives, CM:676-678); pooled_out_host[l] uint8
  * (B, level_h[l], level_w[l]) = the codes OR-pooled over adaptive_max_pool2d's windows. */
@@ -80,7 +82,7 @@ size_t rgbd_depth_decompose_workspace_bytes(int B);
 int rgbd_depth_decompose(const float* depth3, long long depth_batch_stride, long long depth_channel_stride,
                          const float* gray_in, const float* ratio, int B, int H, int W, int num_modes, float* gray_out,
                          long long* hist_out, float* edges_out, int* n_modes_out, int* peak_bins_out, float* centres_out,
-                         float* windows_out, int* status_out, uint8_t* codes_out, int n_levels, const int* level_h_host,
+                         float* windows_out, int* status_out, int* bias_variant_out, uint8_t* codes_out, int n_levels, const int* level_h_host,
                          const int* level_w_host, uint8_t* const* pooled_out_host, void* workspace, rgbd_stream_t stream);
 
 /* ---- E-DSAM: tensor-core building blocks ------------------------------------------------------------------------

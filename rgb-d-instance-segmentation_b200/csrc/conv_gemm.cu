@@ -46,6 +46,9 @@ struct KParams {
     float* pool;
     int cells_y, cells_x;
     int total_tiles;
+    int staging_bytes;    // epi_mode 0: swizzled bf16 output tile staged for TMA stores
+    int gate_bytes;       // epi_mode 0 with gate: TMA-loaded gate tile (same layout)
+    int ss_in_smem;       // scale/shift of the (single) N tile cached in shared memory
 };
 
 struct SmemCtl {
@@ -53,6 +56,8 @@ struct SmemCtl {
     uint64_t empty[kMaxStages];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
+    uint64_t gate_full;
+    uint64_t gate_empty;
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -71,22 +76,229 @@ __device__ __forceinline__ void decode_tile(const KParams& p, int t, int& img, i
     }
 }
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-    if (act == 1) return fmaxf(x, 0.f);
-    if (act == 2) return 1.0f / (1.0f + __expf(-x));
+struct EpiCtx {
+    uint8_t* smem;
+    uint8_t* s_staging;
+    uint8_t* s_gate;
+    SmemCtl* ctl;
+    float* s_scale;
+    float* s_shift;
+    uint32_t tmem_base;
+    int t_begin, t_end, warp, lane;
+};
+
+template <int ACT>
+__device__ __forceinline__ float act_fn(float x) {
+    if (ACT == 1) return fmaxf(x, 0.f);
+    if (ACT == 2) return __fdividef(1.0f, 1.0f + __expf(-x));
     return x;
+}
+
+// Epilogue warps 4..7: TMEM -> registers -> y = act(acc*scale + shift) -> mode-specific output.
+// MODE and ACT are compile-time so the per-element code is branch-free and the loads are batched.
+template <int MODE, int ACT>
+__device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c, const CUtensorMap* tmap_out) {
+    SmemCtl* ctl = c.ctl;
+    const int warp = c.warp, lane = c.lane;
+    const int q = warp - 4;                    // TMEM lane quarter
+    const int row = q * 32 + lane;
+    const int lx = row % p.BX, ly = row / p.BX;
+    const int n_chunks = p.BLOCK_N >> 5;
+    const int epi_tid = row;                   // 0..127
+    int as = 0;
+    uint32_t aphase = 0, gphase = 0;
+    float acc[8];                              // pooled-mode running sums (lane L owns column 32*k + L)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    int cur_key = -1, cur_nt = 0;
+    const int cell_h = p.cells_y ? p.out_h / p.cells_y : 1, cell_w = p.cells_x ? p.out_w / p.cells_x : 1;
+    const int ncells = p.cells_y * p.cells_x;
+    int ss_key = -1;                           // (variant, nt) whose scale/shift currently sit in shared memory
+
+    for (int t = c.t_begin; t < c.t_end; ++t) {
+        int img, ty, tx, nt;
+        decode_tile(p, t, img, ty, tx, nt);
+        const int ox = tx * p.BX + lx, oy = ty * p.BY + ly;
+        const bool valid = ox < p.out_w && oy < p.out_h;
+
+        // scale / shift of this (variant, N tile) -> shared memory (reloaded only when they change)
+        const int var = p.variant ? __ldg(p.variant + img) : 0;
+        const int want = var * p.n_tiles_n + nt;
+        if (want != ss_key) {
+            asm volatile("bar.sync 2, 128;" ::: "memory");          // everyone is done with the old table
+            for (int i = epi_tid; i < p.BLOCK_N; i += 128) {
+                c.s_scale[i] = p.scale ? __ldg(p.scale + nt * p.BLOCK_N + i) : 1.0f;
+                c.s_shift[i] = __ldg(p.shift + (size_t)var * p.N_pad + nt * p.BLOCK_N + i);
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            ss_key = want;
+        }
+
+        tc::mbar_wait(&ctl->tmem_full[as], aphase);
+        tc::tc_fence_after();
+        const uint32_t taddr0 = c.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BLOCK_N);
+
+        int key = -1;
+        bool uniform = false;
+        if (MODE == 2) {
+            key = valid ? img * ncells + (oy / cell_h) * p.cells_x + (ox / cell_w) : -1;
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            const int leader_key = vm ? __shfl_sync(0xffffffffu, key, __ffs(vm) - 1) : -1;
+            uniform = __all_sync(0xffffffffu, !valid || key == leader_key);
+            if (uniform && vm && (leader_key != cur_key || nt != cur_nt)) {
+                if (cur_key >= 0) {
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        if (kk < n_chunks) {
+                            atomicAdd(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
+                            acc[kk] = 0.f;
+                        }
+                    }
+                }
+                cur_key = leader_key;
+                cur_nt = nt;
+            }
+            if (!vm) uniform = false;
+        }
+        if (MODE == 0) {
+            if (p.gate_bytes) tc::mbar_wait(&ctl->gate_full, gphase);
+            // the previous tile's TMA stores must have finished reading the staging buffer
+            if (warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+
+#pragma unroll 1
+        for (int k = 0; k < n_chunks; ++k) {
+            uint32_t v[32];
+            tc::tmem_ld_32x32(taddr0 + (uint32_t)(k * 32), v);
+            float sc[32], sh[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 a = *reinterpret_cast<const float4*>(c.s_scale + k * 32 + j4 * 4);
+                const float4 b = *reinterpret_cast<const float4*>(c.s_shift + k * 32 + j4 * 4);
+                sc[j4 * 4] = a.x; sc[j4 * 4 + 1] = a.y; sc[j4 * 4 + 2] = a.z; sc[j4 * 4 + 3] = a.w;
+                sh[j4 * 4] = b.x; sh[j4 * 4 + 1] = b.y; sh[j4 * 4 + 2] = b.z; sh[j4 * 4 + 3] = b.w;
+            }
+            tc::tmem_ld_wait();
+            const int n0 = nt * p.BLOCK_N + k * 32;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = act_fn<ACT>(fmaf(__uint_as_float(v[j]), sc[j], sh[j]));
+
+            if (MODE == 0) {
+                // stage the bf16 tile in shared memory (128B-swizzled rows of 64 channels) for TMA stores
+                const int grp = k >> 1;
+                uint8_t* rowp = c.s_staging + grp * (kBlockM * 128) + row * 128;
+                if (p.gate_bytes) {
+                    const uint8_t* grow = c.s_gate + grp * (kBlockM * 128) + row * 128;
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        const int piece = ((k & 1) * 4 + g4) ^ (row & 7);
+                        const uint4 gv = *reinterpret_cast<const uint4*>(grow + piece * 16);
+                        const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float2 gf = __bfloat1622float2(g2[e]);
+                            f[g4 * 8 + e * 2] *= gf.x;
+                            f[g4 * 8 + e * 2 + 1] *= gf.y;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    uint4 o;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[g4 * 8 + 0], f[g4 * 8 + 1]);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(f[g4 * 8 + 2], f[g4 * 8 + 3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g4 * 8 + 4], f[g4 * 8 + 5]);
+                    __nv_bfloat162 h3 = __floats2bfloat162_rn(f[g4 * 8 + 6], f[g4 * 8 + 7]);
+                    o.x = *reinterpret_cast<uint32_t*>(&h0);
+                    o.y = *reinterpret_cast<uint32_t*>(&h1);
+                    o.z = *reinterpret_cast<uint32_t*>(&h2);
+                    o.w = *reinterpret_cast<uint32_t*>(&h3);
+                    const int piece = ((k & 1) * 4 + g4) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(rowp + piece * 16) = o;
+                }
+            } else if (MODE == 1) {
+                if (valid) {
+                    const size_t plane = (size_t)p.out_h * p.out_w;
+                    const size_t base = (size_t)img * p.N * plane + (size_t)oy * p.out_w + ox;
+                    float* o = reinterpret_cast<float*>(p.out);
+                    if (p.residual) {
+                        float r[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = (n0 + j < p.N) ? __ldg(p.residual + base + (size_t)(n0 + j) * plane) : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] += r[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + j < p.N) o[base + (size_t)(n0 + j) * plane] = f[j];
+                }
+            } else {
+                if (uniform) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = valid ? f[j] : 0.f;
+#pragma unroll
+                    for (int s = 16; s >= 1; s >>= 1) {
+                        const bool upper = (lane & s) != 0;
+#pragma unroll
+                        for (int i = 0; i < s; ++i) {
+                            const float send = upper ? f[i] : f[i + s];
+                            const float keep = upper ? f[i + s] : f[i];
+                            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                        }
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        if (kk == k) acc[kk] += f[0];
+                } else if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(p.pool + (size_t)key * p.N_pad + n0 + j, f[j]);
+                }
+            }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&ctl->tmem_empty[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        if (MODE == 0) {
+            if (p.gate_bytes) {
+                tc::mbar_arrive(&ctl->gate_empty);
+                gphase ^= 1;
+            }
+            tc::fence_proxy_async();               // generic-proxy smem writes -> visible to the TMA engine
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 4 && lane == 0) {
+                for (int g = 0; g < (p.BLOCK_N >> 6); ++g)
+                    tc::tma_store_4d(tmap_out, c.s_staging + g * (kBlockM * 128), nt * p.BLOCK_N + g * 64, tx * p.BX,
+                                     ty * p.BY, img);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
+    if (MODE == 0 && warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (MODE == 2 && cur_key >= 0) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+            if (kk < n_chunks)
+                atomicAdd(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_gate,
                  const __grid_constant__ KParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     const int a_bytes = kBlockM * p.kb_bytes;
     const int b_bytes = p.BLOCK_N * p.kb_bytes;
     const int stage_bytes = a_bytes + b_bytes;             // multiples of 1024 by construction
-    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + (size_t)p.stages * stage_bytes);
+    uint8_t* s_staging = smem + (size_t)p.stages * stage_bytes;            // 1024-aligned
+    uint8_t* s_gate = s_staging + p.staging_bytes;                           // 1024-aligned
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_gate + p.gate_bytes);
     int4* s_slices = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(ctl) + sizeof(SmemCtl));
+    float* s_scale = reinterpret_cast<float*>(s_slices + p.n_slices);
+    float* s_shift = s_scale + p.BLOCK_N;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -94,6 +306,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmap_a);
         tc::prefetch_tmap(&tmap_b);
+        if (p.staging_bytes) tc::prefetch_tmap(&tmap_out);
+        if (p.gate_bytes) tc::prefetch_tmap(&tmap_gate);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -104,6 +318,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tc::mbar_init(&ctl->tmem_full[s], 1);
             tc::mbar_init(&ctl->tmem_empty[s], 128);
         }
+        tc::mbar_init(&ctl->gate_full, 1);
+        tc::mbar_init(&ctl->gate_empty, 128);
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc(&ctl->tmem_base, kTmemCols);
@@ -120,11 +336,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0 && lane == 0) {
         // ================= TMA producer =================
         int stage = 0;
-        uint32_t phase = 0;
+        uint32_t phase = 0, gphase = 0;
         for (int t = t_begin; t < t_end; ++t) {
             int img, ty, tx, nt;
             decode_tile(p, t, img, ty, tx, nt);
             const int x0 = tx * p.BX, y0 = ty * p.BY, pl0 = img * p.plane_per_img;
+            if (p.gate_bytes) {
+                tc::mbar_wait(&ctl->gate_empty, gphase ^ 1);
+                tc::mbar_expect_tx(&ctl->gate_full, (uint32_t)p.gate_bytes);
+                for (int g = 0; g < (p.BLOCK_N >> 6); ++g)
+                    tc::tma_load_4d(s_gate + g * (kBlockM * 128), &tmap_gate, &ctl->gate_full, nt * p.BLOCK_N + g * 64, x0,
+                                    y0, img);
+                gphase ^= 1;
+            }
             for (int j = 0; j < p.n_slices; ++j) {
                 tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
                 uint8_t* sa = smem + (size_t)stage * stage_bytes;
@@ -165,146 +389,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
-        const int q = warp - 4;                    // TMEM lane quarter
-        const int row = q * 32 + lane;
-        const int lx = row % p.BX, ly = row / p.BX;
-        const int n_chunks = p.BLOCK_N >> 5;
-        int as = 0;
-        uint32_t aphase = 0;
-        // pooled-mode running sums (lane L owns column 32*k + L of the current N tile)
-        float acc[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-        int cur_key = -1, cur_nt = 0;
-        const int cell_h = p.cells_y ? p.out_h / p.cells_y : 1, cell_w = p.cells_x ? p.out_w / p.cells_x : 1;
-        const int ncells = p.cells_y * p.cells_x;
-
-        for (int t = t_begin; t < t_end; ++t) {
-            int img, ty, tx, nt;
-            decode_tile(p, t, img, ty, tx, nt);
-            const int ox = tx * p.BX + lx, oy = ty * p.BY + ly;
-            const bool valid = ox < p.out_w && oy < p.out_h;
-            const float* shift = p.shift + (size_t)(p.variant ? p.variant[img] : 0) * p.N_pad;
-            tc::mbar_wait(&ctl->tmem_full[as], aphase);
-            tc::tc_fence_after();
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BLOCK_N);
-
-            int key = -1;
-            bool uniform = false;
-            if (p.epi_mode == 2) {
-                key = valid ? img * ncells + (oy / cell_h) * p.cells_x + (ox / cell_w) : -1;
-                const unsigned vm = __ballot_sync(0xffffffffu, valid);
-                const int leader_key = vm ? __shfl_sync(0xffffffffu, key, __ffs(vm) - 1) : -1;
-                uniform = __all_sync(0xffffffffu, !valid || key == leader_key);
-                if (uniform && vm && (leader_key != cur_key || nt != cur_nt)) {
-                    if (cur_key >= 0) {
-#pragma unroll
-                        for (int kk = 0; kk < 8; ++kk) {
-                            if (kk < n_chunks) {
-                                atomicAdd(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
-                                acc[kk] = 0.f;
-                            }
-                        }
-                    }
-                    cur_key = leader_key;
-                    cur_nt = nt;
-                }
-                if (!vm) uniform = false;   // nothing to add; skip below
-            }
-
-#pragma unroll 1
-            for (int k = 0; k < n_chunks; ++k) {
-                uint32_t v[32];
-                tc::tmem_ld_32x32(taddr0 + (uint32_t)(k * 32), v);
-                tc::tmem_ld_wait();
-                const int n0 = nt * p.BLOCK_N + k * 32;
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]);
-                    const float sc = p.scale ? __ldg(p.scale + n0 + j) : 1.0f;
-                    x = fmaf(x, sc, __ldg(shift + n0 + j));
-                    f[j] = apply_act(x, p.act);
-                }
-                if (p.epi_mode == 0) {
-                    if (valid) {
-                        const size_t off = ((size_t)(img * p.out_h + oy) * p.out_w + ox) * p.N_pad + n0;
-                        if (p.gate) {
-                            const uint4* gp = reinterpret_cast<const uint4*>(p.gate + off);
-#pragma unroll
-                            for (int g4 = 0; g4 < 4; ++g4) {
-                                uint4 gv = __ldg(gp + g4);
-                                const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    float2 gf = __bfloat1622float2(g2[e]);
-                                    f[g4 * 8 + e * 2] *= gf.x;
-                                    f[g4 * 8 + e * 2 + 1] *= gf.y;
-                                }
-                            }
-                        }
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
-#pragma unroll
-                        for (int g4 = 0; g4 < 4; ++g4) {
-                            uint4 o;
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[g4 * 8 + 0], f[g4 * 8 + 1]);
-                            __nv_bfloat162 h1 = __floats2bfloat162_rn(f[g4 * 8 + 2], f[g4 * 8 + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g4 * 8 + 4], f[g4 * 8 + 5]);
-                            __nv_bfloat162 h3 = __floats2bfloat162_rn(f[g4 * 8 + 6], f[g4 * 8 + 7]);
-                            o.x = *reinterpret_cast<uint32_t*>(&h0);
-                            o.y = *reinterpret_cast<uint32_t*>(&h1);
-                            o.z = *reinterpret_cast<uint32_t*>(&h2);
-                            o.w = *reinterpret_cast<uint32_t*>(&h3);
-                            op[g4] = o;
-                        }
-                    }
-                } else if (p.epi_mode == 1) {
-                    if (valid) {
-                        const size_t plane = (size_t)p.out_h * p.out_w;
-                        const size_t base = (size_t)img * p.N * plane + (size_t)oy * p.out_w + ox;
-                        float* o = reinterpret_cast<float*>(p.out);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n = n0 + j;
-                            if (n < p.N) {
-                                float r = f[j];
-                                if (p.residual) r += __ldg(p.residual + base + (size_t)n * plane);
-                                o[base + (size_t)n * plane] = r;
-                            }
-                        }
-                    }
-                } else {
-                    if (uniform) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = valid ? f[j] : 0.f;
-#pragma unroll
-                        for (int s = 16; s >= 1; s >>= 1) {
-                            const bool upper = (lane & s) != 0;
-#pragma unroll
-                            for (int i = 0; i < s; ++i) {
-                                const float send = upper ? f[i] : f[i + s];
-                                const float keep = upper ? f[i + s] : f[i];
-                                f[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-                            }
-                        }
-#pragma unroll
-                        for (int kk = 0; kk < 8; ++kk)
-                            if (kk == k) acc[kk] += f[0];
-                    } else if (valid) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) atomicAdd(p.pool + (size_t)key * p.N_pad + n0 + j, f[j]);
-                    }
-                }
-            }
-            tc::tc_fence_before();
-            tc::mbar_arrive(&ctl->tmem_empty[as]);
-            if (++as == 2) { as = 0; aphase ^= 1; }
-        }
-        if (p.epi_mode == 2 && cur_key >= 0) {
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-                if (kk < n_chunks)
-                    atomicAdd(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
+        EpiCtx c{smem, s_staging, s_gate, ctl, s_scale, s_shift, tmem_base, t_begin, t_end, warp, lane};
+        if (p.epi_mode == 0) {
+            if (p.act == 2) epilogue_loop<0, 2>(p, c, &tmap_out);
+            else if (p.act == 1) epilogue_loop<0, 1>(p, c, &tmap_out);
+            else epilogue_loop<0, 0>(p, c, &tmap_out);
+        } else if (p.epi_mode == 1) {
+            if (p.act == 1) epilogue_loop<1, 1>(p, c, &tmap_out);
+            else epilogue_loop<1, 0>(p, c, &tmap_out);
+        } else {
+            if (p.act == 1) epilogue_loop<2, 1>(p, c, &tmap_out);
+            else epilogue_loop<2, 0>(p, c, &tmap_out);
         }
     }
 
@@ -357,6 +452,9 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     } else {
         RGBD_CHECK_ARG(d->out, "conv_gemm: null output");
     }
+    if (d->epi_mode == 0)
+        RGBD_CHECK_ARG(d->block_n % 64 == 0, "conv_gemm: the channels-last epilogue needs BLOCK_N %% 64 == 0 (got %d)", d->block_n);
+    RGBD_CHECK_ARG(d->epi_mode == 0 || !d->gate, "conv_gemm: gate is only supported by epilogue mode 0");
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) {
         rgbd_set_error("conv_gemm: cuTensorMapEncodeTiled is not available from the driver");
@@ -395,6 +493,26 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         }
     }
 
+    CUtensorMap tmap_out = tmap_a, tmap_gate = tmap_a;   // placeholders unless epilogue mode 0 uses them
+    if (d->epi_mode == 0) {
+        cuuint64_t dims[4] = {(cuuint64_t)d->n_pad, (cuuint64_t)d->out_w, (cuuint64_t)d->out_h, (cuuint64_t)d->n_img};
+        cuuint64_t strides[3] = {(cuuint64_t)d->n_pad * 2, (cuuint64_t)d->n_pad * 2 * d->out_w,
+                                 (cuuint64_t)d->n_pad * 2 * d->out_w * d->out_h};
+        cuuint32_t box[4] = {64, (cuuint32_t)d->bx, (cuuint32_t)d->by, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&tmap_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS && d->gate)
+            r = encode(&tmap_gate, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->gate), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            rgbd_set_error("conv_gemm: cuTensorMapEncodeTiled(out/gate) failed with %d", (int)r);
+            return RGBD_ERR_CUDA;
+        }
+    }
+
     KParams p;
     p.n_img = d->n_img;
     p.BX = d->bx; p.BY = d->by;
@@ -426,7 +544,11 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
     const int stage_bytes = kBlockM * kb_bytes + p.BLOCK_N * kb_bytes;
-    const int fixed = 1024 + (int)sizeof(SmemCtl) + p.n_slices * 16 + 64;
+    p.staging_bytes = d->epi_mode == 0 ? (p.BLOCK_N / 64) * kBlockM * 128 : 0;
+    p.gate_bytes = (d->epi_mode == 0 && d->gate) ? p.staging_bytes : 0;
+    p.ss_in_smem = (!d->variant && p.n_tiles_n == 1) ? 1 : 0;
+    const int fixed = 1024 + (int)sizeof(SmemCtl) + p.n_slices * 16 + 64 + p.staging_bytes + p.gate_bytes +
+                      2 * p.BLOCK_N * (int)sizeof(float);
     int stages = (max_smem - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     RGBD_CHECK_ARG(stages >= 2, "conv_gemm: not enough shared memory for 2 stages");
@@ -435,7 +557,7 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     int smem_bytes = fixed + stages * stage_bytes;
     if (smem_bytes < 160 * 1024) smem_bytes = 160 * 1024;
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-    conv_gemm_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmap_a, tmap_b, p);
+    conv_gemm_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmap_a, tmap_b, tmap_out, tmap_gate, p);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }

@@ -281,13 +281,16 @@ __global__ void __launch_bounds__(256) decomp_pool_kernel(const uint8_t* __restr
     }
 }
 
-__global__ void decomp_export_kernel(const ImgState* __restrict__ st, int B, int* n_modes, int* peak_bins, float* centres,
-                                     float* windows, float* edges_first_last, int* status) {
+__global__ void decomp_export_kernel(const ImgState* __restrict__ st, int B, int num_modes, int* n_modes, int* peak_bins,
+                                     float* centres, float* windows, float* edges_first_last, int* status,
+                                     int* bias_variant) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const ImgState& s = st[b];
     if (n_modes) n_modes[b] = s.n_modes;
     if (status) status[b] = s.status;
+    // number of conv biases the reference adds: m+1 used regions, or all R+1 when no mode survives (CM:676-691)
+    if (bias_variant) bias_variant[b] = s.n_modes == 0 ? num_modes + 1 : s.n_modes + 1;
     for (int k = 0; k < 3; ++k) {
         if (peak_bins) peak_bins[b * 3 + k] = s.peak_bin[k];
         if (centres) centres[b * 3 + k] = s.centre[k];
@@ -313,7 +316,7 @@ extern "C" int rgbd_depth_decompose(const float* depth3, long long depth_batch_s
                                     const float* gray_in, const float* ratio, int B, int H, int W, int num_modes,
                                     float* gray_out, long long* hist_out, float* edges_out, int* n_modes_out,
                                     int* peak_bins_out, float* centres_out, float* windows_out, int* status_out,
-                                    uint8_t* codes_out, int n_levels, const int* level_h, const int* level_w,
+                                    int* bias_variant_out, uint8_t* codes_out, int n_levels, const int* level_h, const int* level_w,
                                     uint8_t* const* pooled_out, void* workspace, rgbd_stream_t stream) {
     RGBD_CHECK_ARG((depth3 != nullptr) != (gray_in != nullptr), "depth_decompose: pass exactly one of depth3 / gray_in");
     RGBD_CHECK_ARG(ratio && workspace && codes_out, "depth_decompose: null ratio / workspace / codes_out");
@@ -351,8 +354,8 @@ extern "C" int rgbd_depth_decompose(const float* depth3, long long depth_batch_s
         decomp_pool_kernel<<<g, 256, 0, s>>>(codes_out, pooled_out[l], H, W, level_h[l], level_w[l]);
         RGBD_CHECK_LAUNCH();
     }
-    decomp_export_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B, n_modes_out, peak_bins_out, centres_out, windows_out,
-                                                         nullptr, status_out);
+    decomp_export_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B, num_modes, n_modes_out, peak_bins_out, centres_out,
+                                                         windows_out, nullptr, status_out, bias_variant_out);
     RGBD_CHECK_LAUNCH();
     if (hist_out)
         RGBD_CHECK_CUDA(cudaMemcpyAsync(hist_out, hist, sizeof(long long) * (size_t)B * kBins, cudaMemcpyDeviceToDevice, s));

@@ -164,6 +164,7 @@ class Decomposition:
     windows: torch.Tensor              # (B,3,2) f32
     peak_bins: torch.Tensor            # (B,3) i32
     status: torch.Tensor               # (B) i32
+    bias_variant: torch.Tensor         # (B) i32: number of DSAM conv biases the reference adds for the image
     hist: Optional[torch.Tensor] = None    # (B,512) i64
     edges: Optional[torch.Tensor] = None   # (B,513) f32
 
@@ -199,6 +200,7 @@ def depth_decompose(ratio: torch.Tensor, levels: Sequence[Tuple[int, int]], dept
     n_modes = torch.empty(B, **i32)
     peak_bins = torch.empty(B, 3, **i32)
     status = torch.empty(B, **i32)
+    bias_variant = torch.empty(B, **i32)
     centres = torch.empty(B, 3, device=dev, dtype=torch.float32)
     windows = torch.empty(B, 3, 2, device=dev, dtype=torch.float32)
     hist = torch.empty(B, HIST_BINS, device=dev, dtype=torch.int64) if debug else None
@@ -209,11 +211,11 @@ def depth_decompose(ratio: torch.Tensor, levels: Sequence[Tuple[int, int]], dept
         gray_out.data_ptr() if depth3 is not None else None,
         hist.data_ptr() if debug else None, edges.data_ptr() if debug else None,
         n_modes.data_ptr(), peak_bins.data_ptr(), centres.data_ptr(), windows.data_ptr(), status.data_ptr(),
-        codes.data_ptr(), len(levels), int_array([h for h, _ in levels]), int_array([w for _, w in levels]),
+        bias_variant.data_ptr(), codes.data_ptr(), len(levels), int_array([h for h, _ in levels]), int_array([w for _, w in levels]),
         ptr_array([p.data_ptr() for p in pooled]), ws.data_ptr(), _stream())
     check(rc, "rgbd_depth_decompose")
     _count(7 + len(levels) + (1 if debug else 0))
-    return Decomposition(gray_out, codes, pooled, n_modes, centres, windows, peak_bins, status, hist, edges)
+    return Decomposition(gray_out, codes, pooled, n_modes, centres, windows, peak_bins, status, bias_variant, hist, edges)
 
 
 # ------------------------------------------------------------------------------------------------

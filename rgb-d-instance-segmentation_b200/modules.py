@@ -206,10 +206,11 @@ class DSAModule(nn.Module):
             self._ws = {key: torch.zeros(shape, device=dev, dtype=torch.bfloat16)}   # keep one shape alive
         return self._ws[key]
 
-    def stage_forward(self, rgb_features: torch.Tensor, codes: torch.Tensor, n_modes: torch.Tensor,
+    def stage_forward(self, rgb_features: torch.Tensor, codes: torch.Tensor, bias_variant: torch.Tensor,
                       residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Batched tensor-core path: features (B,C_in,H,W) fp32, pooled region codes (B,H,W) uint8 and the
-        per-image mode count -> sum_t conv_t(F*p_t) + projection(F) [+ residual]  (fp32, bf16 operands)."""
+        per-image bias count (Decomposition.bias_variant) -> sum_t conv_t(F*p_t) + projection(F) [+ residual]
+        (fp32 result, bf16 operands)."""
         pk = self._refresh()
         x = Fn._req(rgb_features.contiguous(), "rgb_features", torch.float32)
         B, Cc, H, W = x.shape
@@ -229,8 +230,7 @@ class DSAModule(nn.Module):
             ppi = n_seg
             residual = x if residual is None else residual + x
         out = torch.empty(B, self.out_channels, Ho, Wo, device=x.device, dtype=torch.float32)
-        # no surviving mode -> R+1 all-zero masks, every conv still adds its bias (CM:676-678)
-        variant = torch.where(n_modes == 0, torch.full_like(n_modes, R + 1), n_modes + 1).to(torch.int32).contiguous()
+        variant = bias_variant
         Fn.conv_gemm(packed, a_dims, ppi, pk["w"], pk["slices"], kb, B, (Ho, Wo), _best_box(Ho, Wo), self.out_channels,
                      pk["bias"], variant=variant, epi_mode=1, out=out,
                      residual=residual.contiguous() if residual is not None else None)
@@ -250,7 +250,7 @@ class DSAModule(nn.Module):
         ratio = torch.tensor([float(window_size_ratio)], device=rgb_features.device, dtype=torch.float32)
         dec = Fn.depth_decompose(ratio, [(H, W)], gray=gray, num_modes=self.num_depth_regions)
         codes = dec.pooled[0].expand(B, H, W).contiguous()
-        return self.stage_forward(rgb_features, codes, dec.n_modes.expand(B).contiguous())
+        return self.stage_forward(rgb_features, codes, dec.bias_variant.expand(B).contiguous())
 
     # ---- reference helper API (CM:701-798), computed by the device kernel --------------------------
     def _calculate_depth_histogram(self, depth_map, bins=512, value_range=None):
@@ -429,7 +429,7 @@ class DepthGuidance(nn.Module):
         cp1 = [feats[0]]
         x = feats[0]
         for k, dsam in enumerate((self.dsam0, self.dsam1, self.dsam2)):        # CM:339-352
-            x = dsam.stage_forward(x, dec.pooled[k], dec.n_modes, residual=feats[k + 1])
+            x = dsam.stage_forward(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1])
             cp1.append(x)
         # CM:354-355: cp2 = DGGM(feats); out = cp1 + cp2, fused into the DGGM kernel
         return self.depth_gradient_injection.forward_fused_sum(feats, cp1, gradient_depth, gradient_mask)

@@ -201,7 +201,7 @@ def test_dggm_param_gradients(mods):
 # tensor-core implicit GEMM (tcgen05) against a float64 reference of the same bf16 operands
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kb,c,n,hw", [(64, 128, 64, (4, 128)), (64, 64, 256, (8, 64)), (32, 96, 192, (16, 24)),
-                                       (64, 192, 32, (5, 50))])
+                                       (64, 192, 64, (5, 50))])
 def test_conv_gemm_1x1(fn, kb, c, n, hw):
     rs = np.random.RandomState(1)
     B, (H, W) = 2, hw
