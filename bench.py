@@ -321,7 +321,7 @@ class PerKernel:
             pk, ws = rp._refresh(), rp._workspace(B, H, W, pv.device)
             box = _best_box(H, W)
             out["ratio_conv3x3"] = self._time(lambda: Fn.conv_gemm(
-                ws["x4"], (B, H, W, 128), 1, pk["w5"], pk["sl5"], 64, B, (H, W), box, 256, pk["sh5"], scale=pk["sc5"],
+                ws["x4"], (B, H, W, 128), 1, pk["w5"], pk["sl5"], 64, B, (H, W), box, 256, pk["sh5"],
                 act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), tile_order=1))
             ratios = rp(pv[:, 3:6])
             levels = [tuple(f.shape[2:]) for f in feats[:3]]

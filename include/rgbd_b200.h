@@ -127,6 +127,15 @@ typedef struct rgbd_conv_gemm_desc {
 } rgbd_conv_gemm_desc;
 int rgbd_conv_gemm(const rgbd_conv_gemm_desc* desc_host, rgbd_stream_t stream);
 
+/* Fused point-wise middle of EnhancedDepthImageRatioPredictor.forward (CM:1466-1470): feature_fusion (1x1 192->128 +
+ * folded BN + ReLU), attention (1x1 128->64 + ReLU, 1x1 64->128 + sigmoid) and the gating multiply, as three chained
+ * tcgen05 GEMMs per 128-pixel tile with the intermediates kept in tensor memory.  x1: bf16 (B,H,W,192);
+ * w2 (128,192) with the folded BN scale multiplied in, w3 (64,128), w4 (128,64) bf16; sh2 (128): folded BN shift;
+ * sh3 (64), sh4 (128): conv biases; out: bf16 (B,H,W,128).  Tile = bx*by (=128) pixels. */
+int rgbd_ratio_chain(const void* x1_bf16, const void* w2_bf16, const void* w3_bf16, const void* w4_bf16, const float* sh2,
+                     const float* sh3, const float* sh4, void* out_bf16, int B, int H, int W, int bx, int by,
+                     rgbd_stream_t stream);
+
 /* Tail of EnhancedDepthImageRatioPredictor.forward (CM:1473-1485): pooled sums -> conv3x3 256->512 + folded BN +
  * ReLU -> GAP -> MLP -> 0.01 + 0.49*sigmoid.  conv_w (512,256,3,3) fp32; fc_w_host/fc_b_host: 4 layers. */
 int rgbd_ratio_tail(const float* pool_sums, int pool_stride, int cell_pixels, const float* conv_w, const float* conv_scale,

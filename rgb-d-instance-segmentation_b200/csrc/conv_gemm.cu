@@ -25,7 +25,7 @@
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kMaxSlices = 1024;
 constexpr int kThreads = 256;
 constexpr int kTmemCols = 512;
@@ -48,16 +48,19 @@ struct KParams {
     int total_tiles;
     int staging_bytes;    // epi_mode 0: swizzled bf16 output tile staged for TMA stores
     int gate_bytes;       // epi_mode 0 with gate: TMA-loaded gate tile (same layout)
-    int ss_in_smem;       // scale/shift of the (single) N tile cached in shared memory
+    int ss_in_smem;       // (unused)
+    int b_resident;       // whole weight matrix stays in shared memory (single N tile); the ring carries A only
+    int b_res_bytes;
 };
 
-struct SmemCtl {
+struct alignas(16) SmemCtl {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint64_t gate_full;
     uint64_t gate_empty;
+    uint64_t b_full;
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -90,13 +93,13 @@ struct EpiCtx {
 template <int ACT>
 __device__ __forceinline__ float act_fn(float x) {
     if (ACT == 1) return fmaxf(x, 0.f);
-    if (ACT == 2) return __fdividef(1.0f, 1.0f + __expf(-x));
+    if (ACT == 2) return tc::fast_sigmoid(x);
     return x;
 }
 
 // Epilogue warps 4..7: TMEM -> registers -> y = act(acc*scale + shift) -> mode-specific output.
 // MODE and ACT are compile-time so the per-element code is branch-free and the loads are batched.
-template <int MODE, int ACT>
+template <int MODE, int ACT, bool SCALE>
 __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c, const CUtensorMap* tmap_out) {
     SmemCtl* ctl = c.ctl;
     const int warp = c.warp, lane = c.lane;
@@ -127,7 +130,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
         if (want != ss_key) {
             asm volatile("bar.sync 2, 128;" ::: "memory");          // everyone is done with the old table
             for (int i = epi_tid; i < p.BLOCK_N; i += 128) {
-                c.s_scale[i] = p.scale ? __ldg(p.scale + nt * p.BLOCK_N + i) : 1.0f;
+                if (p.scale) c.s_scale[i] = __ldg(p.scale + nt * p.BLOCK_N + i);
                 c.s_shift[i] = __ldg(p.shift + (size_t)var * p.N_pad + nt * p.BLOCK_N + i);
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -171,25 +174,43 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
         for (int k = 0; k < n_chunks; ++k) {
             uint32_t v[32];
             tc::tmem_ld_32x32(taddr0 + (uint32_t)(k * 32), v);
-            float sc[32], sh[32];
+            float sh[32], f[32];
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 a = *reinterpret_cast<const float4*>(c.s_scale + k * 32 + j4 * 4);
                 const float4 b = *reinterpret_cast<const float4*>(c.s_shift + k * 32 + j4 * 4);
-                sc[j4 * 4] = a.x; sc[j4 * 4 + 1] = a.y; sc[j4 * 4 + 2] = a.z; sc[j4 * 4 + 3] = a.w;
                 sh[j4 * 4] = b.x; sh[j4 * 4 + 1] = b.y; sh[j4 * 4 + 2] = b.z; sh[j4 * 4 + 3] = b.w;
             }
-            tc::tmem_ld_wait();
-            const int n0 = nt * p.BLOCK_N + k * 32;
-            float f[32];
+            if (SCALE) {
+                float sc[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = act_fn<ACT>(fmaf(__uint_as_float(v[j]), sc[j], sh[j]));
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 a = *reinterpret_cast<const float4*>(c.s_scale + k * 32 + j4 * 4);
+                    sc[j4 * 4] = a.x; sc[j4 * 4 + 1] = a.y; sc[j4 * 4 + 2] = a.z; sc[j4 * 4 + 3] = a.w;
+                }
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), sc[j], sh[j]);
+            } else {
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + sh[j];
+            }
+            const int n0 = nt * p.BLOCK_N + k * 32;
+            // ReLU of the channels-last store is fused into the bf16 pack below
+            if (!(MODE == 0 && ACT == 1)) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = act_fn<ACT>(f[j]);
+            }
 
             if (MODE == 0) {
                 // stage the bf16 tile in shared memory (128B-swizzled rows of 64 channels) for TMA stores
                 const int grp = k >> 1;
                 uint8_t* rowp = c.s_staging + grp * (kBlockM * 128) + row * 128;
                 if (p.gate_bytes) {
+                    if (ACT == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
                     const uint8_t* grow = c.s_gate + grp * (kBlockM * 128) + row * 128;
 #pragma unroll
                     for (int g4 = 0; g4 < 4; ++g4) {
@@ -207,14 +228,17 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
                     uint4 o;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[g4 * 8 + 0], f[g4 * 8 + 1]);
-                    __nv_bfloat162 h1 = __floats2bfloat162_rn(f[g4 * 8 + 2], f[g4 * 8 + 3]);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g4 * 8 + 4], f[g4 * 8 + 5]);
-                    __nv_bfloat162 h3 = __floats2bfloat162_rn(f[g4 * 8 + 6], f[g4 * 8 + 7]);
-                    o.x = *reinterpret_cast<uint32_t*>(&h0);
-                    o.y = *reinterpret_cast<uint32_t*>(&h1);
-                    o.z = *reinterpret_cast<uint32_t*>(&h2);
-                    o.w = *reinterpret_cast<uint32_t*>(&h3);
+                    if (ACT == 1 && !p.gate_bytes) {
+                        o.x = tc::pack_bf16x2_relu(f[g4 * 8 + 0], f[g4 * 8 + 1]);
+                        o.y = tc::pack_bf16x2_relu(f[g4 * 8 + 2], f[g4 * 8 + 3]);
+                        o.z = tc::pack_bf16x2_relu(f[g4 * 8 + 4], f[g4 * 8 + 5]);
+                        o.w = tc::pack_bf16x2_relu(f[g4 * 8 + 6], f[g4 * 8 + 7]);
+                    } else {
+                        o.x = tc::pack_bf16x2(f[g4 * 8 + 0], f[g4 * 8 + 1]);
+                        o.y = tc::pack_bf16x2(f[g4 * 8 + 2], f[g4 * 8 + 3]);
+                        o.z = tc::pack_bf16x2(f[g4 * 8 + 4], f[g4 * 8 + 5]);
+                        o.w = tc::pack_bf16x2(f[g4 * 8 + 6], f[g4 * 8 + 7]);
+                    }
                     const int piece = ((k & 1) * 4 + g4) ^ (row & 7);
                     *reinterpret_cast<uint4*>(rowp + piece * 16) = o;
                 }
@@ -292,8 +316,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     const int a_bytes = kBlockM * p.kb_bytes;
     const int b_bytes = p.BLOCK_N * p.kb_bytes;
-    const int stage_bytes = a_bytes + b_bytes;             // multiples of 1024 by construction
-    uint8_t* s_staging = smem + (size_t)p.stages * stage_bytes;            // 1024-aligned
+    const int stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;   // multiples of 1024 by construction
+    uint8_t* s_bres = smem;                                                  // resident weights (b_resident)
+    uint8_t* s_ring = smem + p.b_res_bytes;
+    uint8_t* s_staging = s_ring + (size_t)p.stages * stage_bytes;            // 1024-aligned
     uint8_t* s_gate = s_staging + p.staging_bytes;                           // 1024-aligned
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_gate + p.gate_bytes);
     int4* s_slices = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(ctl) + sizeof(SmemCtl));
@@ -318,6 +344,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tc::mbar_init(&ctl->tmem_full[s], 1);
             tc::mbar_init(&ctl->tmem_empty[s], 128);
         }
+        tc::mbar_init(&ctl->b_full, 1);
         tc::mbar_init(&ctl->gate_full, 1);
         tc::mbar_init(&ctl->gate_empty, 128);
         tc::fence_barrier_init();
@@ -337,6 +364,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // ================= TMA producer =================
         int stage = 0;
         uint32_t phase = 0, gphase = 0;
+        if (p.b_resident) {
+            tc::mbar_expect_tx(&ctl->b_full, (uint32_t)p.b_res_bytes);
+            for (int j = 0; j < p.n_slices; ++j)
+                tc::tma_load_2d(s_bres + (size_t)j * b_bytes, &tmap_b, &ctl->b_full, j * (p.kb_bytes >> 1), 0);
+        }
         for (int t = t_begin; t < t_end; ++t) {
             int img, ty, tx, nt;
             decode_tile(p, t, img, ty, tx, nt);
@@ -351,12 +383,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             for (int j = 0; j < p.n_slices; ++j) {
                 tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
-                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                uint8_t* sa = s_ring + (size_t)stage * stage_bytes;
                 uint8_t* sb = sa + a_bytes;
                 tc::mbar_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
                 const int4 sl = s_slices[j];
                 tc::tma_load_4d(sa, &tmap_a, &ctl->full[stage], sl.x, x0 + sl.y, y0 + sl.z, pl0 + sl.w);
-                tc::tma_load_2d(sb, &tmap_b, &ctl->full[stage], j * (p.kb_bytes >> 1), nt * p.BLOCK_N);
+                if (!p.b_resident)
+                    tc::tma_load_2d(sb, &tmap_b, &ctl->full[stage], j * (p.kb_bytes >> 1), nt * p.BLOCK_N);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -368,6 +401,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t phase = 0;
         int as = 0;
         uint32_t aphase = 0;
+        if (p.b_resident) tc::mbar_wait(&ctl->b_full, 0);
         for (int t = t_begin; t < t_end; ++t) {
             tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
             tc::tc_fence_after();
@@ -375,8 +409,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 0; j < p.n_slices; ++j) {
                 tc::mbar_wait(&ctl->full[stage], phase);
                 tc::tc_fence_after();
-                const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint32_t sb = sa + a_bytes;
+                const uint32_t sa = tc::smem_u32(s_ring + (size_t)stage * stage_bytes);
+                const uint32_t sb = p.b_resident ? tc::smem_u32(s_bres + (size_t)j * b_bytes) : sa + a_bytes;
                 const uint64_t adesc = tc::make_kmajor_desc(sa, p.kb_bytes);
                 const uint64_t bdesc = tc::make_kmajor_desc(sb, p.kb_bytes);
                 for (int k = 0; k < k_per_block; ++k)
@@ -390,16 +424,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp >= 4) {
         // ================= epilogue =================
         EpiCtx c{smem, s_staging, s_gate, ctl, s_scale, s_shift, tmem_base, t_begin, t_end, warp, lane};
+        const bool sc = p.scale != nullptr;
         if (p.epi_mode == 0) {
-            if (p.act == 2) epilogue_loop<0, 2>(p, c, &tmap_out);
-            else if (p.act == 1) epilogue_loop<0, 1>(p, c, &tmap_out);
-            else epilogue_loop<0, 0>(p, c, &tmap_out);
+            if (p.act == 2) epilogue_loop<0, 2, false>(p, c, &tmap_out);
+            else if (p.act == 1 && sc) epilogue_loop<0, 1, true>(p, c, &tmap_out);
+            else if (p.act == 1) epilogue_loop<0, 1, false>(p, c, &tmap_out);
+            else epilogue_loop<0, 0, true>(p, c, &tmap_out);
         } else if (p.epi_mode == 1) {
-            if (p.act == 1) epilogue_loop<1, 1>(p, c, &tmap_out);
-            else epilogue_loop<1, 0>(p, c, &tmap_out);
+            epilogue_loop<1, 0, false>(p, c, &tmap_out);
         } else {
-            if (p.act == 1) epilogue_loop<2, 1>(p, c, &tmap_out);
-            else epilogue_loop<2, 0>(p, c, &tmap_out);
+            if (sc) epilogue_loop<2, 1, true>(p, c, &tmap_out);
+            else epilogue_loop<2, 1, false>(p, c, &tmap_out);
         }
     }
 
@@ -543,12 +578,15 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
-    const int stage_bytes = kBlockM * kb_bytes + p.BLOCK_N * kb_bytes;
+    const int b_total = p.n_slices * p.BLOCK_N * kb_bytes;
+    p.b_resident = (p.n_tiles_n == 1 && b_total <= 100 * 1024) ? 1 : 0;
+    p.b_res_bytes = p.b_resident ? b_total : 0;
+    const int stage_bytes = kBlockM * kb_bytes + (p.b_resident ? 0 : p.BLOCK_N * kb_bytes);
     p.staging_bytes = d->epi_mode == 0 ? (p.BLOCK_N / 64) * kBlockM * 128 : 0;
     p.gate_bytes = (d->epi_mode == 0 && d->gate) ? p.staging_bytes : 0;
     p.ss_in_smem = (!d->variant && p.n_tiles_n == 1) ? 1 : 0;
     const int fixed = 1024 + (int)sizeof(SmemCtl) + p.n_slices * 16 + 64 + p.staging_bytes + p.gate_bytes +
-                      2 * p.BLOCK_N * (int)sizeof(float);
+                      2 * p.BLOCK_N * (int)sizeof(float) + p.b_res_bytes;
     int stages = (max_smem - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     RGBD_CHECK_ARG(stages >= 2, "conv_gemm: not enough shared memory for 2 stages");

@@ -131,4 +131,22 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// pack two floats to bf16x2 (first -> low half), optionally with a fused ReLU
+__device__ __forceinline__ uint32_t pack_bf16x2(float first, float second) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float first, float second) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
+    return d;
+}
+// sigmoid(x) = 0.5*tanh(0.5x) + 0.5 : one MUFU op
+__device__ __forceinline__ float fast_sigmoid(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+}
+
 }  // namespace tc

@@ -294,6 +294,30 @@ def ratio_stem_pack(depth3: torch.Tensor, out: torch.Tensor) -> None:
     _count(1)
 
 
+def ratio_chain(x1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor, w4: torch.Tensor, sh2: torch.Tensor,
+                sh3: torch.Tensor, sh4: torch.Tensor, out: torch.Tensor, box: Tuple[int, int]) -> None:
+    """K4b.  x1 (B,H,W,192) bf16 -> out (B,H,W,128) bf16 = f * sigmoid(W4 relu(W3 f + b3) + b4), f = relu(W2' x1 + sh2)
+    where W2' already carries the folded BatchNorm scale."""
+    lib = _lib.load()
+    _req(x1, "x1", torch.bfloat16)
+    _req(out, "out", torch.bfloat16)
+    B, H, W, c = x1.shape
+    if c != 192 or out.shape != (B, H, W, 128):
+        raise RgbdB200Error("ratio_chain: x1 must be (B,H,W,192) and out (B,H,W,128)")
+    for t, shp in ((w2, (128, 192)), (w3, (64, 128)), (w4, (128, 64))):
+        _req(t, "chain weight", torch.bfloat16)
+        if tuple(t.shape) != shp:
+            raise RgbdB200Error(f"ratio_chain: weight shape {tuple(t.shape)} != {shp}")
+    for t, n in ((sh2, 128), (sh3, 64), (sh4, 128)):
+        _req(t, "chain scale/shift", torch.float32)
+        if t.numel() != n:
+            raise RgbdB200Error("ratio_chain: bad scale/shift length")
+    check(lib.rgbd_ratio_chain(x1.data_ptr(), w2.data_ptr(), w3.data_ptr(), w4.data_ptr(), sh2.data_ptr(),
+                               sh3.data_ptr(), sh4.data_ptr(), out.data_ptr(), B, H, W, box[0], box[1], _stream()),
+          "rgbd_ratio_chain")
+    _count(1)
+
+
 def ratio_tail(pool: torch.Tensor, cell_pixels: int, conv_w: torch.Tensor, conv_scale: torch.Tensor,
                conv_shift: torch.Tensor, fc_w: Sequence[torch.Tensor], fc_b: Sequence[torch.Tensor],
                out_min: float, out_max: float) -> torch.Tensor:

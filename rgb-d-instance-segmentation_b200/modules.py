@@ -298,6 +298,7 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         self.output_min = 0.01
         self.output_max = 0.5
         self.sigmoid = nn.Sigmoid()
+        self.use_fused_chain = True        # False: three separate GEMM launches (kept for cross-checks)
         self._ver = _Versioned()
         self._packed: Dict[str, torch.Tensor] = {}
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
@@ -322,16 +323,19 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
                 s, h = _fold_bn(seq[0].bias, seq[1])
                 sc1.append(s)
                 sh1.append(h)
-            pk = {"w1": w1.reshape(192, 256).to(bf).contiguous(), "sc1": torch.cat(sc1), "sh1": torch.cat(sh1)}
-            pk["w2"] = self.feature_fusion[0].weight.float().reshape(128, 192).to(bf).contiguous()
-            pk["sc2"], pk["sh2"] = _fold_bn(self.feature_fusion[0].bias, self.feature_fusion[1])
+            # folded BatchNorm scales are multiplied into the weights before the bf16 rounding, so the
+            # epilogues only add the shift
+            sc1 = torch.cat(sc1)
+            pk = {"w1": (w1.reshape(192, 256) * sc1[:, None]).to(bf).contiguous(), "sh1": torch.cat(sh1)}
+            sc2, pk["sh2"] = _fold_bn(self.feature_fusion[0].bias, self.feature_fusion[1])
+            pk["w2"] = (self.feature_fusion[0].weight.float().reshape(128, 192) * sc2[:, None]).to(bf).contiguous()
             pk["w3"] = self.attention[0].weight.float().reshape(64, 128).to(bf).contiguous()
             pk["sh3"] = self.attention[0].bias.detach().float().contiguous()
             pk["w4"] = self.attention[2].weight.float().reshape(128, 64).to(bf).contiguous()
             pk["sh4"] = self.attention[2].bias.detach().float().contiguous()
             c5 = self.feature_extractor[0]
-            pk["w5"] = c5.weight.float().permute(0, 2, 3, 1).reshape(256, 9 * 128).to(bf).contiguous()   # K = (tap, c)
-            pk["sc5"], pk["sh5"] = _fold_bn(c5.bias, self.feature_extractor[1])
+            sc5, pk["sh5"] = _fold_bn(c5.bias, self.feature_extractor[1])
+            pk["w5"] = (c5.weight.float().permute(0, 2, 3, 1).reshape(256, 9 * 128) * sc5[:, None]).to(bf).contiguous()  # K = (tap, c)
             c6 = self.feature_extractor[4]
             pk["w6"] = c6.weight.detach().float().contiguous()
             pk["sc6"], pk["sh6"] = _fold_bn(c6.bias, self.feature_extractor[5])
@@ -350,14 +354,14 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         return pk
 
     def _workspace(self, B, H, W, dev):
-        key = (B, H, W, str(dev))
+        key = (B, H, W, str(dev), self.use_fused_chain)
         if key not in self._ws:
             bf = dict(device=dev, dtype=torch.bfloat16)
             self._ws = {key: {
                 "stem": torch.empty(B, H + 6, W, 64, **bf),
                 "x1": torch.empty(B, H, W, 192, **bf),
-                "x2": torch.empty(B, H, W, 128, **bf),
-                "x3": torch.empty(B, H, W, 64, **bf),
+                "x2": torch.empty(B, H, W, 128, **bf) if not self.use_fused_chain else None,
+                "x3": torch.empty(B, H, W, 64, **bf) if not self.use_fused_chain else None,
                 "x4": torch.empty(B, H, W, 128, **bf),
                 "pool": torch.empty(B, 16, 256, device=dev, dtype=torch.float32),
             }}
@@ -379,19 +383,23 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         Fn.ratio_stem_pack(d, ws["stem"])
         # multi-scale stem (CM:1458-1463) + BN + ReLU -> 192 channels
         Fn.conv_gemm(ws["stem"], (B, H + 6, W, 64), 1, pk["w1"], pk["sl1"], 64, B, (H, W), box, 192, pk["sh1"],
-                     scale=pk["sc1"], act=1, out=ws["x1"])
-        # feature_fusion (CM:1466)
-        Fn.conv_gemm(ws["x1"], (B, H, W, 192), 1, pk["w2"], pk["sl2"], 64, B, (H, W), box, 128, pk["sh2"],
-                     scale=pk["sc2"], act=1, out=ws["x2"])
-        # attention (CM:1469-1470): sigmoid(conv(relu(conv(f)))) * f
-        Fn.conv_gemm(ws["x2"], (B, H, W, 128), 1, pk["w3"], pk["sl3"], 64, B, (H, W), box, 64, pk["sh3"], act=1,
-                     out=ws["x3"])
-        Fn.conv_gemm(ws["x3"], (B, H, W, 64), 1, pk["w4"], pk["sl4"], 64, B, (H, W), box, 128, pk["sh4"], act=2,
-                     gate=ws["x2"], out=ws["x4"])
+                     act=1, out=ws["x1"])
+        if self.use_fused_chain:
+            # feature_fusion + attention + gating (CM:1466-1470) as one kernel, intermediates in tensor memory
+            Fn.ratio_chain(ws["x1"], pk["w2"], pk["w3"], pk["w4"], pk["sh2"], pk["sh3"], pk["sh4"], ws["x4"], box)
+        else:
+            # feature_fusion (CM:1466)
+            Fn.conv_gemm(ws["x1"], (B, H, W, 192), 1, pk["w2"], pk["sl2"], 64, B, (H, W), box, 128, pk["sh2"],
+                         act=1, out=ws["x2"])
+            # attention (CM:1469-1470): sigmoid(conv(relu(conv(f)))) * f
+            Fn.conv_gemm(ws["x2"], (B, H, W, 128), 1, pk["w3"], pk["sl3"], 64, B, (H, W), box, 64, pk["sh3"], act=1,
+                         out=ws["x3"])
+            Fn.conv_gemm(ws["x3"], (B, H, W, 64), 1, pk["w4"], pk["sl4"], 64, B, (H, W), box, 128, pk["sh4"], act=2,
+                         gate=ws["x2"], out=ws["x4"])
         # feature_extractor[0:4] (CM:1412-1416): conv3x3 + BN + ReLU + AdaptiveAvgPool2d(4), pooled in the epilogue
         ws["pool"].zero_()
         Fn.conv_gemm(ws["x4"], (B, H, W, 128), 1, pk["w5"], pk["sl5"], 64, B, (H, W), box, 256, pk["sh5"],
-                     scale=pk["sc5"], act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), tile_order=1)
+                     act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), tile_order=1)
         return Fn.ratio_tail(ws["pool"], (H // 4) * (W // 4), pk["w6"], pk["sc6"], pk["sh6"],
                              [pk[f"fw{j}"] for j in range(4)], [pk[f"fb{j}"] for j in range(4)],
                              self.output_min, self.output_max)

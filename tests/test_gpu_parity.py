@@ -242,6 +242,47 @@ def test_conv_gemm_3x3_pool(fn):
     assert rel_err(pool, ref) < 1e-4
 
 
+@pytest.mark.parametrize("hw", [(4, 128), (9, 50), (16, 200)])
+def test_ratio_chain_fused(fn, hw):
+    """Three chained GEMMs with TMEM-resident intermediates vs float64 math on the same bf16 operands."""
+    rs = np.random.RandomState(3)
+    B, (H, W) = 2, hw
+    bf = torch.bfloat16
+    x1 = torch.from_numpy(np.abs(rs.randn(B, H, W, 192)).astype(np.float32)).cuda().to(bf)
+    w2 = torch.from_numpy((rs.randn(128, 192) / np.sqrt(192)).astype(np.float32)).cuda().to(bf)
+    w3 = torch.from_numpy((rs.randn(64, 128) / np.sqrt(128)).astype(np.float32)).cuda().to(bf)
+    w4 = torch.from_numpy((rs.randn(128, 64) / np.sqrt(64)).astype(np.float32)).cuda().to(bf)
+    sc2 = torch.from_numpy(rs.uniform(0.5, 1.5, 128).astype(np.float32)).cuda()
+    sh2, sh4 = (torch.from_numpy((rs.randn(128) * 0.2).astype(np.float32)).cuda() for _ in range(2))
+    sh3 = torch.from_numpy((rs.randn(64) * 0.2).astype(np.float32)).cuda()
+    out = torch.zeros(B, H, W, 128, device="cuda", dtype=bf)
+    from rgbd_b200.modules import _best_box
+    w2 = (w2.float() * sc2[:, None]).to(bf)          # the BN scale is folded into the weights
+    fn.ratio_chain(x1, w2, w3, w4, sh2, sh3, sh4, out, _best_box(H, W))
+    f = torch.relu(x1.double() @ w2.double().T + sh2.double()).to(bf).double()   # kernel rounds f to bf16
+    a = torch.relu(f @ w3.double().T + sh3.double()).to(bf).double()
+    ref = f * torch.sigmoid(a @ w4.double().T + sh4.double())
+    assert rel_err(out.double(), ref) < 8e-3
+
+
+def test_ratio_predictor_fused_chain_matches_unfused(mods):
+    w = OW.ratio_weights(seed=500)
+    frames = []
+    for j in range(2):
+        _, d = synthetic.synth_rgbd_u8(60 + j, 48, 64, "nyu")
+        frames.append(synthetic.normalise_u8(np.repeat(d[:, :, None], 3, axis=2)))
+    x = torch.from_numpy(np.stack(frames)).cuda()
+    res = []
+    for fused in (True, False):
+        m = mods.EnhancedDepthImageRatioPredictor(3)
+        m.use_fused_chain = fused
+        m.load_state_dict(w)
+        m.cuda().eval()
+        with torch.no_grad():
+            res.append(m(x).cpu())
+    assert float(((res[0] - res[1]).abs() / res[1]).max()) < 2e-3
+
+
 # ---------------------------------------------------------------------------------------------------
 # E-DSAM: DSAModule / ratio predictor / v0.4.0 wiring
 # ---------------------------------------------------------------------------------------------------

@@ -166,11 +166,11 @@ def test_ratio_predictor_packing_reproduces_the_reference_chain():
         y = y * (f(pk[sc]) if sc else 1.0) + f(pk[sh])
         return np.maximum(y, 0) if act == 1 else (1 / (1 + np.exp(-y)) if act == 2 else y)
 
-    x1 = layer(stem, "w1", "sl1", 64, 192, "sc1", "sh1", 1)
-    x2 = layer(x1, "w2", "sl2", 64, 128, "sc2", "sh2", 1)
+    x1 = layer(stem, "w1", "sl1", 64, 192, None, "sh1", 1)
+    x2 = layer(x1, "w2", "sl2", 64, 128, None, "sh2", 1)
     x3 = layer(x2, "w3", "sl3", 64, 64, None, "sh3", 1)
     x4 = layer(x3, "w4", "sl4", 64, 128, None, "sh4", 2) * x2
-    y5 = layer(x4, "w5", "sl5", 64, 256, "sc5", "sh5", 1)            # (1,H,W,256)
+    y5 = layer(x4, "w5", "sl5", 64, 256, None, "sh5", 1)            # (1,H,W,256)
     pooled = torch.nn.functional.adaptive_avg_pool2d(torch.from_numpy(y5).permute(0, 3, 1, 2), 4)
     z = torch.nn.functional.conv2d(pooled.float(), pk["w6"], None, padding=1) * pk["sc6"][None, :, None, None] \
         + pk["sh6"][None, :, None, None]
