@@ -13,8 +13,8 @@
 // bf16 weights [N][K] (K-major), K ordered like the slice table.  D: fp32 accumulators in TMEM,
 // 128 pixels x BLOCK_N channels, double buffered so the epilogue of tile i overlaps the MMAs of i+1.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (TMEM -> registers -> fused scale/shift/activation -> global).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
+// allocator, warps 4-11 = epilogue, two per TMEM lane quarter (TMEM -> registers -> fused scale/shift/activation -> global).
 // Epilogues: (0) bf16 channels-last store with optional gating multiply, (1) fp32 NCHW store with
 // optional residual add, (2) adaptive-average-pool accumulation (the 256-channel map of the ratio
 // predictor is never written: CM:1412-1416 BN/ReLU/AdaptiveAvgPool2d(4) are fused here).
@@ -27,7 +27,8 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kMaxStages = 12;
 constexpr int kMaxSlices = 1024;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;        // 4 control warps + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
 
 struct KParams {
@@ -97,17 +98,18 @@ __device__ __forceinline__ float act_fn(float x) {
     return x;
 }
 
-// Epilogue warps 4..7: TMEM -> registers -> y = act(acc*scale + shift) -> mode-specific output.
+// Epilogue warps 4..11: TMEM -> registers -> y = act(acc*scale + shift) -> mode-specific output.
 // MODE and ACT are compile-time so the per-element code is branch-free and the loads are batched.
 template <int MODE, int ACT, bool SCALE>
 __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c, const CUtensorMap* tmap_out) {
     SmemCtl* ctl = c.ctl;
     const int warp = c.warp, lane = c.lane;
-    const int q = warp - 4;                    // TMEM lane quarter
+    const int q = warp & 3;                    // TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..)
+    const int half = (warp - 4) >> 2;          // two warps per quarter: chunks k = half, half+2, ...
     const int row = q * 32 + lane;
     const int lx = row % p.BX, ly = row / p.BX;
     const int n_chunks = p.BLOCK_N >> 5;
-    const int epi_tid = row;                   // 0..127
+    const int epi_tid = (int)threadIdx.x - 128;   // 0..255
     int as = 0;
     uint32_t aphase = 0, gphase = 0;
     float acc[8];                              // pooled-mode running sums (lane L owns column 32*k + L)
@@ -128,12 +130,12 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
         const int var = p.variant ? __ldg(p.variant + img) : 0;
         const int want = var * p.n_tiles_n + nt;
         if (want != ss_key) {
-            asm volatile("bar.sync 2, 128;" ::: "memory");          // everyone is done with the old table
-            for (int i = epi_tid; i < p.BLOCK_N; i += 128) {
+            asm volatile("bar.sync 2, 256;" ::: "memory");          // everyone is done with the old table
+            for (int i = epi_tid; i < p.BLOCK_N; i += kEpiThreads) {
                 if (p.scale) c.s_scale[i] = __ldg(p.scale + nt * p.BLOCK_N + i);
                 c.s_shift[i] = __ldg(p.shift + (size_t)var * p.N_pad + nt * p.BLOCK_N + i);
             }
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+            asm volatile("bar.sync 2, 256;" ::: "memory");
             ss_key = want;
         }
 
@@ -152,7 +154,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
                 if (cur_key >= 0) {
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {
-                        if (kk < n_chunks) {
+                        if (kk < n_chunks && (kk & 1) == half) {
                             atomicAdd(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
                             acc[kk] = 0.f;
                         }
@@ -167,11 +169,11 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
             if (p.gate_bytes) tc::mbar_wait(&ctl->gate_full, gphase);
             // the previous tile's TMA stores must have finished reading the staging buffer
             if (warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
 
 #pragma unroll 1
-        for (int k = 0; k < n_chunks; ++k) {
+        for (int k = half; k < n_chunks; k += 2) {
             uint32_t v[32];
             tc::tmem_ld_32x32(taddr0 + (uint32_t)(k * 32), v);
             float sh[32], f[32];
@@ -290,7 +292,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
                 gphase ^= 1;
             }
             tc::fence_proxy_async();               // generic-proxy smem writes -> visible to the TMA engine
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (warp == 4 && lane == 0) {
                 for (int g = 0; g < (p.BLOCK_N >> 6); ++g)
                     tc::tma_store_4d(tmap_out, c.s_staging + g * (kBlockM * 128), nt * p.BLOCK_N + g * 64, tx * p.BX,
@@ -303,7 +305,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
     if (MODE == 2 && cur_key >= 0) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-            if (kk < n_chunks)
+            if (kk < n_chunks && (kk & 1) == half)
                 atomicAdd(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
     }
 }
@@ -342,11 +344,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&ctl->tmem_full[s], 1);
-            tc::mbar_init(&ctl->tmem_empty[s], 128);
+            tc::mbar_init(&ctl->tmem_empty[s], kEpiThreads);
         }
         tc::mbar_init(&ctl->b_full, 1);
         tc::mbar_init(&ctl->gate_full, 1);
-        tc::mbar_init(&ctl->gate_empty, 128);
+        tc::mbar_init(&ctl->gate_empty, kEpiThreads);
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc(&ctl->tmem_base, kTmemCols);

@@ -18,7 +18,7 @@
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;               // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kStages = 6;                 // 16 KB each: two tiles of three 64-channel slices
 constexpr int kSliceBytes = kBlockM * 128; // 16 KB
 constexpr int kW2Bytes = 3 * 128 * 128;    // 48 KB
@@ -113,8 +113,8 @@ ratio_chain_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_con
         tc::mbar_init(&ctl->acc2_full, 1);
         tc::mbar_init(&ctl->acc3_full, 1);
         tc::mbar_init(&ctl->acc4_full, 1);
-        tc::mbar_init(&ctl->x2_ready, 128);
-        tc::mbar_init(&ctl->x3_ready, 128);
+        tc::mbar_init(&ctl->x2_ready, 256);
+        tc::mbar_init(&ctl->x3_ready, 256);
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc(&ctl->tmem_base, 512);
@@ -187,7 +187,8 @@ ratio_chain_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_con
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
-        const int q = warp - 4;
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;           // chunks k = half, half+2 (E2, E4) / k = half (E3)
         const int row = q * 32 + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t tphase = 0;
@@ -201,7 +202,7 @@ ratio_chain_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_con
             tc::mbar_wait(&ctl->acc2_full, tphase);
             tc::tc_fence_after();
 #pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
+            for (int k = half; k < 4; k += 2) {
                 uint32_t v[32];
                 tc::tmem_ld_32x32(lane_base + kColAcc2 + k * 32, v);
                 tc::tmem_ld_wait();
@@ -221,8 +222,8 @@ ratio_chain_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_con
             // ---- E3: relu(acc3 + b3) -> bf16 -> TMEM
             tc::mbar_wait(&ctl->acc3_full, tphase);
             tc::tc_fence_after();
-#pragma unroll 1
-            for (int k = 0; k < 2; ++k) {
+            {
+                const int k = half;
                 uint32_t v[32];
                 tc::tmem_ld_32x32(lane_base + kColAcc3 + k * 32, v);
                 tc::tmem_ld_wait();
@@ -243,9 +244,9 @@ ratio_chain_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_con
             tc::mbar_wait(&ctl->acc4_full, tphase);
             tc::tc_fence_after();
             if (warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
+            for (int k = half; k < 4; k += 2) {
                 uint32_t v[32], g[16];
                 tc::tmem_ld_32x32(lane_base + kColAcc4 + k * 32, v);
                 tmem_ld_32x16(lane_base + kColX2 + k * 16, g);
@@ -271,7 +272,7 @@ ratio_chain_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_con
             }
             tc::tc_fence_before();
             tc::fence_proxy_async();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (warp == 4 && lane == 0) {
                 for (int g2 = 0; g2 < 2; ++g2)
                     tc::tma_store_4d(&tmap_out, s_staging + g2 * kSliceBytes, g2 * 64, tx * p.BX, ty * p.BY, img);

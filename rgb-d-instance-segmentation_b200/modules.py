@@ -383,7 +383,7 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         Fn.ratio_stem_pack(d, ws["stem"])
         # multi-scale stem (CM:1458-1463) + BN + ReLU -> 192 channels
         Fn.conv_gemm(ws["stem"], (B, H + 6, W, 64), 1, pk["w1"], pk["sl1"], 64, B, (H, W), box, 192, pk["sh1"],
-                     act=1, out=ws["x1"])
+                     act=1, out=ws["x1"], tile_order=1)   # walk down columns: the 4 row taps re-hit L2
         if self.use_fused_chain:
             # feature_fusion + attention + gating (CM:1466-1470) as one kernel, intermediates in tensor memory
             Fn.ratio_chain(ws["x1"], pk["w2"], pk["w3"], pk["w4"], pk["sh2"], pk["sh3"], pk["sh4"], ws["x4"], box)
