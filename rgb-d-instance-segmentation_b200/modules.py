@@ -426,18 +426,27 @@ class DepthGuidance(nn.Module):
 
     def forward(self, pixel_values: torch.Tensor, color_feature_map: Sequence[torch.Tensor],
                 ratios: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
-        depth = pixel_values[:, 3:6]
-        gradient_depth = pixel_values[:, 6:9]
-        gradient_mask = pixel_values[:, 9:10]
-        feats = [f.detach().contiguous() for f in color_feature_map]          # CM:332-333 (detach; no clone needed)
-        if ratios is None:
-            ratios = self.ratio_predictor(depth)                                # CM:336
-        levels = [tuple(f.shape[2:]) for f in feats[:3]]
-        dec = Fn.depth_decompose(ratios.reshape(-1).contiguous(), levels, depth3=depth)
-        cp1 = [feats[0]]
-        x = feats[0]
-        for k, dsam in enumerate((self.dsam0, self.dsam1, self.dsam2)):        # CM:339-352
-            x = dsam.stage_forward(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1])
-            cp1.append(x)
-        # CM:354-355: cp2 = DGGM(feats); out = cp1 + cp2, fused into the DGGM kernel
-        return self.depth_gradient_injection.forward_fused_sum(feats, cp1, gradient_depth, gradient_mask)
+        return depth_guidance_forward(self.ratio_predictor, (self.dsam0, self.dsam1, self.dsam2),
+                                      self.depth_gradient_injection, pixel_values, color_feature_map, ratios)
+
+
+def depth_guidance_forward(ratio_predictor: EnhancedDepthImageRatioPredictor, dsams: Sequence[DSAModule],
+                           dggm: DepthGradientInjectionResidual, pixel_values: torch.Tensor,
+                           color_feature_map: Sequence[torch.Tensor], ratios: Optional[torch.Tensor] = None
+                           ) -> List[torch.Tensor]:
+    """CM:324-355 from the encoder's feature maps to the list handed to the pixel decoder (inference path)."""
+    depth = pixel_values[:, 3:6]
+    gradient_depth = pixel_values[:, 6:9]
+    gradient_mask = pixel_values[:, 9:10]
+    feats = [f.detach().contiguous().float() for f in color_feature_map]   # CM:332-333 (detach; no clone needed)
+    if ratios is None:
+        ratios = ratio_predictor(depth)                                     # CM:336
+    levels = [tuple(f.shape[2:]) for f in feats[:3]]
+    dec = Fn.depth_decompose(ratios.reshape(-1).contiguous(), levels, depth3=depth)
+    cp1 = [feats[0]]
+    x = feats[0]
+    for k, dsam in enumerate(dsams):                                        # CM:339-352
+        x = dsam.stage_forward(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1])
+        cp1.append(x)
+    # CM:354-355: cp2 = DGGM(feats); out = cp1 + cp2, fused into the DGGM kernel
+    return dggm.forward_fused_sum(feats, cp1, gradient_depth, gradient_mask)

@@ -359,3 +359,53 @@ def test_depth_guidance_wiring(mods, golden_dir):
         assert rel_l2(fused_given[i], ref) < BF16_TOL
         # with our own ratio a few boundary pixels of the region masks may flip
         assert rel_l2(fused_own[i], ref) < 3 * BF16_TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole model: HF Mask2Former (stock Swin / pixel decoder / transformer decoder) + CUDA depth guidance
+# ---------------------------------------------------------------------------------------------------
+def test_whole_model_logits_match_cpu_oracle_model(mods):
+    """BASELINE configs[0] in miniature: the v0.4.0 model on one synthetic RGB-D frame, GPU (CUDA hot path)
+    against the same weights on CPU with the oracle hot path (reference predictor path)."""
+    import copy
+    from rgbd_b200 import pixel_level
+    torch.manual_seed(0)
+    cfg = pixel_level.swin_tiny_mask2former_config(num_labels=8)
+    model = pixel_level.build_rgbd_mask2former(cfg).eval()
+    w = OW.guidance_weights(seed=700)
+    plm = model.model.pixel_level_module
+    missing = plm.load_state_dict(w, strict=False)
+    assert not missing.unexpected_keys
+    H, W = 128, 160
+    pvs = []
+    for j in range(2):
+        rgb, d = synthetic.synth_rgbd_u8(90 + j, H, W, "nyu")
+        pvs.append(synthetic.assemble_pixel_values(rgb, d, O.gradient_features))
+    pv = torch.from_numpy(np.stack(pvs))
+
+    cpu_model = copy.deepcopy(model)
+    cpu_plm = cpu_model.model.pixel_level_module
+
+    def oracle_forward(pixel_values, output_hidden_states=False):
+        feats = cpu_plm.encoder(pixel_values[:, 0:3]).feature_maps
+        fused, _ = O.depth_guidance_forward(w, pixel_values, list(feats))
+        dec = cpu_plm.decoder(fused, output_hidden_states=output_hidden_states)
+        from transformers.models.mask2former.modeling_mask2former import Mask2FormerPixelLevelModuleOutput
+        return Mask2FormerPixelLevelModuleOutput(encoder_last_hidden_state=fused[-1], encoder_hidden_states=None,
+                                                 decoder_last_hidden_state=dec.mask_features,
+                                                 decoder_hidden_states=dec.multi_scale_features)
+    cpu_plm.forward = oracle_forward
+    with torch.no_grad():
+        ref = cpu_model(pixel_values=pv)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        out = model.cuda()(pixel_values=pv.cuda())
+    for name in ("class_queries_logits", "masks_queries_logits"):
+        a, b = getattr(out, name), getattr(ref, name)
+        assert a.shape == b.shape
+        assert rel_l2(a, b) < 2e-2, (name, rel_l2(a, b))
+    # instance masks after the reference's post-processing threshold agree (mask parity, PR:701-703)
+    pa = (out.masks_queries_logits.cpu().sigmoid() > 0.5)
+    pb = (ref.masks_queries_logits.sigmoid() > 0.5)
+    agree = float((pa == pb).float().mean())
+    assert agree > 0.995, agree
