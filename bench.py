@@ -121,7 +121,7 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -216,7 +216,6 @@ def run_own(args):
     e1.record()
     barrier()
     launches = Fn.LAUNCHES
-    clocks = sampler.stop()
     elapsed = e0.elapsed_time(e1) / 1e3
     t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
     if world > 1:
@@ -224,28 +223,56 @@ def run_own(args):
     elapsed = float(t.item())
     value = world * B * args.steps / elapsed
 
-    # ---- e2e: pinned host inputs -> device, hot path, fused features -> host, every step
-    copy_stream = torch.cuda.current_stream()
+    # ---- e2e: every step copies its inputs from pinned host memory, runs the hot path through the nn.Module API and
+    # reads the fused features back to pinned host memory.  The three legs run on their own streams with two input
+    # buffers, so step i's H2D overlaps step i-1's compute and step i-2's D2H (how a serving loop would drive it).
     h2d = pv_host.numel() * 4 + sum(f.numel() * 4 for f in feats_host)
     d2h = sum(f.numel() * 4 for f in feats_host)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    s_main = torch.cuda.current_stream()
+    pv_buf = [pv, torch.empty_like(pv)]
+    ft_buf = [feats, [torch.empty_like(f) for f in feats]]
+    out_host2 = [out_host, [torch.empty_like(f).pin_memory() for f in feats_host]]
 
-    def e2e_step():
-        pv.copy_(pv_host, non_blocking=True)
-        for f, fh in zip(feats, feats_host):
-            f.copy_(fh, non_blocking=True)
-        with torch.no_grad():
-            outs = model(pv, feats)
-        for o, oh in zip(outs, out_host):
-            oh.copy_(o, non_blocking=True)
-        copy_stream.synchronize()
+    def e2e_run(n_steps):
+        ev_in = [None, None]
+        ev_free = [None, None]       # compute finished reading input buffer b
+        ev_d2h = [None, None]        # D2H finished reading the outputs written into host buffer b
+        keep = []
+        for i in range(n_steps):
+            b = i & 1
+            with torch.cuda.stream(s_in):
+                if ev_free[b] is not None:
+                    s_in.wait_event(ev_free[b])
+                pv_buf[b].copy_(pv_host, non_blocking=True)
+                for f, fh in zip(ft_buf[b], feats_host):
+                    f.copy_(fh, non_blocking=True)
+                ev_in[b] = s_in.record_event()
+            s_main.wait_event(ev_in[b])
+            with torch.no_grad():
+                outs = model(pv_buf[b], ft_buf[b])
+            ev_free[b] = s_main.record_event()
+            keep.append(outs)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_free[b])
+                if ev_d2h[b] is not None:
+                    s_out.wait_event(ev_d2h[b])
+                for o, oh in zip(outs, out_host2[b]):
+                    oh.copy_(o, non_blocking=True)
+                ev_d2h[b] = s_out.record_event()
+        for e in ev_d2h:
+            if e is not None:
+                s_main.wait_event(e)
+        return keep
 
-    e2e_step()
+    e2e_run(2)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    kept = e2e_run(args.steps)
     e1.record()
     barrier()
+    del kept
+    clocks = sampler.stop()          # sampled over the device-resident and the e2e timed regions
     t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -279,7 +306,8 @@ def run_own(args):
             "config": {"workload": "configs[1]: batch-32/GPU inference, 480x640 RGB-D, Swin-T pyramid, depth-guidance hot path",
                        "batch_per_gpu": B, "frame": [H, W], "channels": list(CHANS),
                        "l2": "per-step inputs (835 MB) exceed the 126 MB L2; no flush needed"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "how": "DepthGuidance.forward on pinned-host inputs; H2D / compute / D2H on 3 streams, 2 input buffers"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,
