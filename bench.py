@@ -350,7 +350,7 @@ class PerKernel:
             box = _best_box(H, W)
             out["ratio_conv3x3"] = self._time(lambda: Fn.conv_gemm(
                 ws["x4"], (B, H, W, 128), 1, pk["w5"], pk["sl5"], 64, B, (H, W), box, 256, pk["sh5"],
-                act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), tile_order=1))
+                act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), tile_order=1, conv3x3_reuse=(box == (128, 1))))
             ratios = rp(pv[:, 3:6])
             levels = [tuple(f.shape[2:]) for f in feats[:3]]
             out["depth_decompose"] = self._time(lambda: Fn.depth_decompose(ratios.reshape(-1), levels, depth3=pv[:, 3:6]))

@@ -124,6 +124,9 @@ typedef struct rgbd_conv_gemm_desc {
     const float* residual;
     float* pool;
     int cells_y, cells_x;
+    int conv3x3_reuse; /* 1: 3x3 stride-1 pad-1 conv over a (n_img, a_y, a_x, a_c) tensor with shared-memory reuse of the
+                          A tile across the dx taps; W is (n_pad, 9*a_c) ordered (dy, dx, c); slices are ignored;
+                          needs kb_elems=64, bx=128, by=1 */
 } rgbd_conv_gemm_desc;
 int rgbd_conv_gemm(const rgbd_conv_gemm_desc* desc_host, rgbd_stream_t stream);
 

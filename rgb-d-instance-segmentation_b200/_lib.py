@@ -26,7 +26,7 @@ class ConvGemmDesc(C.Structure):
         ("tile_order", C.c_int), ("epi_mode", C.c_int), ("act", C.c_int),
         ("scale", C.c_void_p), ("shift", C.c_void_p), ("variant", C.c_void_p), ("gate", C.c_void_p),
         ("out", C.c_void_p), ("residual", C.c_void_p), ("pool", C.c_void_p),
-        ("cells_y", C.c_int), ("cells_x", C.c_int),
+        ("cells_y", C.c_int), ("cells_x", C.c_int), ("conv3x3_reuse", C.c_int),
     ]
 
 

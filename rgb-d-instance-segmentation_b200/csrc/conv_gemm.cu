@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "rgbd_b200.h"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -52,6 +53,8 @@ struct KParams {
     int ss_in_smem;       // (unused)
     int b_resident;       // whole weight matrix stays in shared memory (single N tile); the ring carries A only
     int b_res_bytes;
+    int c_blocks, sa_stages, a_stage_bytes;   // conv3x3_kernel: 64-channel blocks, A-ring depth, bytes per A stage
+    int dbg_shift, dbg_bo;   // experiment: A tile loaded `dbg_shift` pixels early, descriptor start advanced by as many rows
 };
 
 struct alignas(16) SmemCtl {
@@ -62,6 +65,8 @@ struct alignas(16) SmemCtl {
     uint64_t gate_full;
     uint64_t gate_empty;
     uint64_t b_full;
+    uint64_t a_full[4];       // conv3x3_kernel: separate ring for the (128+2)-pixel A tiles
+    uint64_t a_empty[4];
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -389,7 +394,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 uint8_t* sb = sa + a_bytes;
                 tc::mbar_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
                 const int4 sl = s_slices[j];
-                tc::tma_load_4d(sa, &tmap_a, &ctl->full[stage], sl.x, x0 + sl.y, y0 + sl.z, pl0 + sl.w);
+                tc::tma_load_4d(sa, &tmap_a, &ctl->full[stage], sl.x, x0 + sl.y - p.dbg_shift, y0 + sl.z, pl0 + sl.w);
                 if (!p.b_resident)
                     tc::tma_load_2d(sb, &tmap_b, &ctl->full[stage], j * (p.kb_bytes >> 1), nt * p.BLOCK_N);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -413,7 +418,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 tc::tc_fence_after();
                 const uint32_t sa = tc::smem_u32(s_ring + (size_t)stage * stage_bytes);
                 const uint32_t sb = p.b_resident ? tc::smem_u32(s_bres + (size_t)j * b_bytes) : sa + a_bytes;
-                const uint64_t adesc = tc::make_kmajor_desc(sa, p.kb_bytes);
+                uint64_t adesc = tc::make_kmajor_desc(sa + (uint32_t)(p.dbg_shift * p.kb_bytes), p.kb_bytes);
+                if (p.dbg_bo) adesc |= (uint64_t)(p.dbg_shift & 7) << 49;
                 const uint64_t bdesc = tc::make_kmajor_desc(sb, p.kb_bytes);
                 for (int k = 0; k < k_per_block; ++k)
                     tc::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (j | k) != 0);
@@ -431,7 +437,144 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (p.act == 2) epilogue_loop<0, 2, false>(p, c, &tmap_out);
             else if (p.act == 1 && sc) epilogue_loop<0, 1, true>(p, c, &tmap_out);
             else if (p.act == 1) epilogue_loop<0, 1, false>(p, c, &tmap_out);
-            else epilogue_loop<0, 0, true>(p, c, &tmap_out);
+            else if (sc) epilogue_loop<0, 0, true>(p, c, &tmap_out);
+            else epilogue_loop<0, 0, false>(p, c, &tmap_out);
+        } else if (p.epi_mode == 1) {
+            if (sc) epilogue_loop<1, 0, true>(p, c, &tmap_out);
+            else epilogue_loop<1, 0, false>(p, c, &tmap_out);
+        } else {
+            if (sc) epilogue_loop<2, 1, true>(p, c, &tmap_out);
+            else epilogue_loop<2, 1, false>(p, c, &tmap_out);
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+
+// 3x3 stride-1 pad-1 convolution with shared-memory reuse of the A operand across the three dx taps
+// (reference CM:1412-1416, the 128->256 conv that carries 84 % of the ratio predictor's FLOPs).
+// For every (dy, 64-channel block) ONE tile of 130 pixels (x0-1 .. x0+128) is loaded; the MMAs of tap dx read it
+// through a descriptor whose start address is advanced by dx rows of 128 bytes (the 128B swizzle is a function of
+// the absolute shared-memory address, profiles/r01_notes.md).  Per output tile the SM receives 6 A tiles instead
+// of 18, i.e. 676 KB instead of 864 KB over its 64 B/clk L2 port (MMA time: 9216 cycles = 590 KB at 64 B/clk).
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_gate,
+               const __grid_constant__ KParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int b_bytes = p.BLOCK_N * 128;
+    uint8_t* s_a = smem;
+    uint8_t* s_b = s_a + (size_t)p.sa_stages * p.a_stage_bytes;
+    uint8_t* s_staging = s_b + (size_t)p.stages * b_bytes;
+    uint8_t* s_gate = s_staging + p.staging_bytes;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_gate + p.gate_bytes);
+    int4* s_slices = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(ctl) + sizeof(SmemCtl));
+    float* s_scale = reinterpret_cast<float*>(s_slices + p.n_slices);
+    float* s_shift = s_scale + p.BLOCK_N;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_a);
+        tc::prefetch_tmap(&tmap_b);
+        if (p.staging_bytes) tc::prefetch_tmap(&tmap_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            tc::mbar_init(&ctl->full[s], 1);
+            tc::mbar_init(&ctl->empty[s], 1);
+        }
+        for (int s = 0; s < p.sa_stages; ++s) {
+            tc::mbar_init(&ctl->a_full[s], 1);
+            tc::mbar_init(&ctl->a_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&ctl->tmem_full[s], 1);
+            tc::mbar_init(&ctl->tmem_empty[s], kEpiThreads);
+        }
+        tc::mbar_init(&ctl->gate_full, 1);
+        tc::mbar_init(&ctl->gate_empty, kEpiThreads);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(&ctl->tmem_base, kTmemCols);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    const int per = p.total_tiles / gridDim.x, rem = p.total_tiles % gridDim.x;
+    const int t_begin = blockIdx.x * per + min((int)blockIdx.x, rem);
+    const int t_end = t_begin + per + ((int)blockIdx.x < rem ? 1 : 0);
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            int img, ty, tx, nt;
+            decode_tile(p, t, img, ty, tx, nt);
+            const int x0 = tx * p.BX, y0 = ty;
+            for (int dy = 0; dy < 3; ++dy) {
+                for (int cb = 0; cb < p.c_blocks; ++cb) {
+                    tc::mbar_wait(&ctl->a_empty[sa], pa ^ 1);
+                    tc::mbar_expect_tx(&ctl->a_full[sa], (uint32_t)((kBlockM + 2) * 128));
+                    tc::tma_load_4d(s_a + (size_t)sa * p.a_stage_bytes, &tmap_a, &ctl->a_full[sa], cb * 64, x0 - 1, y0 + dy - 1, img);
+                    if (++sa == p.sa_stages) { sa = 0; pa ^= 1; }
+                    for (int dx = 0; dx < 3; ++dx) {
+                        tc::mbar_wait(&ctl->empty[sb], pb ^ 1);
+                        tc::mbar_expect_tx(&ctl->full[sb], (uint32_t)b_bytes);
+                        tc::tma_load_2d(s_b + (size_t)sb * b_bytes, &tmap_b, &ctl->full[sb],
+                                        ((dy * 3 + dx) * p.c_blocks + cb) * 64, nt * p.BLOCK_N);
+                        if (++sb == p.stages) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = tc::make_idesc_bf16(kBlockM, p.BLOCK_N);
+        int sa = 0, sb = 0, as = 0;
+        uint32_t pa = 0, pb = 0, aphase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
+            tc::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BLOCK_N);
+            uint32_t first = 1;
+            for (int dy = 0; dy < 3; ++dy) {
+                for (int cb = 0; cb < p.c_blocks; ++cb) {
+                    tc::mbar_wait(&ctl->a_full[sa], pa);
+                    const uint32_t a_base = tc::smem_u32(s_a + (size_t)sa * p.a_stage_bytes);
+                    for (int dx = 0; dx < 3; ++dx) {
+                        tc::mbar_wait(&ctl->full[sb], pb);
+                        tc::tc_fence_after();
+                        const uint64_t adesc = tc::make_kmajor_desc(a_base + (uint32_t)(dx * 128), 128);
+                        const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_b + (size_t)sb * b_bytes), 128);
+                        for (int k = 0; k < 4; ++k) {
+                            tc::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                        tc::umma_commit(&ctl->empty[sb]);
+                        if (++sb == p.stages) { sb = 0; pb ^= 1; }
+                    }
+                    tc::umma_commit(&ctl->a_empty[sa]);
+                    if (++sa == p.sa_stages) { sa = 0; pa ^= 1; }
+                }
+            }
+            tc::umma_commit(&ctl->tmem_full[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        EpiCtx c{smem, s_staging, s_gate, ctl, s_scale, s_shift, tmem_base, t_begin, t_end, warp, lane};
+        const bool sc = p.scale != nullptr;
+        if (p.epi_mode == 0) {
+            if (p.act == 1 && !sc) epilogue_loop<0, 1, false>(p, c, &tmap_out);
+            else epilogue_loop<0, 0, false>(p, c, &tmap_out);
         } else if (p.epi_mode == 1) {
             epilogue_loop<1, 0, false>(p, c, &tmap_out);
         } else {
@@ -469,12 +612,16 @@ EncodeTiledFn get_encode_fn() {
 
 extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream) {
     RGBD_CHECK_ARG(d, "conv_gemm: null descriptor");
-    RGBD_CHECK_ARG(d->a && d->w && d->slices, "conv_gemm: null operand pointer");
+    RGBD_CHECK_ARG(d->a && d->w && (d->slices || d->conv3x3_reuse), "conv_gemm: null operand pointer");
     RGBD_CHECK_ARG(d->kb_elems == 64 || d->kb_elems == 32, "conv_gemm: kb_elems must be 64 or 32 (got %d)", d->kb_elems);
     RGBD_CHECK_ARG(d->a_c % 8 == 0 && d->a_c >= d->kb_elems, "conv_gemm: A channel count %d must be a multiple of 8 and >= kb", d->a_c);
     RGBD_CHECK_ARG(d->bx >= 1 && d->by >= 1 && d->bx * d->by == kBlockM && d->bx <= 256 && d->by <= 256,
                    "conv_gemm: box %dx%d must cover exactly %d pixels", d->bx, d->by, kBlockM);
-    RGBD_CHECK_ARG(d->n_slices >= 1 && d->n_slices <= kMaxSlices, "conv_gemm: n_slices %d out of range", d->n_slices);
+    RGBD_CHECK_ARG(d->conv3x3_reuse || (d->n_slices >= 1 && d->n_slices <= kMaxSlices), "conv_gemm: n_slices %d out of range",
+                   d->n_slices);
+    if (d->conv3x3_reuse)
+        RGBD_CHECK_ARG(d->kb_elems == 64 && d->bx == kBlockM && d->by == 1 && d->a_c % 64 == 0 && d->plane_per_img == 1,
+                       "conv_gemm: the 3x3 A-reuse path needs kb=64, a 128x1 box, C %% 64 == 0 and one plane per image");
     RGBD_CHECK_ARG(d->n_pad % 32 == 0 && d->block_n % 32 == 0 && d->block_n >= 32 && d->block_n <= 256 &&
                        d->n_pad % d->block_n == 0 && d->n <= d->n_pad && d->n >= 1,
                    "conv_gemm: bad N tiling (N=%d N_pad=%d BLOCK_N=%d)", d->n, d->n_pad, d->block_n);
@@ -505,7 +652,7 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         cuuint64_t dims[4] = {(cuuint64_t)d->a_c, (cuuint64_t)d->a_x, (cuuint64_t)d->a_y, (cuuint64_t)d->a_planes};
         cuuint64_t strides[3] = {(cuuint64_t)d->a_c * 2, (cuuint64_t)d->a_c * 2 * d->a_x,
                                  (cuuint64_t)d->a_c * 2 * d->a_x * d->a_y};
-        cuuint32_t box[4] = {(cuuint32_t)d->kb_elems, (cuuint32_t)d->bx, (cuuint32_t)d->by, 1};
+        cuuint32_t box[4] = {(cuuint32_t)d->kb_elems, (cuuint32_t)(d->conv3x3_reuse ? d->bx + 2 : d->bx), (cuuint32_t)d->by, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->a), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -515,7 +662,7 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
             return RGBD_ERR_CUDA;
         }
     }
-    const long long k_total = (long long)d->n_slices * d->kb_elems;
+    const long long k_total = d->conv3x3_reuse ? 9ll * d->a_c : (long long)d->n_slices * d->kb_elems;
     {
         cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->n_pad};
         cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
@@ -556,8 +703,11 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     p.out_w = d->out_w; p.out_h = d->out_h;
     p.tiles_x = ceil_div(d->out_w, d->bx);
     p.tiles_y = ceil_div(d->out_h, d->by);
-    p.n_slices = d->n_slices;
+    p.n_slices = d->conv3x3_reuse ? 0 : d->n_slices;
     p.kb_bytes = kb_bytes;
+    p.c_blocks = d->a_c / 64;
+    p.sa_stages = 0;
+    p.a_stage_bytes = 0;
     p.N = d->n; p.N_pad = d->n_pad; p.BLOCK_N = d->block_n; p.n_tiles_n = d->n_pad / d->block_n;
     p.plane_per_img = d->plane_per_img;
     p.tile_order = d->tile_order;
@@ -579,6 +729,32 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    }
+    const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+    if (d->conv3x3_reuse) {
+        p.b_resident = 0; p.b_res_bytes = 0; p.ss_in_smem = 0; p.dbg_shift = 0; p.dbg_bo = 0;
+        p.staging_bytes = d->epi_mode == 0 ? (p.BLOCK_N / 64) * kBlockM * 128 : 0;
+        p.gate_bytes = 0;
+        p.sa_stages = 3;
+        p.a_stage_bytes = 17 * 1024;                      // (128+2) rows x 128 B, rounded up to the swizzle period
+        const int b_stage = p.BLOCK_N * 128;
+        const int fixed3 = 1024 + (int)sizeof(SmemCtl) + 64 + p.staging_bytes + 2 * p.BLOCK_N * (int)sizeof(float) +
+                           p.sa_stages * p.a_stage_bytes;
+        int sb = (max_smem - fixed3) / b_stage;
+        if (sb > kMaxStages) sb = kMaxStages;
+        RGBD_CHECK_ARG(sb >= 2, "conv_gemm: not enough shared memory for the 3x3 A-reuse pipeline");
+        p.stages = sb;
+        const int smem3 = fixed3 + sb * b_stage;
+        conv3x3_kernel<<<grid, kThreads, smem3, (cudaStream_t)stream>>>(tmap_a, tmap_b, tmap_out, tmap_gate, p);
+        RGBD_CHECK_LAUNCH();
+        return RGBD_OK;
+    }
+    {
+        const char* e1 = getenv("RGBD_DBG_SHIFT");
+        const char* e2 = getenv("RGBD_DBG_BO");
+        p.dbg_shift = e1 ? atoi(e1) : 0;
+        p.dbg_bo = e2 ? atoi(e2) : 0;
     }
     const int b_total = p.n_slices * p.BLOCK_N * kb_bytes;
     p.b_resident = (p.n_tiles_n == 1 && b_total <= 100 * 1024) ? 1 : 0;
@@ -596,7 +772,6 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     // always take (almost) the whole SM so exactly one CTA (and its 512 TMEM columns) is resident
     int smem_bytes = fixed + stages * stage_bytes;
     if (smem_bytes < 160 * 1024) smem_bytes = 160 * 1024;
-    const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     conv_gemm_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmap_a, tmap_b, tmap_out, tmap_gate, p);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;

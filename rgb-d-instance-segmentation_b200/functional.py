@@ -235,18 +235,21 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
               shift: torch.Tensor, *, scale: Optional[torch.Tensor] = None, variant: Optional[torch.Tensor] = None,
               act: int = 0, epi_mode: int = 0, gate: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
               residual: Optional[torch.Tensor] = None, pool: Optional[torch.Tensor] = None,
-              cells: Tuple[int, int] = (0, 0), tile_order: int = 0, block_n: Optional[int] = None) -> None:
-    """Launch the tcgen05 implicit-GEMM kernel.  a_dims = (planes, y, x, c) of the bf16 channels-last operand."""
+              cells: Tuple[int, int] = (0, 0), tile_order: int = 0, block_n: Optional[int] = None,
+              conv3x3_reuse: bool = False) -> None:
+    """Launch the tcgen05 implicit-GEMM kernel.  a_dims = (planes, y, x, c) of the bf16 channels-last operand.
+    ``conv3x3_reuse``: 3x3 stride-1 conv whose A tile is shared by the three dx taps (``slices`` may be None)."""
     lib = _lib.load()
     _req(a, "a", torch.bfloat16)
     _req(w, "w", torch.bfloat16)
-    _req(slices, "slices", torch.int32)
+    if slices is not None:
+        _req(slices, "slices", torch.int32)
     _req(shift, "shift", torch.float32)
     n_pad = w.shape[0]
     planes, ay, ax, ac = a_dims
     if a.numel() != planes * ay * ax * ac:
         raise RgbdB200Error("conv_gemm: operand size does not match a_dims")
-    n_slices = slices.shape[0]
+    n_slices = slices.shape[0] if slices is not None else 9 * ac // kb
     if w.shape[1] != n_slices * kb:
         raise RgbdB200Error(f"conv_gemm: weight K {w.shape[1]} != n_slices*kb {n_slices * kb}")
     if shift.shape[-1] != n_pad or (scale is not None and scale.numel() != n_pad):
@@ -254,7 +257,9 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
     d = ConvGemmDesc()
     d.a = a.data_ptr(); d.a_c = ac; d.a_x = ax; d.a_y = ay; d.a_planes = planes
     d.plane_per_img = plane_per_img
-    d.w = w.data_ptr(); d.slices = slices.data_ptr(); d.n_slices = n_slices; d.kb_elems = kb
+    d.w = w.data_ptr(); d.slices = slices.data_ptr() if slices is not None else None
+    d.n_slices = n_slices; d.kb_elems = kb
+    d.conv3x3_reuse = 1 if conv3x3_reuse else 0
     d.n_img = n_img; d.out_h, d.out_w = out_hw; d.bx, d.by = box
     d.n = n; d.n_pad = n_pad; d.block_n = block_n or pick_block_n(n_pad)
     d.tile_order = tile_order; d.epi_mode = epi_mode; d.act = act

@@ -399,7 +399,8 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         # feature_extractor[0:4] (CM:1412-1416): conv3x3 + BN + ReLU + AdaptiveAvgPool2d(4), pooled in the epilogue
         ws["pool"].zero_()
         Fn.conv_gemm(ws["x4"], (B, H, W, 128), 1, pk["w5"], pk["sl5"], 64, B, (H, W), box, 256, pk["sh5"],
-                     act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), tile_order=1)
+                     act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), tile_order=1,
+                     conv3x3_reuse=(box == (128, 1)))      # one 130-pixel smem tile serves the three dx taps
         return Fn.ratio_tail(ws["pool"], (H // 4) * (W // 4), pk["w6"], pk["sc6"], pk["sh6"],
                              [pk[f"fw{j}"] for j in range(4)], [pk[f"fb{j}"] for j in range(4)],
                              self.output_min, self.output_max)

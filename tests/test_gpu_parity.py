@@ -242,6 +242,26 @@ def test_conv_gemm_3x3_pool(fn):
     assert rel_err(pool, ref) < 1e-4
 
 
+@pytest.mark.parametrize("c,n,hw", [(128, 256, (8, 256)), (64, 128, (12, 200)), (192, 64, (4, 128))])
+def test_conv3x3_a_reuse_path(fn, c, n, hw):
+    """3x3 conv whose 130-pixel smem tile serves the three dx taps (row-shifted UMMA descriptors)."""
+    rs = np.random.RandomState(4)
+    B, (H, W) = 2, hw
+    a = torch.from_numpy(rs.randn(B, H, W, c).astype(np.float32)).cuda().to(torch.bfloat16)
+    wt = torch.from_numpy((rs.randn(n, c, 3, 3) / np.sqrt(9 * c)).astype(np.float32)).cuda().to(torch.bfloat16)
+    w = wt.permute(0, 2, 3, 1).reshape(n, 9 * c).contiguous()
+    shift = torch.from_numpy(rs.randn(n).astype(np.float32) * 0.1).cuda()
+    y = torch.relu(torch.nn.functional.conv2d(a.double().permute(0, 3, 1, 2), wt.double(), shift.double(), padding=1))
+    pool = torch.zeros(B, 16, n, device="cuda")
+    fn.conv_gemm(a, (B, H, W, c), 1, w, None, 64, B, (H, W), (128, 1), n, shift, act=1, epi_mode=2, pool=pool,
+                 cells=(4, 4), tile_order=1, conv3x3_reuse=True)
+    ref = (torch.nn.functional.adaptive_avg_pool2d(y, 4) * (H // 4) * (W // 4)).permute(0, 2, 3, 1).reshape(B, 16, n)
+    assert rel_err(pool, ref) < 1e-4
+    out = torch.zeros(B, H, W, n, device="cuda", dtype=torch.bfloat16)
+    fn.conv_gemm(a, (B, H, W, c), 1, w, None, 64, B, (H, W), (128, 1), n, shift, act=1, out=out, conv3x3_reuse=True)
+    assert rel_err(out.double(), y.permute(0, 2, 3, 1)) < 8e-3
+
+
 @pytest.mark.parametrize("hw", [(4, 128), (9, 50), (16, 200)])
 def test_ratio_chain_fused(fn, hw):
     """Three chained GEMMs with TMEM-resident intermediates vs float64 math on the same bf16 operands."""
