@@ -87,7 +87,8 @@ __device__ __forceinline__ const DggmScale& find_scale(const DggmParams& p, int&
     return p.s[si];
 }
 
-__global__ void __launch_bounds__(kThreads) dggm_fwd_kernel(const __grid_constant__ DggmParams p) {
+template <int DMAX>
+__global__ void __launch_bounds__(kThreads, DMAX <= 4 ? 4 : 2) dggm_fwd_kernel(const __grid_constant__ DggmParams p) {
     __shared__ __align__(16) float g_s[kMaxD][kTP];
     int t = blockIdx.x;
     const DggmScale& S = find_scale(p, t);
@@ -110,9 +111,9 @@ __global__ void __launch_bounds__(kThreads) dggm_fwd_kernel(const __grid_constan
         const int f = threadIdx.x & 63;
         const int lane_c = threadIdx.x >> 6;           // 4 channel lanes
         if (f >= nf4) return;
-        float4 g[kMaxD];
+        float4 g[DMAX];
 #pragma unroll
-        for (int d = 0; d < kMaxD; ++d)
+        for (int d = 0; d < DMAX; ++d)
             if (d < D) g[d] = *reinterpret_cast<const float4*>(&g_s[d][f * 4]);
         constexpr int U = 4;
         for (int c = c0 + lane_c; c < c1; c += 4 * U) {
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(kThreads) dggm_fwd_kernel(const __grid_constan
                     float bias = __ldg(S.b + cc);
                     float4 e = make_float4(bias, bias, bias, bias);
 #pragma unroll
-                    for (int d = 0; d < kMaxD; ++d) {
+                    for (int d = 0; d < DMAX; ++d) {
                         if (d < D) {
                             float w = __ldg(S.w + cc * D + d);
                             e.x = fmaf(w, g[d].x, e.x);
@@ -305,7 +306,8 @@ extern "C" int rgbd_dggm_fwd(int n_scales, const float* const* color, const floa
         tiles += (long long)B * S.tiles_p * S.tiles_c;
     }
     RGBD_CHECK_ARG(tiles < (1ll << 31), "dggm: too many tiles");
-    dggm_fwd_kernel<<<(unsigned)tiles, kThreads, 0, (cudaStream_t)stream>>>(p);
+    if (D <= 4) dggm_fwd_kernel<4><<<(unsigned)tiles, kThreads, 0, (cudaStream_t)stream>>>(p);
+    else dggm_fwd_kernel<kMaxD><<<(unsigned)tiles, kThreads, 0, (cudaStream_t)stream>>>(p);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }

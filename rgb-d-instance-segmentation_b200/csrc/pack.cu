@@ -18,6 +18,8 @@ namespace {
 __global__ void __launch_bounds__(256) dsam_pack_kernel(const float* __restrict__ feat, const uint8_t* __restrict__ codes,
                                                         __nv_bfloat16* __restrict__ out, int C, int Cp, int H, int W,
                                                         int n_seg, int masked_segs, int split) {
+    // CTA: 32 pixels of one row x 64 channels.  Load NCHW coalesced along x, transpose through shared memory, then each
+    // thread owns (pixel, 8 channels) and writes one 16-byte piece per segment: 8 lanes = one 128-byte channels-last row.
     __shared__ float tile[64][33];
     const int img = blockIdx.z;
     const int y = blockIdx.y;
@@ -32,59 +34,64 @@ __global__ void __launch_bounds__(256) dsam_pack_kernel(const float* __restrict_
     __syncthreads();
     const int H2 = split ? (H + 1) / 2 : H, W2 = split ? (W + 1) / 2 : W;
     const int n_par = split ? 4 : 1;
-    for (int px = tyy; px < 32; px += 8) {
-        const int x = x0 + px;
-        if (x >= W) continue;
-        const unsigned code = codes[(size_t)img * plane + (size_t)y * W + x];
-        const int par = split ? ((y & 1) * 2 + (x & 1)) : 0;
-        const int yy = split ? (y >> 1) : y, xx = split ? (x >> 1) : x;
-        const int c = c0 + tx * 2;
-        if (c >= Cp) continue;
-        const float v0 = tile[tx * 2][px], v1 = tile[tx * 2 + 1][px];
-        for (int s = 0; s < n_seg; ++s) {
-            const bool keep = s >= masked_segs || ((code >> s) & 1u);
-            __nv_bfloat162 h = keep ? __floats2bfloat162_rn(v0, v1) : __floats2bfloat162_rn(0.f, 0.f);
-            const size_t pl = ((size_t)img * n_seg + s) * n_par + par;
-            const size_t off = ((pl * H2 + yy) * W2 + xx) * Cp + c;
-            *reinterpret_cast<__nv_bfloat162*>(out + off) = h;
-        }
+    const int px = threadIdx.x >> 3, cg = threadIdx.x & 7;     // pixel 0..31, channel group of 8
+    const int x = x0 + px;
+    const int c = c0 + cg * 8;
+    if (x >= W || c >= Cp) return;
+    const unsigned code = codes[(size_t)img * plane + (size_t)y * W + x];
+    const int par = split ? ((y & 1) * 2 + (x & 1)) : 0;
+    const int yy = split ? (y >> 1) : y, xx = split ? (x >> 1) : x;
+    uint4 v;
+    {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(tile[cg * 8 + 0][px], tile[cg * 8 + 1][px]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(tile[cg * 8 + 2][px], tile[cg * 8 + 3][px]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(tile[cg * 8 + 4][px], tile[cg * 8 + 5][px]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(tile[cg * 8 + 6][px], tile[cg * 8 + 7][px]);
+        v.x = *reinterpret_cast<uint32_t*>(&h0);
+        v.y = *reinterpret_cast<uint32_t*>(&h1);
+        v.z = *reinterpret_cast<uint32_t*>(&h2);
+        v.w = *reinterpret_cast<uint32_t*>(&h3);
+    }
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int s = 0; s < n_seg; ++s) {
+        const bool keep = s >= masked_segs || ((code >> s) & 1u);
+        const size_t pl = ((size_t)img * n_seg + s) * n_par + par;
+        const size_t off = ((pl * H2 + yy) * W2 + xx) * Cp + c;
+        *reinterpret_cast<uint4*>(out + off) = keep ? v : zero;
     }
 }
 
-__global__ void __launch_bounds__(128) ratio_stem_pack_kernel(const float* __restrict__ depth, long long bs, long long cs,
+__global__ void __launch_bounds__(256) ratio_stem_pack_kernel(const float* __restrict__ depth, long long bs, long long cs,
                                                               __nv_bfloat16* __restrict__ out, int H, int W) {
+    // thread = (pixel, piece): piece p of 8 holds taps dx = 2*(p&3), 2*(p&3)+1 of row j = p>>2  (8 bf16 = 16 bytes);
+    // the 8 lanes of a pixel write its 128-byte row contiguously, a warp writes 4 pixels = 512 contiguous bytes
     const int img = blockIdx.z;
     const int r = blockIdx.y;                                 // 0 .. H+5
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = gid >> 3, piece = gid & 7;
     if (x >= W) return;
+    const int j = piece >> 2, dxp = piece & 3;
     const float* d = depth + (size_t)img * bs;
-    uint4* o = reinterpret_cast<uint4*>(out + (((size_t)img * (H + 6) + r) * W + x) * 64);
+    const int y = r - 3 + j;
+    const bool yok = y >= 0 && y < H;
+    float v[8];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int y = r - 3 + j;
-        const bool yok = y >= 0 && y < H;
+    for (int e = 0; e < 2; ++e) {
+        const int dx = dxp * 2 + e;
+        const int xs = x + dx - 3;
+        const bool ok = yok && dx < 7 && xs >= 0 && xs < W;
 #pragma unroll
-        for (int dxp = 0; dxp < 4; ++dxp) {                   // two taps (8 bf16 = 16 bytes) per store
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int dx = dxp * 2 + e;
-                const int xs = x + dx - 3;
-                const bool ok = yok && dx < 7 && xs >= 0 && xs < W;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) v[e * 4 + c] = ok ? __ldg(d + c * cs + (size_t)y * W + xs) : 0.f;
-                v[e * 4 + 3] = 0.f;
-            }
-            uint4 w;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-            w.x = *reinterpret_cast<uint32_t*>(&h0);
-            w.y = *reinterpret_cast<uint32_t*>(&h1);
-            w.z = *reinterpret_cast<uint32_t*>(&h2);
-            w.w = *reinterpret_cast<uint32_t*>(&h3);
-            o[j * 4 + dxp] = w;
-        }
+        for (int c = 0; c < 3; ++c) v[e * 4 + c] = ok ? __ldg(d + c * cs + (size_t)y * W + xs) : 0.f;
+        v[e * 4 + 3] = 0.f;
     }
+    uint4 w;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    w.x = *reinterpret_cast<uint32_t*>(&h0);
+    w.y = *reinterpret_cast<uint32_t*>(&h1);
+    w.z = *reinterpret_cast<uint32_t*>(&h2);
+    w.w = *reinterpret_cast<uint32_t*>(&h3);
+    reinterpret_cast<uint4*>(out + (((size_t)img * (H + 6) + r) * W + x) * 64)[piece] = w;
 }
 
 }  // namespace
@@ -107,8 +114,8 @@ extern "C" int rgbd_ratio_stem_pack(const float* depth3, long long batch_stride,
                                     int B, int H, int W, rgbd_stream_t stream) {
     RGBD_CHECK_ARG(depth3 && out_bf16, "ratio_stem_pack: null pointer");
     RGBD_CHECK_ARG(B >= 1 && H >= 1 && W >= 1, "ratio_stem_pack: bad geometry");
-    dim3 grid(ceil_div(W, 128), H + 6, B);
-    ratio_stem_pack_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(depth3, batch_stride, channel_stride,
+    dim3 grid(ceil_div(W * 8, 256), H + 6, B);
+    ratio_stem_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(depth3, batch_stride, channel_stride,
                                                                    (__nv_bfloat16*)out_bf16, H, W);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
