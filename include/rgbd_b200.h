@@ -104,7 +104,8 @@ int rgbd_ratio_stem_pack(const float* depth3, long long batch_stride, long long 
  * Output tile = bx*by (=128) pixels of one image x block_n channels.  y = act(acc*scale[n] + shift[variant][n]);
  * epi_mode 0: bf16 (n_img, out_h, out_w, n_pad) store, optionally multiplied by `gate` (same layout);
  * epi_mode 1: fp32 (n_img, n, out_h, out_w) store, optionally + residual (same layout);
- * epi_mode 2: sums over the cells of a cells_y x cells_x grid into pool (n_img, cells, n_pad) (caller zeroes). */
+ * epi_mode 2: sums over the cells of a cells_y x cells_x grid into pool (n_img, cells, n_pad) (caller zeroes);
+ * epi_mode 3: masked segment sum (see the codes / m3_* fields). */
 typedef struct rgbd_conv_gemm_desc {
     const void* a; /* bf16 */
     int a_c, a_x, a_y, a_planes;
@@ -127,8 +128,27 @@ typedef struct rgbd_conv_gemm_desc {
     int conv3x3_reuse; /* 1: 3x3 stride-1 pad-1 conv over a (n_img, a_y, a_x, a_c) tensor with shared-memory reuse of the
                           A tile across the dx taps; W is (n_pad, 9*a_c) ordered (dy, dx, c); slices are ignored;
                           needs kb_elems=64, bx=128, by=1 */
+    /* epi_mode 3 (input gradient of a DSAM stage): the N axis is (channel block of 32, segment, 32 channels),
+       block_n = 32*m3_n_seg; out/residual are fp32 (n_img, n, in_h, in_w); GEMM pixel (oy, ox) is input pixel
+       (oy*m3_stride + m3_py, ox*m3_stride + m3_px); segment s < m3_masked_segs is kept where bit s of codes is set */
+    const void* codes;
+    int in_h, in_w, m3_py, m3_px, m3_stride, m3_masked_segs, m3_n_seg;
 } rgbd_conv_gemm_desc;
 int rgbd_conv_gemm(const rgbd_conv_gemm_desc* desc_host, rgbd_stream_t stream);
+
+/* ---- E-DSAM backward (autograd of DSAModule.forward CM:683-696; colour features of stage 0 are detached CM:332) ----
+ * rgbd_cast_bf16_pitched: (rows, W) fp32 -> bf16 with row pitch W_pitch (multiple of 8, zero padded).
+ * rgbd_dsam_pack_t: like rgbd_dsam_pack but pixel-contiguous: out[img][seg][parity][C_pad][H2][W2_pitch] (zeroed by caller).
+ * rgbd_dsam_dbias: db[t][n] = sum over images that use region t (t < variant[b]) of sum_pixels g[b][n]; db overwritten.
+ * rgbd_dsam_wgrad: dw[n][seg][tap][C_pad] (fp32, overwritten) = sum_pixels g[b][n][oy][ox] * x_t[b][seg][tap-shifted pixel][c];
+ *   g_bf16: (B, N_out, Ho, g_w_pitch); xt_bf16: output of rgbd_dsam_pack_t with plane height x_h.
+ * The input gradient runs through rgbd_conv_gemm with epi_mode 3. */
+int rgbd_cast_bf16_pitched(const float* src, void* dst_bf16, long long rows, int W, int W_pitch, rgbd_stream_t stream);
+int rgbd_dsam_pack_t(const float* feat, const uint8_t* codes, void* out_bf16, int B, int C, int C_pad, int H, int W,
+                     int W2_pitch, int n_seg, int masked_segs, int parity_split, rgbd_stream_t stream);
+int rgbd_dsam_dbias(const float* g, const int* variant, float* db, int B, int N, int HW, int n_bias, rgbd_stream_t stream);
+int rgbd_dsam_wgrad(const void* g_bf16, int g_w_pitch, const void* xt_bf16, int x_w_pitch, int x_h, float* dw, int B,
+                    int N_out, int C_pad, int Ho, int Wo, int n_seg, int parity_split, rgbd_stream_t stream);
 
 /* Fused point-wise middle of EnhancedDepthImageRatioPredictor.forward (CM:1466-1470): feature_fusion (1x1 192->128 +
  * folded BN + ReLU), attention (1x1 128->64 + ReLU, 1x1 64->128 + sigmoid) and the gating multiply, as three chained

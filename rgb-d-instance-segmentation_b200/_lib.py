@@ -27,6 +27,8 @@ class ConvGemmDesc(C.Structure):
         ("scale", C.c_void_p), ("shift", C.c_void_p), ("variant", C.c_void_p), ("gate", C.c_void_p),
         ("out", C.c_void_p), ("residual", C.c_void_p), ("pool", C.c_void_p),
         ("cells_y", C.c_int), ("cells_x", C.c_int), ("conv3x3_reuse", C.c_int),
+        ("codes", C.c_void_p), ("in_h", C.c_int), ("in_w", C.c_int), ("m3_py", C.c_int), ("m3_px", C.c_int),
+        ("m3_stride", C.c_int), ("m3_masked_segs", C.c_int), ("m3_n_seg", C.c_int),
     ]
 
 
@@ -53,6 +55,12 @@ SIGNATURES = {
     "rgbd_ratio_stem_pack": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p]),
     "rgbd_conv_gemm": (C.c_int, [C.POINTER(ConvGemmDesc), C.c_void_p]),
+    "rgbd_cast_bf16_pitched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "rgbd_dsam_pack_t": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "rgbd_dsam_dbias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "rgbd_dsam_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "rgbd_ratio_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "rgbd_ratio_tail": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_void_pp, c_void_pp,

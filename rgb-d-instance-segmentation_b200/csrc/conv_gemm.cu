@@ -53,6 +53,8 @@ struct KParams {
     int ss_in_smem;       // (unused)
     int b_resident;       // whole weight matrix stays in shared memory (single N tile); the ring carries A only
     int b_res_bytes;
+    const uint8_t* codes;     // epilogue mode 3: region codes at the resolution of dX
+    int in_h, in_w, m3_py, m3_px, m3_stride, m3_masked_segs, m3_n_seg;
     int c_blocks, sa_stages, a_stage_bytes;   // conv3x3_kernel: 64-channel blocks, A-ring depth, bytes per A stage
     int dbg_shift, dbg_bo;   // experiment: A tile loaded `dbg_shift` pixels early, descriptor start advanced by as many rows
 };
@@ -134,7 +136,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
         // scale / shift of this (variant, N tile) -> shared memory (reloaded only when they change)
         const int var = p.variant ? __ldg(p.variant + img) : 0;
         const int want = var * p.n_tiles_n + nt;
-        if (want != ss_key) {
+        if (MODE != 3 && want != ss_key) {
             asm volatile("bar.sync 2, 256;" ::: "memory");          // everyone is done with the old table
             for (int i = epi_tid; i < p.BLOCK_N; i += kEpiThreads) {
                 if (p.scale) c.s_scale[i] = __ldg(p.scale + nt * p.BLOCK_N + i);
@@ -177,8 +179,42 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
 
+        if (MODE == 3) {
+            // dF tile: columns are (segment, 32 channels); each warp half owns 16 channels and sums the
+            // segments under the region masks of the INPUT pixel (y, x) = (oy*stride+py, ox*stride+px)
+            const int y = oy * p.m3_stride + p.m3_py, x = ox * p.m3_stride + p.m3_px;
+            const bool ok = valid && y < p.in_h && x < p.in_w;
+            const unsigned code = ok ? p.codes[((size_t)img * p.in_h + y) * p.in_w + x] : 0u;
+            float a16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a16[j] = 0.f;
+            for (int sgm = 0; sgm < p.m3_n_seg; ++sgm) {
+                uint32_t v16[16];
+                tc::tmem_ld_32x16(taddr0 + (uint32_t)(sgm * 32 + half * 16), v16);
+                tc::tmem_ld_wait();
+                const bool keep = sgm >= p.m3_masked_segs || ((code >> sgm) & 1u);
+                if (keep) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) a16[j] += __uint_as_float(v16[j]);
+                }
+            }
+            if (ok) {
+                const size_t plane = (size_t)p.in_h * p.in_w;
+                const size_t base = (size_t)img * p.N * plane + (size_t)y * p.in_w + x;
+                float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int ch = nt * 32 + half * 16 + j;
+                    if (ch < p.N) {
+                        float r = a16[j];
+                        if (p.residual) r += __ldg(p.residual + base + (size_t)ch * plane);
+                        o[base + (size_t)ch * plane] = r;
+                    }
+                }
+            }
+        }
 #pragma unroll 1
-        for (int k = half; k < n_chunks; k += 2) {
+        for (int k = (MODE == 3 ? n_chunks : half); k < n_chunks; k += 2) {
             uint32_t v[32];
             tc::tmem_ld_32x32(taddr0 + (uint32_t)(k * 32), v);
             float sh[32], f[32];
@@ -625,8 +661,12 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     RGBD_CHECK_ARG(d->n_pad % 32 == 0 && d->block_n % 32 == 0 && d->block_n >= 32 && d->block_n <= 256 &&
                        d->n_pad % d->block_n == 0 && d->n <= d->n_pad && d->n >= 1,
                    "conv_gemm: bad N tiling (N=%d N_pad=%d BLOCK_N=%d)", d->n, d->n_pad, d->block_n);
-    RGBD_CHECK_ARG(d->epi_mode >= 0 && d->epi_mode <= 2, "conv_gemm: bad epilogue mode %d", d->epi_mode);
-    RGBD_CHECK_ARG(d->shift, "conv_gemm: shift table is required");
+    RGBD_CHECK_ARG(d->epi_mode >= 0 && d->epi_mode <= 3, "conv_gemm: bad epilogue mode %d", d->epi_mode);
+    RGBD_CHECK_ARG(d->shift || d->epi_mode == 3, "conv_gemm: shift table is required");
+    if (d->epi_mode == 3)
+        RGBD_CHECK_ARG(d->codes && d->m3_n_seg >= 1 && d->m3_n_seg <= 8 && d->block_n == 32 * d->m3_n_seg && d->in_h >= 1 &&
+                           d->in_w >= 1 && (d->m3_stride == 1 || d->m3_stride == 2) && !d->conv3x3_reuse,
+                       "conv_gemm: epilogue mode 3 needs codes, block_n == 32*n_seg and the dX geometry");
     RGBD_CHECK_ARG(d->n_img >= 1 && d->out_w >= 1 && d->out_h >= 1, "conv_gemm: bad output geometry");
     if (d->epi_mode == 2) {
         RGBD_CHECK_ARG(d->pool && d->cells_x >= 1 && d->cells_y >= 1, "conv_gemm: pool epilogue needs pool buffer and cells");
@@ -717,6 +757,9 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     p.gate = reinterpret_cast<const __nv_bfloat16*>(d->gate);
     p.out = d->out; p.residual = d->residual; p.pool = d->pool;
     p.cells_y = d->cells_y; p.cells_x = d->cells_x;
+    p.codes = reinterpret_cast<const uint8_t*>(d->codes);
+    p.in_h = d->in_h; p.in_w = d->in_w; p.m3_py = d->m3_py; p.m3_px = d->m3_px; p.m3_stride = d->m3_stride;
+    p.m3_masked_segs = d->m3_masked_segs; p.m3_n_seg = d->m3_n_seg;
     const long long total = (long long)p.n_img * p.tiles_x * p.tiles_y * p.n_tiles_n;
     RGBD_CHECK_ARG(total < (1ll << 31), "conv_gemm: too many tiles");
     p.total_tiles = (int)total;

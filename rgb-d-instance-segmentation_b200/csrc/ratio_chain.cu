@@ -53,23 +53,6 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
         : "memory");
 }
 
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -213,9 +196,9 @@ ratio_chain_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_con
                     o[j4 * 2] = tc::pack_bf16x2_relu(__uint_as_float(v[j4 * 4]) + b.x, __uint_as_float(v[j4 * 4 + 1]) + b.y);
                     o[j4 * 2 + 1] = tc::pack_bf16x2_relu(__uint_as_float(v[j4 * 4 + 2]) + b.z, __uint_as_float(v[j4 * 4 + 3]) + b.w);
                 }
-                tmem_st_32x16(lane_base + kColX2 + k * 16, o);
+                tc::tmem_st_32x16(lane_base + kColX2 + k * 16, o);
             }
-            tmem_st_wait();
+            tc::tmem_st_wait();
             tc::tc_fence_before();
             tc::mbar_arrive(&ctl->x2_ready);
 
@@ -234,9 +217,9 @@ ratio_chain_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_con
                     o[j4 * 2] = tc::pack_bf16x2_relu(__uint_as_float(v[j4 * 4]) + b.x, __uint_as_float(v[j4 * 4 + 1]) + b.y);
                     o[j4 * 2 + 1] = tc::pack_bf16x2_relu(__uint_as_float(v[j4 * 4 + 2]) + b.z, __uint_as_float(v[j4 * 4 + 3]) + b.w);
                 }
-                tmem_st_32x16(lane_base + kColX3 + k * 16, o);
+                tc::tmem_st_32x16(lane_base + kColX3 + k * 16, o);
             }
-            tmem_st_wait();
+            tc::tmem_st_wait();
             tc::tc_fence_before();
             tc::mbar_arrive(&ctl->x3_ready);
 
@@ -249,7 +232,7 @@ ratio_chain_kernel(const __grid_constant__ CUtensorMap tmap_x1, const __grid_con
             for (int k = half; k < 4; k += 2) {
                 uint32_t v[32], g[16];
                 tc::tmem_ld_32x32(lane_base + kColAcc4 + k * 32, v);
-                tmem_ld_32x16(lane_base + kColX2 + k * 16, g);
+                tc::tmem_ld_32x16(lane_base + kColX2 + k * 16, g);
                 tc::tmem_ld_wait();
                 uint8_t* rowp = s_staging + (k >> 1) * kSliceBytes + row * 128;
 #pragma unroll

@@ -236,7 +236,8 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
               act: int = 0, epi_mode: int = 0, gate: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
               residual: Optional[torch.Tensor] = None, pool: Optional[torch.Tensor] = None,
               cells: Tuple[int, int] = (0, 0), tile_order: int = 0, block_n: Optional[int] = None,
-              conv3x3_reuse: bool = False) -> None:
+              conv3x3_reuse: bool = False, codes: Optional[torch.Tensor] = None, in_hw: Tuple[int, int] = (0, 0),
+              parity: Tuple[int, int] = (0, 0), m3_stride: int = 1, m3_masked_segs: int = 0, m3_n_seg: int = 0) -> None:
     """Launch the tcgen05 implicit-GEMM kernel.  a_dims = (planes, y, x, c) of the bf16 channels-last operand.
     ``conv3x3_reuse``: 3x3 stride-1 conv whose A tile is shared by the three dx taps (``slices`` may be None)."""
     lib = _lib.load()
@@ -244,7 +245,8 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
     _req(w, "w", torch.bfloat16)
     if slices is not None:
         _req(slices, "slices", torch.int32)
-    _req(shift, "shift", torch.float32)
+    if shift is not None:
+        _req(shift, "shift", torch.float32)
     n_pad = w.shape[0]
     planes, ay, ax, ac = a_dims
     if a.numel() != planes * ay * ax * ac:
@@ -252,7 +254,7 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
     n_slices = slices.shape[0] if slices is not None else 9 * ac // kb
     if w.shape[1] != n_slices * kb:
         raise RgbdB200Error(f"conv_gemm: weight K {w.shape[1]} != n_slices*kb {n_slices * kb}")
-    if shift.shape[-1] != n_pad or (scale is not None and scale.numel() != n_pad):
+    if (shift is not None and shift.shape[-1] != n_pad) or (scale is not None and scale.numel() != n_pad):
         raise RgbdB200Error("conv_gemm: scale/shift must have n_pad entries")
     d = ConvGemmDesc()
     d.a = a.data_ptr(); d.a_c = ac; d.a_x = ax; d.a_y = ay; d.a_planes = planes
@@ -264,7 +266,11 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
     d.n = n; d.n_pad = n_pad; d.block_n = block_n or pick_block_n(n_pad)
     d.tile_order = tile_order; d.epi_mode = epi_mode; d.act = act
     d.scale = _req(scale, "scale", torch.float32).data_ptr() if scale is not None else None
-    d.shift = shift.data_ptr()
+    d.shift = shift.data_ptr() if shift is not None else None
+    d.codes = _req(codes, "codes", torch.uint8).data_ptr() if codes is not None else None
+    d.in_h, d.in_w = in_hw
+    d.m3_py, d.m3_px = parity
+    d.m3_stride = m3_stride; d.m3_masked_segs = m3_masked_segs; d.m3_n_seg = m3_n_seg
     d.variant = _req(variant, "variant", torch.int32).data_ptr() if variant is not None else None
     d.gate = _req(gate, "gate", torch.bfloat16).data_ptr() if gate is not None else None
     d.out = out.data_ptr() if out is not None else None
@@ -287,6 +293,57 @@ def dsam_pack(feat: torch.Tensor, codes: torch.Tensor, out: torch.Tensor, c_pad:
     check(lib.rgbd_dsam_pack(feat.data_ptr(), codes.data_ptr(), out.data_ptr(), B, Cc, c_pad, H, W, n_seg, masked_segs,
                              1 if parity_split else 0, _stream()), "rgbd_dsam_pack")
     _count(1)
+
+
+def cast_bf16_pitched(src: torch.Tensor, w_pitch: int) -> torch.Tensor:
+    """(..., W) fp32 -> (..., w_pitch) bf16, zero padded (TMA row strides must be multiples of 16 bytes)."""
+    lib = _lib.load()
+    _req(src, "src", torch.float32)
+    W = src.shape[-1]
+    rows = src.numel() // W
+    out = torch.empty(*src.shape[:-1], w_pitch, device=src.device, dtype=torch.bfloat16)
+    check(lib.rgbd_cast_bf16_pitched(src.data_ptr(), out.data_ptr(), rows, W, w_pitch, _stream()), "rgbd_cast_bf16_pitched")
+    _count(1)
+    return out
+
+
+def dsam_pack_t(feat: torch.Tensor, codes: torch.Tensor, out: torch.Tensor, c_pad: int, w2_pitch: int, n_seg: int,
+                masked_segs: int, parity_split: bool) -> None:
+    lib = _lib.load()
+    _req(feat, "feat", torch.float32)
+    _req(codes, "codes", torch.uint8)
+    _req(out, "packed", torch.bfloat16)
+    B, Cc, H, W = feat.shape
+    check(lib.rgbd_dsam_pack_t(feat.data_ptr(), codes.data_ptr(), out.data_ptr(), B, Cc, c_pad, H, W, w2_pitch, n_seg,
+                               masked_segs, 1 if parity_split else 0, _stream()), "rgbd_dsam_pack_t")
+    _count(1)
+
+
+def dsam_dbias(g: torch.Tensor, variant: Optional[torch.Tensor], n_bias: int) -> torch.Tensor:
+    lib = _lib.load()
+    _req(g, "grad_output", torch.float32)
+    B, N, Ho, Wo = g.shape
+    db = torch.empty(n_bias, N, device=g.device, dtype=torch.float32)
+    check(lib.rgbd_dsam_dbias(g.data_ptr(), _req(variant, "variant", torch.int32).data_ptr() if variant is not None else None,
+                              db.data_ptr(), B, N, Ho * Wo, n_bias, _stream()), "rgbd_dsam_dbias")
+    _count(1)
+    return db
+
+
+def dsam_wgrad(g_bf16: torch.Tensor, xt: torch.Tensor, n_out: int, c_pad: int, out_hw: Tuple[int, int], n_seg: int,
+               parity_split: bool) -> torch.Tensor:
+    """dW[n][seg][tap][c_pad] fp32.  g_bf16: (B, n_out, Ho, Wp); xt: (B, n_seg, n_par, c_pad, H2, W2p)."""
+    lib = _lib.load()
+    _req(g_bf16, "g", torch.bfloat16)
+    _req(xt, "x_t", torch.bfloat16)
+    B = g_bf16.shape[0]
+    taps = 9 if parity_split else 1
+    dw = torch.empty(n_out, n_seg, taps, c_pad, device=g_bf16.device, dtype=torch.float32)
+    check(lib.rgbd_dsam_wgrad(g_bf16.data_ptr(), g_bf16.shape[-1], xt.data_ptr(), xt.shape[-1], xt.shape[-2], dw.data_ptr(), B,
+                              n_out, c_pad, out_hw[0], out_hw[1], n_seg, 1 if parity_split else 0, _stream()),
+          "rgbd_dsam_wgrad")
+    _count(1)
+    return dw
 
 
 def ratio_stem_pack(depth3: torch.Tensor, out: torch.Tensor) -> None:

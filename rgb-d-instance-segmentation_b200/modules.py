@@ -119,6 +119,26 @@ class DepthGradientInjectionResidual(nn.Module):
 # =====================================================================================================
 # E-DSAM core
 # =====================================================================================================
+class _DsamStageFunction(torch.autograd.Function):
+    """Autograd of one DSAM stage (masks are constants): wgrad + dbias always, dgrad only when the
+    stage input requires grad (stage 0's input is a detached clone, CM:332)."""
+
+    @staticmethod
+    def forward(ctx, module, x, codes, variant, residual, *params):
+        out = module._stage_forward_impl(x, codes, variant, residual)
+        ctx.module = module
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, codes, variant)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, codes, variant = ctx.saved_tensors
+        m = ctx.module
+        dx, grads = m._stage_backward_impl(x, codes, variant, g.contiguous().float(), need_dx=ctx.needs_input_grad[1])
+        return (None, dx, None, None, g if ctx.has_res else None, *grads)
+
+
 class DSAModule(nn.Module):
     """CM:622-799.  Depth-sensitive attention: depth histogram modes -> depth-interval region masks ->
     sum_t Conv_t(mask_t * F) + projection(F).  ``in != out``: 3x3 stride-2 convs + bias-free 3x3 stride-2
@@ -142,6 +162,9 @@ class DSAModule(nn.Module):
         self._ver = _Versioned()
         self._packed: Dict[str, torch.Tensor] = {}
         self._ws: Dict[tuple, torch.Tensor] = {}
+        self._ver_bwd = _Versioned()
+        self._packed_bwd: Dict = {}
+        self._ws_t: Dict[tuple, torch.Tensor] = {}
 
     # ---- operand packing -------------------------------------------------------------------------
     @property
@@ -206,13 +229,108 @@ class DSAModule(nn.Module):
             self._ws = {key: torch.zeros(shape, device=dev, dtype=torch.bfloat16)}   # keep one shape alive
         return self._ws[key]
 
+    def _param_list(self):
+        ps = []
+        for conv in self.conv_layers:
+            ps += [conv.weight, conv.bias]
+        if self._proj:
+            ps.append(self.rgb_projection.weight)
+        return ps
+
     def stage_forward(self, rgb_features: torch.Tensor, codes: torch.Tensor, bias_variant: torch.Tensor,
                       residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Batched tensor-core path (see ``_stage_forward_impl``); differentiable w.r.t. the stage's parameters,
+        its input features and the residual when autograd is recording."""
+        ps = self._param_list()
+        if torch.is_grad_enabled() and (rgb_features.requires_grad or any(p.requires_grad for p in ps)
+                                        or (residual is not None and residual.requires_grad)):
+            return _DsamStageFunction.apply(self, rgb_features, codes, bias_variant, residual, *ps)
+        return self._stage_forward_impl(rgb_features, codes, bias_variant, residual)
+
+    # ---- backward (K3b) ----------------------------------------------------------------------------
+    def _refresh_bwd(self):
+        """Per input-parity class: transposed weights [(channel block, segment, 32 ch)][(tap, n)] and tap offsets."""
+        srcs = [p for p in self.parameters()]
+        if not self._ver_bwd.stale(srcs) and self._packed_bwd:
+            return self._packed_bwd
+        dev = srcs[0].device
+        c_in, c_out, R = self.in_channels, self.out_channels, self.num_depth_regions
+        n_seg = R + 1 + (1 if self._proj else 0)
+        c32 = _round_up(c_in, 32)
+        np64 = _round_up(c_out, 64)
+        ws = [c.weight.detach().float() for c in self.conv_layers] + ([self.rgb_projection.weight.detach().float()] if self._proj else [])
+        classes = []
+        par_list = [(py, px) for py in (0, 1) for px in (0, 1)] if self._proj else [(0, 0)]
+        for py, px in par_list:
+            if self._proj:
+                dys = [(1, 0)] if py == 0 else [(0, 1), (2, 0)]       # (dy, oy offset): input row 2*y2+py = 2*oy+dy-1
+                dxs = [(1, 0)] if px == 0 else [(0, 1), (2, 0)]
+            else:
+                dys, dxs = [(0, 0)], [(0, 0)]
+            taps = [(dy, yo, dx, xo) for dy, yo in dys for dx, xo in dxs]
+            wd = torch.zeros(c32 // 32, n_seg, 32, len(taps), np64, device=dev, dtype=torch.float32)
+            for sg, w in enumerate(ws):
+                for ti, (dy, yo, dx, xo) in enumerate(taps):
+                    wt = torch.zeros(c32, np64, device=dev)
+                    wt[:c_in, :c_out] = w[:, :, dy, dx].t()                 # (c, n)
+                    wd[:, sg, :, ti, :] = wt.reshape(c32 // 32, 32, np64)
+            wd = wd.reshape(c32 // 32 * n_seg * 32, len(taps) * np64).to(torch.bfloat16).contiguous()
+            sl = torch.tensor([(nb * 64, xo, yo, 0) for (dy, yo, dx, xo) in taps for nb in range(np64 // 64)],
+                              device=dev, dtype=torch.int32).contiguous()
+            classes.append({"py": py, "px": px, "w": wd, "slices": sl})
+        self._packed_bwd = {"classes": classes, "n_seg": n_seg, "c32": c32, "np64": np64}
+        return self._packed_bwd
+
+    def _stage_backward_impl(self, x: torch.Tensor, codes: torch.Tensor, variant: torch.Tensor, g: torch.Tensor, need_dx: bool):
+        R, c_in, c_out = self.num_depth_regions, self.in_channels, self.out_channels
+        c_pad, kb, n_pad, n_seg = self._geometry()
+        B, _, H, W = x.shape
+        _, _, Ho, Wo = g.shape
+        x = x.detach().contiguous().float()
+        # ---- bias gradients: images use the first variant[b] biases
+        db = Fn.dsam_dbias(g, variant, R + 1)
+        # ---- weight gradients: GEMM over the output pixels
+        gp = Fn.cast_bf16_pitched(g, _round_up(Wo, 8))
+        H2, W2 = ((H + 1) // 2, (W + 1) // 2) if self._proj else (H, W)
+        key = (B, H, W, str(x.device))
+        if key not in self._ws_t:
+            self._ws_t = {key: torch.zeros(B, n_seg, 4 if self._proj else 1, c_pad, H2, _round_up(W2, 8),
+                                           device=x.device, dtype=torch.bfloat16)}
+        xt = self._ws_t[key]
+        Fn.dsam_pack_t(x, codes, xt, c_pad, xt.shape[-1], n_seg, R + 1, self._proj)
+        dw = Fn.dsam_wgrad(gp, xt, c_out, c_pad, (Ho, Wo), n_seg, self._proj)       # (c_out, n_seg, taps, c_pad)
+        k = 3 if self._proj else 1
+        grads = []
+        for t in range(R + 1):
+            grads.append(dw[:, t, :, :c_in].reshape(c_out, k, k, c_in).permute(0, 3, 1, 2).contiguous())
+            grads.append(db[t])
+        if self._proj:
+            grads.append(dw[:, R + 1, :, :c_in].reshape(c_out, 3, 3, c_in).permute(0, 3, 1, 2).contiguous())
+        # ---- input gradient: one transposed-conv GEMM per input-parity class, masked segment sum in the epilogue
+        dx = None
+        if need_dx:
+            pk = self._refresh_bwd()
+            np64 = pk["np64"]
+            gcl = torch.empty(B, Ho, Wo, np64, device=x.device, dtype=torch.bfloat16)
+            Fn.dsam_pack(g, codes.reshape(-1)[:B * Ho * Wo].reshape(B, Ho, Wo), gcl, np64, 1, 0, False)   # plain NCHW -> channels-last
+            dx = torch.empty_like(x)
+            direct = g if not self._proj else None            # identity residual (out = enh + F)
+            for cl in pk["classes"]:
+                Fn.conv_gemm(gcl, (B, Ho, Wo, np64), 1, cl["w"], cl["slices"], 64, B, (H2, W2), _best_box(H2, W2), c_in, None,
+                             epi_mode=3, out=dx, residual=direct, codes=codes, in_hw=(H, W), parity=(cl["py"], cl["px"]),
+                             m3_stride=2 if self._proj else 1, m3_masked_segs=R + 1, m3_n_seg=n_seg,
+                             block_n=32 * n_seg)
+        return dx, grads
+
+    def _stage_forward_impl(self, rgb_features: torch.Tensor, codes: torch.Tensor, bias_variant: torch.Tensor,
+                            residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Batched tensor-core path: features (B,C_in,H,W) fp32, pooled region codes (B,H,W) uint8 and the
         per-image bias count (Decomposition.bias_variant) -> sum_t conv_t(F*p_t) + projection(F) [+ residual]
         (fp32 result, bf16 operands)."""
         pk = self._refresh()
-        x = Fn._req(rgb_features.contiguous(), "rgb_features", torch.float32)
+        x = Fn._req(rgb_features.detach().contiguous(), "rgb_features", torch.float32)
+        if residual is not None:
+            residual = residual.detach()
         B, Cc, H, W = x.shape
         assert Cc == self.in_channels, f"Expected {self.in_channels} channels, got {Cc}"
         c_pad, kb, n_pad, n_seg = self._geometry()
@@ -442,6 +560,7 @@ def depth_guidance_forward(ratio_predictor: EnhancedDepthImageRatioPredictor, ds
     feats = [f.detach().contiguous().float() for f in color_feature_map]   # CM:332-333 (detach; no clone needed)
     if ratios is None:
         ratios = ratio_predictor(depth)                                     # CM:336
+    ratios = ratios.detach()                                                # consumed through .item() in CM:339
     levels = [tuple(f.shape[2:]) for f in feats[:3]]
     dec = Fn.depth_decompose(ratios.reshape(-1).contiguous(), levels, depth3=depth)
     cp1 = [feats[0]]
@@ -449,5 +568,9 @@ def depth_guidance_forward(ratio_predictor: EnhancedDepthImageRatioPredictor, ds
     for k, dsam in enumerate(dsams):                                        # CM:339-352
         x = dsam.stage_forward(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1])
         cp1.append(x)
+    training = torch.is_grad_enabled() and any(p.requires_grad for m in (*dsams, dggm) for p in m.parameters())
+    if training:
+        cp2 = dggm(feats, gradient_depth, gradient_mask)                    # CM:354 (autograd: K1b)
+        return [a + b for a, b in zip(cp1, cp2)]                            # CM:355
     # CM:354-355: cp2 = DGGM(feats); out = cp1 + cp2, fused into the DGGM kernel
     return dggm.forward_fused_sum(feats, cp1, gradient_depth, gradient_mask)

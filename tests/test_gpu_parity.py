@@ -429,3 +429,72 @@ def test_whole_model_logits_match_cpu_oracle_model(mods):
     pb = (ref.masks_queries_logits.sigmoid() > 0.5)
     agree = float((pa == pb).float().mean())
     assert agree > 0.995, agree
+
+
+# ---------------------------------------------------------------------------------------------------
+# K3b: DSAM backward (wgrad / dbias / dgrad) and the training-mode cascade against oracle autograd
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ci,co,hw,dhw", [(32, 64, (24, 32), (96, 128)), (96, 192, (30, 40), (120, 160)),
+                                          (64, 64, (12, 16), (48, 64)), (40, 72, (15, 20), (60, 80))])
+def test_dsam_stage_backward(mods, fn, ci, co, hw, dhw):
+    w = OW.dsam_weights(ci, co, seed=200 + ci + co)
+    m = mods.DSAModule(ci, co, 3)
+    m.load_state_dict(w)
+    m.cuda().train()
+    rs = np.random.RandomState(6)
+    B = 3
+    feat = torch.from_numpy(rs.randn(B, ci, *hw).astype(np.float32))
+    kinds = ["nyu", "constant", "two_valued"]
+    grays = [_gray_for(j, kinds[j], dhw) for j in range(B)]
+    ratios = [0.3, 0.2, 0.4]
+    dec = fn.depth_decompose(torch.tensor(ratios, device="cuda"), [hw], gray=torch.from_numpy(np.stack(grays)).cuda())
+    x = feat.cuda().requires_grad_(True)
+    out = m.stage_forward(x, dec.pooled[0], dec.bias_variant)
+    dout = torch.from_numpy(rs.randn(*out.shape).astype(np.float32))
+    (out * dout.cuda()).sum().backward()
+    # oracle: torch autograd through the CPU restatement
+    wr = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    xr = feat.clone().requires_grad_(True)
+    ref = torch.cat([O.dsam_forward(wr, xr[b:b + 1], grays[b], ratios[b]) for b in range(B)])
+    (ref * dout).sum().backward()
+    assert rel_l2(out, ref) < BF16_TOL
+    assert rel_l2(x.grad, xr.grad) < 2e-2, rel_l2(x.grad, xr.grad)
+    for name, p in m.named_parameters():
+        g_ref = wr[name].grad
+        if g_ref is None:            # region never used by any image: the reference leaves it without gradient
+            assert float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert rel_l2(p.grad, g_ref) < 2e-2, (name, rel_l2(p.grad, g_ref))
+
+
+def test_depth_guidance_training_gradients(mods, golden_dir):
+    """Fine-tuning semantics of CM:324-355: gradients reach all DSAM and DGGM parameters, none reach the encoder
+    features or the ratio predictor."""
+    g = np.load(os.path.join(golden_dir, "wiring.npz"))
+    w = OW.guidance_weights(seed=700)
+    m = mods.DepthGuidance((96, 192, 384, 768))
+    m.load_state_dict(w)
+    m.cuda().train()
+    pvs = []
+    for j in range(2):
+        rgb, d = synthetic.synth_rgbd_u8(80 + j, 64, 96, "nyu")
+        pvs.append(synthetic.assemble_pixel_values(rgb, d, O.gradient_features))
+    pv = torch.from_numpy(np.stack(pvs))
+    feats = [torch.from_numpy(g[f"feat{i}"]) for i in range(4)]
+    ratios = torch.from_numpy(g["ratios"])
+    rs = np.random.RandomState(8)
+    douts = [torch.from_numpy(rs.randn(*f.shape).astype(np.float32)) for f in feats]
+    feats_gpu = [f.cuda().requires_grad_(True) for f in feats]
+    out = m(pv.cuda(), feats_gpu, ratios=ratios.cuda())
+    sum((o * d.cuda()).sum() for o, d in zip(out, douts)).backward()
+    wr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in w.items()}
+    ref, _ = O.depth_guidance_forward(wr, pv, feats, ratios=ratios)
+    sum((o * d).sum() for o, d in zip(ref, douts)).backward()
+    assert all(f.grad is None for f in feats_gpu)                               # detached (CM:332-333)
+    for name, p in m.named_parameters():
+        if name.startswith("ratio_predictor."):
+            assert p.grad is None, name                                          # consumed via .item() (CM:339)
+            continue
+        g_ref = wr[name].grad
+        assert g_ref is not None and p.grad is not None, name
+        assert rel_l2(p.grad, g_ref) < 3e-2, (name, rel_l2(p.grad, g_ref))
