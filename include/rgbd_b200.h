@@ -138,10 +138,13 @@ int rgbd_conv_gemm(const rgbd_conv_gemm_desc* desc_host, rgbd_stream_t stream);
 
 /* ---- E-DSAM backward (autograd of DSAModule.forward CM:683-696; colour features of stage 0 are detached CM:332) ----
  * rgbd_cast_bf16_pitched: (rows, W) fp32 -> bf16 with row pitch W_pitch (multiple of 8, zero padded).
- * rgbd_dsam_pack_t: like rgbd_dsam_pack but pixel-contiguous: out[img][seg][parity][C_pad][H2][W2_pitch] (zeroed by caller).
+ * rgbd_dsam_pack_t: like rgbd_dsam_pack but pixel-contiguous: out[img][seg][plane][C_pad][H2][W2_pitch] (zeroed by caller);
+ *   with parity_split there are 6 planes: the 4 parity planes and right-shifted-by-one copies of the two px=1 planes
+ *   (TMA needs a 16-byte aligned innermost start, so the x-1 tap reads a pre-shifted plane); the last column of a
+ *   shifted plane is dropped when it does not fit the pitch (it never meets a non-zero gradient).
  * rgbd_dsam_dbias: db[t][n] = sum over images that use region t (t < variant[b]) of sum_pixels g[b][n]; db overwritten.
  * rgbd_dsam_wgrad: dw[n][seg][tap][C_pad] (fp32, overwritten) = sum_pixels g[b][n][oy][ox] * x_t[b][seg][tap-shifted pixel][c];
- *   g_bf16: (B, N_out, Ho, g_w_pitch); xt_bf16: output of rgbd_dsam_pack_t with plane height x_h.
+ *   g_bf16: (B, N_out, Ho, g_w_pitch); xt_bf16: output of rgbd_dsam_pack_t with plane height x_h and the SAME row pitch.
  * The input gradient runs through rgbd_conv_gemm with epi_mode 3. */
 int rgbd_cast_bf16_pitched(const float* src, void* dst_bf16, long long rows, int W, int W_pitch, rgbd_stream_t stream);
 int rgbd_dsam_pack_t(const float* feat, const uint8_t* codes, void* out_bf16, int B, int C, int C_pad, int H, int W,

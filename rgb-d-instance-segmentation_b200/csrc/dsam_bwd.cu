@@ -5,27 +5,30 @@
 //   dF              = sum_t p_t * ConvT_t(G) + ProjT(G)   -> conv_gemm.cu, epilogue mode 3 (masked segment sum)
 //
 // wgrad is a GEMM whose reduction dimension is the OUTPUT PIXELS: M = C_out rows of G^T, N = C_in rows of the
-// masked input, K = B*Ho*Wo.  Both operands are staged pixel-contiguous (bf16, "NCHW"), so a K block of 64 pixels
-// is a (kx x ky) TMA box; the input box is shifted by the filter tap inside its parity plane and out-of-range
-// pixels are zero-filled (= conv padding).  One CTA tile = (segment, tap, 128 output channels, BLOCK_N input
+// masked input, K = B*Ho*Wo.  Both operands are staged pixel-contiguous (bf16, "NCHW") with the SAME row pitch, so
+// a K block is 64 consecutive flattened pixels (one 128-byte swizzled TMA row per channel); a filter tap is a
+// constant shift of the flattened index inside the tap's parity plane (rows: -pitch; columns: a pre-shifted copy
+// of the plane, because TMA needs a 16-byte aligned innermost start) and out-of-range pixels are zero-filled
+// (= conv padding; the pitch padding of G is zero, so pad columns never contribute).  One CTA tile = (segment, tap, 128 output channels, BLOCK_N input
 // channels, image range); tcgen05.mma accumulates in TMEM over the whole K loop; the epilogue adds the fp32 tile
 // into dW with red.global (split-K over images keeps all SMs busy).
 #include "common.cuh"
 #include "rgbd_b200.h"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kThreads = 192;          // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int kThreads = 224;          // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc/dealloc (never diverges), warps 3-6 epilogue
 constexpr int kMaxStagesW = 8;
 
 struct WgradParams {
-    int B, Ho, Wo, kx, ky, kbx, kby;
+    int B, Ho, Wo, Wp, k_blocks;
     int n_seg, n_par, taps;
     int m_tiles, n_tiles, BLOCK_N, ksplit;
     int N_out, Cp, stages;
-    int taps_tbl[9][3];                // (parity plane, x offset, y offset) per tap
+    int taps_tbl[9][2];                // (plane, flattened pixel offset) per tap
     float* dw;                         // [N_out][n_seg][taps][Cp]
     int total_tiles;
 };
@@ -66,7 +69,7 @@ dsam_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         tc::mbar_init(&ctl->acc_empty, 128);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, 256);
+    if (warp == 2) tc::tmem_alloc(&ctl->tmem_base, 256);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -79,19 +82,16 @@ dsam_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
             int ks, seg, tap, mt, nt;
             decode_wtile(p, t, ks, seg, tap, mt, nt);
             const int b0 = (int)(((long long)p.B * ks) / p.ksplit), b1 = (int)(((long long)p.B * (ks + 1)) / p.ksplit);
-            const int par = p.taps_tbl[tap][0], xo = p.taps_tbl[tap][1], yo = p.taps_tbl[tap][2];
+            const int par = p.taps_tbl[tap][0], off = p.taps_tbl[tap][1];
             for (int b = b0; b < b1; ++b) {
                 const int plane = (b * p.n_seg + seg) * p.n_par + par;
-                for (int kyb = 0; kyb < p.kby; ++kyb) {
-                    for (int kxb = 0; kxb < p.kbx; ++kxb) {
-                        tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
-                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                        tc::mbar_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
-                        tc::tma_load_4d(sa, &tmap_g, &ctl->full[stage], kxb * p.kx, kyb * p.ky, mt * kBlockM, b);
-                        tc::tma_load_4d(sa + a_bytes, &tmap_x, &ctl->full[stage], kxb * p.kx + xo, kyb * p.ky + yo,
-                                        nt * p.BLOCK_N, plane);
-                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                    }
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    tc::mbar_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
+                    tc::tma_load_3d(sa, &tmap_g, &ctl->full[stage], kb * 64, mt * kBlockM, b);
+                    tc::tma_load_3d(sa + a_bytes, &tmap_x, &ctl->full[stage], kb * 64 + off, nt * p.BLOCK_N, plane);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -103,7 +103,7 @@ dsam_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
             int ks, seg, tap, mt, nt;
             decode_wtile(p, t, ks, seg, tap, mt, nt);
             const int b0 = (int)(((long long)p.B * ks) / p.ksplit), b1 = (int)(((long long)p.B * (ks + 1)) / p.ksplit);
-            const int n_kblocks = (b1 - b0) * p.kby * p.kbx;
+            const int n_kblocks = (b1 - b0) * p.k_blocks;
             tc::mbar_wait(&ctl->acc_empty, aphase ^ 1);
             tc::tc_fence_after();
             for (int j = 0; j < n_kblocks; ++j) {
@@ -119,7 +119,7 @@ dsam_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
             tc::umma_commit(&ctl->acc_full);
             aphase ^= 1;
         }
-    } else if (warp >= 2) {
+    } else if (warp >= 3) {
         const int q = warp & 3;                    // TMEM lane quarter of this warp
         const int row = q * 32 + lane;
         uint32_t aphase = 0;
@@ -147,7 +147,8 @@ dsam_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 2) {
+        __syncwarp();
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem, 256);
     }
@@ -165,12 +166,14 @@ __global__ void __launch_bounds__(256) cast_pitched_kernel(const float* __restri
     dst[i] = __float2bfloat16(x < W ? src[r * W + x] : 0.f);
 }
 
-// masked, parity-split, pixel-contiguous input: out[b][seg][par][c][y2][x2 (pitch W2p)] = bf16(F[b][c][y][x] * bit(code,seg))
+// masked, parity-split, pixel-contiguous input: out[b][seg][par][c][y2][x2 (pitch W2p)] = bf16(F[b][c][y][x] * bit(code,seg)).
+// TMA needs the innermost (x) start coordinate 16-byte aligned, so the x-1 tap cannot be a box shifted by one pixel:
+// planes 4 and 5 are copies of the px=1 planes (py=0 / py=1) shifted right by one pixel (x2 -> x2+1).
 __global__ void __launch_bounds__(256) dsam_pack_t_kernel(const float* __restrict__ feat, const uint8_t* __restrict__ codes,
                                                           __nv_bfloat16* __restrict__ out, int C, int Cp, int H, int W,
                                                           int H2, int W2p, int n_seg, int masked_segs, int split) {
     const int b = blockIdx.z, c = blockIdx.y;
-    const int n_par = split ? 4 : 1;
+    const int n_par = split ? 6 : 1;
     const size_t plane = (size_t)H * W;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
         const int y = i / W, x = i - y * W;
@@ -180,8 +183,11 @@ __global__ void __launch_bounds__(256) dsam_pack_t_kernel(const float* __restric
         const int yy = split ? (y >> 1) : y, xx = split ? (x >> 1) : x;
         for (int s = 0; s < n_seg; ++s) {
             const bool keep = s >= masked_segs || ((code >> s) & 1u);
-            const size_t pl = ((size_t)b * n_seg + s) * n_par + par;
-            out[((pl * Cp + c) * H2 + yy) * W2p + xx] = __float2bfloat16(keep ? v : 0.f);
+            const __nv_bfloat16 h = __float2bfloat16(keep ? v : 0.f);
+            const size_t pl = ((size_t)b * n_seg + s) * n_par;
+            out[(((pl + par) * Cp + c) * H2 + yy) * W2p + xx] = h;
+            if (split && (x & 1) && xx + 1 < W2p)
+                out[(((pl + 4 + (y & 1)) * Cp + c) * H2 + yy) * W2p + xx + 1] = h;
         }
     }
 }
@@ -221,13 +227,12 @@ EncodeTiledFn wg_encode_fn() {
     return fn;
 }
 
-bool make_pix_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int wp, int h, int rows, int planes, int kx, int ky,
-                  int box_rows) {
-    cuuint64_t dims[4] = {(cuuint64_t)wp, (cuuint64_t)h, (cuuint64_t)rows, (cuuint64_t)planes};
-    cuuint64_t strides[3] = {(cuuint64_t)wp * 2, (cuuint64_t)wp * 2 * h, (cuuint64_t)wp * 2 * h * rows};
-    cuuint32_t box[4] = {(cuuint32_t)kx, (cuuint32_t)ky, (cuuint32_t)box_rows, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+bool make_pix_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, long long pix, int rows, int planes, int box_rows) {
+    cuuint64_t dims[3] = {(cuuint64_t)pix, (cuuint64_t)rows, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)pix * 2, (cuuint64_t)pix * 2 * rows};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -281,28 +286,21 @@ extern "C" int rgbd_dsam_wgrad(const void* g_bf16, int g_w_pitch, const void* xt
     WgradParams p;
     p.B = B; p.Ho = Ho; p.Wo = Wo; p.N_out = N_out; p.Cp = C_pad;
     p.n_seg = n_seg;
-    p.n_par = parity_split ? 4 : 1;
+    p.n_par = parity_split ? 6 : 1;
     p.taps = parity_split ? 9 : 1;
-    // K box: kx*ky = 64 pixels, kx a multiple of 8 (16-byte inner box), chosen to waste the fewest pixels
-    int best_kx = 8;
-    double best_eff = -1;
-    for (int kx = 8; kx <= 64; kx *= 2) {
-        const int ky = 64 / kx;
-        const double eff = (double)Wo * Ho / ((double)ceil_div(Wo, kx) * kx * ceil_div(Ho, ky) * ky);
-        if (eff > best_eff + 1e-9) { best_eff = eff; best_kx = kx; }
-    }
-    p.kx = best_kx; p.ky = 64 / best_kx;
-    p.kbx = ceil_div(Wo, p.kx); p.kby = ceil_div(Ho, p.ky);
+    RGBD_CHECK_ARG(g_w_pitch == x_w_pitch && x_h >= Ho, "dsam_wgrad: G and X^T must share the row pitch (got %d / %d)", g_w_pitch,
+                   x_w_pitch);
+    p.Wp = g_w_pitch;
+    p.k_blocks = ceil_div(Ho * p.Wp, 64);
     for (int tap = 0; tap < p.taps; ++tap) {
-        int par = 0, xo = 0, yo = 0;
+        int par = 0, off = 0;
         if (parity_split) {
             const int dy = tap / 3, dx = tap % 3;           // input row 2*oy+dy-1: dy=0 -> odd plane, row oy-1; 1 -> even, oy; 2 -> odd, oy
             const int py = dy == 1 ? 0 : 1, px = dx == 1 ? 0 : 1;
-            par = py * 2 + px;
-            yo = dy == 0 ? -1 : 0;
-            xo = dx == 0 ? -1 : 0;
+            par = dx == 0 ? 4 + py : py * 2 + px;           // dx == 0 reads pixel x2-1: the right-shifted copy of the px=1 plane
+            off = dy == 0 ? -p.Wp : 0;
         }
-        p.taps_tbl[tap][0] = par; p.taps_tbl[tap][1] = xo; p.taps_tbl[tap][2] = yo;
+        p.taps_tbl[tap][0] = par; p.taps_tbl[tap][1] = off;
     }
     p.BLOCK_N = C_pad <= 256 ? C_pad : 0;
     if (!p.BLOCK_N)
@@ -331,8 +329,8 @@ extern "C" int rgbd_dsam_wgrad(const void* g_bf16, int g_w_pitch, const void* xt
     p.stages = stages;
     CUtensorMap m_g, m_x;
     const int x_planes = B * n_seg * p.n_par;
-    if (!make_pix_map(enc, &m_g, g_bf16, g_w_pitch, Ho, N_out, B, p.kx, p.ky, kBlockM) ||
-        !make_pix_map(enc, &m_x, xt_bf16, x_w_pitch, x_h, C_pad, x_planes, p.kx, p.ky, p.BLOCK_N)) {
+    if (!make_pix_map(enc, &m_g, g_bf16, (long long)Ho * g_w_pitch, N_out, B, kBlockM) ||
+        !make_pix_map(enc, &m_x, xt_bf16, (long long)x_h * x_w_pitch, C_pad, x_planes, p.BLOCK_N)) {
         rgbd_set_error("dsam_wgrad: cuTensorMapEncodeTiled failed");
         return RGBD_ERR_CUDA;
     }

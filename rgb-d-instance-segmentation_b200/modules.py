@@ -294,7 +294,8 @@ class DSAModule(nn.Module):
         H2, W2 = ((H + 1) // 2, (W + 1) // 2) if self._proj else (H, W)
         key = (B, H, W, str(x.device))
         if key not in self._ws_t:
-            self._ws_t = {key: torch.zeros(B, n_seg, 4 if self._proj else 1, c_pad, H2, _round_up(W2, 8),
+            self._ws_t = {key: torch.zeros(B, n_seg, 6 if self._proj else 1, c_pad, H2,
+                                           _round_up(W2, 8),
                                            device=x.device, dtype=torch.bfloat16)}
         xt = self._ws_t[key]
         Fn.dsam_pack_t(x, codes, xt, c_pad, xt.shape[-1], n_seg, R + 1, self._proj)
