@@ -478,6 +478,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         } else if (p.epi_mode == 1) {
             if (sc) epilogue_loop<1, 0, true>(p, c, &tmap_out);
             else epilogue_loop<1, 0, false>(p, c, &tmap_out);
+        } else if (p.epi_mode == 3) {
+            epilogue_loop<3, 0, false>(p, c, &tmap_out);
         } else {
             if (sc) epilogue_loop<2, 1, true>(p, c, &tmap_out);
             else epilogue_loop<2, 1, false>(p, c, &tmap_out);
