@@ -323,6 +323,71 @@ def run_own(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE configs[3] restricted to the hot path: one fine-tuning step of the depth-guidance modules (forward +
+    backward: DSAM wgrad/dgrad/dbias, DGGM dW/db) at batch 8 per GPU, gradients all-reduced over NCCL when N > 1.
+    Reported as an extra JSON line (`"mode": "train"`); the headline metric stays the inference line."""
+    import torch.distributed as dist
+    import rgbd_b200  # noqa: F401
+    from rgbd_b200 import functional as Fn, modules, synthetic
+    from oracle import weights as OW
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = 8
+    model = modules.DepthGuidance(CHANS)
+    model.load_state_dict(OW.guidance_weights(seed=42, channels=CHANS))
+    model.to(dev).train()
+    rgb_u8, depth_u8 = make_frames(B, first=rank * 1000)
+    pv = torch.empty(B, 10, H, W, device=dev)
+    for j in range(B):
+        pv[j, 0:3] = torch.from_numpy(synthetic.normalise_u8(rgb_u8[j])).to(dev)
+        pv[j, 3:6] = torch.from_numpy(synthetic.normalise_u8(np.repeat(depth_u8[j][:, :, None], 3, axis=2))).to(dev)
+    Fn.gradient_features(torch.from_numpy(depth_u8).to(dev), norm_out=pv[:, 6:9], vmask_out=pv[:, 9:10])
+    feats = make_features(B, 7 + rank, dev)
+    douts = [torch.randn_like(f) for f in feats]
+    params = [p for n, p in model.named_parameters() if not n.startswith("ratio_predictor.")]
+
+    def step():
+        for p in params:
+            p.grad = None
+        out = model(pv, feats)
+        torch.autograd.backward(out, douts)
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+        return out
+
+    for _ in range(3):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        emit({"mode": "train", "metric": "rgbd_480x640_train_frames_per_sec_depth_guidance_hot_path",
+              "value": world * B * args.steps / float(t.item()), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+              "ms_per_step": float(t.item()) / args.steps * 1e3, "batch_per_gpu": B,
+              "grad_elements_allreduced": int(sum(p.numel() for p in params)) if world > 1 else 0,
+              "config": {"workload": "configs[3] hot-path share: fwd+bwd of DSAM x3 + DGGM, batch 8/GPU, NCCL grad all-reduce"}})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 class PerKernel:
     """Times the stages of one hot-path step separately with CUDA events (same inputs, same stream)."""
 
@@ -404,9 +469,12 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "train":
+        run_train(args)
     else:
         run_own(args)
 
