@@ -66,6 +66,14 @@ int rgbd_gradient_features(const void* depth, int depth_dtype, long long depth_b
                            long long norm_batch_stride, int n_rep, float* vmask_out, long long vmask_batch_stride, int B,
                            int H, int W, float invalid_value, void* workspace, rgbd_stream_t stream);
 
+/* rgbd_pack_pixel_values builds the whole (B,10,H,W) model input of map_10channel_case2 (DL:386-425) on device from the
+ * already-resized uint8 colour image (B,H,W,3) and uint8 depth image (B,H,W): channels 0:3 / 3:6 = the Hugging Face
+ * processor's rescale + normalize of colour / depth-as-RGB (bit-exact with its numpy arithmetic), 6:9 + 9 = the
+ * gradient features above.  workspace: rgbd_gradient_features_workspace_bytes(B). */
+int rgbd_pack_pixel_values(const uint8_t* rgb_hwc, const uint8_t* depth, float* pixel_values, long long pv_batch_stride,
+                           int B, int H, int W, double rescale_factor, const float* mean3_host, const float* std3_host,
+                           float invalid_value, void* workspace, rgbd_stream_t stream);
+
 /* ---- E-DSAM: depth decomposition ------------------------------------------------------------------------------
  * rgbd_depth_decompose replaces, for a whole batch and without host round trips, to_grayscale (CM:466-480) and
  * DSAModule._calculate_depth_histogram / _select_depth_distribution_modes / _define_depth_interval_windows /

@@ -45,6 +45,8 @@ SIGNATURES = {
     "rgbd_gradient_features_workspace_bytes": (C.c_size_t, [C.c_int]),
     "rgbd_gradient_features": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p,
                                          C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "rgbd_pack_pixel_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                         C.c_double, c_float_p, c_float_p, C.c_float, C.c_void_p, C.c_void_p]),
     "rgbd_depth_decompose_workspace_bytes": (C.c_size_t, [C.c_int]),
     "rgbd_depth_decompose": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

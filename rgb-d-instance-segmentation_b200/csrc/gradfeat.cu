@@ -116,7 +116,45 @@ __global__ void gradfeat_pass2_kernel(float* __restrict__ norm, long long norm_b
     }
 }
 
+// uint8 RGB (B,H,W,3) + uint8 depth (B,H,W) -> channels 0:6 of pixel_values (B,10,H,W): the Hugging Face
+// processor's rescale (float32(double(x) * rescale_factor)) and normalize ((x - mean) / std, float32) applied to the
+// colour image and to the depth image replicated to three channels (DL:389-410).  Bit-exact with the numpy path.
+__global__ void __launch_bounds__(256) pack_rgbd_kernel(const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ depth,
+                                                        float* __restrict__ pv, long long pv_bs, int HW, double rescale,
+                                                        float m0, float m1, float m2, float s0, float s1, float s2) {
+    const int b = blockIdx.y;
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+    float* out = pv + (long long)b * pv_bs;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const uint8_t* px = rgb + ((long long)b * HW + i) * 3;
+        const float d = (float)((double)depth[(long long)b * HW + i] * rescale);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = (float)((double)px[c] * rescale);
+            out[(long long)c * HW + i] = __fdiv_rn(v - mean[c], stdv[c]);
+            out[(long long)(3 + c) * HW + i] = __fdiv_rn(d - mean[c], stdv[c]);
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int rgbd_pack_pixel_values(const uint8_t* rgb_hwc, const uint8_t* depth, float* pixel_values,
+                                      long long pv_batch_stride, int B, int H, int W, double rescale_factor,
+                                      const float* mean3_host, const float* std3_host, float invalid_value, void* workspace,
+                                      rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(rgb_hwc && depth && pixel_values && mean3_host && std3_host && workspace, "pack_pixel_values: null pointer");
+    RGBD_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && pv_batch_stride >= 10ll * H * W, "pack_pixel_values: bad geometry");
+    const int HW = H * W;
+    dim3 grid(min(ceil_div(HW, 256), 1024), B);
+    pack_rgbd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rgb_hwc, depth, pixel_values, pv_batch_stride, HW, rescale_factor,
+                                                           mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0],
+                                                           std3_host[1], std3_host[2]);
+    RGBD_CHECK_LAUNCH();
+    // channels 6:9 (normalised Sobel magnitude x3) and 9 (valid-gradient mask): K0 on the raw uint8 depth (DL:412-421)
+    return rgbd_gradient_features(depth, RGBD_DTYPE_U8, HW, pixel_values + 6ll * HW, pv_batch_stride, 3,
+                                  pixel_values + 9ll * HW, pv_batch_stride, B, H, W, invalid_value, workspace, stream);
+}
 
 extern "C" size_t rgbd_gradient_features_workspace_bytes(int B) { return sizeof(ImgStats) * (size_t)(B > 0 ? B : 0); }
 

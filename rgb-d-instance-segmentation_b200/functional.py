@@ -151,6 +151,30 @@ def gradient_features(depth: torch.Tensor, n_rep: int = 3, invalid_value: float 
     return norm_out, vmask_out
 
 
+def pack_pixel_values(rgb_u8: torch.Tensor, depth_u8: torch.Tensor, out: Optional[torch.Tensor] = None,
+                      mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225),
+                      rescale_factor: float = 0.00392156862745098, invalid_value: float = 0.0) -> torch.Tensor:
+    """Front-end of ``map_10channel_case2`` (DL:386-425) on device: uint8 colour (B,H,W,3) + uint8 depth (B,H,W), already
+    at the model resolution -> ``pixel_values`` (B,10,H,W) float32."""
+    lib = _lib.load()
+    _req(rgb_u8, "rgb", torch.uint8)
+    _req(depth_u8, "depth", torch.uint8)
+    B, H, W = depth_u8.shape
+    if rgb_u8.shape != (B, H, W, 3):
+        raise RgbdB200Error(f"rgb must be {(B, H, W, 3)}, got {tuple(rgb_u8.shape)}")
+    if out is None:
+        out = torch.empty(B, 10, H, W, device=depth_u8.device, dtype=torch.float32)
+    _req(out, "pixel_values", torch.float32)
+    ws = torch.empty(max(int(lib.rgbd_gradient_features_workspace_bytes(B)), 16), device=depth_u8.device, dtype=torch.uint8)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    check(lib.rgbd_pack_pixel_values(rgb_u8.data_ptr(), depth_u8.data_ptr(), out.data_ptr(), out.stride(0), B, H, W,
+                                     float(rescale_factor), m, s, float(invalid_value), ws.data_ptr(), _stream()),
+          "rgbd_pack_pixel_values")
+    _count(4)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # E-DSAM depth decomposition
 # ------------------------------------------------------------------------------------------------

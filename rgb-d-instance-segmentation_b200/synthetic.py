@@ -49,9 +49,14 @@ def synth_rgbd_u8(frame_idx: int, height: int = 480, width: int = 640, kind: str
     return rgb, depth
 
 
+RESCALE_FACTOR = 0.00392156862745098       # preprocessor_config.json "rescale_factor" (1/255 as a double)
+
+
 def normalise_u8(img_hwc_u8: np.ndarray) -> np.ndarray:
-    """HF image-processor arithmetic: rescale by 1/255 then (x-mean)/std, float32, (3,H,W)."""
-    x = img_hwc_u8.astype(np.float32) * np.float32(1.0 / 255.0)
+    """The Hugging Face image processor's arithmetic as ``map_10channel_case2`` (DL:405-410) invokes it:
+    ``rescale`` = float32(float64(x) * rescale_factor), then ``normalize`` = (x - mean) / std in float32 with
+    float32 mean/std (transformers.image_transforms.rescale / normalize).  Returns (3,H,W) float32."""
+    x = (img_hwc_u8.astype(np.float64) * RESCALE_FACTOR).astype(np.float32)
     x = (x - IMAGE_MEAN) / IMAGE_STD
     return np.ascontiguousarray(x.transpose(2, 0, 1)).astype(np.float32)
 

@@ -75,6 +75,18 @@ def test_gradient_features_into_pixel_values_view(fn):
     assert float(pv[:, :6].abs().max()) == 0.0
 
 
+def test_pack_pixel_values_front_end_bit_exact(fn):
+    """uint8 colour + uint8 depth -> the whole 10-channel model input (DL:386-425), bit-exact with the numpy/HF path."""
+    rgbs, ds, refs = [], [], []
+    for j, kind in enumerate(["nyu", "uniform", "all_invalid"]):
+        rgb, d = synthetic.synth_rgbd_u8(200 + j, 60, 84, kind)
+        rgbs.append(rgb)
+        ds.append(d)
+        refs.append(synthetic.assemble_pixel_values(rgb, d, O.gradient_features))
+    pv = fn.pack_pixel_values(torch.from_numpy(np.stack(rgbs)).cuda(), torch.from_numpy(np.stack(ds)).cuda())
+    np.testing.assert_array_equal(pv.cpu().numpy(), np.stack(refs))
+
+
 # ---------------------------------------------------------------------------------------------------
 # K2 depth decomposition: bit-exact histogram / modes / windows / masks / pooled masks
 # ---------------------------------------------------------------------------------------------------
@@ -498,3 +510,32 @@ def test_depth_guidance_training_gradients(mods, golden_dir):
         g_ref = wr[name].grad
         assert g_ref is not None and p.grad is not None, name
         assert rel_l2(p.grad, g_ref) < 3e-2, (name, rel_l2(p.grad, g_ref))
+
+
+# ---------------------------------------------------------------------------------------------------
+# other geometries: Swin-B channels (BASELINE configs[4]) and image sizes that do not tile evenly
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("chans,hw", [((128, 256, 512, 1024), (96, 128)), ((96, 192, 384, 768), (100, 132)),
+                                      ((32, 64, 96, 160), (72, 88))])
+def test_depth_guidance_other_geometries(mods, chans, hw):
+    H, W = hw
+    w = OW.guidance_weights(seed=900, channels=chans)
+    m = mods.DepthGuidance(chans)
+    m.load_state_dict(w)
+    m.cuda().eval()
+    pvs = []
+    for j in range(2):
+        rgb, d = synthetic.synth_rgbd_u8(120 + j, H, W, "nyu")
+        pvs.append(synthetic.assemble_pixel_values(rgb, d, O.gradient_features))
+    pv = torch.from_numpy(np.stack(pvs))
+    rs = np.random.RandomState(1)
+    sizes = [(-(-H // s), -(-W // s)) for s in (4, 8, 16, 32)]           # Swin pads: ceil division
+    feats = [torch.from_numpy(rs.randn(2, c, h, ww).astype(np.float32)) for c, (h, ww) in zip(chans, sizes)]
+    ref, ref_ratio = O.depth_guidance_forward(w, pv, feats)
+    with torch.no_grad():
+        ratio = m.ratio_predictor(pv.cuda()[:, 3:6])
+        out = m(pv.cuda(), [f.cuda() for f in feats], ratios=ref_ratio.cuda())
+    assert float(((ratio.cpu() - ref_ratio).abs() / ref_ratio).max()) < BF16_TOL
+    for i in range(4):
+        assert out[i].shape == ref[i].shape
+        assert rel_err(out[i], ref[i]) < BF16_TOL, (i, rel_err(out[i], ref[i]))
