@@ -158,6 +158,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pin this rank's host threads (and therefore its pinned staging buffers, first-touch) to the CPUs NVML reports as
+    local to its GPU, so H2D/D2H copies do not cross the socket interconnect.  Best effort; returns the old mask."""
+    try:
+        import pynvml
+        old = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * wi + b for wi, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= old
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return old
+    except Exception:
+        return None
+
+
 def run_own(args):
     import torch.distributed as dist
     import rgbd_b200  # noqa: F401
@@ -170,6 +192,7 @@ def run_own(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    old_affinity = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -268,7 +291,7 @@ def run_own(args):
                 s_main.wait_event(e)
         return keep
 
-    e2e_run(2)
+    e2e_run(4)
     barrier()
     e0.record()
     kept = e2e_run(args.steps)
@@ -299,9 +322,9 @@ def run_own(args):
          "peak": pkv["tf_sustained"], "unit": "TFLOP/s", "frac": dsam_tf / pkv["tf_sustained"]},
     ]
     if rank == 0:
-        cpu_base = None
-        if world == 1 or True:
-            cpu_base, _ = cpu_reference(args.cpu_steps, 1)
+        if old_affinity:
+            os.sched_setaffinity(0, old_affinity)          # the CPU baseline uses every host core
+        cpu_base, _ = cpu_reference(args.cpu_steps, 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
