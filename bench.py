@@ -313,13 +313,15 @@ def run_own(args):
     dggm_gbs = BYTES_DGGM * B / kt["dggm"] / 1e9
     dsam_tf = FLOP_DSAM * B / kt["dsam_gemm"] / 1e12
     roof = {"kernel": "conv3x3_kernel (ratio predictor 3x3 128->256 conv + BN + ReLU + AdaptiveAvgPool2d(4))", "bound": "tensor",
-            "achieved": conv5_tf, "peak": pkv["tf_sustained"], "unit": "TFLOP/s", "frac": conv5_tf / pkv["tf_sustained"],
-            "traffic": TRAFFIC_CONV5_B32 if B == 32 else None, "peak_source": pkv["source"] + " sustained bf16 (kernel timed inside the step)"}
+            "achieved": conv5_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": conv5_tf / pkv["tf_burst"],
+            "frac_of_sustained": conv5_tf / pkv["tf_sustained"],
+            "traffic": TRAFFIC_CONV5_B32 if B == 32 else None,
+            "peak_source": pkv["source"] + " burst bf16 cuBLAS (the kernel is timed alone, back to back)"}
     extra = [
         {"kernel": "dggm_fwd_kernel (DGGM + branch sum)", "bound": "hbm", "achieved": dggm_gbs, "peak": pkv["hbm_gbs"],
          "unit": "GB/s", "frac": dggm_gbs / pkv["hbm_gbs"], "bytes_per_frame": BYTES_DGGM},
         {"kernel": "conv_gemm_kernel (3 DSAM stages)", "bound": "tensor", "achieved": dsam_tf,
-         "peak": pkv["tf_sustained"], "unit": "TFLOP/s", "frac": dsam_tf / pkv["tf_sustained"]},
+         "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": dsam_tf / pkv["tf_burst"]},
     ]
     if rank == 0:
         if old_affinity:

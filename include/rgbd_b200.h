@@ -97,9 +97,10 @@ int rgbd_depth_decompose(const float* depth3, long long depth_batch_stride, long
  * rgbd_dsam_pack builds the masked, K-concatenated bf16 operand of a DSAM stage (CM:683-696) from NCHW fp32
  * features and the pooled region codes: out[img][seg][parity][y2][x2][C_pad] (parity_split=1, 3x3 stride 2) or
  * out[img][seg][y][x][C_pad] (parity_split=0, 1x1).  Segments < masked_segs are multiplied by bit(code, seg);
- * the others are plain copies.  The caller zero-initialises `out` once (padding stays zero). */
+ * the others are plain copies.  The caller zero-initialises `out` once (padding stays zero).  hi_lo=1 writes every
+ * segment twice -- bf16(v) and bf16(v - bf16(v)), segment index 2*seg / 2*seg+1 -- for the split-precision ("fp32") mode. */
 int rgbd_dsam_pack(const float* feat, const uint8_t* codes, void* out_bf16, int B, int C, int C_pad, int H, int W, int n_seg,
-                   int masked_segs, int parity_split, rgbd_stream_t stream);
+                   int masked_segs, int parity_split, int hi_lo, rgbd_stream_t stream);
 
 /* Row-im2col of the 3-channel depth image for the predictor's multi-scale stem (CM:1458-1460):
  * out[img][H+6][W][64] bf16, channel (j*8+dx)*4+c = depth[img][c][r-3+j][x+dx-3]. */

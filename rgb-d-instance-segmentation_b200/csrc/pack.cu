@@ -17,7 +17,7 @@ namespace {
 
 __global__ void __launch_bounds__(256) dsam_pack_kernel(const float* __restrict__ feat, const uint8_t* __restrict__ codes,
                                                         __nv_bfloat16* __restrict__ out, int C, int Cp, int H, int W,
-                                                        int n_seg, int masked_segs, int split) {
+                                                        int n_seg, int masked_segs, int split, int hi_lo) {
     // CTA: 32 pixels of one row x 64 channels.  Load NCHW coalesced along x, transpose through shared memory, then each
     // thread owns (pixel, 8 channels) and writes one 16-byte piece per segment: 8 lanes = one 128-byte channels-last row.
     __shared__ float tile[64][33];
@@ -41,23 +41,32 @@ __global__ void __launch_bounds__(256) dsam_pack_kernel(const float* __restrict_
     const unsigned code = codes[(size_t)img * plane + (size_t)y * W + x];
     const int par = split ? ((y & 1) * 2 + (x & 1)) : 0;
     const int yy = split ? (y >> 1) : y, xx = split ? (x >> 1) : x;
-    uint4 v;
+    // hi = bf16(v); lo = bf16(v - hi): with W = W_hi + W_lo the three products hi*W_hi + lo*W_hi + hi*W_lo carry ~16
+    // mantissa bits through the bf16 tensor cores (the "fp32" precision mode of DSAModule)
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = tile[cg * 8 + k][px];
+    uint4 v, vl;
     {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(tile[cg * 8 + 0][px], tile[cg * 8 + 1][px]);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(tile[cg * 8 + 2][px], tile[cg * 8 + 3][px]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(tile[cg * 8 + 4][px], tile[cg * 8 + 5][px]);
-        __nv_bfloat162 h3 = __floats2bfloat162_rn(tile[cg * 8 + 6][px], tile[cg * 8 + 7][px]);
-        v.x = *reinterpret_cast<uint32_t*>(&h0);
-        v.y = *reinterpret_cast<uint32_t*>(&h1);
-        v.z = *reinterpret_cast<uint32_t*>(&h2);
-        v.w = *reinterpret_cast<uint32_t*>(&h3);
+        uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
+        uint32_t* pl = reinterpret_cast<uint32_t*>(&vl);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+            pv[k] = *reinterpret_cast<uint32_t*>(&h);
+            const float2 hf = __bfloat1622float2(h);
+            __nv_bfloat162 l = __floats2bfloat162_rn(f[2 * k] - hf.x, f[2 * k + 1] - hf.y);
+            pl[k] = *reinterpret_cast<uint32_t*>(&l);
+        }
     }
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const int mult = hi_lo ? 2 : 1;
     for (int s = 0; s < n_seg; ++s) {
         const bool keep = s >= masked_segs || ((code >> s) & 1u);
-        const size_t pl = ((size_t)img * n_seg + s) * n_par + par;
+        const size_t pl = ((size_t)img * n_seg * mult + s * mult) * n_par + par;
         const size_t off = ((pl * H2 + yy) * W2 + xx) * Cp + c;
         *reinterpret_cast<uint4*>(out + off) = keep ? v : zero;
+        if (hi_lo) *reinterpret_cast<uint4*>(out + off + (size_t)n_par * H2 * W2 * Cp) = keep ? vl : zero;
     }
 }
 
@@ -97,7 +106,7 @@ __global__ void __launch_bounds__(256) ratio_stem_pack_kernel(const float* __res
 }  // namespace
 
 extern "C" int rgbd_dsam_pack(const float* feat, const uint8_t* codes, void* out_bf16, int B, int C, int C_pad, int H, int W,
-                              int n_seg, int masked_segs, int parity_split, rgbd_stream_t stream) {
+                              int n_seg, int masked_segs, int parity_split, int hi_lo, rgbd_stream_t stream) {
     RGBD_CHECK_ARG(feat && codes && out_bf16, "dsam_pack: null pointer");
     RGBD_CHECK_ARG(B >= 1 && C >= 1 && H >= 1 && W >= 1, "dsam_pack: bad geometry");
     RGBD_CHECK_ARG(C_pad >= C && C_pad % 32 == 0, "dsam_pack: C_pad %d must be a multiple of 32 and >= C", C_pad);
@@ -105,7 +114,7 @@ extern "C" int rgbd_dsam_pack(const float* feat, const uint8_t* codes, void* out
                    "dsam_pack: bad segment counts");
     dim3 grid(ceil_div(W, 32) * ceil_div(C_pad, 64), H, B);
     dsam_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feat, codes, (__nv_bfloat16*)out_bf16, C, C_pad, H, W, n_seg,
-                                                            masked_segs, parity_split ? 1 : 0);
+                                                            masked_segs, parity_split ? 1 : 0, hi_lo ? 1 : 0);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }

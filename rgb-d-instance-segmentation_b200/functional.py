@@ -306,7 +306,7 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
 
 
 def dsam_pack(feat: torch.Tensor, codes: torch.Tensor, out: torch.Tensor, c_pad: int, n_seg: int, masked_segs: int,
-              parity_split: bool) -> None:
+              parity_split: bool, hi_lo: bool = False) -> None:
     lib = _lib.load()
     _req(feat, "feat", torch.float32)
     _req(codes, "codes", torch.uint8)
@@ -315,7 +315,7 @@ def dsam_pack(feat: torch.Tensor, codes: torch.Tensor, out: torch.Tensor, c_pad:
     if codes.shape != (B, H, W):
         raise RgbdB200Error(f"codes must be {(B, H, W)}, got {tuple(codes.shape)}")
     check(lib.rgbd_dsam_pack(feat.data_ptr(), codes.data_ptr(), out.data_ptr(), B, Cc, c_pad, H, W, n_seg, masked_segs,
-                             1 if parity_split else 0, _stream()), "rgbd_dsam_pack")
+                             1 if parity_split else 0, 1 if hi_lo else 0, _stream()), "rgbd_dsam_pack")
     _count(1)
 
 

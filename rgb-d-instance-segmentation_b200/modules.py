@@ -144,6 +144,11 @@ class DSAModule(nn.Module):
     sum_t Conv_t(mask_t * F) + projection(F).  ``in != out``: 3x3 stride-2 convs + bias-free 3x3 stride-2
     ``rgb_projection``; ``in == out``: 1x1 convs + identity residual."""
 
+    #: "bf16": bf16 operands, fp32 accumulate (what torch.autocast gives the reference; ~1e-3 relative).
+    #: "fp32": split precision -- activations and weights as bf16 hi + lo parts, three tensor-core products per term
+    #: (~2^-16 relative, inside the 1e-4 fp32 bar) at three times the GEMM work.  Forward only; gradients stay bf16.
+    precision = "bf16"
+
     def __init__(self, in_channels, out_channels, num_depth_regions=3):
         super().__init__()
         if not 1 <= num_depth_regions <= 3:
@@ -180,7 +185,8 @@ class DSAModule(nn.Module):
 
     def _refresh(self):
         srcs = [p for p in self.parameters()]
-        if not self._ver.stale(srcs) and self._packed:
+        split = self.precision == "fp32"
+        if not self._ver.stale(srcs) and self._packed and self._packed.get("split") == split:
             return self._packed
         dev = srcs[0].device
         c_in, c_out, R = self.in_channels, self.out_channels, self.num_depth_regions
@@ -193,7 +199,13 @@ class DSAModule(nn.Module):
                 w[:c_out, t, :, :c_in] = self.conv_layers[t].weight.reshape(c_out, c_in, k * k).permute(0, 2, 1)
             if self._proj:
                 w[:c_out, R + 1, :, :c_in] = self.rgb_projection.weight.reshape(c_out, c_in, 9).permute(0, 2, 1)
-            w_cat = w.reshape(n_pad, n_seg * taps * c_pad).to(torch.bfloat16).contiguous()
+            if split:
+                # K blocks per (segment, tap): [x_hi . W_hi | x_lo . W_hi | x_hi . W_lo]
+                w_hi = w.to(torch.bfloat16)
+                w_lo = (w - w_hi.float()).to(torch.bfloat16)
+                w_cat = torch.stack([w_hi, w_hi, w_lo], dim=3).reshape(n_pad, n_seg * taps * 3 * c_pad).contiguous()
+            else:
+                w_cat = w.reshape(n_pad, n_seg * taps * c_pad).to(torch.bfloat16).contiguous()
             # bias table: variant v = sum of the first v conv biases (CM:683-691: only used regions add a bias)
             bias = torch.zeros(R + 2, n_pad, device=dev, dtype=torch.float32)
             run = torch.zeros(c_out, device=dev, dtype=torch.float32)
@@ -212,20 +224,26 @@ class DSAModule(nn.Module):
                     par = py * 2 + px
                 else:
                     par, yo, xo = 0, 0, 0
-                for cb in range(c_pad // kb):
-                    sl.append((cb * kb, xo, yo, seg * n_par + par))
+                if split:       # operand segments are stored (hi, lo) interleaved: segment index 2*seg + {0, 1}
+                    for a_seg in (2 * seg, 2 * seg + 1, 2 * seg):
+                        for cb in range(c_pad // kb):
+                            sl.append((cb * kb, xo, yo, a_seg * n_par + par))
+                else:
+                    for cb in range(c_pad // kb):
+                        sl.append((cb * kb, xo, yo, seg * n_par + par))
         slices = torch.tensor(sl, device=dev, dtype=torch.int32).contiguous()
-        self._packed = {"w": w_cat, "bias": bias, "slices": slices}
+        self._packed = {"w": w_cat, "bias": bias, "slices": slices, "split": split}
         return self._packed
 
     def _workspace(self, B, H, W, dev):
         c_pad, kb, n_pad, n_seg = self._geometry()
-        key = (B, H, W, str(dev))
+        n_op = n_seg * (2 if self.precision == "fp32" else 1)
+        key = (B, H, W, str(dev), n_op)
         if key not in self._ws:
             if self._proj:
-                shape = (B, n_seg, 4, (H + 1) // 2, (W + 1) // 2, c_pad)
+                shape = (B, n_op, 4, (H + 1) // 2, (W + 1) // 2, c_pad)
             else:
-                shape = (B, n_seg, 1, H, W, c_pad)
+                shape = (B, n_op, 1, H, W, c_pad)
             self._ws = {key: torch.zeros(shape, device=dev, dtype=torch.bfloat16)}   # keep one shape alive
         return self._ws[key]
 
@@ -338,15 +356,16 @@ class DSAModule(nn.Module):
         R = self.num_depth_regions
         packed = self._workspace(B, H, W, x.device)
         if not getattr(self, "_gemm_only", False):        # bench.py times the GEMM alone on packed operands
-            Fn.dsam_pack(x, codes, packed, c_pad, n_seg, R + 1, self._proj)
+            Fn.dsam_pack(x, codes, packed, c_pad, n_seg, R + 1, self._proj, hi_lo=pk["split"])
+        n_op = n_seg * (2 if pk["split"] else 1)
         if self._proj:
             Ho, Wo = (H + 1) // 2, (W + 1) // 2
-            a_dims = (B * n_seg * 4, Ho, Wo, c_pad)
-            ppi = n_seg * 4
+            a_dims = (B * n_op * 4, Ho, Wo, c_pad)
+            ppi = n_op * 4
         else:
             Ho, Wo = H, W
-            a_dims = (B * n_seg, H, W, c_pad)
-            ppi = n_seg
+            a_dims = (B * n_op, H, W, c_pad)
+            ppi = n_op
             residual = x if residual is None else residual + x
         out = torch.empty(B, self.out_channels, Ho, Wo, device=x.device, dtype=torch.float32)
         variant = bias_variant
@@ -534,15 +553,18 @@ class DepthGuidance(nn.Module):
     stages -> DGGM injection fused with the branch sum.  Child names match the reference's pixel-level
     module (``ratio_predictor, dsam0, dsam1, dsam2, depth_gradient_injection``)."""
 
-    def __init__(self, color_channels: Sequence[int] = (96, 192, 384, 768)):
+    def __init__(self, color_channels: Sequence[int] = (96, 192, 384, 768), precision: str = "bf16"):
         super().__init__()
         c = list(color_channels)
         assert len(c) == 4
+        assert precision in ("bf16", "fp32")
         self.ratio_predictor = EnhancedDepthImageRatioPredictor(3)
         self.dsam0 = DSAModule(in_channels=c[0], out_channels=c[1], num_depth_regions=3)
         self.dsam1 = DSAModule(in_channels=c[1], out_channels=c[2], num_depth_regions=3)
         self.dsam2 = DSAModule(in_channels=c[2], out_channels=c[3], num_depth_regions=3)
         self.depth_gradient_injection = DepthGradientInjectionResidual(c, 3)
+        for d in (self.dsam0, self.dsam1, self.dsam2):
+            d.precision = precision            # DSAM convolutions; DGGM is fp32 arithmetic in either mode
 
     def forward(self, pixel_values: torch.Tensor, color_feature_map: Sequence[torch.Tensor],
                 ratios: Optional[torch.Tensor] = None) -> List[torch.Tensor]:

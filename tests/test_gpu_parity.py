@@ -346,6 +346,43 @@ def test_dsam_module(mods, ci, co, hw, dhw):
         m(feat.cuda(), [[0.0]], 0.3)
 
 
+@pytest.mark.parametrize("ci,co,hw,dhw", [(8, 16, (24, 32), (96, 128)), (96, 192, (30, 40), (120, 160)),
+                                          (64, 64, (12, 20), (48, 80)), (40, 72, (15, 21), (60, 84))])
+def test_dsam_module_fp32_precision_mode(mods, ci, co, hw, dhw):
+    """Split-precision tensor-core path (x_hi W_hi + x_lo W_hi + x_hi W_lo): inside the fp32 bar of 1e-4."""
+    w = OW.dsam_weights(ci, co, seed=100 + ci + co)
+    m = mods.DSAModule(ci, co, 3)
+    m.precision = "fp32"
+    m.load_state_dict(w)
+    m.cuda().eval()
+    feat = torch.from_numpy(np.random.RandomState(5).randn(2, ci, *hw).astype(np.float32))
+    for j, kind in enumerate(["nyu", "constant", "two_valued"]):
+        gray = _gray_for(j, kind, dhw)
+        with torch.no_grad():
+            y = m(feat.cuda(), torch.from_numpy(gray)[None].cuda(), 0.3)
+        ref = torch.cat([O.dsam_forward(w, feat[b:b + 1], gray, 0.3) for b in range(2)])
+        assert rel_err(y, ref) < FP32_TOL, (kind, rel_err(y, ref))
+
+
+def test_depth_guidance_fp32_precision_mode(mods, golden_dir):
+    """fp32 bar of the north star (1e-4 relative) on the fused features handed to the pixel decoder."""
+    g = np.load(os.path.join(golden_dir, "wiring.npz"))
+    m = mods.DepthGuidance((96, 192, 384, 768), precision="fp32")
+    m.load_state_dict(OW.guidance_weights(seed=700))
+    m.cuda().eval()
+    pvs = []
+    for j in range(2):
+        rgb, d = synthetic.synth_rgbd_u8(80 + j, 64, 96, "nyu")
+        pvs.append(synthetic.assemble_pixel_values(rgb, d, O.gradient_features))
+    pv = torch.from_numpy(np.stack(pvs)).cuda()
+    feats = [torch.from_numpy(g[f"feat{i}"]).cuda() for i in range(4)]
+    with torch.no_grad():
+        fused = m(pv, feats, ratios=torch.from_numpy(g["ratios"]).cuda())
+    for i in range(4):
+        ref = torch.from_numpy(g[f"fused{i}"])
+        assert rel_err(fused[i], ref) < FP32_TOL, (i, rel_err(fused[i], ref))
+
+
 @pytest.mark.parametrize("hw", [(48, 64), (96, 160)])
 def test_ratio_predictor(mods, hw):
     w = OW.ratio_weights(seed=500)
