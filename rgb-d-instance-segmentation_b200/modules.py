@@ -177,7 +177,9 @@ class DSAModule(nn.Module):
         return self.in_channels != self.out_channels
 
     def _geometry(self):
-        c_pad = _round_up(self.in_channels, 32)
+        # 128-byte K rows (64 channels) keep TMA/L2 requests full-width; 96 channels are padded to 128 rather than
+        # split into 64-byte rows (measured: fewer, wider K blocks win although 1/4 of the stage-0 MMAs multiply zeros)
+        c_pad = _round_up(self.in_channels, 64) if self.in_channels > 32 else 32
         kb = 64 if c_pad % 64 == 0 else 32
         n_pad = _round_up(self.out_channels, 32)
         n_seg = self.num_depth_regions + 1 + (1 if self._proj else 0)
@@ -597,3 +599,28 @@ def depth_guidance_forward(ratio_predictor: EnhancedDepthImageRatioPredictor, ds
         return [a + b for a, b in zip(cp1, cp2)]                            # CM:355
     # CM:354-355: cp2 = DGGM(feats); out = cp1 + cp2, fused into the DGGM kernel
     return dggm.forward_fused_sum(feats, cp1, gradient_depth, gradient_mask)
+
+
+class GraphedDepthGuidance:
+    """The inference hot path captured once into a CUDA graph (static shapes, static input tensors): one graph launch
+    replaces ~40 kernel launches per step.  ``inputs`` are the tensors captured; copy new data into them (or pass them
+    as views of a staging buffer) and call the object to replay.  Outputs are the same tensors on every replay."""
+
+    def __init__(self, module: DepthGuidance, pixel_values: torch.Tensor, color_feature_map: Sequence[torch.Tensor],
+                 warmup: int = 2):
+        self.module = module
+        self.pixel_values = pixel_values
+        self.features = list(color_feature_map)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):                       # allocates workspaces / packs weights outside the capture
+                module(self.pixel_values, self.features)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.outputs = module(self.pixel_values, self.features)
+
+    def __call__(self) -> List[torch.Tensor]:
+        self.graph.replay()
+        return self.outputs
