@@ -576,3 +576,97 @@ def test_depth_guidance_other_geometries(mods, chans, hw):
     for i in range(4):
         assert out[i].shape == ref[i].shape
         assert rel_err(out[i], ref[i]) < BF16_TOL, (i, rel_err(out[i], ref[i]))
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at the full BASELINE size (batch 32, 480x640, Swin-T pyramid)
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_size(fn):
+    B, H, W = 32, 480, 640
+    rgbs, ds = [], []
+    for j in range(4):
+        rgb, d = synthetic.synth_rgbd_u8(300 + j, H, W, ["nyu", "nyu", "uniform", "two_valued"][j])
+        rgbs.append(rgb)
+        ds.append(d)
+    idx = torch.arange(B) % 4
+    rgb = torch.from_numpy(np.stack(rgbs)).cuda()[idx].contiguous()
+    depth = torch.from_numpy(np.stack(ds)).cuda()[idx].contiguous()
+    pv = fn.pack_pixel_values(rgb, depth)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    feats = [torch.randn(B, c, H // s, W // s, generator=g).cuda() for c, s in zip((96, 192, 384, 768), (4, 8, 16, 32))]
+    return pv, feats, depth
+
+
+def test_full_size_decomposition_invariants(fn, full_size):
+    pv, feats, depth = full_size
+    B, _, H, W = pv.shape
+    ratio = torch.linspace(0.01, 0.5, B, device="cuda")
+    dec = fn.depth_decompose(ratio, [(120, 160), (60, 80), (30, 40)], depth3=pv[:, 3:6], debug=True)
+    gray = dec.gray
+    # every finite pixel lands in exactly one histogram bin; edges are monotone and span [nanmin, nanmax]
+    assert torch.equal(dec.hist.sum(1), torch.isfinite(gray).flatten(1).sum(1))
+    assert bool((dec.edges[:, 1:] > dec.edges[:, :-1]).all())
+    assert torch.equal(dec.edges[:, 0], gray.flatten(1).min(1).values) and torch.equal(dec.edges[:, -1], gray.flatten(1).max(1).values)
+    # identical images give identical artefacts (the batch repeats 4 frames); the ratio only moves the windows
+    assert torch.equal(dec.hist[0], dec.hist[4]) and torch.equal(dec.peak_bins[1], dec.peak_bins[5])
+    # region codes: with m >= 1 modes every pixel carries a bit, and the "remaining" bit m excludes the window bits
+    m = dec.n_modes.view(B, 1, 1).to(torch.int32)
+    codes = dec.codes.to(torch.int32)
+    has_modes = m > 0
+    assert bool(((codes > 0) | ~has_modes).all()) and bool(((codes == 0) | has_modes).all())
+    rem = (codes >> m) & 1
+    assert bool((((rem == 1) & ((codes & ((1 << m) - 1)) != 0)) == 0).all())
+    assert bool((codes < (1 << (m + 1))).all())
+    # pooled codes are the bitwise OR over the pooling window == per-bit max pooling
+    for lvl, s in enumerate((4, 8, 16)):
+        ref = torch.zeros_like(dec.pooled[lvl], dtype=torch.int32)
+        for t in range(4):
+            bit = ((codes >> t) & 1).float()[:, None]
+            ref |= (torch.nn.functional.max_pool2d(bit, s)[:, 0].to(torch.int32) << t)
+        assert torch.equal(dec.pooled[lvl].to(torch.int32), ref)
+    # windows: lo = max(0, c - hw), hi = c + hw with hw = c*ratio/2 -> hi - c is proportional to the ratio
+    hw_ = dec.windows[:, :, 1] - dec.centres
+    k = dec.n_modes.min().item()
+    if k > 0:
+        assert torch.allclose(hw_[:, :k], dec.centres[:, :k] * ratio[:, None] / 2, rtol=1e-5, atol=1e-6)
+
+
+def test_full_size_dggm_and_dsam_linearity(mods, fn, full_size):
+    pv, feats, depth = full_size
+    B = pv.shape[0]
+    chans = (96, 192, 384, 768)
+    m = mods.DepthGuidance(chans)
+    m.load_state_dict(OW.guidance_weights(seed=11, channels=chans))
+    m.cuda().eval()
+    with torch.no_grad():
+        # DGGM: the enhancement depends on grad/mask/weights only -> out(f) - f is the same for any f; zero mask -> relu(bias)
+        dg = m.depth_gradient_injection
+        a = dg(feats, pv[:, 6:9], pv[:, 9:10])
+        b = dg([2 * f for f in feats], pv[:, 6:9], pv[:, 9:10])
+        for i in range(4):
+            assert rel_err(b[i] - 2 * feats[i], a[i] - feats[i]) < 1e-5
+        z = dg(feats, pv[:, 6:9], torch.zeros_like(pv[:, 9:10]))
+        for i in range(4):
+            bias = torch.relu(dg.depth_enhancement_layers[i][0].bias).view(1, -1, 1, 1)
+            assert rel_err(z[i], feats[i] + bias) < 1e-6
+        # DSAM stage: linear in the features once the bias is removed (masks are data): f(2x) - f(0) = 2 (f(x) - f(0))
+        ratio = torch.full((B,), 0.3, device="cuda")
+        dec = fn.depth_decompose(ratio, [(120, 160)], depth3=pv[:, 3:6])
+        d0 = m.dsam0
+        y0 = d0.stage_forward(torch.zeros_like(feats[0]), dec.pooled[0], dec.bias_variant)
+        y1 = d0.stage_forward(feats[0], dec.pooled[0], dec.bias_variant)
+        y2 = d0.stage_forward(2 * feats[0], dec.pooled[0], dec.bias_variant)
+        assert rel_err(y2 - y0, 2 * (y1 - y0)) < 1e-5          # scaling by 2 is exact in bf16
+        # whole path: finite, right shapes, ratios inside the constrained range (CM:1485)
+        r = m.ratio_predictor(pv[:, 3:6])
+        assert bool(((r >= 0.01) & (r <= 0.5)).all())
+        out = m(pv, feats)
+        for o, f in zip(out, feats):
+            assert o.shape == f.shape and bool(torch.isfinite(o).all())
+        # identical frames (batch repeats 4) with identical features give identical outputs: no cross-image leakage
+        same = [f.clone() for f in feats]
+        for f in same:
+            f[4] = f[0]
+        out2 = m(pv, same)
+        assert torch.equal(out2[3][0], out2[3][4]) and torch.equal(out2[0][0], out2[0][4])
