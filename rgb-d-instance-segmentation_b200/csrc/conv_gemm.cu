@@ -95,6 +95,8 @@ struct EpiCtx {
     float* s_shift;
     uint32_t tmem_base;
     int t_begin, t_end, warp, lane;
+    int t_step;                       // 1, or 2 when a CTA pair alternates tiles (t = 2*pair + rank)
+    uint32_t tmem_empty_remote[2];    // shared::cluster addresses of the leader's tmem_empty barriers (0: arrive locally)
 };
 
 template <int ACT>
@@ -126,14 +128,14 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
     const int ncells = p.cells_y * p.cells_x;
     int ss_key = -1;                           // (variant, nt) whose scale/shift currently sit in shared memory
 
-    for (int t = c.t_begin; t < c.t_end; ++t) {
+    for (int t = c.t_begin; t < c.t_end; t += c.t_step) {
         int img, ty, tx, nt;
         decode_tile(p, t, img, ty, tx, nt);
         const int ox = tx * p.BX + lx, oy = ty * p.BY + ly;
-        const bool valid = ox < p.out_w && oy < p.out_h;
+        const bool valid = ox < p.out_w && oy < p.out_h && img < p.n_img;   // img >= n_img: padding tile of an odd pair
 
         // scale / shift of this (variant, N tile) -> shared memory (reloaded only when they change)
-        const int var = p.variant ? __ldg(p.variant + img) : 0;
+        const int var = (p.variant && img < p.n_img) ? __ldg(p.variant + img) : 0;
         const int want = var * p.n_tiles_n + nt;
         if (MODE != 3 && want != ss_key) {
             asm volatile("bar.sync 2, 256;" ::: "memory");          // everyone is done with the old table
@@ -324,7 +326,8 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
             }
         }
         tc::tc_fence_before();
-        tc::mbar_arrive(&ctl->tmem_empty[as]);
+        if (c.tmem_empty_remote[as]) tc::mbar_arrive_cluster(c.tmem_empty_remote[as]);
+        else tc::mbar_arrive(&ctl->tmem_empty[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
         if (MODE == 0) {
             if (p.gate_bytes) {
@@ -466,7 +469,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
-        EpiCtx c{smem, s_staging, s_gate, ctl, s_scale, s_shift, tmem_base, t_begin, t_end, warp, lane};
+        EpiCtx c{smem, s_staging, s_gate, ctl, s_scale, s_shift, tmem_base, t_begin, t_end, warp, lane, 1, {0u, 0u}};
         const bool sc = p.scale != nullptr;
         if (p.epi_mode == 0) {
             if (p.act == 2) epilogue_loop<0, 2, false>(p, c, &tmap_out);
@@ -607,7 +610,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 4) {
-        EpiCtx c{smem, s_staging, s_gate, ctl, s_scale, s_shift, tmem_base, t_begin, t_end, warp, lane};
+        EpiCtx c{smem, s_staging, s_gate, ctl, s_scale, s_shift, tmem_base, t_begin, t_end, warp, lane, 1, {0u, 0u}};
         const bool sc = p.scale != nullptr;
         if (p.epi_mode == 0) {
             if (p.act == 1 && !sc) epilogue_loop<0, 1, false>(p, c, &tmap_out);
@@ -625,6 +628,134 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 2) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// The same 3x3 convolution on a CTA PAIR (tcgen05 cta_group::2): the two CTAs of a cluster work on two consecutive
+// output tiles (rows y, y+1 of one column strip) as ONE M=256 MMA.  Each CTA stages its own A tiles and only HALF of
+// every B tile (128 of the 256 output channels); the tensor cores of both SMs read both halves.  Per tile the SM's
+// L2 inbound drops from 676 KB to 388 KB (64 B/clk port; 9216 MMA cycles = 590 KB) and its shared-memory operand
+// reads from 96 to 64 B/clk, so the kernel becomes MMA-bound.  Leader (cluster rank 0) issues the MMAs; both CTAs
+// issue TMA loads (bytes counted on the leader's barriers) and run their own epilogue on their own TMEM half.
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ KParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int b_bytes = (p.BLOCK_N / 2) * 128;                 // this CTA's half of a B tile
+    uint8_t* s_a = smem;
+    uint8_t* s_b = s_a + (size_t)p.sa_stages * p.a_stage_bytes;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b + (size_t)p.stages * b_bytes);
+    float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + sizeof(SmemCtl));
+    float* s_shift = s_scale + p.BLOCK_N;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const bool leader = rank == 0;
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_a);
+        tc::prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            tc::mbar_init(&ctl->full[s], 1);
+            tc::mbar_init(&ctl->empty[s], 1);
+        }
+        for (int s = 0; s < p.sa_stages; ++s) {
+            tc::mbar_init(&ctl->a_full[s], 1);
+            tc::mbar_init(&ctl->a_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&ctl->tmem_full[s], 1);
+            tc::mbar_init(&ctl->tmem_empty[s], 2 * kEpiThreads);       // the epilogue threads of BOTH CTAs
+        }
+        tc::fence_barrier_init();
+    }
+    tc::cluster_sync_all();                                            // barriers of both CTAs exist before any remote use
+    if (warp == 2) tc::tmem_alloc_2cta(&ctl->tmem_base, kTmemCols);
+    tc::tc_fence_before();
+    tc::cluster_sync_all();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    // pairs of tiles (2u, 2u+1) are split contiguously over the clusters
+    const int n_pairs = (p.total_tiles + 1) / 2;
+    const int n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
+    const int per = n_pairs / n_clusters, rem = n_pairs % n_clusters;
+    const int u_begin = cid * per + min(cid, rem);
+    const int u_end = u_begin + per + (cid < rem ? 1 : 0);
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer (both CTAs) =================
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            int img, ty, tx, nt;
+            decode_tile(p, 2 * u + (int)rank, img, ty, tx, nt);
+            const int x0 = tx * p.BX, y0 = ty;
+            for (int dy = 0; dy < 3; ++dy) {
+                for (int cb = 0; cb < p.c_blocks; ++cb) {
+                    tc::mbar_wait(&ctl->a_empty[sa], pa ^ 1);
+                    if (leader) tc::mbar_expect_tx(&ctl->a_full[sa], 2u * (uint32_t)((kBlockM + 2) * 128));
+                    tc::tma_load_4d_2cta(s_a + (size_t)sa * p.a_stage_bytes, &tmap_a, &ctl->a_full[sa], cb * 64, x0 - 1,
+                                         y0 + dy - 1, img);
+                    if (++sa == p.sa_stages) { sa = 0; pa ^= 1; }
+                    for (int dx = 0; dx < 3; ++dx) {
+                        tc::mbar_wait(&ctl->empty[sb], pb ^ 1);
+                        if (leader) tc::mbar_expect_tx(&ctl->full[sb], 2u * (uint32_t)b_bytes);
+                        tc::tma_load_2d_2cta(s_b + (size_t)sb * b_bytes, &tmap_b, &ctl->full[sb],
+                                             ((dy * 3 + dx) * p.c_blocks + cb) * 64, (int)rank * (p.BLOCK_N / 2));
+                        if (++sb == p.stages) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ================= MMA issuer (leader CTA only) =================
+        const uint32_t idesc = tc::make_idesc_bf16(2 * kBlockM, p.BLOCK_N);
+        int sa = 0, sb = 0, as = 0;
+        uint32_t pa = 0, pb = 0, aphase = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
+            tc::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BLOCK_N);
+            uint32_t first = 1;
+            for (int dy = 0; dy < 3; ++dy) {
+                for (int cb = 0; cb < p.c_blocks; ++cb) {
+                    tc::mbar_wait(&ctl->a_full[sa], pa);
+                    const uint32_t a_base = tc::smem_u32(s_a + (size_t)sa * p.a_stage_bytes);
+                    for (int dx = 0; dx < 3; ++dx) {
+                        tc::mbar_wait(&ctl->full[sb], pb);
+                        tc::tc_fence_after();
+                        const uint64_t adesc = tc::make_kmajor_desc(a_base + (uint32_t)(dx * 128), 128);
+                        const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_b + (size_t)sb * b_bytes), 128);
+                        for (int k = 0; k < 4; ++k) {
+                            tc::umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                        tc::umma_commit_2cta(&ctl->empty[sb]);
+                        if (++sb == p.stages) { sb = 0; pb ^= 1; }
+                    }
+                    tc::umma_commit_2cta(&ctl->a_empty[sa]);
+                    if (++sa == p.sa_stages) { sa = 0; pa ^= 1; }
+                }
+            }
+            tc::umma_commit_2cta(&ctl->tmem_full[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue (both CTAs, each on its own 128 TMEM lanes) =================
+        EpiCtx c{smem, nullptr, nullptr, ctl, s_scale, s_shift, tmem_base, 2 * u_begin + (int)rank, 2 * u_end, warp, lane, 2,
+                 {tc::mapa(tc::smem_u32(&ctl->tmem_empty[0]), 0), tc::mapa(tc::smem_u32(&ctl->tmem_empty[1]), 0)}};
+        if (p.scale) epilogue_loop<2, 1, true>(p, c, &tmap_a);
+        else epilogue_loop<2, 1, false>(p, c, &tmap_a);
+    }
+
+    tc::tc_fence_before();
+    tc::cluster_sync_all();                       // the peer's smem / TMEM stay alive until the leader's MMAs are done
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc_2cta(tmem_base, kTmemCols);
     }
 }
 
@@ -774,6 +905,7 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     if (d->conv3x3_reuse) {
@@ -790,6 +922,42 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         RGBD_CHECK_ARG(sb >= 2, "conv_gemm: not enough shared memory for the 3x3 A-reuse pipeline");
         p.stages = sb;
         const int smem3 = fixed3 + sb * b_stage;
+        static const bool no_pair = getenv("RGBD_NO_CTA_PAIR") != nullptr;
+        if (d->epi_mode == 2 && p.n_tiles_n == 1 && p.BLOCK_N % 32 == 0 && (p.BLOCK_N / 2) % 8 == 0 && p.total_tiles >= 2 && !no_pair) {
+            // CTA-pair kernel: each CTA stages half of every B tile (box rows = BLOCK_N/2)
+            CUtensorMap tmap_b2;
+            cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->n_pad};
+            cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+            cuuint32_t box[2] = {64, (cuuint32_t)(p.BLOCK_N / 2)};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = encode(&tmap_b2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                rgbd_set_error("conv_gemm: cuTensorMapEncodeTiled(B half) failed with %d", (int)r);
+                return RGBD_ERR_CUDA;
+            }
+            const int b_half = (p.BLOCK_N / 2) * 128;
+            const int fixed2 = 1024 + (int)sizeof(SmemCtl) + 64 + 2 * p.BLOCK_N * (int)sizeof(float) + p.sa_stages * p.a_stage_bytes;
+            int sb2 = (max_smem - fixed2) / b_half;
+            if (sb2 > kMaxStages) sb2 = kMaxStages;
+            p.stages = sb2;
+            const int n_pairs = (p.total_tiles + 1) / 2;
+            int clusters = num_sms / 2;
+            if (clusters > n_pairs) clusters = n_pairs;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * clusters);
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = fixed2 + sb2 * b_half;
+            cfg.stream = (cudaStream_t)stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_2cta_kernel, tmap_a, tmap_b2, p));
+            return RGBD_OK;
+        }
         conv3x3_kernel<<<grid, kThreads, smem3, (cudaStream_t)stream>>>(tmap_a, tmap_b, tmap_out, tmap_gate, p);
         RGBD_CHECK_LAUNCH();
         return RGBD_OK;
