@@ -42,9 +42,9 @@ FLOP_DSAM = sum(5 * 2.0 * (H // (2 * s)) * (W // (2 * s)) * co * 9 * ci
                 for s, ci, co in zip(STRIDES[:3], CHANS[:3], CHANS[1:]))      # 23.89 GFLOP
 FEAT_ELEMS = sum(c * (H // s) * (W // s) for c, s in zip(CHANS, STRIDES))      # 3 456 000
 BYTES_DGGM = 3 * 4 * FEAT_ELEMS + 4 * 4 * H * W               # read colour + branch-1, write fused, read grad+mask
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE conv3x3_kernel launch at batch 32, from the ncu --set full capture
-# profiles/r01_ncu_full_b32_conv3x3_dggm.txt (the bf16 128-channel input is 2.517 GB: it is read from DRAM once)
-TRAFFIC_CONV5_B32 = 2.560253e9 + 6.634752e6
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE conv3x3_2cta_kernel launch at batch 32, from the ncu --set full
+# capture profiles/r01_ncu_full_b32_conv3x3_2cta.txt (the bf16 128-channel input is 2.517 GB: it is read from DRAM once)
+TRAFFIC_CONV5_B32 = 2.555123e9 + 7.578368e6
 
 
 def peaks():
@@ -323,7 +323,7 @@ def run_own(args):
     conv5_tf = FLOP_CONV5 * B / kt["ratio_conv3x3"] / 1e12
     dggm_gbs = BYTES_DGGM * B / kt["dggm"] / 1e9
     dsam_tf = FLOP_DSAM * B / kt["dsam_gemm"] / 1e12
-    roof = {"kernel": "conv3x3_kernel (ratio predictor 3x3 128->256 conv + BN + ReLU + AdaptiveAvgPool2d(4))", "bound": "tensor",
+    roof = {"kernel": "conv3x3_2cta_kernel (ratio predictor 3x3 128->256 conv + BN + ReLU + AdaptiveAvgPool2d(4), CTA pairs)", "bound": "tensor",
             "achieved": conv5_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": conv5_tf / pkv["tf_burst"],
             "frac_of_sustained": conv5_tf / pkv["tf_sustained"],
             "traffic": TRAFFIC_CONV5_B32 if B == 32 else None,
