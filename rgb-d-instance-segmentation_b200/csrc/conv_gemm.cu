@@ -94,10 +94,15 @@ struct EpiCtx {
     float* s_scale;
     float* s_shift;
     uint32_t tmem_base;
-    int t_begin, t_end, warp, lane;
-    int t_step;                       // 1, or 2 when a CTA pair alternates tiles (t = 2*pair + rank)
+    int t_begin, t_end, warp, lane;   // work units [t_begin, t_end): tiles, or tile PAIRS when pair_rank >= 0
+    int pair_rank;                    // -1: one CTA per tile; 0/1: rank of this CTA in a CTA pair (see pair_tile)
     uint32_t tmem_empty_remote[2];    // shared::cluster addresses of the leader's tmem_empty barriers (0: arrive locally)
 };
+
+// tile of CTA `rank` in pair unit u: the two CTAs take adjacent M tiles of the SAME N tile (they share the B operand)
+__device__ __forceinline__ int pair_tile(const KParams& p, int u, int rank) {
+    return (2 * (u / p.n_tiles_n) + rank) * p.n_tiles_n + (u % p.n_tiles_n);
+}
 
 template <int ACT>
 __device__ __forceinline__ float act_fn(float x) {
@@ -128,7 +133,8 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
     const int ncells = p.cells_y * p.cells_x;
     int ss_key = -1;                           // (variant, nt) whose scale/shift currently sit in shared memory
 
-    for (int t = c.t_begin; t < c.t_end; t += c.t_step) {
+    for (int unit = c.t_begin; unit < c.t_end; ++unit) {
+        const int t = c.pair_rank < 0 ? unit : pair_tile(p, unit, c.pair_rank);
         int img, ty, tx, nt;
         decode_tile(p, t, img, ty, tx, nt);
         const int ox = tx * p.BX + lx, oy = ty * p.BY + ly;
@@ -469,7 +475,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
-        EpiCtx c{smem, s_staging, s_gate, ctl, s_scale, s_shift, tmem_base, t_begin, t_end, warp, lane, 1, {0u, 0u}};
+        EpiCtx c{smem, s_staging, s_gate, ctl, s_scale, s_shift, tmem_base, t_begin, t_end, warp, lane, -1, {0u, 0u}};
         const bool sc = p.scale != nullptr;
         if (p.epi_mode == 0) {
             if (p.act == 2) epilogue_loop<0, 2, false>(p, c, &tmap_out);
@@ -610,7 +616,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 4) {
-        EpiCtx c{smem, s_staging, s_gate, ctl, s_scale, s_shift, tmem_base, t_begin, t_end, warp, lane, 1, {0u, 0u}};
+        EpiCtx c{smem, s_staging, s_gate, ctl, s_scale, s_shift, tmem_base, t_begin, t_end, warp, lane, -1, {0u, 0u}};
         const bool sc = p.scale != nullptr;
         if (p.epi_mode == 0) {
             if (p.act == 1 && !sc) epilogue_loop<0, 1, false>(p, c, &tmap_out);
@@ -628,6 +634,111 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 2) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// conv_gemm_kernel on CTA pairs (tcgen05 cta_group::2) for the DSAM stages (epilogue modes 1 and 3): the two CTAs of a
+// cluster take adjacent M tiles of the same N tile, so each stages only half of every B (weight) K block.
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ KParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int a_bytes = kBlockM * p.kb_bytes;
+    const int b_bytes = (p.BLOCK_N / 2) * p.kb_bytes;          // this CTA's half of a B K block
+    const int stage_bytes = a_bytes + b_bytes;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + (size_t)p.stages * stage_bytes);
+    int4* s_slices = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(ctl) + sizeof(SmemCtl));
+    float* s_scale = reinterpret_cast<float*>(s_slices + p.n_slices);
+    float* s_shift = s_scale + p.BLOCK_N;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const bool leader = rank == 0;
+    for (int i = threadIdx.x; i < p.n_slices; i += blockDim.x) s_slices[i] = p.slices[i];
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_a);
+        tc::prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            tc::mbar_init(&ctl->full[s], 1);
+            tc::mbar_init(&ctl->empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&ctl->tmem_full[s], 1);
+            tc::mbar_init(&ctl->tmem_empty[s], 2 * kEpiThreads);
+        }
+        tc::fence_barrier_init();
+    }
+    tc::cluster_sync_all();
+    if (warp == 2) tc::tmem_alloc_2cta(&ctl->tmem_base, kTmemCols);
+    tc::tc_fence_before();
+    tc::cluster_sync_all();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    const int total_m = p.total_tiles / p.n_tiles_n;
+    const int n_units = ((total_m + 1) / 2) * p.n_tiles_n;
+    const int n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
+    const int per = n_units / n_clusters, rem = n_units % n_clusters;
+    const int u_begin = cid * per + min(cid, rem);
+    const int u_end = u_begin + per + (cid < rem ? 1 : 0);
+
+    if (warp == 0 && lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            int img, ty, tx, nt;
+            decode_tile(p, pair_tile(p, u, (int)rank), img, ty, tx, nt);
+            const int x0 = tx * p.BX, y0 = ty * p.BY, pl0 = img * p.plane_per_img;
+            for (int j = 0; j < p.n_slices; ++j) {
+                tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                if (leader) tc::mbar_expect_tx(&ctl->full[stage], 2u * (uint32_t)stage_bytes);
+                const int4 sl = s_slices[j];
+                tc::tma_load_4d_2cta(sa, &tmap_a, &ctl->full[stage], sl.x, x0 + sl.y, y0 + sl.z, pl0 + sl.w);
+                tc::tma_load_2d_2cta(sa + a_bytes, &tmap_b, &ctl->full[stage], j * (p.kb_bytes >> 1),
+                                     nt * p.BLOCK_N + (int)rank * (p.BLOCK_N / 2));
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        const uint32_t idesc = tc::make_idesc_bf16(2 * kBlockM, p.BLOCK_N);
+        const int k_per_block = p.kb_bytes >> 5;
+        int stage = 0, as = 0;
+        uint32_t phase = 0, aphase = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
+            tc::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BLOCK_N);
+            for (int j = 0; j < p.n_slices; ++j) {
+                tc::mbar_wait(&ctl->full[stage], phase);
+                tc::tc_fence_after();
+                const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t adesc = tc::make_kmajor_desc(sa, p.kb_bytes);
+                const uint64_t bdesc = tc::make_kmajor_desc(sa + a_bytes, p.kb_bytes);
+                for (int k = 0; k < k_per_block; ++k)
+                    tc::umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (j | k) != 0);
+                tc::umma_commit_2cta(&ctl->empty[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            tc::umma_commit_2cta(&ctl->tmem_full[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        EpiCtx c{smem, nullptr, nullptr, ctl, s_scale, s_shift, tmem_base, u_begin, u_end, warp, lane, (int)rank,
+                 {tc::mapa(tc::smem_u32(&ctl->tmem_empty[0]), 0), tc::mapa(tc::smem_u32(&ctl->tmem_empty[1]), 0)}};
+        if (p.epi_mode == 3) epilogue_loop<3, 0, false>(p, c, &tmap_a);
+        else if (p.scale) epilogue_loop<1, 0, true>(p, c, &tmap_a);
+        else epilogue_loop<1, 0, false>(p, c, &tmap_a);
+    }
+
+    tc::tc_fence_before();
+    tc::cluster_sync_all();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc_2cta(tmem_base, kTmemCols);
     }
 }
 
@@ -691,7 +802,7 @@ conv3x3_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t pa = 0, pb = 0;
         for (int u = u_begin; u < u_end; ++u) {
             int img, ty, tx, nt;
-            decode_tile(p, 2 * u + (int)rank, img, ty, tx, nt);
+            decode_tile(p, pair_tile(p, u, (int)rank), img, ty, tx, nt);
             const int x0 = tx * p.BX, y0 = ty;
             for (int dy = 0; dy < 3; ++dy) {
                 for (int cb = 0; cb < p.c_blocks; ++cb) {
@@ -745,7 +856,7 @@ conv3x3_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp >= 4) {
         // ================= epilogue (both CTAs, each on its own 128 TMEM lanes) =================
-        EpiCtx c{smem, nullptr, nullptr, ctl, s_scale, s_shift, tmem_base, 2 * u_begin + (int)rank, 2 * u_end, warp, lane, 2,
+        EpiCtx c{smem, nullptr, nullptr, ctl, s_scale, s_shift, tmem_base, u_begin, u_end, warp, lane, (int)rank,
                  {tc::mapa(tc::smem_u32(&ctl->tmem_empty[0]), 0), tc::mapa(tc::smem_u32(&ctl->tmem_empty[1]), 0)}};
         if (p.scale) epilogue_loop<2, 1, true>(p, c, &tmap_a);
         else epilogue_loop<2, 1, false>(p, c, &tmap_a);
@@ -906,6 +1017,7 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     if (d->conv3x3_reuse) {
@@ -983,6 +1095,45 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     // always take (almost) the whole SM so exactly one CTA (and its 512 TMEM columns) is resident
     int smem_bytes = fixed + stages * stage_bytes;
     if (smem_bytes < 160 * 1024) smem_bytes = 160 * 1024;
+    static const bool no_pair_g = getenv("RGBD_NO_CTA_PAIR") != nullptr;
+    const int total_m = p.total_tiles / p.n_tiles_n;
+    if ((d->epi_mode == 1 || d->epi_mode == 3) && !p.b_resident && !no_pair_g && total_m >= 2 && (p.BLOCK_N / 2) % 16 == 0 &&
+        p.dbg_shift == 0) {
+        CUtensorMap tmap_b2;
+        cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->n_pad};
+        cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+        cuuint32_t box[2] = {(cuuint32_t)d->kb_elems, (cuuint32_t)(p.BLOCK_N / 2)};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmap_b2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            rgbd_set_error("conv_gemm: cuTensorMapEncodeTiled(B half) failed with %d", (int)r);
+            return RGBD_ERR_CUDA;
+        }
+        const int stage2 = kBlockM * kb_bytes + (p.BLOCK_N / 2) * kb_bytes;
+        const int fixed2 = 1024 + (int)sizeof(SmemCtl) + p.n_slices * 16 + 64 + 2 * p.BLOCK_N * (int)sizeof(float);
+        int st2 = (max_smem - fixed2) / stage2;
+        if (st2 > kMaxStages) st2 = kMaxStages;
+        p.stages = st2;
+        const int n_units = ((total_m + 1) / 2) * p.n_tiles_n;
+        int clusters = num_sms / 2;
+        if (clusters > n_units) clusters = n_units;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(kThreads);
+        int smem2 = fixed2 + st2 * stage2;
+        if (smem2 < 160 * 1024) smem2 = 160 * 1024;
+        cfg.dynamicSmemBytes = smem2;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_2cta_kernel, tmap_a, tmap_b2, p));
+        return RGBD_OK;
+    }
     conv_gemm_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmap_a, tmap_b, tmap_out, tmap_gate, p);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
