@@ -194,6 +194,27 @@ def main():
         out[f"feat{i}"] = captured["feats"][i].numpy()
         out[f"fused{i}"] = captured["fused"][i].numpy()
     np.savez_compressed(os.path.join(GOLD, "wiring.npz"), **out)
+    # ---- 8. other version branches that reuse DGGM / DSAM (CM:156-163, CM:234-256) ---------------------------
+    for version, nch in (("0.0.3", 7), ("0.1.2", 6)):
+        torch.manual_seed(42)
+        plm = cm.CustomMask2FormerPixelLevelModule(cfg, version=version)
+        missing = plm.load_state_dict({k: v for k, v in w.items() if k.split(".")[0] in dict(plm.named_children())}, strict=False)
+        assert not missing.unexpected_keys, missing.unexpected_keys
+        plm.eval()
+        if version == "0.0.3":      # rgb, gradient map (3 ch), gradient mask
+            pvv = torch.cat([pv[:, 0:3], pv[:, 6:9], pv[:, 9:10]], dim=1)
+        else:                        # rgb, depth
+            pvv = pv[:, 0:6].clone()
+        cap = {}
+        plm.encoder.register_forward_hook(lambda mod, a, o: cap.__setitem__("feats", [t.detach().clone() for t in o.feature_maps]))
+        plm.decoder.register_forward_pre_hook(lambda mod, a: cap.__setitem__("fused", [t.detach().clone() for t in a[0]]))
+        with torch.no_grad():
+            plm(pvv)
+        out = {}
+        for i in range(4):
+            out[f"feat{i}"] = cap["feats"][i].numpy()
+            out[f"fused{i}"] = cap["fused"][i].numpy()
+        np.savez_compressed(os.path.join(GOLD, f"wiring_v{version.replace('.', '')}.npz"), **out)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

@@ -18,25 +18,52 @@ from .modules import (DepthGradientInjectionResidual, DSAModule, EnhancedDepthIm
 class CustomMask2FormerPixelLevelModule(Mask2FormerPixelLevelModule):
     main_input_name = "pixel_values"
 
+    DGGM_ONLY = ("0.0.3", "0.0.4", "0.0.5", "0.0.6")     # CM:73-75, 156-163: 7-channel input, DGGM on the raw features
+    DSAM_ONLY = ("0.1.2",)                                # CM:97-100, 234-256: 6-channel input, DSAM cascade, ratio 0.1
+    SUPPORTED = ("0.0.0", "0.4.0") + DGGM_ONLY + DSAM_ONLY
+
     def __init__(self, config, version: str = "0.4.0"):
         super().__init__(config)
-        if version != "0.4.0":
+        if version not in self.SUPPORTED:
             raise NotImplementedError(
-                f"rgbd_b200 implements the paper's final variant (version '0.4.0', DGGM + E-DSAM); got {version!r}")
+                f"rgbd_b200 builds the version branches made of DGGM / E-DSAM ({', '.join(self.SUPPORTED)}); the dual-backbone "
+                f"and surface-normal ablations are out of scope (SURVEY section 2 row 7); got {version!r}")
         self.version = version
         c = list(self.encoder.channels)
-        self.ratio_predictor = EnhancedDepthImageRatioPredictor(3)
-        self.dsam0 = DSAModule(in_channels=c[0], out_channels=c[1], num_depth_regions=3)
-        self.dsam1 = DSAModule(in_channels=c[1], out_channels=c[2], num_depth_regions=3)
-        self.dsam2 = DSAModule(in_channels=c[2], out_channels=c[3], num_depth_regions=3)
-        self.depth_gradient_injection = DepthGradientInjectionResidual(c, 3)
+        if version == "0.4.0":
+            self.ratio_predictor = EnhancedDepthImageRatioPredictor(3)
+        if version == "0.4.0" or version in self.DSAM_ONLY:
+            self.dsam0 = DSAModule(in_channels=c[0], out_channels=c[1], num_depth_regions=3)
+            self.dsam1 = DSAModule(in_channels=c[1], out_channels=c[2], num_depth_regions=3)
+            self.dsam2 = DSAModule(in_channels=c[2], out_channels=c[3], num_depth_regions=3)
+        if version == "0.4.0" or version in self.DGGM_ONLY:
+            self.depth_gradient_injection = DepthGradientInjectionResidual(c, 3)
+
+    def _dsam_only(self, pixel_values: Tensor, feats):
+        """CM:234-256 batched: cp[k+1] += dsam_k(cp[k], gray(depth), window_size_ratio=0.1) with no detach."""
+        from . import functional as Fn
+        B = pixel_values.shape[0]
+        ratio = torch.full((B,), 0.1, device=pixel_values.device, dtype=torch.float32)       # CM:647 default argument
+        cp = [f.float().contiguous() for f in feats]
+        dec = Fn.depth_decompose(ratio, [tuple(f.shape[2:]) for f in cp[:3]], depth3=pixel_values[:, 3:6].float())
+        for k, dsam in enumerate((self.dsam0, self.dsam1, self.dsam2)):
+            cp[k + 1] = dsam.stage_forward(cp[k], dec.pooled[k], dec.bias_variant, residual=cp[k + 1])
+        return cp
 
     def forward(self, pixel_values: Tensor, output_hidden_states: bool = False) -> Mask2FormerPixelLevelModuleOutput:
         rgb = pixel_values[:, 0:3, :, :]
         color_feature_map = self.encoder(rgb).feature_maps                                  # CM:330
-        backbone_features = depth_guidance_forward(
-            self.ratio_predictor, (self.dsam0, self.dsam1, self.dsam2), self.depth_gradient_injection,
-            pixel_values.float(), color_feature_map)                                        # CM:332-355
+        if self.version == "0.0.0":
+            backbone_features = list(color_feature_map)                                     # CM:145-146
+        elif self.version in self.DGGM_ONLY:
+            backbone_features = self.depth_gradient_injection(
+                [f.float() for f in color_feature_map], pixel_values[:, 3:6].float(), pixel_values[:, 6:7].float())
+        elif self.version in self.DSAM_ONLY:
+            backbone_features = self._dsam_only(pixel_values, color_feature_map)
+        else:
+            backbone_features = depth_guidance_forward(
+                self.ratio_predictor, (self.dsam0, self.dsam1, self.dsam2), self.depth_gradient_injection,
+                pixel_values.float(), color_feature_map)                                    # CM:332-355
         backbone_features = [f.to(color_feature_map[0].dtype) for f in backbone_features]
         decoder_output = self.decoder(backbone_features, output_hidden_states=output_hidden_states)   # CM:383
         return Mask2FormerPixelLevelModuleOutput(

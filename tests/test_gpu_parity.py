@@ -670,3 +670,35 @@ def test_full_size_dggm_and_dsam_linearity(mods, fn, full_size):
             f[4] = f[0]
         out2 = m(pv, same)
         assert torch.equal(out2[3][0], out2[3][4]) and torch.equal(out2[0][0], out2[0][4])
+
+
+@pytest.mark.parametrize("version", ["0.0.3", "0.1.2"])
+def test_other_version_branches(mods, golden_dir, version):
+    """the version branches built from the same kernels (DGGM only / DSAM cascade only)."""
+    from rgbd_b200 import pixel_level
+    g = np.load(os.path.join(golden_dir, f"wiring_v{version.replace('.', '')}.npz"))
+    cfg = pixel_level.swin_tiny_mask2former_config(num_labels=8)
+    plm = pixel_level.CustomMask2FormerPixelLevelModule(cfg, version=version)
+    w = OW.guidance_weights(seed=700)
+    own = dict(plm.named_children())
+    missing = plm.load_state_dict({k: v for k, v in w.items() if k.split(".")[0] in own}, strict=False)
+    assert not missing.unexpected_keys
+    assert ("ratio_predictor" in own) == (version == "0.4.0")
+    plm.cuda().eval()
+    pvs = []
+    for j in range(2):
+        rgb, d = synthetic.synth_rgbd_u8(80 + j, 64, 96, "nyu")
+        pvs.append(synthetic.assemble_pixel_values(rgb, d, O.gradient_features))
+    pv = torch.from_numpy(np.stack(pvs)).cuda()
+    pvv = torch.cat([pv[:, 0:3], pv[:, 6:9], pv[:, 9:10]], dim=1) if version == "0.0.3" else pv[:, 0:6].contiguous()
+    feats = [torch.from_numpy(g[f"feat{i}"]).cuda() for i in range(4)]
+    with torch.no_grad():
+        if version == "0.0.3":
+            fused = plm.depth_gradient_injection(feats, pvv[:, 3:6], pvv[:, 6:7])
+        else:
+            fused = plm._dsam_only(pvv, feats)
+    tol = FP32_TOL if version == "0.0.3" else BF16_TOL
+    for i in range(4):
+        assert rel_err(fused[i], torch.from_numpy(g[f"fused{i}"])) < tol, (version, i)
+    with pytest.raises(NotImplementedError):
+        pixel_level.CustomMask2FormerPixelLevelModule(cfg, version="0.3.0")

@@ -152,3 +152,20 @@ def test_wiring(golden_dir):
     for i in range(4):
         ref = g[f"fused{i}"]
         np.testing.assert_allclose(fused[i].numpy(), ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("version", ["0.0.3", "0.1.2"])
+def test_other_version_wiring(golden_dir, version):
+    g = _load(golden_dir, f"wiring_v{version.replace('.', '')}.npz")
+    w = OW.guidance_weights(seed=700)
+    pvs = []
+    for j in range(2):
+        rgb, d = synthetic.synth_rgbd_u8(80 + j, 64, 96, "nyu")
+        pvs.append(synthetic.assemble_pixel_values(rgb, d, O.gradient_features))
+    pv = torch.from_numpy(np.stack(pvs))
+    pvv = torch.cat([pv[:, 0:3], pv[:, 6:9], pv[:, 9:10]], dim=1) if version == "0.0.3" else pv[:, 0:6]
+    feats = [torch.from_numpy(g[f"feat{i}"]) for i in range(4)]
+    fused = O.version_forward(version, w, pvv, feats)
+    for i in range(4):
+        ref = g[f"fused{i}"]
+        np.testing.assert_allclose(fused[i].numpy(), ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
