@@ -142,6 +142,12 @@ typedef struct rgbd_conv_gemm_desc {
        (oy*m3_stride + m3_py, ox*m3_stride + m3_px); segment s < m3_masked_segs is kept where bit s of codes is set */
     const void* codes;
     int in_h, in_w, m3_py, m3_px, m3_stride, m3_masked_segs, m3_n_seg;
+    /* dsam_masked = 1 (forward of a stride-2 DSAM stage, CM:683-696, masking done in shared memory): a is the UNMASKED
+       parity-split operand (n_img*4 planes, rgbd_dsam_pack with n_seg=1, masked_segs=0); codes are the pooled region
+       codes (n_img, in_h, in_w) at the INPUT resolution; W is (n_pad, 9*(a_c/64)*m3_n_seg*64) ordered
+       (tap, channel block, segment, 64 channels), segment m3_n_seg-1 = rgb_projection, m3_masked_segs = m3_n_seg-1;
+       needs epi_mode 1, kb_elems 64, plane_per_img 4; slices are ignored. */
+    int dsam_masked;
 } rgbd_conv_gemm_desc;
 int rgbd_conv_gemm(const rgbd_conv_gemm_desc* desc_host, rgbd_stream_t stream);
 

@@ -29,6 +29,7 @@ class ConvGemmDesc(C.Structure):
         ("cells_y", C.c_int), ("cells_x", C.c_int), ("conv3x3_reuse", C.c_int),
         ("codes", C.c_void_p), ("in_h", C.c_int), ("in_w", C.c_int), ("m3_py", C.c_int), ("m3_px", C.c_int),
         ("m3_stride", C.c_int), ("m3_masked_segs", C.c_int), ("m3_n_seg", C.c_int),
+        ("dsam_masked", C.c_int),
     ]
 
 

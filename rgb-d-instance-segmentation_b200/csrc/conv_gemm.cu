@@ -54,6 +54,7 @@ struct KParams {
     int b_res_bytes;
     const uint8_t* codes;     // epilogue mode 3: region codes at the resolution of dX
     int in_h, in_w, m3_py, m3_px, m3_stride, m3_masked_segs, m3_n_seg;
+    int dsam_taps;            // dsam_fwd_kernel: 9 (3x3 stride 2 on parity planes)
     int c_blocks, sa_stages, a_stage_bytes;   // conv3x3_kernel: 64-channel blocks, A-ring depth, bytes per A stage
     int dbg_shift, dbg_bo;   // experiment: A tile loaded `dbg_shift` pixels early, descriptor start advanced by as many rows
 };
@@ -68,6 +69,8 @@ struct alignas(16) SmemCtl {
     uint64_t b_full;
     uint64_t a_full[4];       // conv3x3_kernel: separate ring for the (128+2)-pixel A tiles
     uint64_t a_empty[4];
+    uint64_t masked_full[2];  // dsam_fwd_kernel: the masked copies of an A group are written (both CTAs of the pair)
+    uint64_t masked_empty[2]; // ... and consumed by the pair's MMAs
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -637,6 +640,194 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 }
 
+// DSAModule.forward (CM:683-696) without the five-fold masked operand in HBM: the UNMASKED feature tile of a
+// (tap, 64-channel block) is loaded once by TMA; four "mask warps" write the region-masked copies
+// (mask_t * F = the tile with the rows of pixels outside region t zeroed, region bits from the pooled code of the
+// INPUT pixel the tap reads) into shared memory; the MMA then runs the five K blocks [p0*F | p1*F | p2*F | p3*F | F]
+// against the five weight tiles.  Versus conv_gemm on a pre-masked operand this loads 128 + 5*BLOCK_N/2 TMA rows per
+// 5 K blocks instead of 5*(128 + BLOCK_N/2) and the pack kernel writes one copy instead of five.  CTA pairs
+// (cta_group::2): every CTA masks its own tile, the weight tiles are split between the two CTAs.
+constexpr int kDsamThreads = 512;            // 4 control warps + 8 epilogue warps + 4 mask warps
+constexpr int kDsamRaw = 3;                  // raw (unmasked) tile ring: prefetched ahead of the masking
+__global__ void __launch_bounds__(kDsamThreads, 1)
+dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const __grid_constant__ KParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int kTile = kBlockM * 128;                       // 16 KB: 128 pixels x 64 channels
+    const int n_seg = p.m3_n_seg;                              // 5: four masked segments + the projection copy
+    const int n_msk = p.m3_masked_segs;
+    const int b_bytes = (p.BLOCK_N / 2) * 128;
+    uint8_t* s_rawt = smem;                                    // kDsamRaw raw tiles (TMA targets; also the projection operand)
+    uint8_t* s_msk = s_rawt + kDsamRaw * kTile;                // 2 groups x n_msk masked copies
+    uint8_t* s_b = s_msk + 2 * n_msk * kTile;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b + (size_t)p.stages * b_bytes);
+    float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + sizeof(SmemCtl));
+    float* s_shift = s_scale + p.BLOCK_N;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const bool leader = rank == 0;
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_a);
+        tc::prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            tc::mbar_init(&ctl->full[s], 1);
+            tc::mbar_init(&ctl->empty[s], 1);
+        }
+        for (int r = 0; r < kDsamRaw; ++r) {
+            tc::mbar_init(&ctl->a_full[r], 1);                 // raw tile landed (local TMA)
+            tc::mbar_init(&ctl->a_empty[r], 1);                // released by the pair's MMAs (multicast commit)
+        }
+        for (int g = 0; g < 2; ++g) {
+            tc::mbar_init(&ctl->masked_full[g], 2 * 128);      // mask threads of BOTH CTAs (counted in the leader)
+            tc::mbar_init(&ctl->masked_empty[g], 1);           // multicast commit
+            tc::mbar_init(&ctl->tmem_full[g], 1);
+            tc::mbar_init(&ctl->tmem_empty[g], 2 * kEpiThreads);
+        }
+        tc::fence_barrier_init();
+    }
+    tc::cluster_sync_all();
+    if (warp == 2) tc::tmem_alloc_2cta(&ctl->tmem_base, kTmemCols);
+    tc::tc_fence_before();
+    tc::cluster_sync_all();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    const int total_m = p.total_tiles / p.n_tiles_n;
+    const int n_units = ((total_m + 1) / 2) * p.n_tiles_n;
+    const int n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
+    const int per = n_units / n_clusters, rem = n_units % n_clusters;
+    const int u_begin = cid * per + min(cid, rem);
+    const int u_end = u_begin + per + (cid < rem ? 1 : 0);
+    const int groups_per_tile = p.dsam_taps * p.c_blocks;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer: weight tiles =================
+        int sb = 0;
+        uint32_t pb = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            const int nt = pair_tile(p, u, (int)rank) % p.n_tiles_n;
+            for (int gi = 0; gi < groups_per_tile; ++gi) {
+                for (int sg = 0; sg < n_seg; ++sg) {
+                    tc::mbar_wait(&ctl->empty[sb], pb ^ 1);
+                    if (leader) tc::mbar_expect_tx(&ctl->full[sb], 2u * (uint32_t)b_bytes);
+                    tc::tma_load_2d_2cta(s_b + (size_t)sb * b_bytes, &tmap_b, &ctl->full[sb], (gi * n_seg + sg) * 64,
+                                         nt * p.BLOCK_N + (int)rank * (p.BLOCK_N / 2));
+                    if (++sb == p.stages) { sb = 0; pb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 3 && lane == 0) {
+        // ================= TMA producer: raw feature tiles (own ring, runs ahead of the masking) =================
+        int r = 0;
+        uint32_t pr = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            int img, ty, tx, nt;
+            decode_tile(p, pair_tile(p, u, (int)rank), img, ty, tx, nt);
+            const int x0 = tx * p.BX, y0 = ty * p.BY;
+            for (int tap = 0; tap < p.dsam_taps; ++tap) {
+                const int dy = tap / 3, dx = tap % 3;
+                // input row 2*oy+dy-1: dy=0 -> odd plane, row oy-1; dy=1 -> even plane, row oy; dy=2 -> odd plane, row oy
+                const int par = (dy == 1 ? 0 : 2) + (dx == 1 ? 0 : 1);
+                const int yo = dy == 0 ? -1 : 0, xo = dx == 0 ? -1 : 0;
+                for (int cb = 0; cb < p.c_blocks; ++cb) {
+                    tc::mbar_wait(&ctl->a_empty[r], pr ^ 1);
+                    tc::mbar_expect_tx(&ctl->a_full[r], kTile);
+                    tc::tma_load_4d(s_rawt + (size_t)r * kTile, &tmap_a, &ctl->a_full[r], cb * 64, x0 + xo, y0 + yo, img * 4 + par);
+                    if (++r == kDsamRaw) { r = 0; pr ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ================= MMA issuer (leader) =================
+        const uint32_t idesc = tc::make_idesc_bf16(2 * kBlockM, p.BLOCK_N);
+        int g = 0, r = 0, sb = 0, as = 0;
+        uint32_t pg = 0, pb = 0, aphase = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
+            tc::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BLOCK_N);
+            uint32_t first = 1;
+            for (int gi = 0; gi < groups_per_tile; ++gi) {
+                tc::mbar_wait(&ctl->masked_full[g], pg);       // both CTAs: raw tile landed and masked copies written
+                tc::tc_fence_after();
+                for (int sg = 0; sg < n_seg; ++sg) {
+                    tc::mbar_wait(&ctl->full[sb], pb);
+                    tc::tc_fence_after();
+                    const uint8_t* a_tile = sg < n_msk ? s_msk + (size_t)(g * n_msk + sg) * kTile : s_rawt + (size_t)r * kTile;
+                    const uint64_t adesc = tc::make_kmajor_desc(tc::smem_u32(a_tile), 128);
+                    const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_b + (size_t)sb * b_bytes), 128);
+                    for (int k = 0; k < 4; ++k) {
+                        tc::umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
+                        first = 0;
+                    }
+                    tc::umma_commit_2cta(&ctl->empty[sb]);
+                    if (++sb == p.stages) { sb = 0; pb ^= 1; }
+                }
+                tc::umma_commit_2cta(&ctl->masked_empty[g]);
+                tc::umma_commit_2cta(&ctl->a_empty[r]);
+                if (++g == 2) { g = 0; pg ^= 1; }
+                if (++r == kDsamRaw) r = 0;
+            }
+            tc::umma_commit_2cta(&ctl->tmem_full[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    } else if (warp >= 12) {
+        // ================= mask warps: masked copies of the raw tile =================
+        const int row = (warp - 12) * 32 + lane;               // pixel row of the tile
+        const int lx = row % p.BX, ly = row / p.BX;
+        const uint32_t masked_full_remote[2] = {tc::mapa(tc::smem_u32(&ctl->masked_full[0]), 0),
+                                                tc::mapa(tc::smem_u32(&ctl->masked_full[1]), 0)};
+        int g = 0, r = 0;
+        uint32_t pg = 0, pr = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            int img, ty, tx, nt;
+            decode_tile(p, pair_tile(p, u, (int)rank), img, ty, tx, nt);
+            const int oy = ty * p.BY + ly, ox = tx * p.BX + lx;
+            const bool img_ok = img < p.n_img;
+            for (int tap = 0; tap < p.dsam_taps; ++tap) {
+                const int iy = 2 * oy + tap / 3 - 1, ix = 2 * ox + tap % 3 - 1;
+                unsigned code = 0;
+                if (img_ok && iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w)
+                    code = p.codes[((size_t)img * p.in_h + iy) * p.in_w + ix];
+                for (int cb = 0; cb < p.c_blocks; ++cb) {
+                    tc::mbar_wait(&ctl->a_full[r], pr);
+                    const uint8_t* src = s_rawt + (size_t)r * kTile + row * 128;
+                    uint4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (((j + row) & 7) << 4));   // rotated: bank-conflict free
+                    tc::mbar_wait(&ctl->masked_empty[g], pg ^ 1);
+                    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+                    for (int sg = 0; sg < n_msk; ++sg) {
+                        uint8_t* dst = s_msk + (size_t)(g * n_msk + sg) * kTile + row * 128;
+                        const bool keep = (code >> sg) & 1u;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(dst + (((j + row) & 7) << 4)) = keep ? v[j] : zero;
+                    }
+                    tc::fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's smem reads
+                    tc::mbar_arrive_cluster(masked_full_remote[g]);
+                    if (++g == 2) { g = 0; pg ^= 1; }
+                    if (++r == kDsamRaw) { r = 0; pr ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        EpiCtx c{smem, nullptr, nullptr, ctl, s_scale, s_shift, tmem_base, u_begin, u_end, warp, lane, (int)rank,
+                 {tc::mapa(tc::smem_u32(&ctl->tmem_empty[0]), 0), tc::mapa(tc::smem_u32(&ctl->tmem_empty[1]), 0)}};
+        epilogue_loop<1, 0, false>(p, c, &tmap_a);
+    }
+
+    tc::tc_fence_before();
+    tc::cluster_sync_all();
+    if (warp == 2) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc_2cta(tmem_base, kTmemCols);
+    }
+}
+
 // conv_gemm_kernel on CTA pairs (tcgen05 cta_group::2) for the DSAM stages (epilogue modes 1 and 3): the two CTAs of a
 // cluster take adjacent M tiles of the same N tile, so each stages only half of every B (weight) K block.
 __global__ void __launch_bounds__(kThreads, 1)
@@ -891,12 +1082,12 @@ EncodeTiledFn get_encode_fn() {
 
 extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream) {
     RGBD_CHECK_ARG(d, "conv_gemm: null descriptor");
-    RGBD_CHECK_ARG(d->a && d->w && (d->slices || d->conv3x3_reuse), "conv_gemm: null operand pointer");
+    RGBD_CHECK_ARG(d->a && d->w && (d->slices || d->conv3x3_reuse || d->dsam_masked), "conv_gemm: null operand pointer");
     RGBD_CHECK_ARG(d->kb_elems == 64 || d->kb_elems == 32, "conv_gemm: kb_elems must be 64 or 32 (got %d)", d->kb_elems);
     RGBD_CHECK_ARG(d->a_c % 8 == 0 && d->a_c >= d->kb_elems, "conv_gemm: A channel count %d must be a multiple of 8 and >= kb", d->a_c);
     RGBD_CHECK_ARG(d->bx >= 1 && d->by >= 1 && d->bx * d->by == kBlockM && d->bx <= 256 && d->by <= 256,
                    "conv_gemm: box %dx%d must cover exactly %d pixels", d->bx, d->by, kBlockM);
-    RGBD_CHECK_ARG(d->conv3x3_reuse || (d->n_slices >= 1 && d->n_slices <= kMaxSlices), "conv_gemm: n_slices %d out of range",
+    RGBD_CHECK_ARG(d->conv3x3_reuse || d->dsam_masked || (d->n_slices >= 1 && d->n_slices <= kMaxSlices), "conv_gemm: n_slices %d out of range",
                    d->n_slices);
     if (d->conv3x3_reuse)
         RGBD_CHECK_ARG(d->kb_elems == 64 && d->bx == kBlockM && d->by == 1 && d->a_c % 64 == 0 && d->plane_per_img == 1,
@@ -906,6 +1097,13 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
                    "conv_gemm: bad N tiling (N=%d N_pad=%d BLOCK_N=%d)", d->n, d->n_pad, d->block_n);
     RGBD_CHECK_ARG(d->epi_mode >= 0 && d->epi_mode <= 3, "conv_gemm: bad epilogue mode %d", d->epi_mode);
     RGBD_CHECK_ARG(d->shift || d->epi_mode == 3, "conv_gemm: shift table is required");
+    if (d->dsam_masked)
+        RGBD_CHECK_ARG(d->epi_mode == 1 && d->kb_elems == 64 && d->a_c % 64 == 0 && d->plane_per_img == 4 && d->codes &&
+                           d->m3_n_seg >= 2 && d->m3_n_seg <= 5 && d->m3_masked_segs == d->m3_n_seg - 1 && d->in_h >= 1 &&
+                           d->in_w >= 1 && !d->conv3x3_reuse && (d->block_n / 2) % 16 == 0 &&
+                           (long long)d->n_img * ceil_div(d->out_w, d->bx) * ceil_div(d->out_h, d->by) >= 2,
+                       "conv_gemm: dsam_masked needs epilogue mode 1, kb=64, C %% 64 == 0, 4 parity planes, codes, "
+                       "2..5 segments and at least two pixel tiles");
     if (d->epi_mode == 3)
         RGBD_CHECK_ARG(d->codes && d->m3_n_seg >= 1 && d->m3_n_seg <= 8 && d->block_n == 32 * d->m3_n_seg && d->in_h >= 1 &&
                            d->in_w >= 1 && (d->m3_stride == 1 || d->m3_stride == 2) && !d->conv3x3_reuse,
@@ -945,7 +1143,8 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
             return RGBD_ERR_CUDA;
         }
     }
-    const long long k_total = d->conv3x3_reuse ? 9ll * d->a_c : (long long)d->n_slices * d->kb_elems;
+    const long long k_total = d->conv3x3_reuse ? 9ll * d->a_c
+                              : d->dsam_masked ? 9ll * d->a_c * d->m3_n_seg : (long long)d->n_slices * d->kb_elems;
     {
         cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->n_pad};
         cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
@@ -986,7 +1185,8 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     p.out_w = d->out_w; p.out_h = d->out_h;
     p.tiles_x = ceil_div(d->out_w, d->bx);
     p.tiles_y = ceil_div(d->out_h, d->by);
-    p.n_slices = d->conv3x3_reuse ? 0 : d->n_slices;
+    p.n_slices = (d->conv3x3_reuse || d->dsam_masked) ? 0 : d->n_slices;
+    p.dsam_taps = 9;
     p.kb_bytes = kb_bytes;
     p.c_blocks = d->a_c / 64;
     p.sa_stages = 0;
@@ -1018,6 +1218,7 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(dsam_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     if (d->conv3x3_reuse) {
@@ -1072,6 +1273,44 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         }
         conv3x3_kernel<<<grid, kThreads, smem3, (cudaStream_t)stream>>>(tmap_a, tmap_b, tmap_out, tmap_gate, p);
         RGBD_CHECK_LAUNCH();
+        return RGBD_OK;
+    }
+    if (d->dsam_masked) {
+        p.b_resident = 0; p.b_res_bytes = 0; p.dbg_shift = 0; p.dbg_bo = 0; p.staging_bytes = 0; p.gate_bytes = 0;
+        CUtensorMap tmap_b2;
+        cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->n_pad};
+        cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)(p.BLOCK_N / 2)};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmap_b2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            rgbd_set_error("conv_gemm: cuTensorMapEncodeTiled(B half) failed with %d", (int)r);
+            return RGBD_ERR_CUDA;
+        }
+        const int b_half = (p.BLOCK_N / 2) * 128;
+        const int fixedm = 1024 + (int)sizeof(SmemCtl) + 64 + 2 * p.BLOCK_N * (int)sizeof(float) +
+                           (kDsamRaw + 2 * p.m3_masked_segs) * kBlockM * 128;
+        int sbm = (max_smem - fixedm) / b_half;
+        if (sbm > kMaxStages) sbm = kMaxStages;
+        RGBD_CHECK_ARG(sbm >= 2, "conv_gemm: not enough shared memory for the masked DSAM pipeline");
+        p.stages = sbm;
+        const int total_m = p.total_tiles / p.n_tiles_n;
+        const int n_units = ((total_m + 1) / 2) * p.n_tiles_n;
+        int clusters = num_sms / 2;
+        if (clusters > n_units) clusters = n_units;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(kDsamThreads);
+        cfg.dynamicSmemBytes = fixedm + sbm * b_half;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dsam_fwd_kernel, tmap_a, tmap_b2, p));
         return RGBD_OK;
     }
     {   // measurement hook of profiles/dbg_shift.py (row-shifted descriptor experiment); 0 in normal operation

@@ -261,9 +261,11 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
               residual: Optional[torch.Tensor] = None, pool: Optional[torch.Tensor] = None,
               cells: Tuple[int, int] = (0, 0), tile_order: int = 0, block_n: Optional[int] = None,
               conv3x3_reuse: bool = False, codes: Optional[torch.Tensor] = None, in_hw: Tuple[int, int] = (0, 0),
-              parity: Tuple[int, int] = (0, 0), m3_stride: int = 1, m3_masked_segs: int = 0, m3_n_seg: int = 0) -> None:
+              parity: Tuple[int, int] = (0, 0), m3_stride: int = 1, m3_masked_segs: int = 0, m3_n_seg: int = 0,
+              dsam_masked: bool = False) -> None:
     """Launch the tcgen05 implicit-GEMM kernel.  a_dims = (planes, y, x, c) of the bf16 channels-last operand.
-    ``conv3x3_reuse``: 3x3 stride-1 conv whose A tile is shared by the three dx taps (``slices`` may be None)."""
+    ``conv3x3_reuse``: 3x3 stride-1 conv whose A tile is shared by the three dx taps (``slices`` may be None).
+    ``dsam_masked``: stride-2 DSAM stage on the unmasked operand, region masking in shared memory (``slices`` None)."""
     lib = _lib.load()
     _req(a, "a", torch.bfloat16)
     _req(w, "w", torch.bfloat16)
@@ -275,7 +277,10 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
     planes, ay, ax, ac = a_dims
     if a.numel() != planes * ay * ax * ac:
         raise RgbdB200Error("conv_gemm: operand size does not match a_dims")
-    n_slices = slices.shape[0] if slices is not None else 9 * ac // kb
+    if dsam_masked:
+        n_slices = 9 * (ac // 64) * m3_n_seg
+    else:
+        n_slices = slices.shape[0] if slices is not None else 9 * ac // kb
     if w.shape[1] != n_slices * kb:
         raise RgbdB200Error(f"conv_gemm: weight K {w.shape[1]} != n_slices*kb {n_slices * kb}")
     if (shift is not None and shift.shape[-1] != n_pad) or (scale is not None and scale.numel() != n_pad):
@@ -286,6 +291,7 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
     d.w = w.data_ptr(); d.slices = slices.data_ptr() if slices is not None else None
     d.n_slices = n_slices; d.kb_elems = kb
     d.conv3x3_reuse = 1 if conv3x3_reuse else 0
+    d.dsam_masked = 1 if dsam_masked else 0
     d.n_img = n_img; d.out_h, d.out_w = out_hw; d.bx, d.by = box
     d.n = n; d.n_pad = n_pad; d.block_n = block_n or pick_block_n(n_pad)
     d.tile_order = tile_order; d.epi_mode = epi_mode; d.act = act

@@ -346,6 +346,28 @@ def test_dsam_module(mods, ci, co, hw, dhw):
         m(feat.cuda(), [[0.0]], 0.3)
 
 
+@pytest.mark.parametrize("ci,co,hw,dhw", [(96, 192, (30, 40), (120, 160)), (64, 128, (15, 21), (60, 84)),
+                                          (192, 384, (31, 17), (124, 68)), (128, 96, (9, 130), (36, 520))])
+def test_dsam_shared_memory_masking_matches_premasked_layout(mods, monkeypatch, ci, co, hw, dhw):
+    """dsam_fwd_kernel (region masks applied to the tile in shared memory) against the five-fold pre-masked operand
+    + generic GEMM, and both against the oracle; odd sizes exercise the parity-plane edges and half-empty pairs."""
+    w = OW.dsam_weights(ci, co, seed=300 + ci + co)
+    m = mods.DSAModule(ci, co, 3)
+    m.load_state_dict(w)
+    m.cuda().eval()
+    feat = torch.from_numpy(np.random.RandomState(6).randn(3, ci, *hw).astype(np.float32))
+    for j, kind in enumerate(["nyu", "two_valued"]):
+        gray = _gray_for(j, kind, dhw)
+        outs = []
+        for premasked in (False, True):
+            monkeypatch.setattr(mods, "_PREMASKED", premasked)
+            with torch.no_grad():
+                outs.append(m(feat.cuda(), torch.from_numpy(gray)[None].cuda(), 0.25))
+        ref = torch.cat([O.dsam_forward(w, feat[b:b + 1], gray, 0.25) for b in range(3)])
+        assert rel_err(outs[0], ref) < BF16_TOL and rel_err(outs[1], ref) < BF16_TOL
+        assert rel_err(outs[0], outs[1]) < 1e-5, rel_err(outs[0], outs[1])     # same bf16 operands, other K order
+
+
 @pytest.mark.parametrize("ci,co,hw,dhw", [(8, 16, (24, 32), (96, 128)), (96, 192, (30, 40), (120, 160)),
                                           (64, 64, (12, 20), (48, 80)), (40, 72, (15, 21), (60, 84))])
 def test_dsam_module_fp32_precision_mode(mods, ci, co, hw, dhw):
