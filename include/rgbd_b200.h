@@ -177,6 +177,15 @@ int rgbd_ratio_chain(const void* x1_bf16, const void* w2_bf16, const void* w3_bf
                      const float* sh3, const float* sh4, void* out_bf16, int B, int H, int W, int bx, int by,
                      rgbd_stream_t stream);
 
+/* Multi-scale stem + point-wise middle of EnhancedDepthImageRatioPredictor.forward (CM:1458-1470) as ONE kernel on CTA
+ * pairs: the stem GEMM (K = 256 row-im2col, N = 192) feeds rgbd_ratio_chain's three GEMMs through tensor memory, so the
+ * 192-channel stem output never reaches HBM.  r: output of rgbd_ratio_stem_pack, bf16 (B,H+6,W,64); w1 (192,256) bf16 with
+ * the folded BN scale multiplied in (K order = 4 slices x (j, dx8, c4), tap dy = 2*slice + j); sh1 (192): folded BN
+ * shift; the other arguments as for rgbd_ratio_chain. */
+int rgbd_ratio_front(const void* r_bf16, const void* w1_bf16, const void* w2_bf16, const void* w3_bf16, const void* w4_bf16,
+                     const float* sh1, const float* sh2, const float* sh3, const float* sh4, void* out_bf16, int B, int H,
+                     int W, int bx, int by, rgbd_stream_t stream);
+
 /* Tail of EnhancedDepthImageRatioPredictor.forward (CM:1473-1485): pooled sums -> conv3x3 256->512 + folded BN +
  * ReLU -> GAP -> MLP -> 0.01 + 0.49*sigmoid.  conv_w (512,256,3,3) fp32; fc_w_host/fc_b_host: 4 layers. */
 int rgbd_ratio_tail(const float* pool_sums, int pool_stride, int cell_pixels, const float* conv_w, const float* conv_scale,

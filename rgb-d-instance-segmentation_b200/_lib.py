@@ -66,6 +66,7 @@ SIGNATURES = {
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "rgbd_ratio_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "rgbd_ratio_front": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 5 + [C.c_void_p]),
     "rgbd_ratio_tail": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_void_pp, c_void_pp,
                                   C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 }

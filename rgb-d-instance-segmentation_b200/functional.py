@@ -386,6 +386,31 @@ def ratio_stem_pack(depth3: torch.Tensor, out: torch.Tensor) -> None:
     _count(1)
 
 
+def ratio_front(r: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor, w4: torch.Tensor, sh1: torch.Tensor,
+                sh2: torch.Tensor, sh3: torch.Tensor, sh4: torch.Tensor, out: torch.Tensor, box: Tuple[int, int]) -> None:
+    """K4a+K4b in one kernel.  r (B,H+6,W,64) bf16 row-im2col depth -> out (B,H,W,128) bf16: stem GEMM + BN + ReLU,
+    feature_fusion, attention and gating (CM:1458-1470) with every intermediate in tensor memory."""
+    lib = _lib.load()
+    _req(r, "r", torch.bfloat16)
+    _req(out, "out", torch.bfloat16)
+    B, H6, W, c = r.shape
+    H = H6 - 6
+    if c != 64 or H < 1 or out.shape != (B, H, W, 128):
+        raise RgbdB200Error("ratio_front: r must be (B,H+6,W,64) and out (B,H,W,128)")
+    for t, shp in ((w1, (192, 256)), (w2, (128, 192)), (w3, (64, 128)), (w4, (128, 64))):
+        _req(t, "front weight", torch.bfloat16)
+        if tuple(t.shape) != shp:
+            raise RgbdB200Error(f"ratio_front: weight shape {tuple(t.shape)} != {shp}")
+    for t, n in ((sh1, 192), (sh2, 128), (sh3, 64), (sh4, 128)):
+        _req(t, "front shift", torch.float32)
+        if t.numel() != n:
+            raise RgbdB200Error("ratio_front: bad shift length")
+    check(lib.rgbd_ratio_front(r.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), w4.data_ptr(), sh1.data_ptr(),
+                               sh2.data_ptr(), sh3.data_ptr(), sh4.data_ptr(), out.data_ptr(), B, H, W, box[0], box[1],
+                               _stream()), "rgbd_ratio_front")
+    _count(1)
+
+
 def ratio_chain(x1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor, w4: torch.Tensor, sh2: torch.Tensor,
                 sh3: torch.Tensor, sh4: torch.Tensor, out: torch.Tensor, box: Tuple[int, int]) -> None:
     """K4b.  x1 (B,H,W,192) bf16 -> out (B,H,W,128) bf16 = f * sigmoid(W4 relu(W3 f + b3) + b4), f = relu(W2' x1 + sh2)

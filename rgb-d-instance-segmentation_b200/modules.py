@@ -465,7 +465,8 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         self.output_min = 0.01
         self.output_max = 0.5
         self.sigmoid = nn.Sigmoid()
-        self.use_fused_chain = True        # False: three separate GEMM launches (kept for cross-checks)
+        self.use_fused_front = True        # stem GEMM + chain in one kernel; False: stem GEMM, then ...
+        self.use_fused_chain = True        # ... the fused chain, or (False) three separate GEMM launches (cross-checks)
         self._ver = _Versioned()
         self._packed: Dict[str, torch.Tensor] = {}
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
@@ -521,14 +522,14 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         return pk
 
     def _workspace(self, B, H, W, dev):
-        key = (B, H, W, str(dev), self.use_fused_chain)
+        key = (B, H, W, str(dev), self.use_fused_chain, self.use_fused_front)
         if key not in self._ws:
             bf = dict(device=dev, dtype=torch.bfloat16)
             self._ws = {key: {
                 "stem": torch.empty(B, H + 6, W, 64, **bf),
-                "x1": torch.empty(B, H, W, 192, **bf),
-                "x2": torch.empty(B, H, W, 128, **bf) if not self.use_fused_chain else None,
-                "x3": torch.empty(B, H, W, 64, **bf) if not self.use_fused_chain else None,
+                "x1": torch.empty(B, H, W, 192, **bf) if not self.use_fused_front else None,
+                "x2": torch.empty(B, H, W, 128, **bf) if not (self.use_fused_chain or self.use_fused_front) else None,
+                "x3": torch.empty(B, H, W, 64, **bf) if not (self.use_fused_chain or self.use_fused_front) else None,
                 "x4": torch.empty(B, H, W, 128, **bf),
                 "pool": torch.empty(B, 16, 256, device=dev, dtype=torch.float32),
             }}
@@ -548,10 +549,17 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
             d = d.float()
         box = _best_box(H, W)
         Fn.ratio_stem_pack(d, ws["stem"])
-        # multi-scale stem (CM:1458-1463) + BN + ReLU -> 192 channels
-        Fn.conv_gemm(ws["stem"], (B, H + 6, W, 64), 1, pk["w1"], pk["sl1"], 64, B, (H, W), box, 192, pk["sh1"],
-                     act=1, out=ws["x1"], tile_order=1)   # walk down columns: the 4 row taps re-hit L2
-        if self.use_fused_chain:
+        if self.use_fused_front:
+            # stem + feature_fusion + attention + gating (CM:1458-1470) in one kernel; intermediates in tensor memory
+            Fn.ratio_front(ws["stem"], pk["w1"], pk["w2"], pk["w3"], pk["w4"], pk["sh1"], pk["sh2"], pk["sh3"], pk["sh4"],
+                           ws["x4"], box)
+        else:
+            # multi-scale stem (CM:1458-1463) + BN + ReLU -> 192 channels
+            Fn.conv_gemm(ws["stem"], (B, H + 6, W, 64), 1, pk["w1"], pk["sl1"], 64, B, (H, W), box, 192, pk["sh1"],
+                         act=1, out=ws["x1"], tile_order=1)   # walk down columns: the 4 row taps re-hit L2
+        if self.use_fused_front:
+            pass
+        elif self.use_fused_chain:
             # feature_fusion + attention + gating (CM:1466-1470) as one kernel, intermediates in tensor memory
             Fn.ratio_chain(ws["x1"], pk["w2"], pk["w3"], pk["w4"], pk["sh2"], pk["sh3"], pk["sh4"], ws["x4"], box)
         else:

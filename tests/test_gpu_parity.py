@@ -307,12 +307,37 @@ def test_ratio_predictor_fused_chain_matches_unfused(mods):
     res = []
     for fused in (True, False):
         m = mods.EnhancedDepthImageRatioPredictor(3)
+        m.use_fused_front = False
         m.use_fused_chain = fused
         m.load_state_dict(w)
         m.cuda().eval()
         with torch.no_grad():
             res.append(m(x).cpu())
     assert float(((res[0] - res[1]).abs() / res[1]).max()) < 2e-3
+
+
+@pytest.mark.parametrize("B,hw", [(1, (4, 128)), (2, (48, 64)), (3, (20, 36)), (5, (8, 256))])
+def test_ratio_front_fused_matches_stem_gemm_plus_chain(mods, fn, B, hw):
+    """ratio_front_kernel (stem GEMM + chain, two tile chains per CTA pair, all intermediates in tensor memory) against
+    the two-kernel path on the same packed operands: identical bf16 rounding points, so the gated 128-channel map must
+    agree to bf16 resolution; odd tile counts leave the last pair half empty."""
+    w = OW.ratio_weights(seed=501)
+    H, W = hw
+    rs = np.random.RandomState(B)
+    x = torch.from_numpy(rs.uniform(-2, 2, (B, 3, H, W)).astype(np.float32)).cuda()
+    outs, ratios = [], []
+    for fused in (True, False):
+        m = mods.EnhancedDepthImageRatioPredictor(3)
+        m.use_fused_front = fused
+        m.load_state_dict(w)
+        m.cuda().eval()
+        with torch.no_grad():
+            ratios.append(m(x).cpu())
+        outs.append(next(iter(m._ws.values()))["x4"].float().cpu())
+    assert outs[0].shape == (B, H, W, 128)
+    assert rel_err(outs[0], outs[1]) < 1e-2, rel_err(outs[0], outs[1])
+    assert rel_l2(outs[0], outs[1]) < 2e-3
+    assert float(((ratios[0] - ratios[1]).abs() / ratios[1]).max()) < 2e-3
 
 
 # ---------------------------------------------------------------------------------------------------
