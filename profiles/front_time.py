@@ -1,0 +1,34 @@
+"""Time rgbd_ratio_front (stem GEMM + chain, one kernel) alone at the bench shape; never a bench number."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rgbd_b200
+from rgbd_b200 import functional as Fn
+from rgbd_b200.modules import EnhancedDepthImageRatioPredictor, _best_box
+from oracle import weights as OW
+
+B, H, W = int(os.environ.get("B", 32)), 480, 640
+m = EnhancedDepthImageRatioPredictor(3)
+m.load_state_dict(OW.ratio_weights(seed=1))
+m.cuda().eval()
+pk = m._refresh()
+x = torch.randn(B, 3, H, W, device="cuda")
+r = torch.empty(B, H + 6, W, 64, device="cuda", dtype=torch.bfloat16)
+out = torch.empty(B, H, W, 128, device="cuda", dtype=torch.bfloat16)
+Fn.ratio_stem_pack(x, r)
+box = _best_box(H, W)
+args = (r, pk["w1"], pk["w2"], pk["w3"], pk["w4"], pk["sh1"], pk["sh2"], pk["sh3"], pk["sh4"], out, box)
+for _ in range(3):
+    Fn.ratio_front(*args)
+ts = []
+for _ in range(5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        Fn.ratio_front(*args)
+    e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1) / 10)
+tiles = B * H * W / 128
+print(f"ratio_front B={B}: {min(ts)*1e3:.1f} us (median {sorted(ts)[2]*1e3:.1f}); "
+      f"{min(ts)*1e-3*1.9e9/(tiles/148):.0f} cycles/tile/SM @1.9GHz")

@@ -11,7 +11,7 @@
 //
 // The epilogues are bound by the TMEM read rate (~64 B/clk/SM: 512 accumulator columns per tile = 4096 cycles) while
 // the MMAs need 2816 cycles per tile, so TWO tile chains are kept in flight per CTA, each with its own eight epilogue
-// warps; the single MMA thread interleaves their GEMMs in a fixed order.  TMEM columns (480 of 512):
+// warps.  Three MMA-issuing threads (stem GEMMs; chain 0; chain 1) each block on exactly the barrier they need.  TMEM columns (480 of 512):
 //     P_c = 192*c .. +192   chain c:  acc1 [0,192) -> acc2 [0,128) | f bf16 [128,192) -> acc3 [0,64) | relu bf16 [160,192)
 //                                      -> acc4 [0,128)          (each reuse only after the previous owner was consumed)
 //     Q   = [384,480)       ms as bf16 (A operand of GEMM 2), shared by both chains (the other chain's GEMM 2 must be done)
@@ -115,8 +115,8 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
         tc::mbar_init(&ctl->w_full, 1);
         for (int c = 0; c < 2; ++c) {
             for (int g = 0; g < 4; ++g) tc::mbar_init(&ctl->acc_full[c][g], 1);
-            for (int g = 0; g < 3; ++g) tc::mbar_init(&ctl->x_ready[c][g], 2 * kChainThreads);
-            tc::mbar_init(&ctl->p_free[c], 2 * kChainThreads);
+            for (int g = 0; g < 3; ++g) tc::mbar_init(&ctl->x_ready[c][g], 2 * (kChainThreads / 32));   // one arrive per warp
+            tc::mbar_init(&ctl->p_free[c], 2 * (kChainThreads / 32));
         }
         tc::fence_barrier_init();
     }
@@ -154,17 +154,18 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0 && leader) {
-        // ================= MMA issuer (leader): GEMMs of both chains in a fixed interleaved order =================
+    } else if (warp == 1 && leader) {
+        // ================= MMA issuer 1 (leader): the stem GEMMs of both chains, in the tile order of the TMA ring ======
+        // The tensor pipe executes MMAs in issue order, so a whole GEMM 1 (1536 cycles) queued at once would park the other
+        // chain's short GEMMs 2-4 behind it: issue one K-slice (384 cycles), wait until it has executed, issue the next.
         const uint32_t idesc192 = tc::make_idesc_bf16(2 * kBlockM, 192);
-        const uint32_t idesc128 = tc::make_idesc_bf16(2 * kBlockM, 128);
-        const uint32_t idesc64 = tc::make_idesc_bf16(2 * kBlockM, 64);
         tc::mbar_wait(&ctl->w_full, 0);
         tc::tc_fence_after();
         int stage = 0;
         uint32_t phase = 0;
-        auto gemm1 = [&](int c, int i) {       // acc1 = R . W1^T  (A from the smem ring, 4 slices x 4 MMAs)
-            tc::mbar_wait(&ctl->p_free[c], (uint32_t)((i & 1) ^ 1));
+        for (int n = 0; n < n_mine; ++n) {
+            const int c = n & 1, i = n >> 1;
+            tc::mbar_wait(&ctl->p_free[c], (uint32_t)((i & 1) ^ 1));      // acc4 of the chain's previous tile was read
             tc::tc_fence_after();
             const uint32_t d = tmem + (uint32_t)(c * 192);
             for (int j = 0; j < 4; ++j) {
@@ -172,50 +173,64 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
                 tc::tc_fence_after();
                 const uint64_t adesc = tc::make_kmajor_desc(tc::smem_u32(s_ring + stage * kSliceBytes), 128);
                 const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_w1 + j * (96 * 128)), 128);
-                for (int k = 0; k < 4; ++k)
-                    tc::umma_bf16_2cta(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc192, (j | k) != 0);
-                tc::umma_commit_2cta(&ctl->empty[stage]);
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::umma_bf16_2cta(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc192, (j | k) != 0);
+                    tc::umma_commit_2cta(&ctl->empty[stage]);
+                    if (j == 3) tc::umma_commit_2cta(&ctl->acc_full[c][0]);
+                }
+                __syncwarp();
+                if (j != 3) tc::mbar_wait(&ctl->empty[stage], phase);     // throttle: at most one slice queued
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            tc::umma_commit_2cta(&ctl->acc_full[c][0]);
-        };
-        auto gemm2 = [&](int c, int i) {       // acc2 = ms(bf16, TMEM Q) . W2^T   (K = 192: 12 MMAs, A advances 8 columns each)
-            tc::mbar_wait(&ctl->x_ready[c][0], (uint32_t)(i & 1));
+        }
+    } else if ((warp == 2 || warp == 3) && leader) {
+        // whole warp runs the (uniform) control flow so the descriptors stay in uniform registers; one elected lane issues
+        // ================= MMA issuers 2/3 (leader): GEMMs 2-4 of chain 0 / chain 1, A operand in tensor memory ==========
+        const int c = warp - 2;
+        const uint32_t idesc128 = tc::make_idesc_bf16(2 * kBlockM, 128);
+        const uint32_t idesc64 = tc::make_idesc_bf16(2 * kBlockM, 64);
+        const uint32_t d = tmem + (uint32_t)(c * 192);
+        const uint64_t w2d = tc::make_kmajor_desc(tc::smem_u32(s_w2), 128);
+        const uint64_t w3d = tc::make_kmajor_desc(tc::smem_u32(s_w3), 128);
+        const uint64_t w4d = tc::make_kmajor_desc(tc::smem_u32(s_w4), 128);
+        tc::mbar_wait(&ctl->w_full, 0);
+        tc::tc_fence_after();
+        const int n_c = c == 0 ? n_a : n_b;
+        for (int i = 0; i < n_c; ++i) {
+            const uint32_t ph = (uint32_t)(i & 1);
+            // GEMM 2: acc2 = ms(bf16, TMEM Q) . W2^T   (K = 192: 12 MMAs, A advances 8 columns, B 32 bytes / 8 KB per slice)
+            tc::mbar_wait(&ctl->x_ready[c][0], ph);
             tc::tc_fence_after();
-            const uint32_t d = tmem + (uint32_t)(c * 192);
-            for (int k = 0; k < 12; ++k) {
-                const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_w2 + (k >> 2) * (64 * 128)), 128) + (uint64_t)((k & 3) * 2);
-                umma_bf16_ts_2cta(d, tmem + kColQ + (uint32_t)(k * 8), bdesc, idesc128, k != 0);
+            if (tc::elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k)
+                    umma_bf16_ts_2cta(d, tmem + kColQ + (uint32_t)(k * 8), w2d + (uint64_t)((k >> 2) * ((64 * 128) >> 4) + (k & 3) * 2),
+                                      idesc128, k != 0);
+                tc::umma_commit_2cta(&ctl->acc_full[c][1]);
             }
-            tc::umma_commit_2cta(&ctl->acc_full[c][1]);
-        };
-        auto gemm3 = [&](int c, int i) {       // acc3 = f(bf16, TMEM P+128) . W3^T   (K = 128: 8 MMAs)
-            tc::mbar_wait(&ctl->x_ready[c][1], (uint32_t)(i & 1));
+            __syncwarp();
+            // GEMM 3: acc3 = f(bf16, TMEM P+128) . W3^T   (K = 128: 8 MMAs)
+            tc::mbar_wait(&ctl->x_ready[c][1], ph);
             tc::tc_fence_after();
-            const uint32_t d = tmem + (uint32_t)(c * 192);
-            for (int k = 0; k < 8; ++k) {
-                const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_w3 + (k >> 2) * (32 * 128)), 128) + (uint64_t)((k & 3) * 2);
-                umma_bf16_ts_2cta(d, d + 128u + (uint32_t)(k * 8), bdesc, idesc64, k != 0);
+            if (tc::elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16_ts_2cta(d, d + 128u + (uint32_t)(k * 8), w3d + (uint64_t)((k >> 2) * ((32 * 128) >> 4) + (k & 3) * 2), idesc64,
+                                      k != 0);
+                tc::umma_commit_2cta(&ctl->acc_full[c][2]);
             }
-            tc::umma_commit_2cta(&ctl->acc_full[c][2]);
-        };
-        auto gemm4 = [&](int c, int i) {       // acc4 = relu(.)(bf16, TMEM P+160) . W4^T   (K = 64: 4 MMAs)
-            tc::mbar_wait(&ctl->x_ready[c][2], (uint32_t)(i & 1));
+            __syncwarp();
+            // GEMM 4: acc4 = relu(.)(bf16, TMEM P+160) . W4^T   (K = 64: 4 MMAs)
+            tc::mbar_wait(&ctl->x_ready[c][2], ph);
             tc::tc_fence_after();
-            const uint32_t d = tmem + (uint32_t)(c * 192);
-            for (int k = 0; k < 4; ++k) {
-                const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_w4), 128) + (uint64_t)(k * 2);
-                umma_bf16_ts_2cta(d, d + 160u + (uint32_t)(k * 8), bdesc, idesc128, k != 0);
+            if (tc::elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16_ts_2cta(d, d + 160u + (uint32_t)(k * 8), w4d + (uint64_t)(k * 2), idesc128, k != 0);
+                tc::umma_commit_2cta(&ctl->acc_full[c][3]);
             }
-            tc::umma_commit_2cta(&ctl->acc_full[c][3]);
-        };
-        for (int i = 0; i <= n_a; ++i) {
-            if (i < n_a) gemm1(0, i);
-            if (i >= 1 && i - 1 < n_b) { gemm3(1, i - 1); gemm4(1, i - 1); }
-            if (i < n_a) gemm2(0, i);
-            if (i < n_b) gemm1(1, i);
-            if (i < n_a) { gemm3(0, i); gemm4(0, i); }
-            if (i < n_b) gemm2(1, i);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ================= epilogue: chain c = warps 4..11 / 12..19; a thread owns one pixel row and every other
@@ -239,9 +254,9 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
             decode(p, 2 * (u_begin + 2 * i + c) + (int)rank, img, ty, tx);
 
             // ---- E1: ms = relu(acc1 + sh1) -> bf16 -> TMEM Q (shared: the other chain's GEMM 2 must have read it)
-            tc::mbar_wait(&ctl->acc_full[c][0], ph);
-            if (c == 1) tc::mbar_wait(&ctl->acc_full[0][1], ph);
-            else if (i > 0) tc::mbar_wait(&ctl->acc_full[1][1], ph ^ 1);
+            tc::mbar_wait_sleep(&ctl->acc_full[c][0], ph);
+            if (c == 1) tc::mbar_wait_sleep(&ctl->acc_full[0][1], ph);
+            else if (i > 0) tc::mbar_wait_sleep(&ctl->acc_full[1][1], ph ^ 1);
             tc::tc_fence_after();
 #pragma unroll 1
             for (int k = h; k < 6; k += 2) {
@@ -259,10 +274,11 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
             }
             tc::tmem_st_wait();
             tc::tc_fence_before();
-            tc::mbar_arrive_cluster(x_remote[0]);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster_tmem(x_remote[0]);
 
             // ---- E2: f = relu(acc2 + sh2) -> bf16 -> TMEM P+128 (A of GEMM 3) and the shared-memory stash (gating)
-            tc::mbar_wait(&ctl->acc_full[c][1], ph);
+            tc::mbar_wait_sleep(&ctl->acc_full[c][1], ph);
             tc::tc_fence_after();
             if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous TMA store has read the stash
             asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
@@ -288,10 +304,11 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
             }
             tc::tmem_st_wait();
             tc::tc_fence_before();
-            tc::mbar_arrive_cluster(x_remote[1]);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster_tmem(x_remote[1]);
 
             // ---- E3: relu(acc3 + b3) -> bf16 -> TMEM P+160 (A of GEMM 4)
-            tc::mbar_wait(&ctl->acc_full[c][2], ph);
+            tc::mbar_wait_sleep(&ctl->acc_full[c][2], ph);
             tc::tc_fence_after();
 #pragma unroll 1
             for (int k = h; k < 2; k += 2) {
@@ -309,10 +326,11 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
             }
             tc::tmem_st_wait();
             tc::tc_fence_before();
-            tc::mbar_arrive_cluster(x_remote[2]);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster_tmem(x_remote[2]);
 
             // ---- E4: out = sigmoid(acc4 + b4) * f(stash) -> bf16 -> stash -> TMA store
-            tc::mbar_wait(&ctl->acc_full[c][3], ph);
+            tc::mbar_wait_sleep(&ctl->acc_full[c][3], ph);
             tc::tc_fence_after();
 #pragma unroll 1
             for (int k = h; k < 4; k += 2) {
@@ -341,7 +359,8 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
                 }
             }
             tc::tc_fence_before();
-            tc::mbar_arrive_cluster(p_free_remote);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster_tmem(p_free_remote);
             tc::fence_proxy_async();
             asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
             if (issuer) {

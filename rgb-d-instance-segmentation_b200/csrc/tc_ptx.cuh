@@ -47,6 +47,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// non-blocking phase test (mbarrier.try_wait may suspend the thread for a system-dependent time before it returns
+// false; a polling scheduler must not)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// wait with a suspend-time hint: the thread sleeps in hardware (no issue slots taken from working warps) until the
+// phase completes or ~hint_ns elapse
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 2000) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+            : "memory");
+    } while (!ok);
+}
+
 // ---- TMA ----------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -95,6 +123,11 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// remote arrive whose payload is TENSOR MEMORY only (ordered by tcgen05.wait + tcgen05.fence::before_thread_sync):
+// CTA-scope release, no cluster-wide memory barrier
+__device__ __forceinline__ void mbar_arrive_cluster_tmem(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are counted on the barrier of the
 // pair's leader CTA (peer bit of the barrier address cleared)
