@@ -334,9 +334,16 @@ def run_own(args):
     extra = [
         {"kernel": "dggm_fwd_kernel (DGGM + branch sum)", "bound": "hbm", "achieved": dggm_gbs, "peak": pkv["hbm_gbs"],
          "unit": "GB/s", "frac": dggm_gbs / pkv["hbm_gbs"], "bytes_per_frame": BYTES_DGGM},
-        {"kernel": "conv_gemm_kernel (3 DSAM stages)", "bound": "tensor", "achieved": dsam_tf,
-         "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": dsam_tf / pkv["tf_burst"]},
+        {"kernel": "dsam_fwd_kernel x2 + conv_gemm_2cta_kernel (3 DSAM stages, useful FLOPs: K padding not counted)",
+         "bound": "tensor", "achieved": dsam_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": dsam_tf / pkv["tf_burst"]},
     ]
+    if "ratio_front" in kt:
+        # stem GEMM (K = 147 useful taps of 256) + 192->128 + 128->64 + 64->128 point-wise layers
+        front_tf = 2.0 * (147 * 192 + 192 * 128 + 128 * 64 + 64 * 128) * H * W * B / kt["ratio_front"] / 1e12
+        front_gbs = (128 + 256) * H * W * B / kt["ratio_front"] / 1e9
+        extra.append({"kernel": "ratio_front_kernel (stem + feature fusion + attention, one kernel)", "bound": "tensor",
+                      "achieved": front_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": front_tf / pkv["tf_burst"],
+                      "hbm_gbs": front_gbs, "note": "latency-bound: TMEM->register->TMEM hand-offs between the four chained GEMMs"})
     if rank == 0:
         if old_affinity:
             os.sched_setaffinity(0, old_affinity)          # the CPU baseline uses every host core
@@ -460,6 +467,9 @@ class PerKernel:
             out["ratio_conv3x3"] = self._time(lambda: Fn.conv_gemm(
                 ws["x4"], (B, H, W, 128), 1, pk["w5"], pk["sl5"], 64, B, (H, W), box, 256, pk["sh5"],
                 act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), tile_order=1, conv3x3_reuse=(box == (128, 1))))
+            if rp.use_fused_front:
+                out["ratio_front"] = self._time(lambda: Fn.ratio_front(
+                    ws["stem"], pk["w1"], pk["w2"], pk["w3"], pk["w4"], pk["sh1"], pk["sh2"], pk["sh3"], pk["sh4"], ws["x4"], box))
             ratios = rp(pv[:, 3:6])
             levels = [tuple(f.shape[2:]) for f in feats[:3]]
             out["depth_decompose"] = self._time(lambda: Fn.depth_decompose(ratios.reshape(-1), levels, depth3=pv[:, 3:6]))

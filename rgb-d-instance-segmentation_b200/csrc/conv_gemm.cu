@@ -682,7 +682,7 @@ dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             tc::mbar_init(&ctl->a_empty[r], 1);                // released by the pair's MMAs (multicast commit)
         }
         for (int g = 0; g < 2; ++g) {
-            tc::mbar_init(&ctl->masked_full[g], 2 * 128);      // mask threads of BOTH CTAs (counted in the leader)
+            tc::mbar_init(&ctl->masked_full[g], 2 * 4);        // one arrive per mask warp of BOTH CTAs (counted in the leader)
             tc::mbar_init(&ctl->masked_empty[g], 1);           // multicast commit
             tc::mbar_init(&ctl->tmem_full[g], 1);
             tc::mbar_init(&ctl->tmem_empty[g], 2 * kEpiThreads);
@@ -808,7 +808,8 @@ dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(dst + (((j + row) & 7) << 4)) = keep ? v[j] : zero;
                     }
                     tc::fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's smem reads
-                    tc::mbar_arrive_cluster(masked_full_remote[g]);
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive_cluster(masked_full_remote[g]);   // 1 cluster-scope release per warp, not 32
                     if (++g == 2) { g = 0; pg ^= 1; }
                     if (++r == kDsamRaw) { r = 0; pr ^= 1; }
                 }
