@@ -192,6 +192,26 @@ int rgbd_ratio_tail(const float* pool_sums, int pool_stride, int cell_pixels, co
                     const float* conv_shift, const float* const* fc_w_host, const float* const* fc_b_host, float out_min,
                     float out_max, float* gap_ws, float* ratio_out, int B, rgbd_stream_t stream);
 
+/* ---- instance post-processing: HuggingFace `post_process_instance_segmentation(outputs, threshold,
+ * target_sizes, return_binary_maps=True)` as the reference calls it (mask2former/utils/model_essential_part.py:86-91,
+ * mask2former/predictor.py:34-36, 701-703) for a batch of images that share one target size.
+ * class_logits (B,Q,C1) fp32 (C1 = classes + "no object"), mask_logits (B,Q,h,w) fp32.  Per image the Q best (query,
+ * label) candidates are taken in a DEFINED order (class score descending, flattened index ascending on ties; HF's
+ * topk(sorted=False) order is unspecified), scored with the mean sigmoid of their 384x384-upsampled mask, kept when the
+ * target-size mask is non-empty and score >= threshold, and written compactly in candidate order:
+ * out_masks (B,Q,Ht,Wt) bytes 0/1 (first out_count[b] planes valid), out_labels / out_scores / out_query (B,Q),
+ * out_count (B), out_segmentation (B,Ht,Wt) int32 or NULL: -1 background, else the id of the last kept segment covering
+ * the pixel (HF paints in list order).  Ht = Wt = 384 reproduces target_sizes=None. */
+size_t rgbd_postprocess_workspace_bytes(int B, int Q);
+int rgbd_postprocess_instances(const float* class_logits, const float* mask_logits, int B, int Q, int C1, int h, int w,
+                               int Ht, int Wt, float threshold, void* workspace, uint8_t* out_masks, int* out_labels,
+                               float* out_scores, int* out_query, int* out_count, int* out_segmentation,
+                               rgbd_stream_t stream);
+/* Pairwise mask IoU, the core of the evaluator's segm mAP (mask2former/utils/model_essential_part.py:111-170 through
+ * torchmetrics): pred (P,pixels) and gt (G,pixels) bytes 0/1 -> iou (P,G) fp32 (0 where the union is empty). */
+int rgbd_mask_iou(const uint8_t* pred_masks, const uint8_t* gt_masks, int P, int G, long long pixels, float* iou,
+                  rgbd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

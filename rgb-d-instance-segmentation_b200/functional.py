@@ -451,3 +451,66 @@ def ratio_tail(pool: torch.Tensor, cell_pixels: int, conv_w: torch.Tensor, conv_
                               ratio.data_ptr(), B, _stream()), "rgbd_ratio_tail")
     _count(2)
     return ratio
+
+
+# ------------------------------------------------------------------------------------------------
+# instance post-processing
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class InstanceBatch:
+    """Device-side result of ``post_process_instances``; entries ``[b, :count[b]]`` are valid, in candidate order."""
+    masks: torch.Tensor                # (B,Q,Ht,Wt) u8 0/1
+    labels: torch.Tensor               # (B,Q) i32
+    scores: torch.Tensor               # (B,Q) f32 (unrounded)
+    query: torch.Tensor                # (B,Q) i32  query index of the segment
+    count: torch.Tensor                # (B,) i32
+    segmentation: Optional[torch.Tensor]   # (B,Ht,Wt) i32, -1 background
+
+
+def post_process_instances(class_logits: torch.Tensor, mask_logits: torch.Tensor, threshold: float = 0.5,
+                           target_size: Optional[Tuple[int, int]] = None, want_segmentation: bool = True) -> InstanceBatch:
+    """HF ``post_process_instance_segmentation`` (model_essential_part.py:86-91) for a batch sharing one target size,
+    without host synchronisation.  ``target_size=None`` keeps HF's 384x384 maps."""
+    lib = _lib.load()
+    _req(class_logits, "class_queries_logits", torch.float32)
+    _req(mask_logits, "masks_queries_logits", torch.float32)
+    if class_logits.dim() != 3 or mask_logits.dim() != 4 or class_logits.shape[:2] != mask_logits.shape[:2]:
+        raise RgbdB200Error("post_process_instances: expected (B,Q,C+1) class logits and (B,Q,h,w) mask logits")
+    B, Q, C1 = class_logits.shape
+    h, w = mask_logits.shape[2:]
+    Ht, Wt = (384, 384) if target_size is None else (int(target_size[0]), int(target_size[1]))
+    dev = class_logits.device
+    ws = torch.empty(max(int(lib.rgbd_postprocess_workspace_bytes(B, Q)), 16), device=dev, dtype=torch.uint8)
+    masks = torch.empty(B, Q, Ht, Wt, device=dev, dtype=torch.uint8)
+    labels = torch.empty(B, Q, device=dev, dtype=torch.int32)
+    scores = torch.empty(B, Q, device=dev, dtype=torch.float32)
+    query = torch.empty(B, Q, device=dev, dtype=torch.int32)
+    count = torch.empty(B, device=dev, dtype=torch.int32)
+    seg = torch.empty(B, Ht, Wt, device=dev, dtype=torch.int32) if want_segmentation else None
+    check(lib.rgbd_postprocess_instances(class_logits.data_ptr(), mask_logits.data_ptr(), B, Q, C1, h, w, Ht, Wt,
+                                         float(threshold), ws.data_ptr(), masks.data_ptr(), labels.data_ptr(),
+                                         scores.data_ptr(), query.data_ptr(), count.data_ptr(),
+                                         seg.data_ptr() if seg is not None else None, _stream()),
+          "rgbd_postprocess_instances")
+    _count(5 if want_segmentation else 4)
+    return InstanceBatch(masks, labels, scores, query, count, seg)
+
+
+def mask_iou(pred_masks: torch.Tensor, gt_masks: torch.Tensor) -> torch.Tensor:
+    """(P,H,W) x (G,H,W) 0/1 masks (bool or uint8) -> (P,G) float32 IoU."""
+    lib = _lib.load()
+    if pred_masks.dtype == torch.bool:
+        pred_masks = pred_masks.view(torch.uint8)
+    if gt_masks.dtype == torch.bool:
+        gt_masks = gt_masks.view(torch.uint8)
+    _req(pred_masks, "pred_masks", torch.uint8)
+    _req(gt_masks, "gt_masks", torch.uint8)
+    if pred_masks.dim() != 3 or gt_masks.dim() != 3 or pred_masks.shape[1:] != gt_masks.shape[1:]:
+        raise RgbdB200Error("mask_iou: expected (P,H,W) and (G,H,W) masks of one size")
+    P, G = pred_masks.shape[0], gt_masks.shape[0]
+    iou = torch.zeros(P, G, device=pred_masks.device, dtype=torch.float32)
+    if P and G:
+        check(lib.rgbd_mask_iou(pred_masks.data_ptr(), gt_masks.data_ptr(), P, G, pred_masks.shape[1] * pred_masks.shape[2],
+                                iou.data_ptr(), _stream()), "rgbd_mask_iou")
+        _count(1)
+    return iou

@@ -1,0 +1,126 @@
+"""GPU parity of the instance post-processing kernels (csrc/postproc.cu) through the C ABI: against the CPU oracle
+(oracle/postproc.py, pinned to HuggingFace's routine by tests/golden/postproc.npz) and against those goldens directly."""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+pytestmark = pytest.mark.gpu
+
+from oracle import postproc as OP                                  # noqa: E402
+from oracle.make_golden_postproc import CASES, synth_outputs       # noqa: E402
+from test_postproc_oracle import match_segments                    # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def fn():
+    import rgbd_b200  # noqa: F401
+    from rgbd_b200 import functional
+    functional._lib.load()
+    return functional
+
+
+def check_against_oracle(fn, cls, masks, thr, tgt):
+    B = cls.shape[0]
+    r = fn.post_process_instances(cls.cuda(), masks.cuda(), thr, tgt)
+    ref = OP.post_process_instance_segmentation(cls, masks, thr, None if tgt is None else [tgt] * B)
+    count = r.count.cpu().tolist()
+    for b in range(B):
+        n = len(ref[b]["labels"])
+        assert count[b] == n, (b, count[b], n)
+        assert r.labels[b, :n].cpu().tolist() == ref[b]["labels"].tolist()          # same defined order
+        assert r.query[b, :n].cpu().tolist() == ref[b]["query"].tolist()
+        assert (r.labels[b, n:] == -1).all()
+        if n:
+            got_s, ref_s = r.scores[b, :n].cpu().double(), ref[b]["scores"].double()
+            assert float(((got_s - ref_s).abs() / ref_s.abs().clamp_min(1e-12)).max()) < 1e-5
+            assert torch.equal(r.masks[b, :n].cpu().bool(), ref[b]["masks"])         # bit-exact binary maps
+        assert torch.equal(r.segmentation[b].cpu(), ref[b]["segmentation"])
+    return r, ref
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_postprocess_matches_oracle_and_hf_golden(fn, case):
+    name, seed, B, Q, C, hw, thr, tgt = case
+    cls, masks = synth_outputs(seed, B, Q, C, *hw)
+    r, _ = check_against_oracle(fn, cls, masks, thr, tgt)
+    count = r.count.cpu().tolist()
+    for b in range(B):
+        n = count[b]
+        match_segments({"masks": r.masks[b, :n].cpu().bool().numpy(), "labels": r.labels[b, :n].cpu(),
+                        "scores": r.scores[b, :n].cpu()}, b, name)
+
+
+def test_postprocess_model_sized_batch(fn):
+    """Mask2Former-sized outputs: 100 queries, 48 classes, 120x160 logits -> 480x640 maps, batch 3."""
+    cls, masks = synth_outputs(21, 3, 100, 48, 120, 160)
+    r, ref = check_against_oracle(fn, cls, masks, 0.05, (480, 640))
+    assert sum(r.count.cpu().tolist()) > 10
+    # painted map == id of the last kept segment covering the pixel
+    n0 = int(r.count[0])
+    seg = torch.full((480, 640), -1, dtype=torch.int32)
+    for j in range(n0):
+        seg[r.masks[0, j].cpu().bool()] = j
+    assert torch.equal(seg, r.segmentation[0].cpu())
+
+
+def test_hf_style_entry_point_and_evaluator_mirror(fn):
+    from rgbd_b200 import postprocess as PP
+    name, seed, B, Q, C, hw, thr, tgt = CASES[0]
+    cls, masks = synth_outputs(seed, B, Q, C, *hw)
+    outs = SimpleNamespace(class_queries_logits=cls.cuda(), masks_queries_logits=masks.cuda())
+    res = PP.post_process_instance_segmentation(outs, threshold=thr, target_sizes=[tgt] * B, return_binary_maps=True)
+    for b, r in enumerate(res):
+        info = r["segments_info"]
+        assert [s["id"] for s in info] == list(range(len(info))) and all(s["was_fused"] is False for s in info)
+        match_segments({"masks": r["segmentation"].cpu().bool().numpy(), "labels": np.array([s["label_id"] for s in info]),
+                        "scores": np.array([s["score"] for s in info])}, b, name)
+    # mixed target sizes are grouped; the painted map variant returns (Ht,Wt) float maps with -1 background
+    res2 = PP.post_process_instance_segmentation(outs, threshold=thr, target_sizes=[(480, 640), (120, 160)])
+    assert res2[0]["segmentation"].shape == (480, 640) and res2[1]["segmentation"].shape == (120, 160)
+    ref1 = OP.post_process_image(cls[1], masks[1], thr, (120, 160))
+    assert torch.equal(res2[1]["segmentation"].cpu().int(), ref1["segmentation"])
+    with pytest.raises(ValueError):
+        PP.post_process_instance_segmentation(outs, return_coco_annotation=True, return_binary_maps=True)
+    with pytest.raises(Exception):
+        PP.post_process_instance_segmentation(SimpleNamespace(class_queries_logits=cls, masks_queries_logits=masks))
+    ev = PP.postprocess_prediction_batch((cls.cuda(), masks.cuda()), [tgt] * B, threshold=thr)
+    assert ev[0]["masks"].dtype == torch.bool and ev[0]["masks"].shape[1:] == tgt
+    assert len(ev[0]["labels"]) == len(res[0]["segments_info"])
+
+
+@pytest.mark.parametrize("P,G,hw", [(5, 3, (48, 64)), (7, 7, (33, 31)), (0, 4, (16, 16)), (20, 12, (480, 640))])
+def test_mask_iou_and_map(fn, P, G, hw):
+    from rgbd_b200 import postprocess as PP
+    rs = np.random.RandomState(P * 10 + G)
+    base = rs.rand(max(G, 1), *hw) > 0.6
+    pred = np.stack([np.logical_xor(base[k % max(G, 1)], rs.rand(*hw) > 0.9) for k in range(P)]) if P else np.zeros((0,) + hw, bool)
+    gt = base[:G]
+    if P:
+        pred[0] = False                              # empty prediction: IoU 0
+    iou = fn.mask_iou(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda()).cpu().numpy()
+    ref = OP.mask_iou(pred, gt)
+    assert iou.shape == (P, G)
+    assert np.abs(iou - ref).max(initial=0.0) < 1e-6
+    # non-16-byte-aligned view (scalar path)
+    if P and hw[1] > 4:
+        iou2 = fn.mask_iou(torch.from_numpy(pred[:, :, 1:]).cuda().contiguous(), torch.from_numpy(gt[:, :, 1:]).cuda().contiguous())
+        assert np.abs(iou2.cpu().numpy() - OP.mask_iou(pred[:, :, 1:], gt[:, :, 1:])).max() < 1e-6
+    if P and G:
+        preds = [{"masks": torch.from_numpy(pred), "labels": torch.from_numpy(rs.randint(0, 3, P)),
+                  "scores": torch.from_numpy(rs.rand(P))}]
+        tgts = [{"masks": torch.from_numpy(gt), "labels": torch.from_numpy(rs.randint(0, 3, G))}]
+        m = PP.MaskAP()
+        m.update(preds, tgts)
+        got = m.compute()
+        want = OP.average_precision([{"labels": preds[0]["labels"].numpy(), "scores": preds[0]["scores"].numpy()}],
+                                    [{"labels": tgts[0]["labels"].numpy()}], [ref])
+        for k in ("map", "map_50", "map_75"):
+            assert abs(got[k] - want[k]) < 1e-6, (k, got, want)
