@@ -187,7 +187,9 @@ __global__ void __launch_bounds__(256) postproc_finalize_kernel(PostGeom g, floa
         const float mask_score = sum / ((float)cnt + 1e-6f);
         const float pred = sel_score[(size_t)b * g.Q + j] * mask_score;
         s_pred[j] = pred;
-        s_keep[j] = (any_target[(size_t)b * g.Q + j] != 0u && pred >= threshold) ? 1 : 0;
+        // nearest UPsampling visits every grid point, so the target mask is empty iff the grid mask is
+        const bool nonempty = (g.Ht >= kGrid && g.Wt >= kGrid) ? cnt != 0u : any_target[(size_t)b * g.Q + j] != 0u;
+        s_keep[j] = (nonempty && pred >= threshold) ? 1 : 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -226,9 +228,16 @@ __global__ void __launch_bounds__(256) postproc_masks_kernel(const float* __rest
     if (p0 >= n_t) return;
     unsigned packed = 0;
     const int n = n_t - p0 < 4 ? n_t - p0 : 4;
+    int last_gy = -1, last_gx = -1;
+    float v = 0.f;
     for (int e = 0; e < n; ++e) {
         const int pt = p0 + e;
-        const float v = grid_logit(plane, g, nearest_src(pt / g.Wt, g.sy), nearest_src(pt % g.Wt, g.sx));
+        const int gy = nearest_src(pt / g.Wt, g.sy), gx = nearest_src(pt % g.Wt, g.sx);
+        if (gy != last_gy || gx != last_gx) {
+            v = grid_logit(plane, g, gy, gx);
+            last_gy = gy;
+            last_gx = gx;
+        }
         if (v > 0.f) {
             packed |= 1u << (8 * e);
             if (seg) atomicMax(seg + (size_t)b * n_t + pt, s);
@@ -368,7 +377,7 @@ extern "C" int rgbd_postprocess_instances(const float* class_logits, const float
     RGBD_CHECK_LAUNCH();
     RGBD_CHECK_CUDA(cudaMemsetAsync(any_target, 0, (size_t)B * Q * 4, s));
     const int n_chunk_grid = ceil_div(kGrid * kGrid, kChunk);
-    const int n_chunk_t = ceil_div(Ht * Wt, kChunk);
+    const int n_chunk_t = (Ht >= kGrid && Wt >= kGrid) ? 0 : ceil_div(Ht * Wt, kChunk);
     postproc_stats_kernel<<<dim3(n_chunk_grid + n_chunk_t, Q, B), 256, 0, s>>>(mask_logits, g, sel_query, n_chunk_grid, part_cnt,
                                                                                part_sum, any_target);
     RGBD_CHECK_LAUNCH();
