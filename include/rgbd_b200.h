@@ -192,6 +192,14 @@ int rgbd_ratio_tail(const float* pool_sums, int pool_stride, int cell_pixels, co
                     const float* conv_shift, const float* const* fc_w_host, const float* const* fc_b_host, float out_min,
                     float out_max, float* gap_ws, float* ratio_out, int B, rgbd_stream_t stream);
 
+/* Feature-based window-ratio predictor of the version 0.1.3 / 0.3.0 models (`RatioPredictor.forward`, CM:860-898): global
+ * average pool of n_levels NCHW fp32 depth-feature maps (B,C_l,HW_l), concatenation, MLP sum(C_l)->64->32->1 with ReLU,
+ * ratio = out_min + (out_max - out_min) * sigmoid.  feats_host / C_host / HW_host / fc_*_host are HOST arrays (of device
+ * pointers where they hold pointers); pooled_ws: B*sum(C_l) floats; ratio_out: B floats. */
+int rgbd_ratio_from_features(int n_levels, const float* const* feats_host, const int* C_host, const int* HW_host, int B,
+                             const float* const* fc_w_host, const float* const* fc_b_host, float out_min, float out_max,
+                             float* pooled_ws, float* ratio_out, rgbd_stream_t stream);
+
 /* ---- instance post-processing: HuggingFace `post_process_instance_segmentation(outputs, threshold,
  * target_sizes, return_binary_maps=True)` as the reference calls it (mask2former/utils/model_essential_part.py:86-91,
  * mask2former/predictor.py:34-36, 701-703) for a batch of images that share one target size.

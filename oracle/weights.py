@@ -85,6 +85,24 @@ def ratio_weights(seed: int, c_in: int = 3) -> Dict[str, torch.Tensor]:
     return w
 
 
+def ratio_feat_weights(seed: int, channels=(96, 192, 384, 768)) -> Dict[str, torch.Tensor]:
+    """``RatioPredictor`` (CM:823-858): fc_layers.{0,2,4} = Linear sum(C)->64->32->1."""
+    rs = np.random.RandomState(seed)
+    w: Dict[str, torch.Tensor] = {}
+    w.update(linear_weights(rs, "fc_layers.0", 64, int(sum(channels))))
+    w.update(linear_weights(rs, "fc_layers.2", 32, 64))
+    w.update(linear_weights(rs, "fc_layers.4", 1, 32))
+    return w
+
+
+def guidance_weights_feature_ratio(seed: int, channels=(96, 192, 384, 768)) -> Dict[str, torch.Tensor]:
+    """Parameters of the version 0.1.3 / 0.3.0 hot path: ``guidance_weights`` with the feature-based ratio predictor."""
+    w = {k: v for k, v in guidance_weights(seed, channels).items() if not k.startswith("ratio_predictor.")}
+    for k, v in ratio_feat_weights(seed + 11, channels).items():
+        w["ratio_predictor." + k] = v
+    return w
+
+
 def guidance_weights(seed: int, channels=(96, 192, 384, 768)) -> Dict[str, torch.Tensor]:
     """All hot-path parameters with the pixel-level module's prefixes (CM:123-134)."""
     w: Dict[str, torch.Tensor] = {}

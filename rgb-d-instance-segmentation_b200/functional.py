@@ -453,6 +453,29 @@ def ratio_tail(pool: torch.Tensor, cell_pixels: int, conv_w: torch.Tensor, conv_
     return ratio
 
 
+def ratio_from_features(feats: Sequence[torch.Tensor], fc_w: Sequence[torch.Tensor], fc_b: Sequence[torch.Tensor],
+                        out_min: float, out_max: float) -> torch.Tensor:
+    """K6: ``RatioPredictor.forward`` (CM:860-898) -- GAP of every depth feature map, concat, 3-layer MLP -> (B,1)."""
+    lib = _lib.load()
+    feats = [_req(f.contiguous(), "depth feature map", torch.float32) for f in feats]
+    B = feats[0].shape[0]
+    for t in (*fc_w, *fc_b):
+        _req(t, "ratio predictor parameter", torch.float32)
+    c_total = sum(f.shape[1] for f in feats)
+    if fc_w[0].shape != (64, c_total) or fc_w[1].shape != (32, 64) or fc_w[2].shape != (1, 32):
+        raise RgbdB200Error("ratio_from_features: fc layers must be (64, sum C), (32, 64), (1, 32)")
+    pooled = torch.empty(B, c_total, device=feats[0].device, dtype=torch.float32)
+    ratio = torch.empty(B, 1, device=feats[0].device, dtype=torch.float32)
+    cs = (C.c_int * len(feats))(*[f.shape[1] for f in feats])
+    hws = (C.c_int * len(feats))(*[f.shape[2] * f.shape[3] for f in feats])
+    check(lib.rgbd_ratio_from_features(len(feats), ptr_array([f.data_ptr() for f in feats]), cs, hws, B,
+                                       ptr_array([t.data_ptr() for t in fc_w]), ptr_array([t.data_ptr() for t in fc_b]),
+                                       float(out_min), float(out_max), pooled.data_ptr(), ratio.data_ptr(), _stream()),
+          "rgbd_ratio_from_features")
+    _count(2)
+    return ratio
+
+
 # ------------------------------------------------------------------------------------------------
 # instance post-processing (SURVEY 8f-3)
 # ------------------------------------------------------------------------------------------------

@@ -581,6 +581,34 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
                              self.output_min, self.output_max)
 
 
+class RatioPredictor(nn.Module):
+    """CM:823-898: window_size_ratio from the depth ENCODER's feature maps (versions 0.1.3 / 0.3.0): global average
+    pool per scale, concat, Linear sum(C)->64->32->1 with ReLU, ``output_min + span * sigmoid`` -> (B,1).  Forward only
+    (the reference consumes the result through ``.item()``, CM:275)."""
+
+    def __init__(self, depth_channels_list: List[int]):
+        super().__init__()
+        self.depth_channels_list = list(depth_channels_list)
+        self.num_scales = len(self.depth_channels_list)
+        self.fc_layers = nn.Sequential(nn.Linear(sum(self.depth_channels_list), 64), nn.ReLU(inplace=True),
+                                       nn.Linear(64, 32), nn.ReLU(inplace=True), nn.Linear(32, 1))
+        self.global_avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.output_min = 0.01
+        self.output_max = 0.5
+        self.sigmoid = nn.Sigmoid()
+
+    def forward(self, depth_feature_maps: List[torch.Tensor]) -> torch.Tensor:
+        assert len(depth_feature_maps) == self.num_scales, \
+            f"Expected {self.num_scales} depth feature maps, but got {len(depth_feature_maps)}"
+        for i, f in enumerate(depth_feature_maps):
+            assert f.shape[1] == self.depth_channels_list[i], \
+                f"Expected {self.depth_channels_list[i]} channels for scale {i}, but got {f.shape[1]}"
+        fcs = [self.fc_layers[i] for i in (0, 2, 4)]
+        return Fn.ratio_from_features([f.detach().float() for f in depth_feature_maps],
+                                      [l.weight.detach().float().contiguous() for l in fcs],
+                                      [l.bias.detach().float().contiguous() for l in fcs], self.output_min, self.output_max)
+
+
 # =====================================================================================================
 # v0.4.0 wiring
 # =====================================================================================================

@@ -11,7 +11,9 @@ from torch import Tensor
 from transformers.models.mask2former.modeling_mask2former import (Mask2FormerPixelLevelModule,
                                                                   Mask2FormerPixelLevelModuleOutput)
 
-from .modules import (DepthGradientInjectionResidual, DSAModule, EnhancedDepthImageRatioPredictor,
+from transformers.backbone_utils import load_backbone
+
+from .modules import (DepthGradientInjectionResidual, DSAModule, EnhancedDepthImageRatioPredictor, RatioPredictor,
                       depth_guidance_forward)
 
 
@@ -20,7 +22,9 @@ class CustomMask2FormerPixelLevelModule(Mask2FormerPixelLevelModule):
 
     DGGM_ONLY = ("0.0.3", "0.0.4", "0.0.5", "0.0.6")     # CM:73-75, 156-163: 7-channel input, DGGM on the raw features
     DSAM_ONLY = ("0.1.2",)                                # CM:97-100, 234-256: 6-channel input, DSAM cascade, ratio 0.1
-    SUPPORTED = ("0.0.0", "0.4.0") + DGGM_ONLY + DSAM_ONLY
+    DEPTH_ENCODER = ("0.1.3", "0.3.0")                    # CM:101-116, 258-322: second backbone on the depth image feeds the
+    #                                                       feature-based RatioPredictor; 0.3.0 then applies DGGM to the DSAM result
+    SUPPORTED = ("0.0.0", "0.4.0") + DGGM_ONLY + DSAM_ONLY + DEPTH_ENCODER
 
     def __init__(self, config, version: str = "0.4.0"):
         super().__init__(config)
@@ -32,18 +36,24 @@ class CustomMask2FormerPixelLevelModule(Mask2FormerPixelLevelModule):
         c = list(self.encoder.channels)
         if version == "0.4.0":
             self.ratio_predictor = EnhancedDepthImageRatioPredictor(3)
-        if version == "0.4.0" or version in self.DSAM_ONLY:
+        if version in self.DEPTH_ENCODER:
+            self.depth_encoder = load_backbone(config)
+            self.ratio_predictor = RatioPredictor(depth_channels_list=c)
+        if version == "0.4.0" or version in self.DSAM_ONLY or version in self.DEPTH_ENCODER:
             self.dsam0 = DSAModule(in_channels=c[0], out_channels=c[1], num_depth_regions=3)
             self.dsam1 = DSAModule(in_channels=c[1], out_channels=c[2], num_depth_regions=3)
             self.dsam2 = DSAModule(in_channels=c[2], out_channels=c[3], num_depth_regions=3)
-        if version == "0.4.0" or version in self.DGGM_ONLY:
+        if version in ("0.4.0", "0.3.0") or version in self.DGGM_ONLY:
             self.depth_gradient_injection = DepthGradientInjectionResidual(c, 3)
 
-    def _dsam_only(self, pixel_values: Tensor, feats):
-        """CM:234-256 batched: cp[k+1] += dsam_k(cp[k], gray(depth), window_size_ratio=0.1) with no detach."""
+    def _dsam_only(self, pixel_values: Tensor, feats, ratio=None):
+        """CM:234-256 (ratio 0.1) / CM:258-290 (predicted ratios) batched: cp[k+1] += dsam_k(cp[k], gray(depth), ratio)
+        with no detach."""
         from . import functional as Fn
         B = pixel_values.shape[0]
-        ratio = torch.full((B,), 0.1, device=pixel_values.device, dtype=torch.float32)       # CM:647 default argument
+        if ratio is None:
+            ratio = torch.full((B,), 0.1, device=pixel_values.device, dtype=torch.float32)   # CM:647 default argument
+        ratio = ratio.reshape(-1).float().contiguous()
         cp = [f.float().contiguous() for f in feats]
         dec = Fn.depth_decompose(ratio, [tuple(f.shape[2:]) for f in cp[:3]], depth3=pixel_values[:, 3:6].float())
         for k, dsam in enumerate((self.dsam0, self.dsam1, self.dsam2)):
@@ -60,6 +70,13 @@ class CustomMask2FormerPixelLevelModule(Mask2FormerPixelLevelModule):
                 [f.float() for f in color_feature_map], pixel_values[:, 3:6].float(), pixel_values[:, 6:7].float())
         elif self.version in self.DSAM_ONLY:
             backbone_features = self._dsam_only(pixel_values, color_feature_map)
+        elif self.version in self.DEPTH_ENCODER:
+            depth_feature_map = self.depth_encoder(pixel_values[:, 3:6, :, :]).feature_maps              # CM:262, 299
+            predicted_ratios = self.ratio_predictor(list(depth_feature_map))                             # CM:266, 304
+            backbone_features = self._dsam_only(pixel_values, color_feature_map, predicted_ratios)       # CM:272-290
+            if self.version == "0.3.0":                                                                  # CM:322
+                backbone_features = self.depth_gradient_injection(backbone_features, pixel_values[:, 6:9].float(),
+                                                                  pixel_values[:, 9:10].float())
         else:
             backbone_features = depth_guidance_forward(
                 self.ratio_predictor, (self.dsam0, self.dsam1, self.dsam2), self.depth_gradient_injection,

@@ -748,4 +748,41 @@ def test_other_version_branches(mods, golden_dir, version):
     for i in range(4):
         assert rel_err(fused[i], torch.from_numpy(g[f"fused{i}"])) < tol, (version, i)
     with pytest.raises(NotImplementedError):
-        pixel_level.CustomMask2FormerPixelLevelModule(cfg, version="0.3.0")
+        pixel_level.CustomMask2FormerPixelLevelModule(cfg, version="0.2.0")
+
+
+@pytest.mark.parametrize("version", ["0.1.3", "0.3.0"])
+def test_depth_encoder_version_branches(mods, golden_dir, version):
+    """Versions with a second (depth) encoder and the feature-based RatioPredictor (CM:258-322)."""
+    from rgbd_b200 import pixel_level
+    g = np.load(os.path.join(golden_dir, f"wiring_v{version.replace('.', '')}.npz"))
+    cfg = pixel_level.swin_tiny_mask2former_config(num_labels=8)
+    plm = pixel_level.CustomMask2FormerPixelLevelModule(cfg, version=version)
+    own = dict(plm.named_children())
+    assert "depth_encoder" in own and isinstance(plm.ratio_predictor, mods.RatioPredictor)
+    assert ("depth_gradient_injection" in own) == (version == "0.3.0")
+    w = OW.guidance_weights_feature_ratio(seed=700)
+    missing = plm.load_state_dict({k: v for k, v in w.items() if k.split(".")[0] in own}, strict=False)
+    assert not missing.unexpected_keys
+    plm.cuda().eval()
+    pvs = []
+    for j in range(2):
+        rgb, d = synthetic.synth_rgbd_u8(80 + j, 64, 96, "nyu")
+        pvs.append(synthetic.assemble_pixel_values(rgb, d, O.gradient_features))
+    pv = torch.from_numpy(np.stack(pvs)).cuda()
+    feats = [torch.from_numpy(g[f"feat{i}"]).cuda() for i in range(4)]
+    dfeats = [torch.from_numpy(g[f"dfeat{i}"]).cuda() for i in range(4)]
+    with torch.no_grad():
+        ratios = plm.ratio_predictor(dfeats)
+        assert ratios.shape == (2, 1)
+        assert rel_err(ratios, torch.from_numpy(g["ratios"])) < 1e-5
+        fused = plm._dsam_only(pv, feats, ratios)
+        if version == "0.3.0":
+            fused = plm.depth_gradient_injection(fused, pv[:, 6:9], pv[:, 9:10])
+        for i in range(4):
+            assert rel_err(fused[i], torch.from_numpy(g[f"fused{i}"])) < BF16_TOL, (version, i)
+        # the whole module (stock encoders + decoder around the hot path) runs end to end
+        out = plm(pv if version == "0.3.0" else pv[:, 0:6].contiguous())
+        assert out.decoder_last_hidden_state.shape[0] == 2 and torch.isfinite(out.decoder_last_hidden_state).all()
+    with pytest.raises(AssertionError):
+        plm.ratio_predictor(dfeats[:3])

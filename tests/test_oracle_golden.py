@@ -169,3 +169,24 @@ def test_other_version_wiring(golden_dir, version):
     for i in range(4):
         ref = g[f"fused{i}"]
         np.testing.assert_allclose(fused[i].numpy(), ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("version", ["0.1.3", "0.3.0"])
+def test_depth_encoder_version_wiring(golden_dir, version):
+    """CM:258-322: feature-based RatioPredictor -> DSAM cascade (-> DGGM on the result for 0.3.0), reference goldens."""
+    g = _load(golden_dir, f"wiring_v{version.replace('.', '')}.npz")
+    w = OW.guidance_weights_feature_ratio(seed=700)
+    pvs = []
+    for j in range(2):
+        rgb, d = synthetic.synth_rgbd_u8(80 + j, 64, 96, "nyu")
+        pvs.append(synthetic.assemble_pixel_values(rgb, d, O.gradient_features))
+    pv = torch.from_numpy(np.stack(pvs))
+    feats = [torch.from_numpy(g[f"feat{i}"]) for i in range(4)]
+    dfeats = [torch.from_numpy(g[f"dfeat{i}"]) for i in range(4)]
+    ratios = O.ratio_from_features_forward({k[len("ratio_predictor."):]: v for k, v in w.items()
+                                            if k.startswith("ratio_predictor.")}, dfeats)
+    np.testing.assert_allclose(ratios.numpy(), g["ratios"], rtol=1e-5)
+    fused = O.version_forward(version, w, pv, feats, dfeats)
+    for i in range(4):
+        ref = g[f"fused{i}"]
+        np.testing.assert_allclose(fused[i].numpy(), ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
