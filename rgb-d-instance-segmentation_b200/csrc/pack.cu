@@ -15,7 +15,8 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256) dsam_pack_kernel(const float* __restrict__ feat, const uint8_t* __restrict__ codes,
+// Variant for many segments per pixel (pre-masked five-fold layouts): shared-memory transpose, 128-byte coalesced rows.
+__global__ void __launch_bounds__(256) dsam_pack_tile_kernel(const float* __restrict__ feat, const uint8_t* __restrict__ codes,
                                                         __nv_bfloat16* __restrict__ out, int C, int Cp, int H, int W,
                                                         int n_seg, int masked_segs, int split, int hi_lo) {
     // CTA: 32 pixels of one row x 64 channels.  Load NCHW coalesced along x, transpose through shared memory, then each
@@ -70,6 +71,73 @@ __global__ void __launch_bounds__(256) dsam_pack_kernel(const float* __restrict_
     }
 }
 
+// CTA = 128 consecutive pixels (flattened y*W + x) x 64 channels; warp w owns channels 8w..8w+7, lane L pixels 4L..4L+3.
+// Loads: 8 x 128-bit per thread, each fully coalesced along the NCHW plane (512 B per warp and channel).  Stores: every
+// thread writes its pixel's 8 channels as one 16-byte piece per segment; the 8 warps of the CTA fill the 128-byte
+// channels-last rows of the same pixels together, so the L2 merges them into whole lines.  No shared memory, no syncs.
+template <bool VEC>
+__global__ void __launch_bounds__(256) dsam_pack_kernel(const float* __restrict__ feat, const uint8_t* __restrict__ codes,
+                                                        __nv_bfloat16* __restrict__ out, int C, int Cp, int H, int W,
+                                                        int n_seg, int masked_segs, int split, int hi_lo) {
+    const int img = blockIdx.z;
+    const int c0 = blockIdx.y * 64 + (threadIdx.x >> 5) * 8;
+    const int plane = H * W;
+    const int p0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+    if (p0 >= plane || c0 >= Cp) return;
+    float f[8][4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int cc = c0 + k;
+        if (cc < C) {
+            const float* src = feat + ((size_t)img * C + cc) * plane + p0;
+            if (VEC) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+                f[k][0] = v.x; f[k][1] = v.y; f[k][2] = v.z; f[k][3] = v.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) f[k][e] = p0 + e < plane ? __ldg(src + e) : 0.f;
+            }
+        } else {
+            f[k][0] = f[k][1] = f[k][2] = f[k][3] = 0.f;
+        }
+    }
+    const int H2 = split ? (H + 1) / 2 : H, W2 = split ? (W + 1) / 2 : W;
+    const int n_par = split ? 4 : 1;
+    const int mult = hi_lo ? 2 : 1;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int p = p0 + e;
+        if (p >= plane) break;
+        const int y = p / W, x = p - y * W;
+        const unsigned code = masked_segs ? codes[(size_t)img * plane + p] : 0u;
+        const int par = split ? ((y & 1) * 2 + (x & 1)) : 0;
+        const int yy = split ? (y >> 1) : y, xx = split ? (x >> 1) : x;
+        // hi = bf16(v); lo = bf16(v - hi): with W = W_hi + W_lo the three products hi*W_hi + lo*W_hi + hi*W_lo carry ~16
+        // mantissa bits through the bf16 tensor cores (the "fp32" precision mode of DSAModule)
+        uint4 v, vl;
+        {
+            uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
+            uint32_t* pl = reinterpret_cast<uint32_t*>(&vl);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k][e], f[2 * k + 1][e]);
+                pv[k] = *reinterpret_cast<uint32_t*>(&h);
+                const float2 hf = __bfloat1622float2(h);
+                __nv_bfloat162 l = __floats2bfloat162_rn(f[2 * k][e] - hf.x, f[2 * k + 1][e] - hf.y);
+                pl[k] = *reinterpret_cast<uint32_t*>(&l);
+            }
+        }
+        for (int s = 0; s < n_seg; ++s) {
+            const bool keep = s >= masked_segs || ((code >> s) & 1u);
+            const size_t pln = ((size_t)img * n_seg * mult + s * mult) * n_par + par;
+            const size_t off = ((pln * H2 + yy) * W2 + xx) * Cp + c0;
+            *reinterpret_cast<uint4*>(out + off) = keep ? v : zero;
+            if (hi_lo) *reinterpret_cast<uint4*>(out + off + (size_t)n_par * H2 * W2 * Cp) = keep ? vl : zero;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) ratio_stem_pack_kernel(const float* __restrict__ depth, long long bs, long long cs,
                                                               __nv_bfloat16* __restrict__ out, int H, int W) {
     // thread = (pixel, piece): piece p of 8 holds taps dx = 2*(p&3), 2*(p&3)+1 of row j = p>>2  (8 bf16 = 16 bytes);
@@ -112,9 +180,21 @@ extern "C" int rgbd_dsam_pack(const float* feat, const uint8_t* codes, void* out
     RGBD_CHECK_ARG(C_pad >= C && C_pad % 32 == 0, "dsam_pack: C_pad %d must be a multiple of 32 and >= C", C_pad);
     RGBD_CHECK_ARG(n_seg >= 1 && n_seg <= 8 && masked_segs >= 0 && masked_segs <= n_seg && masked_segs <= 4,
                    "dsam_pack: bad segment counts");
-    dim3 grid(ceil_div(W, 32) * ceil_div(C_pad, 64), H, B);
-    dsam_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feat, codes, (__nv_bfloat16*)out_bf16, C, C_pad, H, W, n_seg,
-                                                            masked_segs, parity_split ? 1 : 0, hi_lo ? 1 : 0);
+    if (n_seg > 2) {
+        dim3 grid_t(ceil_div(W, 32) * ceil_div(C_pad, 64), H, B);
+        dsam_pack_tile_kernel<<<grid_t, 256, 0, (cudaStream_t)stream>>>(feat, codes, (__nv_bfloat16*)out_bf16, C, C_pad, H, W, n_seg,
+                                                                       masked_segs, parity_split ? 1 : 0, hi_lo ? 1 : 0);
+        RGBD_CHECK_LAUNCH();
+        return RGBD_OK;
+    }
+    dim3 grid(ceil_div(H * W, 128), ceil_div(C_pad, 64), B);
+    const bool vec = (H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
+    if (vec)
+        dsam_pack_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, codes, (__nv_bfloat16*)out_bf16, C, C_pad, H, W, n_seg,
+                                                                      masked_segs, parity_split ? 1 : 0, hi_lo ? 1 : 0);
+    else
+        dsam_pack_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, codes, (__nv_bfloat16*)out_bf16, C, C_pad, H, W, n_seg,
+                                                                       masked_segs, parity_split ? 1 : 0, hi_lo ? 1 : 0);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }
