@@ -498,6 +498,10 @@ class PerKernel:
             if rp.use_fused_front:
                 out["ratio_front"] = self._time(lambda: Fn.ratio_front(
                     ws["stem"], pk["w1"], pk["w2"], pk["w3"], pk["w4"], pk["sh1"], pk["sh2"], pk["sh3"], pk["sh4"], ws["x4"], box))
+            out["ratio_stem_pack"] = self._time(lambda: Fn.ratio_stem_pack(pv[:, 3:6], ws["stem"]))
+            out["ratio_tail"] = self._time(lambda: Fn.ratio_tail(
+                ws["pool"], (H // 4) * (W // 4), pk["w6"], pk["sc6"], pk["sh6"], [pk[f"fw{j}"] for j in range(4)],
+                [pk[f"fb{j}"] for j in range(4)], rp.output_min, rp.output_max))
             ratios = rp(pv[:, 3:6])
             levels = [tuple(f.shape[2:]) for f in feats[:3]]
             out["depth_decompose"] = self._time(lambda: Fn.depth_decompose(ratios.reshape(-1), levels, depth3=pv[:, 3:6]))

@@ -3,55 +3,69 @@
 //   pooled sums / cell size -> Conv3x3(256->512, pad 1) on the 4x4 map -> BN (folded) -> ReLU -> global
 //   average pool -> Linear 512->128->64->32->1 with ReLU (Dropout is identity in eval) ->
 //   ratio = 0.01 + 0.49 * sigmoid(raw).
-// 19 MFLOP per image: fp32 CUDA cores, two launches (conv split over 8 channel groups per image so
-// B*8 CTAs run; then one CTA per image for the MLP).
+// 19 MFLOP per image: fp32 CUDA cores, two launches (conv: CTAs of 16 output channels x 4 images so the weights are read
+// once per 4 images; then one CTA per image for the MLP).
 #include "common.cuh"
 #include "rgbd_b200.h"
 
 namespace {
 
-constexpr int kCin = 256, kCout = 512, kGroup = 64;
+constexpr int kCin = 256, kCout = 512;
+constexpr int kOcPerCta = 16, kImgPerCta = 4, kIcChunk = 32;
+constexpr int kXImgStride = kIcChunk * 36 + 8;     // +8 floats: the 4 images of a warp land in different banks
 
+// CTA = 16 output channels x 4 images: the 16 x 2304 weights (147 KB) are read once per 4 images, coalesced, through a
+// shared-memory chunk of 32 input channels; thread = (oc, image, output row) computes the 4 outputs of its row.
 __global__ void __launch_bounds__(256) ratio_tail_conv_kernel(const float* __restrict__ pool, int pool_stride,
                                                               float inv_cell, const float* __restrict__ w,
                                                               const float* __restrict__ scale,
-                                                              const float* __restrict__ shift, float* __restrict__ gap) {
-    __shared__ float x[kCin][6][6];
-    const int b = blockIdx.x, g = blockIdx.y;
-    for (int i = threadIdx.x; i < kCin * 36; i += blockDim.x) {
-        const int ic = i / 36, r = (i % 36) / 6, c = i % 6;
-        float v = 0.f;
-        if (r >= 1 && r <= 4 && c >= 1 && c <= 4)
-            v = pool[((size_t)b * 16 + (r - 1) * 4 + (c - 1)) * pool_stride + ic] * inv_cell;
-        x[ic][r][c] = v;
-    }
-    __syncthreads();
-    const int oc = g * kGroup + (threadIdx.x >> 2);
-    const int oy = threadIdx.x & 3;
+                                                              const float* __restrict__ shift, float* __restrict__ gap, int B) {
+    __shared__ float xs[kImgPerCta * kXImgStride];          // [img][ic][6][6] zero-padded 4x4 maps
+    __shared__ float ws[kOcPerCta * kIcChunk * 9];          // [oc][ic][3][3]
+    const int oc0 = blockIdx.x * kOcPerCta, b0 = blockIdx.y * kImgPerCta;
+    const int oy = threadIdx.x & 3, im = (threadIdx.x >> 2) & 3, ol = threadIdx.x >> 4;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* wr = w + (size_t)oc * kCin * 9;
-    for (int ic = 0; ic < kCin; ++ic) {
-        float wk[9];
+    for (int ic0 = 0; ic0 < kCin; ic0 += kIcChunk) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kImgPerCta * kIcChunk * 36; i += blockDim.x) {
+            const int c = i % 6, r = (i / 6) % 6, ic = (i / 36) % kIcChunk, bi = i / (36 * kIcChunk);
+            float v = 0.f;
+            if (r >= 1 && r <= 4 && c >= 1 && c <= 4 && b0 + bi < B)
+                v = pool[((size_t)(b0 + bi) * 16 + (r - 1) * 4 + (c - 1)) * pool_stride + ic0 + ic] * inv_cell;
+            xs[bi * kXImgStride + ic * 36 + r * 6 + c] = v;
+        }
+        for (int i = threadIdx.x; i < kOcPerCta * kIcChunk * 9; i += blockDim.x) {
+            const int o = i / (kIcChunk * 9), r = i % (kIcChunk * 9);
+            ws[i] = __ldg(w + ((size_t)(oc0 + o) * kCin + ic0) * 9 + r);
+        }
+        __syncthreads();
+        const float* xr = xs + im * kXImgStride + oy * 6;
+        const float* wr = ws + ol * kIcChunk * 9;
+#pragma unroll 4
+        for (int ic = 0; ic < kIcChunk; ++ic) {
+            float wk[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) wk[k] = __ldg(wr + ic * 9 + k);
+            for (int k = 0; k < 9; ++k) wk[k] = wr[ic * 9 + k];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            float row[6];
+            for (int ky = 0; ky < 3; ++ky) {
+                float row[6];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) row[c] = x[ic][oy + ky][c];
+                for (int c = 0; c < 6; ++c) row[c] = xr[ic * 36 + ky * 6 + c];
 #pragma unroll
-            for (int ox = 0; ox < 4; ++ox)
+                for (int ox = 0; ox < 4; ++ox)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) acc[ox] = fmaf(wk[ky * 3 + kx], row[ox + kx], acc[ox]);
+                    for (int kx = 0; kx < 3; ++kx) acc[ox] = fmaf(wk[ky * 3 + kx], row[ox + kx], acc[ox]);
+            }
         }
     }
+    const int oc = oc0 + ol;
     const float sc = scale[oc], sh = shift[oc];
     float s = 0.f;
 #pragma unroll
     for (int ox = 0; ox < 4; ++ox) s += fmaxf(fmaf(acc[ox], sc, sh), 0.f);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (oy == 0) gap[(size_t)b * kCout + oc] = s * (1.0f / 16.0f);
+    if (oy == 0 && b0 + im < B) gap[(size_t)(b0 + im) * kCout + oc] = s * (1.0f / 16.0f);
 }
 
 __device__ __forceinline__ void fc_layer(const float* __restrict__ w, const float* __restrict__ bias, const float* in,
@@ -70,7 +84,7 @@ __device__ __forceinline__ void fc_layer(const float* __restrict__ w, const floa
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(128) ratio_tail_mlp_kernel(const float* __restrict__ gap, const float* w0, const float* b0,
+__global__ void __launch_bounds__(512) ratio_tail_mlp_kernel(const float* __restrict__ gap, const float* w0, const float* b0,
                                                              const float* w1, const float* b1, const float* w2,
                                                              const float* b2, const float* w3, const float* b3,
                                                              float out_min, float out_span, float* __restrict__ ratio) {
@@ -99,10 +113,10 @@ extern "C" int rgbd_ratio_tail(const float* pool_sums, int pool_stride, int cell
     RGBD_CHECK_ARG(B >= 1 && cell_pixels >= 1 && pool_stride >= kCin, "ratio_tail: bad geometry");
     for (int i = 0; i < 4; ++i) RGBD_CHECK_ARG(fc_w[i] && fc_b[i], "ratio_tail: null fc layer %d", i);
     cudaStream_t s = (cudaStream_t)stream;
-    ratio_tail_conv_kernel<<<dim3(B, kCout / kGroup), 256, 0, s>>>(pool_sums, pool_stride, 1.0f / (float)cell_pixels, conv_w,
-                                                                   conv_scale, conv_shift, gap_ws);
+    ratio_tail_conv_kernel<<<dim3(kCout / kOcPerCta, ceil_div(B, kImgPerCta)), 256, 0, s>>>(
+        pool_sums, pool_stride, 1.0f / (float)cell_pixels, conv_w, conv_scale, conv_shift, gap_ws, B);
     RGBD_CHECK_LAUNCH();
-    ratio_tail_mlp_kernel<<<B, 128, 0, s>>>(gap_ws, fc_w[0], fc_b[0], fc_w[1], fc_b[1], fc_w[2], fc_b[2], fc_w[3], fc_b[3],
+    ratio_tail_mlp_kernel<<<B, 512, 0, s>>>(gap_ws, fc_w[0], fc_b[0], fc_w[1], fc_b[1], fc_w[2], fc_b[2], fc_w[3], fc_b[3],
                                             out_min, out_max - out_min, ratio_out);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
