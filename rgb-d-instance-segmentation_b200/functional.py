@@ -152,7 +152,8 @@ def gradient_features(depth: torch.Tensor, n_rep: int = 3, invalid_value: float 
 
 
 def pack_pixel_values(rgb_u8: torch.Tensor, depth_u8: torch.Tensor, out: Optional[torch.Tensor] = None,
-                      mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225),
+                      mean=(0.48500001430511475, 0.4560000002384186, 0.4059999883174896),
+                      std=(0.2290000021457672, 0.2239999920129776, 0.22499999403953552),   # preprocessor_config.json
                       rescale_factor: float = 0.00392156862745098, invalid_value: float = 0.0) -> torch.Tensor:
     """Front-end of ``map_10channel_case2`` (DL:386-425) on device: uint8 colour (B,H,W,3) + uint8 depth (B,H,W), already
     at the model resolution -> ``pixel_values`` (B,10,H,W) float32."""

@@ -13,8 +13,11 @@ from typing import Callable, Tuple
 
 import numpy as np
 
-IMAGE_MEAN = np.array([0.485, 0.456, 0.406], dtype=np.float32)
-IMAGE_STD = np.array([0.229, 0.224, 0.225], dtype=np.float32)
+# image_mean / image_std exactly as the reference's checkpoint stores them (mask2former/checkpoints/standard/
+# preprocessor_config.json).  They are float32-rounded ImageNet statistics; std[1] is 0.2239999920129776, ONE ULP BELOW
+# float32(0.224) -- using the decimal 0.224 changes 27 % of the normalised green/depth values by one ulp.
+IMAGE_MEAN = np.array([0.48500001430511475, 0.4560000002384186, 0.4059999883174896], dtype=np.float32)
+IMAGE_STD = np.array([0.2290000021457672, 0.2239999920129776, 0.22499999403953552], dtype=np.float32)
 
 
 def synth_rgbd_u8(frame_idx: int, height: int = 480, width: int = 640, kind: str = "nyu"

@@ -75,6 +75,16 @@ def test_gradient_features_into_pixel_values_view(fn):
     assert float(pv[:, :6].abs().max()) == 0.0
 
 
+def test_pack_pixel_values_matches_huggingface_processor_golden(fn, golden_dir):
+    """Device front-end against the outputs of the real HF processor + reference mapper (tests/golden/frontend.npz)."""
+    g = np.load(os.path.join(golden_dir, "frontend.npz"))
+    for j in range(3):
+        rgb = torch.from_numpy(g[f"f{j}.rgb"])[None].cuda().contiguous()
+        depth = torch.from_numpy(g[f"f{j}.depth"])[None].cuda().contiguous()
+        pv = fn.pack_pixel_values(rgb, depth)
+        assert torch.equal(pv[0].cpu(), torch.from_numpy(g[f"f{j}.pixel_values"])), j
+
+
 def test_pack_pixel_values_front_end_bit_exact(fn):
     """uint8 colour + uint8 depth -> the whole 10-channel model input (DL:386-425), bit-exact with the numpy/HF path."""
     rgbs, ds, refs = [], [], []

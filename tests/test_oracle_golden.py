@@ -190,3 +190,16 @@ def test_depth_encoder_version_wiring(golden_dir, version):
     for i in range(4):
         ref = g[f"fused{i}"]
         np.testing.assert_allclose(fused[i].numpy(), ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+
+
+def test_front_end_matches_huggingface_processor_and_reference_mapper(golden_dir):
+    """DL:386-425: pixel_values of map_10channel_case2 from the real HF (PIL backend) processor with the reference's
+    preprocessor_config.json + the reference's calculate_gradient_features, against the restatement the synthetic input
+    builder and the device front-end share (bit-exact, including the checkpoint's one-ulp-low std[1])."""
+    g = _load(golden_dir, "frontend.npz")
+    assert np.array_equal(g["image_mean"].astype(np.float32), synthetic.IMAGE_MEAN)
+    assert np.array_equal(g["image_std"].astype(np.float32), synthetic.IMAGE_STD)
+    assert float(g["rescale_factor"]) == synthetic.RESCALE_FACTOR
+    for j in range(3):
+        pv = synthetic.assemble_pixel_values(g[f"f{j}.rgb"], g[f"f{j}.depth"], O.gradient_features)
+        assert pv.dtype == np.float32 and np.array_equal(pv, g[f"f{j}.pixel_values"])
