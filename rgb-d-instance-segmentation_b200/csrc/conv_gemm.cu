@@ -809,7 +809,9 @@ dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     }
                     tc::fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's smem reads
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive_cluster(masked_full_remote[g]);   // 1 cluster-scope release per warp, not 32
+                    // one arrive per warp, CTA-scope release: the copies are read by THIS CTA's tensor core (async proxy,
+                    // ordered by the fence above); the remote barrier only signals the leader's MMA thread
+                    if (lane == 0) tc::mbar_arrive_cluster_tmem(masked_full_remote[g]);
                     if (++g == 2) { g = 0; pg ^= 1; }
                     if (++r == kDsamRaw) { r = 0; pr ^= 1; }
                 }
