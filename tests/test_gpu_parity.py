@@ -797,3 +797,9 @@ def test_depth_encoder_version_branches(mods, golden_dir, version):
         assert out.decoder_last_hidden_state.shape[0] == 2 and torch.isfinite(out.encoder_last_hidden_state).all()
     with pytest.raises(AssertionError):
         plm.ratio_predictor(dfeats[:3])
+    with pytest.raises(AssertionError):                      # CM:876: channel count per scale
+        plm.ratio_predictor([dfeats[1], dfeats[1], dfeats[2], dfeats[3]])
+    # odd plane sizes take the scalar (unaligned) pooling path
+    odd = [torch.randn(3, c, 5, 7, device="cuda") for c in plm.ratio_predictor.depth_channels_list]
+    w_rp = {k[len("ratio_predictor."):]: v for k, v in w.items() if k.startswith("ratio_predictor.")}
+    assert rel_err(plm.ratio_predictor(odd), O.ratio_from_features_forward(w_rp, [t.cpu() for t in odd])) < 1e-5

@@ -124,3 +124,26 @@ def test_mask_iou_and_map(fn, P, G, hw):
                                     [{"labels": tgts[0]["labels"].numpy()}], [ref])
         for k in ("map", "map_50", "map_75"):
             assert abs(got[k] - want[k]) < 1e-6, (k, got, want)
+
+
+def test_postprocess_argument_errors_and_edge_shapes(fn):
+    from rgbd_b200._lib import RgbdB200Error
+    cls, masks = synth_outputs(3, 1, 4, 3, 8, 8)
+    with pytest.raises(RgbdB200Error):                       # CPU tensors: no CPU path
+        fn.post_process_instances(cls, masks)
+    with pytest.raises(RgbdB200Error):                       # query counts disagree
+        fn.post_process_instances(cls.cuda(), masks[:, :3].contiguous().cuda())
+    big_cls = torch.zeros(1, 200, 50, device="cuda")         # 200 * 49 candidates > the in-shared-memory sort
+    with pytest.raises(RgbdB200Error, match="candidates"):
+        fn.post_process_instances(big_cls, torch.zeros(1, 200, 4, 4, device="cuda"))
+    with pytest.raises(RgbdB200Error):
+        fn.mask_iou(torch.zeros(2, 4, 4, dtype=torch.uint8, device="cuda"), torch.zeros(2, 4, 5, dtype=torch.uint8, device="cuda"))
+    # every query background -> nothing kept, map stays -1
+    r = fn.post_process_instances(cls.cuda(), torch.full_like(masks, -3.0).cuda(), 0.0, (20, 24))
+    assert r.count.cpu().tolist() == [0] and bool((r.segmentation == -1).all()) and bool((r.labels == -1).all())
+    # a single query / single class, 1x1 logits, non-multiple-of-4 target
+    one = fn.post_process_instances(torch.tensor([[[2.0, -1.0]]], device="cuda"), torch.full((1, 1, 1, 1), 4.0, device="cuda"),
+                                    0.5, (5, 7))
+    ref = OP.post_process_image(torch.tensor([[2.0, -1.0]]), torch.full((1, 1, 1), 4.0), 0.5, (5, 7))
+    assert one.count.cpu().tolist() == [1] and bool(one.masks[0, 0].all())
+    assert abs(float(one.scores[0, 0]) - float(ref["scores"][0])) < 1e-6
