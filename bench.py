@@ -359,9 +359,10 @@ def run_own(args):
          "bound": "tensor", "achieved": dsam_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": dsam_tf / pkv["tf_burst"]},
     ]
     if "ratio_front" in kt:
+        compact = model.ratio_predictor._compact(H, W)
         # stem GEMM (K = 147 useful taps of 256) + 192->128 + 128->64 + 64->128 point-wise layers
         front_tf = 2.0 * (147 * 192 + 192 * 128 + 128 * 64 + 64 * 128) * H * W * B / kt["ratio_front"] / 1e12
-        front_gbs = (128 + 256) * H * W * B / kt["ratio_front"] / 1e9
+        front_gbs = ((16 if compact else 128) + 256) * H * W * B / kt["ratio_front"] / 1e9
         extra.append({"kernel": "ratio_front_kernel (stem + feature fusion + attention, one kernel)", "bound": "tensor",
                       "achieved": front_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": front_tf / pkv["tf_burst"],
                       "hbm_gbs": front_gbs, "note": "latency-bound: TMEM->register->TMEM hand-offs between the four chained GEMMs"})
@@ -495,10 +496,13 @@ class PerKernel:
             out["ratio_conv3x3"] = self._time(lambda: Fn.conv_gemm(
                 ws["x4"], (B, H, W, 128), 1, pk["w5"], pk["sl5"], 64, B, (H, W), box, 256, pk["sh5"],
                 act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), tile_order=1, conv3x3_reuse=(box == (128, 1))))
+            compact = rp._compact(H, W)
             if rp.use_fused_front:
                 out["ratio_front"] = self._time(lambda: Fn.ratio_front(
-                    ws["stem"], pk["w1"], pk["w2"], pk["w3"], pk["w4"], pk["sh1"], pk["sh2"], pk["sh3"], pk["sh4"], ws["x4"], box))
-            out["ratio_stem_pack"] = self._time(lambda: Fn.ratio_stem_pack(pv[:, 3:6], ws["stem"]))
+                    ws["stem"], pk["w1c"] if compact else pk["w1"], pk["w2"], pk["w3"], pk["w4"], pk["sh1"], pk["sh2"], pk["sh3"],
+                    pk["sh4"], ws["x4"], box))
+            out["ratio_stem_pack"] = self._time(lambda: (Fn.ratio_stem_pack_compact if compact else Fn.ratio_stem_pack)(
+                pv[:, 3:6], ws["stem"]))
             out["ratio_tail"] = self._time(lambda: Fn.ratio_tail(
                 ws["pool"], (H // 4) * (W // 4), pk["w6"], pk["sc6"], pk["sh6"], [pk[f"fw{j}"] for j in range(4)],
                 [pk[f"fb{j}"] for j in range(4)], rp.output_min, rp.output_max))

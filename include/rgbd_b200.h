@@ -184,7 +184,15 @@ int rgbd_ratio_chain(const void* x1_bf16, const void* w2_bf16, const void* w3_bf
  * shift; the other arguments as for rgbd_ratio_chain. */
 int rgbd_ratio_front(const void* r_bf16, const void* w1_bf16, const void* w2_bf16, const void* w3_bf16, const void* w4_bf16,
                      const float* sh1, const float* sh2, const float* sh3, const float* sh4, void* out_bf16, int B, int H,
-                     int W, int bx, int by, rgbd_stream_t stream);
+                     int W, int bx, int by, int compact_operand, rgbd_stream_t stream);
+/* compact_operand = 1: r_bf16 is the output of rgbd_ratio_stem_pack_compact, E (B,2,H+6,Wp,4) bf16 with
+ * Wp = rgbd_ratio_stem_compact_width(W): E[b][s][r][xx][c] = depth[b][c][r-3][xx+s-3] (zero outside, c == 3 zero) -- the
+ * depth image channels-last in two copies shifted by one pixel; the kernel reads it through sliding-window tensor maps
+ * (free im2col along x), so the 128-byte-per-pixel row-im2col tensor is never written.  Then w1 is (192, 224) with K
+ * ordered (dy 7, dx 8, c 4); needs bx = 128, by = 1 and an even W. */
+int rgbd_ratio_stem_compact_width(int W);
+int rgbd_ratio_stem_pack_compact(const float* depth3, long long batch_stride, long long channel_stride, void* out_bf16, int B,
+                                 int H, int W, rgbd_stream_t stream);
 
 /* Tail of EnhancedDepthImageRatioPredictor.forward (CM:1473-1485): pooled sums -> conv3x3 256->512 + folded BN +
  * ReLU -> GAP -> MLP -> 0.01 + 0.49*sigmoid.  conv_w (512,256,3,3) fp32; fc_w_host/fc_b_host: 4 layers. */

@@ -171,7 +171,46 @@ __global__ void __launch_bounds__(256) ratio_stem_pack_kernel(const float* __res
     reinterpret_cast<uint4*>(out + (((size_t)img * (H + 6) + r) * W + x) * 64)[piece] = w;
 }
 
+// Compact stem operand E[img][s][r][xx][4] = depth[img][c][r-3][xx+s-3] (0 outside / for c == 3): the depth image itself,
+// channels-last with zero borders, in two copies shifted by one pixel (ratio_front.cu reads 64-byte sliding windows of it).
+__global__ void __launch_bounds__(256) ratio_stem_pack_compact_kernel(const float* __restrict__ depth, long long bs, long long cs,
+                                                                      __nv_bfloat16* __restrict__ out, int H, int W, int Wp) {
+    const int img = blockIdx.z, r = blockIdx.y;
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xx >= Wp) return;
+    const float* d = depth + (size_t)img * bs;
+    const int y = r - 3;
+    const bool yok = y >= 0 && y < H;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int xs = xx + s - 3;
+        const bool ok = yok && xs >= 0 && xs < W;
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = ok ? __ldg(d + c * cs + (size_t)y * W + xs) : 0.f;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], 0.f);
+        uint2 w;
+        w.x = *reinterpret_cast<uint32_t*>(&h0);
+        w.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(out + ((((size_t)img * 2 + s) * (H + 6) + r) * Wp + xx) * 4) = w;
+    }
+}
+
 }  // namespace
+
+extern "C" int rgbd_ratio_stem_compact_width(int W) { return W + 8; }
+
+extern "C" int rgbd_ratio_stem_pack_compact(const float* depth3, long long batch_stride, long long channel_stride, void* out_bf16,
+                                            int B, int H, int W, rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(depth3 && out_bf16, "ratio_stem_pack_compact: null pointer");
+    RGBD_CHECK_ARG(B >= 1 && H >= 1 && W >= 1, "ratio_stem_pack_compact: bad geometry");
+    const int Wp = rgbd_ratio_stem_compact_width(W);
+    dim3 grid(ceil_div(Wp, 256), H + 6, B);
+    ratio_stem_pack_compact_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(depth3, batch_stride, channel_stride,
+                                                                           (__nv_bfloat16*)out_bf16, H, W, Wp);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}
 
 extern "C" int rgbd_dsam_pack(const float* feat, const uint8_t* codes, void* out_bf16, int B, int C, int C_pad, int H, int W,
                               int n_seg, int masked_segs, int parity_split, int hi_lo, rgbd_stream_t stream) {

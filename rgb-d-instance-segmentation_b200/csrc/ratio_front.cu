@@ -25,13 +25,24 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kThreads = 640;                 // 4 control warps + 2 chains x 8 epilogue warps
 constexpr int kChainThreads = 256;            // epilogue threads per chain: two warps (column halves) per TMEM lane quarter
-constexpr int kStages = 4;                    // 16 KB slices of the row-im2col operand (one tile = 4 slices)
 constexpr int kSliceBytes = kBlockM * 128;    // 16 KB
-constexpr int kW1Half = 4 * 96 * 128;         // per CTA: 96 of 192 rows x 4 K-slices      48 KB
+// Stem operand, two layouts (template parameter EM):
+//  EM = false  R (B,H+6,W,64): row-im2col written by ratio_stem_pack (128 B per pixel and row); 4 K-slices of 64 per tile
+//  EM = true   E (B,2,H+6,Wp,4): the depth image itself, channels-last with c padded to 4 (8 B per pixel) and zero borders,
+//              in two copies shifted by one pixel.  The 8 dx taps x 4 channels of a pixel are 64 CONTIGUOUS bytes of E, so a
+//              tensor map whose pixel dimension has a 16-byte stride (two pixels) under a 64-byte inner box is the im2col
+//              along x for free (overlapping strides are legal for tiled TMA: profiles/micro/tma_overlap.cu); copy 0 serves
+//              the even pixels, copy 1 the odd ones (16-byte alignment).  7 K-blocks of 32 (one per row tap, 64-byte swizzle),
+//              tile rows 0..63 = even pixels, 64..127 = odd pixels; the output store uses pixel-stride-2 tensor maps.
+//              HBM: the 1.27 GB R tensor (batch 32) is replaced by 0.16 GB that stays in L2.
+template <bool EM> struct StemCfg;
+template <> struct StemCfg<false> { static constexpr int kBlocks = 4, kStageBytes = 16384, kStages = 4, kW1Block = 96 * 128, kMmaPerBlock = 4, kRowBytes = 128; };
+template <> struct StemCfg<true> { static constexpr int kBlocks = 7, kStageBytes = 8192, kStages = 9, kW1Block = 96 * 64, kMmaPerBlock = 2, kRowBytes = 64; };
+constexpr int kMaxStages = 12;
 constexpr int kW2Half = 3 * 64 * 128;         //          64 of 128 rows x 3 K-slices      24 KB
 constexpr int kW3Half = 2 * 32 * 128;         //          32 of  64 rows x 2 K-slices       8 KB
 constexpr int kW4Half = 1 * 64 * 128;         //          64 of 128 rows x 1 K-slice        8 KB
-constexpr int kWBytes = kW1Half + kW2Half + kW3Half + kW4Half;
+constexpr int kWRest = kW2Half + kW3Half + kW4Half;
 constexpr int kStashBytes = 2 * kSliceBytes;  // per chain: 128 pixels x 128 channels bf16 (f, then out)
 constexpr uint32_t kColQ = 384;
 
@@ -44,8 +55,8 @@ struct FrontParams {
 };
 
 struct alignas(16) FrontCtl {
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
     uint64_t w_full;
     uint64_t acc_full[2][4];      // [chain][GEMM 1..4]   multicast commit -> both CTAs
     uint64_t x_ready[2][3];       // [chain][after E1..E3] epilogue threads of BOTH CTAs (counted in the leader)
@@ -69,11 +80,16 @@ __device__ __forceinline__ void decode(const FrontParams& p, int t, int& img, in
     img = t / p.tiles_x;
 }
 
+template <bool EM>
 __global__ void __launch_bounds__(kThreads, 1)
-ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_w1,
-                   const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_w3,
-                   const __grid_constant__ CUtensorMap tmap_w4, const __grid_constant__ CUtensorMap tmap_out,
+ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_r1,
+                   const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
+                   const __grid_constant__ CUtensorMap tmap_w3, const __grid_constant__ CUtensorMap tmap_w4,
+                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out1,
                    const __grid_constant__ FrontParams p) {
+    using Cfg = StemCfg<EM>;
+    constexpr int kStages = Cfg::kStages, kStageBytes = Cfg::kStageBytes, kW1Half = Cfg::kBlocks * Cfg::kW1Block;
+    constexpr int kWBytes = kW1Half + kWRest;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* s_w1 = smem;
@@ -81,7 +97,7 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
     uint8_t* s_w3 = s_w2 + kW2Half;
     uint8_t* s_w4 = s_w3 + kW3Half;
     uint8_t* s_ring = s_w4 + kW4Half;
-    uint8_t* s_stash = s_ring + kStages * kSliceBytes;
+    uint8_t* s_stash = s_ring + kStages * kStageBytes;
     FrontCtl* ctl = reinterpret_cast<FrontCtl*>(s_stash + 2 * kStashBytes);
     float* s_sh1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + sizeof(FrontCtl));
     float* s_sh2 = s_sh1 + 192;
@@ -101,6 +117,8 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
     }
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmap_r);
+        if (EM) tc::prefetch_tmap(&tmap_r1);
+        if (EM) tc::prefetch_tmap(&tmap_out1);
         tc::prefetch_tmap(&tmap_w1);
         tc::prefetch_tmap(&tmap_w2);
         tc::prefetch_tmap(&tmap_w3);
@@ -138,7 +156,8 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
     if (warp == 0 && lane == 0) {
         // ================= TMA producer: resident weight halves, then the row-im2col slices =================
         if (leader) tc::mbar_expect_tx(&ctl->w_full, 2u * kWBytes);
-        for (int j = 0; j < 4; ++j) tc::tma_load_2d_2cta(s_w1 + j * (96 * 128), &tmap_w1, &ctl->w_full, j * 64, (int)rank * 96);
+        for (int j = 0; j < Cfg::kBlocks; ++j)
+            tc::tma_load_2d_2cta(s_w1 + j * Cfg::kW1Block, &tmap_w1, &ctl->w_full, j * (Cfg::kRowBytes / 2), (int)rank * 96);
         for (int j = 0; j < 3; ++j) tc::tma_load_2d_2cta(s_w2 + j * (64 * 128), &tmap_w2, &ctl->w_full, j * 64, (int)rank * 64);
         for (int j = 0; j < 2; ++j) tc::tma_load_2d_2cta(s_w3 + j * (32 * 128), &tmap_w3, &ctl->w_full, j * 64, (int)rank * 32);
         tc::tma_load_2d_2cta(s_w4, &tmap_w4, &ctl->w_full, 0, (int)rank * 64);
@@ -147,10 +166,16 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
         for (int n = 0; n < n_mine; ++n) {
             int img, ty, tx;
             decode(p, 2 * (u_begin + n) + (int)rank, img, ty, tx);
-            for (int j = 0; j < 4; ++j) {                       // slice j holds taps dy = 2j, 2j+1: rows y + 2j of R
+            for (int j = 0; j < Cfg::kBlocks; ++j) {
                 tc::mbar_wait(&ctl->empty[stage], phase ^ 1);
-                if (leader) tc::mbar_expect_tx(&ctl->full[stage], 2u * kSliceBytes);
-                tc::tma_load_4d_2cta(s_ring + stage * kSliceBytes, &tmap_r, &ctl->full[stage], 0, tx * p.BX, ty * p.BY + 2 * j, img);
+                if (leader) tc::mbar_expect_tx(&ctl->full[stage], 2u * kStageBytes);
+                if (EM) {       // row tap dy = j: E row y + j; even pixels from copy 0, odd pixels from copy 1 (64 pixel pairs each)
+                    tc::tma_load_4d_2cta(s_ring + stage * kStageBytes, &tmap_r, &ctl->full[stage], 0, tx * 64, ty + j, img);
+                    tc::tma_load_4d_2cta(s_ring + stage * kStageBytes + kStageBytes / 2, &tmap_r1, &ctl->full[stage], 0, tx * 64,
+                                         ty + j, img);
+                } else {        // slice j holds taps dy = 2j, 2j+1: rows y + 2j of R
+                    tc::tma_load_4d_2cta(s_ring + stage * kStageBytes, &tmap_r, &ctl->full[stage], 0, tx * p.BX, ty * p.BY + 2 * j, img);
+                }
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -168,20 +193,21 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
             tc::mbar_wait(&ctl->p_free[c], (uint32_t)((i & 1) ^ 1));      // acc4 of the chain's previous tile was read
             tc::tc_fence_after();
             const uint32_t d = tmem + (uint32_t)(c * 192);
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < Cfg::kBlocks; ++j) {
                 tc::mbar_wait(&ctl->full[stage], phase);
                 tc::tc_fence_after();
-                const uint64_t adesc = tc::make_kmajor_desc(tc::smem_u32(s_ring + stage * kSliceBytes), 128);
-                const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_w1 + j * (96 * 128)), 128);
+                const uint64_t adesc = tc::make_kmajor_desc(tc::smem_u32(s_ring + stage * kStageBytes), Cfg::kRowBytes);
+                const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_w1 + j * Cfg::kW1Block), Cfg::kRowBytes);
                 if (tc::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < Cfg::kMmaPerBlock; ++k)
                         tc::umma_bf16_2cta(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc192, (j | k) != 0);
                     tc::umma_commit_2cta(&ctl->empty[stage]);
-                    if (j == 3) tc::umma_commit_2cta(&ctl->acc_full[c][0]);
+                    if (j == Cfg::kBlocks - 1) tc::umma_commit_2cta(&ctl->acc_full[c][0]);
                 }
                 __syncwarp();
-                if (j != 3) tc::mbar_wait(&ctl->empty[stage], phase);     // throttle: at most one slice queued
+                // throttle: at most ~384 cycles of stem MMAs queued ahead of the other chain's short GEMMs
+                if (j != Cfg::kBlocks - 1 && (!EM || (j & 1))) tc::mbar_wait(&ctl->empty[stage], phase);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -364,8 +390,14 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
             tc::fence_proxy_async();
             asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
             if (issuer) {
-                for (int g2 = 0; g2 < 2; ++g2)
-                    tc::tma_store_4d(&tmap_out, stash + g2 * kSliceBytes, g2 * 64, tx * p.BX, ty * p.BY, img);
+                for (int g2 = 0; g2 < 2; ++g2) {
+                    if (EM) {   // tile rows 0..63 = even pixels, 64..127 = odd pixels: pixel-stride-2 maps
+                        tc::tma_store_4d(&tmap_out, stash + g2 * kSliceBytes, g2 * 64, tx * 64, ty, img);
+                        tc::tma_store_4d(&tmap_out1, stash + g2 * kSliceBytes + kSliceBytes / 2, g2 * 64, tx * 64, ty, img);
+                    } else {
+                        tc::tma_store_4d(&tmap_out, stash + g2 * kSliceBytes, g2 * 64, tx * p.BX, ty * p.BY, img);
+                    }
+                }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
@@ -417,24 +449,98 @@ bool make_weight_half_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, i
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// pixel-pair view: dims (inner, pairs, rows, images) with a 2-pixel stride in dimension 1 (overlapping when the inner
+// extent exceeds it: the sliding window over x)
+bool make_pair_map(EncodeTiledFn enc, CUtensorMap* m, const void* base, int inner_elems, int pixel_bytes, long long row_bytes,
+                   long long img_bytes, int pairs, int rows, int n, int box_inner, CUtensorMapSwizzle swz) {
+    cuuint64_t dims[4] = {(cuuint64_t)inner_elems, (cuuint64_t)pairs, (cuuint64_t)rows, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)(2 * pixel_bytes), (cuuint64_t)row_bytes, (cuuint64_t)img_bytes};
+    cuuint32_t box[4] = {(cuuint32_t)box_inner, 64, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool make_weight_half_map64(EncodeTiledFn enc, CUtensorMap* m, const void* base, int k, int n) {   // 32-element K blocks, SW64
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)n};
+    cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+    cuuint32_t box[2] = {32, (cuuint32_t)(n / 2)};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool EM>
+int launch_front(const CUtensorMap& m_r, const CUtensorMap& m_r1, const CUtensorMap& m_w1, const CUtensorMap& m_w2,
+                 const CUtensorMap& m_w3, const CUtensorMap& m_w4, const CUtensorMap& m_out, const CUtensorMap& m_out1,
+                 const FrontParams& p, cudaStream_t stream) {
+    using Cfg = StemCfg<EM>;
+    static int num_sms = 0;
+    const int smem_bytes = 1024 + Cfg::kBlocks * Cfg::kW1Block + kWRest + Cfg::kStages * Cfg::kStageBytes + 2 * kStashBytes +
+                           (int)sizeof(FrontCtl) + (192 + 128 + 64 + 128) * 4 + 64;
+    if (!num_sms) {
+        int dev = 0;
+        RGBD_CHECK_CUDA(cudaGetDevice(&dev));
+        RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(ratio_front_kernel<EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    }
+    const int n_units = (p.total_tiles + 1) / 2;
+    int clusters = num_sms / 2;
+    if (clusters > n_units) clusters = n_units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ratio_front_kernel<EM>, m_r, m_r1, m_w1, m_w2, m_w3, m_w4, m_out, m_out1, p));
+    return RGBD_OK;
+}
+
 }  // namespace
 
 extern "C" int rgbd_ratio_front(const void* r_bf16, const void* w1_bf16, const void* w2_bf16, const void* w3_bf16,
                                 const void* w4_bf16, const float* sh1, const float* sh2, const float* sh3, const float* sh4,
-                                void* out_bf16, int B, int H, int W, int bx, int by, rgbd_stream_t stream) {
+                                void* out_bf16, int B, int H, int W, int bx, int by, int compact_operand, rgbd_stream_t stream) {
     RGBD_CHECK_ARG(r_bf16 && w1_bf16 && w2_bf16 && w3_bf16 && w4_bf16 && sh1 && sh2 && sh3 && sh4 && out_bf16,
                    "ratio_front: null pointer");
     RGBD_CHECK_ARG(B >= 1 && H >= 1 && W >= 1, "ratio_front: bad geometry");
     RGBD_CHECK_ARG(bx >= 1 && by >= 1 && bx * by == kBlockM && bx <= 256 && by <= 256, "ratio_front: box must cover 128 pixels");
+    if (compact_operand)
+        RGBD_CHECK_ARG(bx == kBlockM && by == 1 && W % 2 == 0, "ratio_front: the compact operand needs a 128x1 box and an even width");
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
         rgbd_set_error("ratio_front: cuTensorMapEncodeTiled is not available from the driver");
         return RGBD_ERR_CUDA;
     }
-    CUtensorMap m_r, m_w1, m_w2, m_w3, m_w4, m_out;
-    if (!make_nhwc_map(enc, &m_r, r_bf16, 64, W, H + 6, B, bx, by) || !make_nhwc_map(enc, &m_out, out_bf16, 128, W, H, B, bx, by) ||
-        !make_weight_half_map(enc, &m_w1, w1_bf16, 256, 192) || !make_weight_half_map(enc, &m_w2, w2_bf16, 192, 128) ||
-        !make_weight_half_map(enc, &m_w3, w3_bf16, 128, 64) || !make_weight_half_map(enc, &m_w4, w4_bf16, 64, 128)) {
+    CUtensorMap m_r, m_r1, m_w1, m_w2, m_w3, m_w4, m_out, m_out1;
+    bool ok = make_weight_half_map(enc, &m_w2, w2_bf16, 192, 128) && make_weight_half_map(enc, &m_w3, w3_bf16, 128, 64) &&
+              make_weight_half_map(enc, &m_w4, w4_bf16, 64, 128);
+    if (compact_operand) {
+        const int Wp = rgbd_ratio_stem_compact_width(W);
+        const long long row_bytes = (long long)Wp * 8, plane = (long long)(H + 6) * row_bytes;
+        const uint8_t* e = reinterpret_cast<const uint8_t*>(r_bf16);
+        ok = ok && make_pair_map(enc, &m_r, e, 32, 8, row_bytes, 2 * plane, W / 2, H + 6, B, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
+             make_pair_map(enc, &m_r1, e + plane, 32, 8, row_bytes, 2 * plane, W / 2, H + 6, B, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
+             make_weight_half_map64(enc, &m_w1, w1_bf16, 224, 192);
+        uint8_t* o = reinterpret_cast<uint8_t*>(out_bf16);
+        ok = ok && make_pair_map(enc, &m_out, o, 128, 256, (long long)W * 256, (long long)H * W * 256, W / 2, H, B, 64,
+                                 CU_TENSOR_MAP_SWIZZLE_128B) &&
+             make_pair_map(enc, &m_out1, o + 256, 128, 256, (long long)W * 256, (long long)H * W * 256, W / 2, H, B, 64,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+        ok = ok && make_nhwc_map(enc, &m_r, r_bf16, 64, W, H + 6, B, bx, by) && make_nhwc_map(enc, &m_out, out_bf16, 128, W, H, B, bx, by) &&
+             make_weight_half_map(enc, &m_w1, w1_bf16, 256, 192);
+        m_r1 = m_r;
+        m_out1 = m_out;
+    }
+    if (!ok) {
         rgbd_set_error("ratio_front: cuTensorMapEncodeTiled failed");
         return RGBD_ERR_CUDA;
     }
@@ -446,28 +552,6 @@ extern "C" int rgbd_ratio_front(const void* r_bf16, const void* w1_bf16, const v
     RGBD_CHECK_ARG(total < (1ll << 30), "ratio_front: too many tiles");
     p.total_tiles = (int)total;
     p.sh1 = sh1; p.sh2 = sh2; p.sh3 = sh3; p.sh4 = sh4;
-    static int num_sms = 0;
-    const int smem_bytes = 1024 + kWBytes + kStages * kSliceBytes + 2 * kStashBytes + (int)sizeof(FrontCtl) +
-                           (192 + 128 + 64 + 128) * 4 + 64;
-    if (!num_sms) {
-        int dev = 0;
-        RGBD_CHECK_CUDA(cudaGetDevice(&dev));
-        RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        RGBD_CHECK_CUDA(cudaFuncSetAttribute(ratio_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    }
-    const int n_units = (p.total_tiles + 1) / 2;
-    int clusters = num_sms / 2;
-    if (clusters > n_units) clusters = n_units;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ratio_front_kernel, m_r, m_w1, m_w2, m_w3, m_w4, m_out, p));
-    return RGBD_OK;
+    return compact_operand ? launch_front<true>(m_r, m_r1, m_w1, m_w2, m_w3, m_w4, m_out, m_out1, p, (cudaStream_t)stream)
+                           : launch_front<false>(m_r, m_r1, m_w1, m_w2, m_w3, m_w4, m_out, m_out1, p, (cudaStream_t)stream);
 }

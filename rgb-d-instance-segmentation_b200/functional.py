@@ -387,18 +387,46 @@ def ratio_stem_pack(depth3: torch.Tensor, out: torch.Tensor) -> None:
     _count(1)
 
 
+def ratio_stem_compact_width(W: int) -> int:
+    return int(_lib.load().rgbd_ratio_stem_compact_width(int(W)))
+
+
+def ratio_stem_pack_compact(depth3: torch.Tensor, out: torch.Tensor) -> None:
+    """depth (B,3,H,W) fp32 -> E (B,2,H+6,Wp,4) bf16: channels-last depth with zero borders, two copies shifted by one pixel."""
+    lib = _lib.load()
+    _req(depth3, "depth", torch.float32, False)
+    _req(out, "compact stem operand", torch.bfloat16)
+    B, c3, H, W = depth3.shape
+    if out.shape != (B, 2, H + 6, ratio_stem_compact_width(W), 4):
+        raise RgbdB200Error("ratio_stem_pack_compact: out must be (B,2,H+6,Wp,4)")
+    bs, cs = _plane_strided(depth3, "depth")
+    check(lib.rgbd_ratio_stem_pack_compact(depth3.data_ptr(), bs, cs, out.data_ptr(), B, H, W, _stream()),
+          "rgbd_ratio_stem_pack_compact")
+    _count(1)
+
+
 def ratio_front(r: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor, w4: torch.Tensor, sh1: torch.Tensor,
                 sh2: torch.Tensor, sh3: torch.Tensor, sh4: torch.Tensor, out: torch.Tensor, box: Tuple[int, int]) -> None:
-    """K4a+K4b in one kernel.  r (B,H+6,W,64) bf16 row-im2col depth -> out (B,H,W,128) bf16: stem GEMM + BN + ReLU,
-    feature_fusion, attention and gating (CM:1458-1470) with every intermediate in tensor memory."""
+    """K4a+K4b in one kernel: stem GEMM + BN + ReLU, feature_fusion, attention and gating (CM:1458-1470) with every
+    intermediate in tensor memory -> out (B,H,W,128) bf16.  ``r`` is either the row-im2col tensor (B,H+6,W,64) with
+    w1 (192,256), or the compact operand (B,2,H+6,Wp,4) of ``ratio_stem_pack_compact`` with w1 (192,224)."""
     lib = _lib.load()
     _req(r, "r", torch.bfloat16)
     _req(out, "out", torch.bfloat16)
-    B, H6, W, c = r.shape
+    compact = r.dim() == 5
+    if compact:
+        B, two, H6, Wp, c = r.shape
+        W = out.shape[2]
+        ok = two == 2 and c == 4 and Wp == ratio_stem_compact_width(W)
+        k1 = 224
+    else:
+        B, H6, W, c = r.shape
+        ok = c == 64
+        k1 = 256
     H = H6 - 6
-    if c != 64 or H < 1 or out.shape != (B, H, W, 128):
-        raise RgbdB200Error("ratio_front: r must be (B,H+6,W,64) and out (B,H,W,128)")
-    for t, shp in ((w1, (192, 256)), (w2, (128, 192)), (w3, (64, 128)), (w4, (128, 64))):
+    if not ok or H < 1 or out.shape != (B, H, W, 128):
+        raise RgbdB200Error("ratio_front: r must be (B,H+6,W,64) or (B,2,H+6,Wp,4) and out (B,H,W,128)")
+    for t, shp in ((w1, (192, k1)), (w2, (128, 192)), (w3, (64, 128)), (w4, (128, 64))):
         _req(t, "front weight", torch.bfloat16)
         if tuple(t.shape) != shp:
             raise RgbdB200Error(f"ratio_front: weight shape {tuple(t.shape)} != {shp}")
@@ -408,7 +436,7 @@ def ratio_front(r: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, w3: torch.T
             raise RgbdB200Error("ratio_front: bad shift length")
     check(lib.rgbd_ratio_front(r.data_ptr(), w1.data_ptr(), w2.data_ptr(), w3.data_ptr(), w4.data_ptr(), sh1.data_ptr(),
                                sh2.data_ptr(), sh3.data_ptr(), sh4.data_ptr(), out.data_ptr(), B, H, W, box[0], box[1],
-                               _stream()), "rgbd_ratio_front")
+                               1 if compact else 0, _stream()), "rgbd_ratio_front")
     _count(1)
 
 

@@ -465,6 +465,7 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         self.output_min = 0.01
         self.output_max = 0.5
         self.sigmoid = nn.Sigmoid()
+        self.use_compact_operand = True    # fused front end reads the depth image itself (sliding-window TMA) when it can
         self.use_fused_front = True        # stem GEMM + chain in one kernel; False: stem GEMM, then ...
         self.use_fused_chain = True        # ... the fused chain, or (False) three separate GEMM launches (cross-checks)
         self._ver = _Versioned()
@@ -495,6 +496,8 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
             # epilogues only add the shift
             sc1 = torch.cat(sc1)
             pk = {"w1": (w1.reshape(192, 256) * sc1[:, None]).to(bf).contiguous(), "sh1": torch.cat(sh1)}
+            # compact-operand layout: K = (dy 7, dx 8, c 4); w1 above is (t, j, dx, c) with dy = 2t + j, row dy = 7 all zero
+            pk["w1c"] = pk["w1"].reshape(192, 8, 32)[:, :7].reshape(192, 224).contiguous()
             sc2, pk["sh2"] = _fold_bn(self.feature_fusion[0].bias, self.feature_fusion[1])
             pk["w2"] = (self.feature_fusion[0].weight.float().reshape(128, 192) * sc2[:, None]).to(bf).contiguous()
             pk["w3"] = self.attention[0].weight.float().reshape(64, 128).to(bf).contiguous()
@@ -522,11 +525,13 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         return pk
 
     def _workspace(self, B, H, W, dev):
-        key = (B, H, W, str(dev), self.use_fused_chain, self.use_fused_front)
+        compact = self._compact(H, W)
+        key = (B, H, W, str(dev), self.use_fused_chain, self.use_fused_front, compact)
         if key not in self._ws:
             bf = dict(device=dev, dtype=torch.bfloat16)
             self._ws = {key: {
-                "stem": torch.empty(B, H + 6, W, 64, **bf),
+                "stem": (torch.empty(B, 2, H + 6, Fn.ratio_stem_compact_width(W), 4, **bf) if compact
+                         else torch.empty(B, H + 6, W, 64, **bf)),
                 "x1": torch.empty(B, H, W, 192, **bf) if not self.use_fused_front else None,
                 "x2": torch.empty(B, H, W, 128, **bf) if not (self.use_fused_chain or self.use_fused_front) else None,
                 "x3": torch.empty(B, H, W, 64, **bf) if not (self.use_fused_chain or self.use_fused_front) else None,
@@ -534,6 +539,11 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
                 "pool": torch.empty(B, 16, 256, device=dev, dtype=torch.float32),
             }}
         return self._ws[key]
+
+    def _compact(self, H: int, W: int) -> bool:
+        """The fused front end can read the depth image through sliding-window tensor maps (no row-im2col tensor in HBM)
+        when its tile is 128 consecutive pixels of a row and the width is even."""
+        return self.use_fused_front and self.use_compact_operand and _best_box(H, W) == (128, 1) and W % 2 == 0
 
     def forward(self, depth_image: torch.Tensor) -> torch.Tensor:
         assert depth_image.dim() == 4, f"Expected 4D tensor, got {depth_image.dim()}D"
@@ -548,11 +558,15 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         if d.dtype != torch.float32:
             d = d.float()
         box = _best_box(H, W)
-        Fn.ratio_stem_pack(d, ws["stem"])
+        compact = self._compact(H, W)
+        if compact:
+            Fn.ratio_stem_pack_compact(d, ws["stem"])
+        else:
+            Fn.ratio_stem_pack(d, ws["stem"])
         if self.use_fused_front:
             # stem + feature_fusion + attention + gating (CM:1458-1470) in one kernel; intermediates in tensor memory
-            Fn.ratio_front(ws["stem"], pk["w1"], pk["w2"], pk["w3"], pk["w4"], pk["sh1"], pk["sh2"], pk["sh3"], pk["sh4"],
-                           ws["x4"], box)
+            Fn.ratio_front(ws["stem"], pk["w1c"] if compact else pk["w1"], pk["w2"], pk["w3"], pk["w4"], pk["sh1"], pk["sh2"],
+                           pk["sh3"], pk["sh4"], ws["x4"], box)
         else:
             # multi-scale stem (CM:1458-1463) + BN + ReLU -> 192 channels
             Fn.conv_gemm(ws["stem"], (B, H + 6, W, 64), 1, pk["w1"], pk["sl1"], 64, B, (H, W), box, 192, pk["sh1"],

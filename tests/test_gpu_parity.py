@@ -326,7 +326,7 @@ def test_ratio_predictor_fused_chain_matches_unfused(mods):
     assert float(((res[0] - res[1]).abs() / res[1]).max()) < 2e-3
 
 
-@pytest.mark.parametrize("B,hw", [(1, (4, 128)), (2, (48, 64)), (3, (20, 36)), (5, (8, 256))])
+@pytest.mark.parametrize("B,hw", [(1, (4, 128)), (2, (48, 64)), (3, (20, 36)), (5, (8, 256)), (2, (12, 640)), (1, (8, 384))])
 def test_ratio_front_fused_matches_stem_gemm_plus_chain(mods, fn, B, hw):
     """ratio_front_kernel (stem GEMM + chain, two tile chains per CTA pair, all intermediates in tensor memory) against
     the two-kernel path on the same packed operands: identical bf16 rounding points, so the gated 128-channel map must
@@ -345,6 +345,8 @@ def test_ratio_front_fused_matches_stem_gemm_plus_chain(mods, fn, B, hw):
             ratios.append(m(x).cpu())
         outs.append(next(iter(m._ws.values()))["x4"].float().cpu())
     assert outs[0].shape == (B, H, W, 128)
+    # widths tiled by 128x1 boxes read the depth image through sliding-window tensor maps (compact operand)
+    assert mods.EnhancedDepthImageRatioPredictor(3)._compact(H, W) == (mods._best_box(H, W) == (128, 1) and W % 2 == 0)
     assert rel_err(outs[0], outs[1]) < 1e-2, rel_err(outs[0], outs[1])
     assert rel_l2(outs[0], outs[1]) < 2e-3
     assert float(((ratios[0] - ratios[1]).abs() / ratios[1]).max()) < 2e-3
