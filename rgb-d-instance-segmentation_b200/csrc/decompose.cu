@@ -42,7 +42,8 @@ __global__ void decomp_init_kernel(ImgState* st, unsigned long long* hist, int B
     if (i < B * kBins) hist[i] = 0ull;
 }
 
-// gray + per-image nanmin/nanmax
+// gray + per-image nanmin/nanmax; 4 pixels per thread (128-bit loads / stores when VEC)
+template <bool VEC>
 __global__ void __launch_bounds__(256) decomp_gray_kernel(const float* __restrict__ depth3, long long bs, long long cs,
                                                           float* __restrict__ gray, ImgState* __restrict__ st, int HW) {
     const int b = blockIdx.y;
@@ -51,15 +52,38 @@ __global__ void __launch_bounds__(256) decomp_gray_kernel(const float* __restric
     const float* bl = g + cs;
     float* out = gray + (long long)b * HW;
     uint32_t lmin = 0xffffffffu, lmax = 0u, nfin = 0u, ninf = 0u;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-        float v = (0.299f * r[i] + 0.587f * g[i]) + 0.114f * bl[i];
-        out[i] = v;
-        if (!isnan(v)) {
-            uint32_t e = f32_to_ordered(v);
-            lmin = min(lmin, e);
-            lmax = max(lmax, e);
-            nfin++;
-            if (isinf(v)) ninf = 1u;
+    for (int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < HW; i4 += gridDim.x * blockDim.x * 4) {
+        float rv[4], gv[4], bv[4], v[4];
+        const int n = HW - i4 < 4 ? HW - i4 : 4;
+        if (VEC) {
+            const float4 a = *reinterpret_cast<const float4*>(r + i4), c = *reinterpret_cast<const float4*>(g + i4),
+                         d = *reinterpret_cast<const float4*>(bl + i4);
+            rv[0] = a.x; rv[1] = a.y; rv[2] = a.z; rv[3] = a.w;
+            gv[0] = c.x; gv[1] = c.y; gv[2] = c.z; gv[3] = c.w;
+            bv[0] = d.x; bv[1] = d.y; bv[2] = d.z; bv[3] = d.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                rv[e] = e < n ? r[i4 + e] : 0.f;
+                gv[e] = e < n ? g[i4 + e] : 0.f;
+                bv[e] = e < n ? bl[i4 + e] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[e] = (0.299f * rv[e] + 0.587f * gv[e]) + 0.114f * bv[e];
+            if (e < n && !isnan(v[e])) {
+                uint32_t enc = f32_to_ordered(v[e]);
+                lmin = min(lmin, enc);
+                lmax = max(lmax, enc);
+                nfin++;
+                if (isinf(v[e])) ninf = 1u;
+            }
+        }
+        if (VEC) {
+            *reinterpret_cast<float4*>(out + i4) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int e = 0; e < n; ++e) out[i4 + e] = v[e];
         }
     }
 #pragma unroll
@@ -253,13 +277,30 @@ __global__ void __launch_bounds__(256) decomp_codes_kernel(const float* __restri
     const ImgState s = st[b];
     const float* in = gray + (long long)b * HW;
     uint8_t* out = codes + (long long)b * HW;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-        float g = in[i];
-        unsigned c = 0;
-        for (int t = 0; t < s.n_modes; ++t)
-            if (g >= s.lo[t] && g <= s.hi[t]) c |= 1u << t;
-        if (s.n_modes > 0 && c == 0) c = 1u << s.n_modes;
-        out[i] = (uint8_t)c;
+    const bool vec = (HW & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
+    for (int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < HW; i4 += gridDim.x * blockDim.x * 4) {
+        const int n = HW - i4 < 4 ? HW - i4 : 4;
+        float g[4];
+        if (vec) {
+            const float4 a = *reinterpret_cast<const float4*>(in + i4);
+            g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
+        } else {
+            for (int e = 0; e < 4; ++e) g[e] = e < n ? in[i4 + e] : 0.f;
+        }
+        unsigned packed = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            unsigned c = 0;
+            for (int t = 0; t < s.n_modes; ++t)
+                if (g[e] >= s.lo[t] && g[e] <= s.hi[t]) c |= 1u << t;
+            if (s.n_modes > 0 && c == 0) c = 1u << s.n_modes;
+            packed |= c << (8 * e);
+        }
+        if (vec) {
+            *reinterpret_cast<unsigned*>(out + i4) = packed;
+        } else {
+            for (int e = 0; e < n; ++e) out[i4 + e] = (uint8_t)((packed >> (8 * e)) & 0xffu);
+        }
     }
 }
 
@@ -270,6 +311,29 @@ __global__ void __launch_bounds__(256) decomp_pool_kernel(const uint8_t* __restr
     const int b = blockIdx.y;
     const uint8_t* in = codes + (long long)b * H * W;
     uint8_t* out = pooled + (long long)b * h * w;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < h * w; o += gridDim.x * blockDim.x) {
+        int i = o / w, j = o - i * w;
+        int y0 = (int)(((long long)i * H) / h), y1 = (int)((((long long)i + 1) * H + h - 1) / h);
+        int x0 = (int)(((long long)j * W) / w), x1 = (int)((((long long)j + 1) * W + w - 1) / w);
+        unsigned c = 0;
+        for (int y = y0; y < y1; ++y)
+            for (int x = x0; x < x1; ++x) c |= in[(long long)y * W + x];
+        out[o] = (uint8_t)c;
+    }
+}
+
+struct PoolLevels {
+    uint8_t* out[8];
+    int h[8], w[8];
+};
+
+// all pyramid levels in one launch (blockIdx.z = level)
+__global__ void __launch_bounds__(256) decomp_pool_levels_kernel(const uint8_t* __restrict__ codes, const __grid_constant__ PoolLevels lv,
+                                                                 int H, int W) {
+    const int b = blockIdx.y, l = blockIdx.z;
+    const int h = lv.h[l], w = lv.w[l];
+    const uint8_t* in = codes + (long long)b * H * W;
+    uint8_t* out = lv.out[l] + (long long)b * h * w;
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < h * w; o += gridDim.x * blockDim.x) {
         int i = o / w, j = o - i * w;
         int y0 = (int)(((long long)i * H) / h), y1 = (int)((((long long)i + 1) * H + h - 1) / h);
@@ -334,7 +398,10 @@ extern "C" int rgbd_depth_decompose(const float* depth3, long long depth_batch_s
     dim3 grid(min(ceil_div(HW, 256 * 4), 296), B);
     const float* gray = gray_in;
     if (depth3) {
-        decomp_gray_kernel<<<grid, 256, 0, s>>>(depth3, depth_batch_stride, depth_channel_stride, gray_out, st, HW);
+        const bool vec = HW % 4 == 0 && depth_batch_stride % 4 == 0 && depth_channel_stride % 4 == 0 &&
+                         ((reinterpret_cast<uintptr_t>(depth3) | reinterpret_cast<uintptr_t>(gray_out)) & 15) == 0;
+        if (vec) decomp_gray_kernel<true><<<grid, 256, 0, s>>>(depth3, depth_batch_stride, depth_channel_stride, gray_out, st, HW);
+        else decomp_gray_kernel<false><<<grid, 256, 0, s>>>(depth3, depth_batch_stride, depth_channel_stride, gray_out, st, HW);
         gray = gray_out;
     } else {
         decomp_minmax_kernel<<<grid, 256, 0, s>>>(gray_in, st, HW);
@@ -348,10 +415,16 @@ extern "C" int rgbd_depth_decompose(const float* depth3, long long depth_batch_s
     RGBD_CHECK_LAUNCH();
     decomp_codes_kernel<<<grid, 256, 0, s>>>(gray, st, codes_out, HW);
     RGBD_CHECK_LAUNCH();
-    for (int l = 0; l < n_levels; ++l) {
-        RGBD_CHECK_ARG(level_h[l] >= 1 && level_w[l] >= 1 && pooled_out[l], "depth_decompose: bad level %d", l);
-        dim3 g(min(ceil_div(level_h[l] * level_w[l], 256), 296), B);
-        decomp_pool_kernel<<<g, 256, 0, s>>>(codes_out, pooled_out[l], H, W, level_h[l], level_w[l]);
+    if (n_levels > 0) {
+        PoolLevels lv;
+        int max_px = 1;
+        for (int l = 0; l < n_levels; ++l) {
+            RGBD_CHECK_ARG(level_h[l] >= 1 && level_w[l] >= 1 && pooled_out[l], "depth_decompose: bad level %d", l);
+            lv.out[l] = pooled_out[l]; lv.h[l] = level_h[l]; lv.w[l] = level_w[l];
+            max_px = max(max_px, level_h[l] * level_w[l]);
+        }
+        dim3 g(min(ceil_div(max_px, 256), 296), B, n_levels);
+        decomp_pool_levels_kernel<<<g, 256, 0, s>>>(codes_out, lv, H, W);
         RGBD_CHECK_LAUNCH();
     }
     decomp_export_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B, num_modes, n_modes_out, peak_bins_out, centres_out,
