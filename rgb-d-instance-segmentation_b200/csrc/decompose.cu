@@ -306,22 +306,6 @@ __global__ void __launch_bounds__(256) decomp_codes_kernel(const float* __restri
 
 // adaptive_max_pool2d of each region mask == bitwise OR of the codes over the window
 // [floor(i*H/h), ceil((i+1)*H/h)) x [floor(j*W/w), ceil((j+1)*W/w))
-__global__ void __launch_bounds__(256) decomp_pool_kernel(const uint8_t* __restrict__ codes, uint8_t* __restrict__ pooled,
-                                                          int H, int W, int h, int w) {
-    const int b = blockIdx.y;
-    const uint8_t* in = codes + (long long)b * H * W;
-    uint8_t* out = pooled + (long long)b * h * w;
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < h * w; o += gridDim.x * blockDim.x) {
-        int i = o / w, j = o - i * w;
-        int y0 = (int)(((long long)i * H) / h), y1 = (int)((((long long)i + 1) * H + h - 1) / h);
-        int x0 = (int)(((long long)j * W) / w), x1 = (int)((((long long)j + 1) * W + w - 1) / w);
-        unsigned c = 0;
-        for (int y = y0; y < y1; ++y)
-            for (int x = x0; x < x1; ++x) c |= in[(long long)y * W + x];
-        out[o] = (uint8_t)c;
-    }
-}
-
 struct PoolLevels {
     uint8_t* out[8];
     int h[8], w[8];
