@@ -52,8 +52,10 @@ def _plane_strided(t: torch.Tensor, name: str) -> Tuple[int, int]:
 # ------------------------------------------------------------------------------------------------
 def dggm_forward(feats: Sequence[torch.Tensor], grad: torch.Tensor, mask: torch.Tensor,
                  weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
-                 branch1: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
-    """K1.  out_i = feats_i + ReLU(conv1x1_i(bilinear(grad) * nearest(mask))) [+ branch1_i]."""
+                 branch1: Optional[Sequence[torch.Tensor]] = None,
+                 outs: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+    """K1.  out_i = feats_i + ReLU(conv1x1_i(bilinear(grad) * nearest(mask))) [+ branch1_i].  ``outs``: preallocated
+    results (e.g. views of one staging slab)."""
     lib = _lib.load()
     n = len(feats)
     _req(grad, "processed_depth_gradient_map", torch.float32, contiguous=False)
@@ -63,6 +65,7 @@ def dggm_forward(feats: Sequence[torch.Tensor], grad: torch.Tensor, mask: torch.
         raise RgbdB200Error(f"gradient_mask must be {(B, 1, H, W)}, got {tuple(mask.shape)}")
     gbs, _ = _plane_strided(grad, "processed_depth_gradient_map")
     mbs, _ = _plane_strided(mask, "gradient_mask")
+    given = outs
     outs = []
     ws, bs = [], []
     for i, f in enumerate(feats):
@@ -75,7 +78,12 @@ def dggm_forward(feats: Sequence[torch.Tensor], grad: torch.Tensor, mask: torch.
             raise RgbdB200Error(f"scale {i}: weight {tuple(w.shape)} / bias {tuple(b.shape)} do not match C={f.shape[1]}, D={D}")
         ws.append(w)
         bs.append(b)
-        outs.append(torch.empty_like(f))
+        if given is not None:
+            if given[i].shape != f.shape:
+                raise RgbdB200Error(f"outs[{i}] must have the shape of color_feature_maps[{i}]")
+            outs.append(_req(given[i], f"outs[{i}]", torch.float32))
+        else:
+            outs.append(torch.empty_like(f))
         if branch1 is not None:
             _req(branch1[i], f"branch1[{i}]", torch.float32)
             if branch1[i].shape != f.shape:

@@ -114,11 +114,11 @@ class DepthGradientInjectionResidual(nn.Module):
         return Fn.dggm_forward([f.contiguous() for f in color_feature_maps], processed_depth_gradient_map,
                                gradient_mask, [w.detach() for w in ws], [b.detach() for b in bs])
 
-    def forward_fused_sum(self, color_feature_maps, branch1, processed_depth_gradient_map, gradient_mask):
+    def forward_fused_sum(self, color_feature_maps, branch1, processed_depth_gradient_map, gradient_mask, outs=None):
         """``branch1_i + (color_i + enh_i)`` in one pass (the v0.4.0 branch sum, CM:354-355). Inference only."""
         ws, bs = self._params()
         return Fn.dggm_forward(color_feature_maps, processed_depth_gradient_map, gradient_mask,
-                               [w.detach() for w in ws], [b.detach() for b in bs], branch1=branch1)
+                               [w.detach() for w in ws], [b.detach() for b in bs], branch1=branch1, outs=outs)
 
 
 # =====================================================================================================
@@ -646,15 +646,17 @@ class DepthGuidance(nn.Module):
             d.precision = precision            # DSAM convolutions; DGGM is fp32 arithmetic in either mode
 
     def forward(self, pixel_values: torch.Tensor, color_feature_map: Sequence[torch.Tensor],
-                ratios: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+                ratios: Optional[torch.Tensor] = None, out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+        """``out``: optional preallocated fused feature maps (inference path), e.g. views of one device slab that a
+        serving loop copies to the host in a single transfer."""
         return depth_guidance_forward(self.ratio_predictor, (self.dsam0, self.dsam1, self.dsam2),
-                                      self.depth_gradient_injection, pixel_values, color_feature_map, ratios)
+                                      self.depth_gradient_injection, pixel_values, color_feature_map, ratios, out)
 
 
 def depth_guidance_forward(ratio_predictor: EnhancedDepthImageRatioPredictor, dsams: Sequence[DSAModule],
                            dggm: DepthGradientInjectionResidual, pixel_values: torch.Tensor,
-                           color_feature_map: Sequence[torch.Tensor], ratios: Optional[torch.Tensor] = None
-                           ) -> List[torch.Tensor]:
+                           color_feature_map: Sequence[torch.Tensor], ratios: Optional[torch.Tensor] = None,
+                           out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
     """CM:324-355 from the encoder's feature maps to the list handed to the pixel decoder (inference path)."""
     depth = pixel_values[:, 3:6]
     gradient_depth = pixel_values[:, 6:9]
@@ -672,10 +674,12 @@ def depth_guidance_forward(ratio_predictor: EnhancedDepthImageRatioPredictor, ds
         cp1.append(x)
     training = torch.is_grad_enabled() and any(p.requires_grad for m in (*dsams, dggm) for p in m.parameters())
     if training:
+        if out is not None:
+            raise RgbdB200Error("preallocated outputs are an inference-path option")
         cp2 = dggm(feats, gradient_depth, gradient_mask)                    # CM:354 (autograd: K1b)
         return [a + b for a, b in zip(cp1, cp2)]                            # CM:355
     # CM:354-355: cp2 = DGGM(feats); out = cp1 + cp2, fused into the DGGM kernel
-    return dggm.forward_fused_sum(feats, cp1, gradient_depth, gradient_mask)
+    return dggm.forward_fused_sum(feats, cp1, gradient_depth, gradient_mask, outs=out)
 
 
 class GraphedDepthGuidance:
