@@ -358,11 +358,16 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
             // ---- E4: out = sigmoid(acc4 + b4) * f(stash) -> bf16 -> stash -> TMA store
             tc::mbar_wait_sleep(&ctl->acc_full[c][3], ph);
             tc::tc_fence_after();
-#pragma unroll 1
-            for (int k = h; k < 4; k += 2) {
-                uint32_t v[32];
-                tc::tmem_ld_32x32(P + k * 32, v);
-                tc::tmem_ld_wait();
+            // both accumulator chunks go to registers first, so the chain's TMEM columns are released (and the stem
+            // GEMM of its next tile starts) BEFORE the sigmoid / gating math, which is bound by the MUFU pipe
+            uint32_t va[32], vb[32];
+            tc::tmem_ld_32x32(P + h * 32, va);
+            tc::tmem_ld_32x32(P + (h + 2) * 32, vb);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster_tmem(p_free_remote);
+            auto gate = [&](const int k, const uint32_t (&v)[32]) {
                 uint8_t* rowp = stash + (k >> 1) * kSliceBytes + row * 128;
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
@@ -383,10 +388,9 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
                     }
                     *reinterpret_cast<uint4*>(rowp + piece * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
-            }
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive_cluster_tmem(p_free_remote);
+            };
+            gate(h, va);
+            gate(h + 2, vb);
             tc::fence_proxy_async();
             asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
             if (issuer) {
