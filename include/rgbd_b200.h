@@ -113,8 +113,11 @@ int rgbd_ratio_stem_pack(const float* depth3, long long batch_stride, long long 
  * Output tile = bx*by (=128) pixels of one image x block_n channels.  y = act(acc*scale[n] + shift[variant][n]);
  * epi_mode 0: bf16 (n_img, out_h, out_w, n_pad) store, optionally multiplied by `gate` (same layout);
  * epi_mode 1: fp32 (n_img, n, out_h, out_w) store, optionally + residual (same layout);
- * epi_mode 2: sums over the cells of a cells_y x cells_x grid into pool (n_img, cells, n_pad) (caller zeroes);
+ * epi_mode 2: sums over the cells of a cells_y x cells_x grid into pool (n_img, cells, n_pad) (caller zeroes), as 64-bit
+ *             FIXED-POINT integers in units of 1/RGBD_POOL_FIXED_ONE: integer atomics make the sums independent of the
+ *             accumulation order, so the ratio (and the integer region codes derived from it) is reproducible run to run;
  * epi_mode 3: masked segment sum (see the codes / m3_* fields). */
+#define RGBD_POOL_FIXED_ONE 16777216.0 /* 2^24 */
 typedef struct rgbd_conv_gemm_desc {
     const void* a; /* bf16 */
     int a_c, a_x, a_y, a_planes;
@@ -132,7 +135,7 @@ typedef struct rgbd_conv_gemm_desc {
     const void* gate;     /* bf16 or NULL */
     void* out;
     const float* residual;
-    float* pool;
+    long long* pool;
     int cells_y, cells_x;
     int conv3x3_reuse; /* 1: 3x3 stride-1 pad-1 conv over a (n_img, a_y, a_x, a_c) tensor with shared-memory reuse of the
                           A tile across the dx taps; W is (n_pad, 9*a_c) ordered (dy, dx, c); slices are ignored;
@@ -196,7 +199,7 @@ int rgbd_ratio_stem_pack_compact(const float* depth3, long long batch_stride, lo
 
 /* Tail of EnhancedDepthImageRatioPredictor.forward (CM:1473-1485): pooled sums -> conv3x3 256->512 + folded BN +
  * ReLU -> GAP -> MLP -> 0.01 + 0.49*sigmoid.  conv_w (512,256,3,3) fp32; fc_w_host/fc_b_host: 4 layers. */
-int rgbd_ratio_tail(const float* pool_sums, int pool_stride, int cell_pixels, const float* conv_w, const float* conv_scale,
+int rgbd_ratio_tail(const long long* pool_sums, int pool_stride, int cell_pixels, const float* conv_w, const float* conv_scale,
                     const float* conv_shift, const float* const* fc_w_host, const float* const* fc_b_host, float out_min,
                     float out_max, float* gap_ws, float* ratio_out, int B, rgbd_stream_t stream);
 

@@ -45,7 +45,7 @@ struct KParams {
     const __nv_bfloat16* gate;
     void* out;
     const float* residual;
-    float* pool;
+    long long* pool;          // fixed-point (1/RGBD_POOL_FIXED_ONE) cell sums: order-independent integer atomics
     int cells_y, cells_x;
     int total_tiles;
     int staging_bytes;    // epi_mode 0: swizzled bf16 output tile staged for TMA stores
@@ -105,6 +105,10 @@ struct EpiCtx {
 // tile of CTA `rank` in pair unit u: the two CTAs take adjacent M tiles of the SAME N tile (they share the B operand)
 __device__ __forceinline__ int pair_tile(const KParams& p, int u, int rank) {
     return (2 * (u / p.n_tiles_n) + rank) * p.n_tiles_n + (u % p.n_tiles_n);
+}
+
+__device__ __forceinline__ void pool_add(long long* dst, float v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__double2ll_rn((double)v * RGBD_POOL_FIXED_ONE));
 }
 
 template <int ACT>
@@ -172,7 +176,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {
                         if (kk < n_chunks && (kk & 1) == half) {
-                            atomicAdd(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
+                            pool_add(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
                             acc[kk] = 0.f;
                         }
                     }
@@ -330,7 +334,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
                         if (kk == k) acc[kk] += f[0];
                 } else if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(p.pool + (size_t)key * p.N_pad + n0 + j, f[j]);
+                    for (int j = 0; j < 32; ++j) pool_add(p.pool + (size_t)key * p.N_pad + n0 + j, f[j]);
                 }
             }
         }
@@ -358,7 +362,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
             if (kk < n_chunks && (kk & 1) == half)
-                atomicAdd(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
+                pool_add(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
     }
 }
 

@@ -1,6 +1,6 @@
 // K4 tail: the small end of EnhancedDepthImageRatioPredictor.forward (reference
 // mask2former/utils/custom_model.py:1473-1485) after the fused 3x3 conv + BN + ReLU + AdaptiveAvgPool2d(4):
-//   pooled sums / cell size -> Conv3x3(256->512, pad 1) on the 4x4 map -> BN (folded) -> ReLU -> global
+//   pooled sums (64-bit fixed point, see rgbd_conv_gemm epi_mode 2) / cell size -> Conv3x3(256->512, pad 1) on the 4x4 map -> BN (folded) -> ReLU -> global
 //   average pool -> Linear 512->128->64->32->1 with ReLU (Dropout is identity in eval) ->
 //   ratio = 0.01 + 0.49 * sigmoid(raw).
 // 19 MFLOP per image: fp32 CUDA cores, two launches (conv: CTAs of 16 output channels x 4 images so the weights are read
@@ -16,7 +16,7 @@ constexpr int kXImgStride = kIcChunk * 36 + 8;     // +8 floats: the 4 images of
 
 // CTA = 16 output channels x 4 images: the 16 x 2304 weights (147 KB) are read once per 4 images, coalesced, through a
 // shared-memory chunk of 32 input channels; thread = (oc, image, output row) computes the 4 outputs of its row.
-__global__ void __launch_bounds__(256) ratio_tail_conv_kernel(const float* __restrict__ pool, int pool_stride,
+__global__ void __launch_bounds__(256) ratio_tail_conv_kernel(const long long* __restrict__ pool, int pool_stride,
                                                               float inv_cell, const float* __restrict__ w,
                                                               const float* __restrict__ scale,
                                                               const float* __restrict__ shift, float* __restrict__ gap, int B) {
@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(256) ratio_tail_conv_kernel(const float* __res
             const int c = i % 6, r = (i / 6) % 6, ic = (i / 36) % kIcChunk, bi = i / (36 * kIcChunk);
             float v = 0.f;
             if (r >= 1 && r <= 4 && c >= 1 && c <= 4 && b0 + bi < B)
-                v = pool[((size_t)(b0 + bi) * 16 + (r - 1) * 4 + (c - 1)) * pool_stride + ic0 + ic] * inv_cell;
+                v = (float)((double)pool[((size_t)(b0 + bi) * 16 + (r - 1) * 4 + (c - 1)) * pool_stride + ic0 + ic] *
+                            (1.0 / RGBD_POOL_FIXED_ONE)) * inv_cell;
             xs[bi * kXImgStride + ic * 36 + r * 6 + c] = v;
         }
         for (int i = threadIdx.x; i < kOcPerCta * kIcChunk * 9; i += blockDim.x) {
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(512) ratio_tail_mlp_kernel(const float* __rest
 
 }  // namespace
 
-extern "C" int rgbd_ratio_tail(const float* pool_sums, int pool_stride, int cell_pixels, const float* conv_w,
+extern "C" int rgbd_ratio_tail(const long long* pool_sums, int pool_stride, int cell_pixels, const float* conv_w,
                                const float* conv_scale, const float* conv_shift, const float* const* fc_w,
                                const float* const* fc_b, float out_min, float out_max, float* gap_ws, float* ratio_out,
                                int B, rgbd_stream_t stream) {

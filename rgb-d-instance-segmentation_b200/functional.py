@@ -254,6 +254,9 @@ def depth_decompose(ratio: torch.Tensor, levels: Sequence[Tuple[int, int]], dept
 # ------------------------------------------------------------------------------------------------
 # tensor-core building blocks
 # ------------------------------------------------------------------------------------------------
+POOL_FIXED_ONE = float(1 << 24)      # RGBD_POOL_FIXED_ONE: unit of the fixed-point cell sums of conv_gemm's epilogue mode 2
+
+
 def pick_block_n(n_pad: int) -> int:
     if n_pad <= 256:
         return n_pad
@@ -314,7 +317,7 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
     d.gate = _req(gate, "gate", torch.bfloat16).data_ptr() if gate is not None else None
     d.out = out.data_ptr() if out is not None else None
     d.residual = _req(residual, "residual", torch.float32).data_ptr() if residual is not None else None
-    d.pool = _req(pool, "pool", torch.float32).data_ptr() if pool is not None else None
+    d.pool = _req(pool, "pool", torch.int64).data_ptr() if pool is not None else None
     d.cells_y, d.cells_x = cells
     check(lib.rgbd_conv_gemm(C.byref(d), _stream()), "rgbd_conv_gemm")
     _count(1)
@@ -476,7 +479,7 @@ def ratio_tail(pool: torch.Tensor, cell_pixels: int, conv_w: torch.Tensor, conv_
                conv_shift: torch.Tensor, fc_w: Sequence[torch.Tensor], fc_b: Sequence[torch.Tensor],
                out_min: float, out_max: float) -> torch.Tensor:
     lib = _lib.load()
-    _req(pool, "pool", torch.float32)
+    _req(pool, "pool", torch.int64)
     B = pool.shape[0]
     gap = torch.empty(B, 512, device=pool.device, dtype=torch.float32)
     ratio = torch.empty(B, 1, device=pool.device, dtype=torch.float32)

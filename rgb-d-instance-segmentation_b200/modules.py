@@ -536,7 +536,7 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
                 "x2": torch.empty(B, H, W, 128, **bf) if not (self.use_fused_chain or self.use_fused_front) else None,
                 "x3": torch.empty(B, H, W, 64, **bf) if not (self.use_fused_chain or self.use_fused_front) else None,
                 "x4": torch.empty(B, H, W, 128, **bf),
-                "pool": torch.empty(B, 16, 256, device=dev, dtype=torch.float32),
+                "pool": torch.empty(B, 16, 256, device=dev, dtype=torch.int64),     # fixed-point cell sums
             }}
         return self._ws[key]
 

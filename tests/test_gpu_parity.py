@@ -254,14 +254,14 @@ def test_conv_gemm_3x3_pool(fn):
     shift = torch.from_numpy(rs.randn(n).astype(np.float32) * 0.1).cuda()
     slices = torch.tensor([(64 * cb, dx - 1, dy - 1, 0) for dy in range(3) for dx in range(3) for cb in range(c // 64)],
                           dtype=torch.int32).cuda()
-    pool = torch.zeros(B, 16, n, device="cuda")
+    pool = torch.zeros(B, 16, n, device="cuda", dtype=torch.int64)        # fixed-point cell sums
     from rgbd_b200.modules import _best_box
     fn.conv_gemm(a, (B, H, W, c), 1, w, slices, 64, B, (H, W), _best_box(H, W), n, shift, act=1, epi_mode=2, pool=pool,
                  cells=(4, 4), tile_order=1)
     y = torch.relu(torch.nn.functional.conv2d(a.double().permute(0, 3, 1, 2), wt.double(), shift.double(), padding=1))
     ref = torch.nn.functional.adaptive_avg_pool2d(y, 4) * (H // 4) * (W // 4)       # sums per cell
     ref = ref.permute(0, 2, 3, 1).reshape(B, 16, n)
-    assert rel_err(pool, ref) < 1e-4
+    assert rel_err(pool.double() / fn.POOL_FIXED_ONE, ref) < 1e-4
 
 
 @pytest.mark.parametrize("c,n,hw", [(128, 256, (8, 256)), (64, 128, (12, 200)), (192, 64, (4, 128))])
@@ -274,11 +274,11 @@ def test_conv3x3_a_reuse_path(fn, c, n, hw):
     w = wt.permute(0, 2, 3, 1).reshape(n, 9 * c).contiguous()
     shift = torch.from_numpy(rs.randn(n).astype(np.float32) * 0.1).cuda()
     y = torch.relu(torch.nn.functional.conv2d(a.double().permute(0, 3, 1, 2), wt.double(), shift.double(), padding=1))
-    pool = torch.zeros(B, 16, n, device="cuda")
+    pool = torch.zeros(B, 16, n, device="cuda", dtype=torch.int64)        # fixed-point cell sums
     fn.conv_gemm(a, (B, H, W, c), 1, w, None, 64, B, (H, W), (128, 1), n, shift, act=1, epi_mode=2, pool=pool,
                  cells=(4, 4), tile_order=1, conv3x3_reuse=True)
     ref = (torch.nn.functional.adaptive_avg_pool2d(y, 4) * (H // 4) * (W // 4)).permute(0, 2, 3, 1).reshape(B, 16, n)
-    assert rel_err(pool, ref) < 1e-4
+    assert rel_err(pool.double() / fn.POOL_FIXED_ONE, ref) < 1e-4
     out = torch.zeros(B, H, W, n, device="cuda", dtype=torch.bfloat16)
     fn.conv_gemm(a, (B, H, W, c), 1, w, None, 64, B, (H, W), (128, 1), n, shift, act=1, out=out, conv3x3_reuse=True)
     assert rel_err(out.double(), y.permute(0, 2, 3, 1)) < 8e-3
@@ -635,6 +635,27 @@ def test_depth_guidance_other_geometries(mods, chans, hw):
     for i in range(4):
         assert out[i].shape == ref[i].shape
         assert rel_err(out[i], ref[i]) < BF16_TOL, (i, rel_err(out[i], ref[i]))
+
+
+def test_hot_path_is_reproducible_run_to_run(mods, fn):
+    """The window ratio feeds integer decisions (region codes), so the whole path must be bit-reproducible: the pooled
+    sums of the 3x3 conv use fixed-point integer atomics, everything else has a fixed summation order."""
+    chans, (H, W), B = (96, 192, 384, 768), (192, 256), 4
+    m = mods.DepthGuidance(chans)
+    m.load_state_dict(OW.guidance_weights(seed=77, channels=chans))
+    m.cuda().eval()
+    rgbs, ds = zip(*[synthetic.synth_rgbd_u8(700 + j, H, W, "nyu") for j in range(B)])
+    pv = fn.pack_pixel_values(torch.from_numpy(np.stack(rgbs)).cuda(), torch.from_numpy(np.stack(ds)).cuda())
+    g = torch.Generator(device="cpu").manual_seed(3)
+    feats = [torch.randn(B, c, H // s, W // s, generator=g).cuda() for c, s in zip(chans, (4, 8, 16, 32))]
+    runs = []
+    for _ in range(3):
+        with torch.no_grad():
+            r = m.ratio_predictor(pv[:, 3:6]).clone()
+            runs.append((r, [o.clone() for o in m(pv, feats)]))
+    for r, outs in runs[1:]:
+        assert torch.equal(r, runs[0][0])
+        assert all(torch.equal(a, b) for a, b in zip(outs, runs[0][1]))
 
 
 def test_large_frame_swin_b_cross_implementation(mods, fn, monkeypatch):
