@@ -238,9 +238,11 @@ __global__ void __launch_bounds__(kBins) decomp_modes_kernel(const unsigned long
     }
     __syncthreads();
     if (i == 0) {
+        ImgState loc = s;                 // one read of the per-image state; the serial part below works on registers
+        const float rt = ratio[b];
         const int nc = n_cand;
         int nm = 0;
-        if (!(s.status & RGBD_DECOMP_RANGE_NOT_FINITE)) {
+        if (!(loc.status & RGBD_DECOMP_RANGE_NOT_FINITE)) {
             // selection by (height desc, centre desc); centres are non-decreasing in the bin index,
             // so (height, bin) descending gives the same centres in the same order
             for (int pick = 0; pick < num_modes && pick < nc; ++pick) {
@@ -253,20 +255,21 @@ __global__ void __launch_bounds__(kBins) decomp_modes_kernel(const unsigned long
                 }
                 int pb = cand_bin[best];
                 cand_bin[best] = -1;
-                float e0 = bin_edge(s, pb), e1 = bin_edge(s, pb + 1);
+                float e0 = bin_edge(loc, pb), e1 = bin_edge(loc, pb + 1);
                 float centre = e0 + (e1 - e0) / 2.0f;
-                float hw = (centre * ratio[b]) / 2.0f;
+                float hw = (centre * rt) / 2.0f;
                 float lo = centre - hw;
                 lo = lo > 0.0f ? lo : 0.0f;          // python max(0, x)
-                s.peak_bin[nm] = pb;
-                s.centre[nm] = centre;
-                s.lo[nm] = lo;
-                s.hi[nm] = centre + hw;
+                loc.peak_bin[nm] = pb;
+                loc.centre[nm] = centre;
+                loc.lo[nm] = lo;
+                loc.hi[nm] = centre + hw;
                 ++nm;
             }
         }
-        s.n_modes = nm;
-        for (int k = nm; k < 3; ++k) { s.peak_bin[k] = -1; s.centre[k] = 0.f; s.lo[k] = 0.f; s.hi[k] = 0.f; }
+        loc.n_modes = nm;
+        for (int k = nm; k < 3; ++k) { loc.peak_bin[k] = -1; loc.centre[k] = 0.f; loc.lo[k] = 0.f; loc.hi[k] = 0.f; }
+        s = loc;
     }
 }
 
