@@ -203,6 +203,18 @@ int rgbd_ratio_tail(const long long* pool_sums, int pool_stride, int cell_pixels
                     const float* conv_shift, const float* const* fc_w_host, const float* const* fc_b_host, float out_min,
                     float out_max, float* gap_ws, float* ratio_out, int B, rgbd_stream_t stream);
 
+/* ---- resize half of the data mapper's front-end (map_10channel_case2, DL:405-414), bit-exact with the libraries the
+ * reference calls.  rgbd_resize_pil_bilinear_u8: Pillow Image.resize((w,h), BILINEAR) for (B,H,W,C) uint8 images, C <= 4
+ * (HF image processor, PIL backend, resample = 2): antialiased triangle filter, 22-bit fixed-point coefficients, horizontal
+ * then vertical pass.  rgbd_resize_cv_linear_u8: cv2.resize(img, (w,h), interpolation=INTER_LINEAR) for (B,H,W) uint8
+ * (the depth map the Sobel features are taken from): 11-bit fixed-point weights, OpenCV's border and rounding rules.
+ * workspace: rgbd_resize_workspace_bytes(B,H,W,C,h,w) bytes (C = 1 for the OpenCV resize). */
+size_t rgbd_resize_workspace_bytes(int B, int H, int W, int C, int h, int w);
+int rgbd_resize_pil_bilinear_u8(const uint8_t* src, uint8_t* dst, int B, int H, int W, int C, int h, int w, void* workspace,
+                                rgbd_stream_t stream);
+int rgbd_resize_cv_linear_u8(const uint8_t* src, uint8_t* dst, int B, int H, int W, int h, int w, void* workspace,
+                             rgbd_stream_t stream);
+
 /* Feature-based window-ratio predictor of the version 0.1.3 / 0.3.0 models (`RatioPredictor.forward`, CM:860-898): global
  * average pool of n_levels NCHW fp32 depth-feature maps (B,C_l,HW_l), concatenation, MLP sum(C_l)->64->32->1 with ReLU,
  * ratio = out_min + (out_max - out_min) * sigmoid.  feats_host / C_host / HW_host / fc_*_host are HOST arrays (of device

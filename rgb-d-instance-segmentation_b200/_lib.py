@@ -70,6 +70,9 @@ SIGNATURES = {
     "rgbd_ratio_stem_compact_width": (C.c_int, [C.c_int]),
     "rgbd_ratio_stem_pack_compact": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                C.c_void_p]),
+    "rgbd_resize_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
+    "rgbd_resize_pil_bilinear_u8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
+    "rgbd_resize_cv_linear_u8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "rgbd_ratio_from_features": (C.c_int, [C.c_int, c_void_pp, c_int_p, c_int_p, C.c_int, c_void_pp, c_void_pp, C.c_float, C.c_float,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "rgbd_postprocess_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),

@@ -184,6 +184,55 @@ def pack_pixel_values(rgb_u8: torch.Tensor, depth_u8: torch.Tensor, out: Optiona
     return out
 
 
+def resize_pil_bilinear(img_u8: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+    """(B,H,W,C) or (B,H,W) uint8 -> (B,h,w[,C]) uint8, bit-exact with ``PIL.Image.resize((w,h), BILINEAR)`` -- the resize
+    of the HF image processor (PIL backend) the reference's mapper runs on the colour image and on ``depth.convert('RGB')``."""
+    lib = _lib.load()
+    _req(img_u8, "image", torch.uint8)
+    squeeze = img_u8.dim() == 3
+    x = img_u8[..., None] if squeeze else img_u8
+    B, H, W, Cc = x.shape
+    h, w = int(size[0]), int(size[1])
+    out = torch.empty(B, h, w, Cc, device=x.device, dtype=torch.uint8)
+    ws = torch.empty(max(int(lib.rgbd_resize_workspace_bytes(B, H, W, Cc, h, w)), 16), device=x.device, dtype=torch.uint8)
+    check(lib.rgbd_resize_pil_bilinear_u8(x.data_ptr(), out.data_ptr(), B, H, W, Cc, h, w, ws.data_ptr(), _stream()),
+          "rgbd_resize_pil_bilinear_u8")
+    _count(4)
+    return out[..., 0] if squeeze else out
+
+
+def resize_cv_linear(img_u8: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+    """(B,H,W) uint8 -> (B,h,w) uint8, bit-exact with ``cv2.resize(img, (w,h), interpolation=cv2.INTER_LINEAR)`` (DL:413)."""
+    lib = _lib.load()
+    _req(img_u8, "image", torch.uint8)
+    B, H, W = img_u8.shape
+    h, w = int(size[0]), int(size[1])
+    out = torch.empty(B, h, w, device=img_u8.device, dtype=torch.uint8)
+    ws = torch.empty(max(int(lib.rgbd_resize_workspace_bytes(B, H, W, 1, h, w)), 16), device=img_u8.device, dtype=torch.uint8)
+    check(lib.rgbd_resize_cv_linear_u8(img_u8.data_ptr(), out.data_ptr(), B, H, W, h, w, ws.data_ptr(), _stream()),
+          "rgbd_resize_cv_linear_u8")
+    _count(3)
+    return out
+
+
+def map_10channel(rgb_u8: torch.Tensor, depth_u8: torch.Tensor, size: Optional[Tuple[int, int]] = (384, 384),
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The whole ``map_10channel_case2`` front-end (DL:386-425) on device: camera-resolution uint8 colour (B,H,W,3) and
+    depth (B,H,W) -> ``pixel_values`` (B,10,h,w): Pillow-bilinear resize of colour and of the 3x-replicated depth (HF
+    processor, ``size`` of preprocessor_config.json), rescale + normalise, OpenCV-linear resize of the depth for the Sobel
+    gradient features (DL:413-414) and the validity mask.  ``size=None`` keeps the input resolution."""
+    B, H, W = depth_u8.shape
+    h, w = (H, W) if size is None else (int(size[0]), int(size[1]))
+    if (h, w) == (H, W):
+        return pack_pixel_values(rgb_u8, depth_u8, out=out)
+    rgb_r = resize_pil_bilinear(rgb_u8, (h, w))
+    depth_pil = resize_pil_bilinear(depth_u8, (h, w))          # per-channel filter: resizing 'L' then replicating == 'RGB'
+    depth_cv = resize_cv_linear(depth_u8, (h, w))
+    pv = pack_pixel_values(rgb_r, depth_pil, out=out)
+    gradient_features(depth_cv, norm_out=pv[:, 6:9], vmask_out=pv[:, 9:10])     # DL:413-414: features of the OpenCV resize
+    return pv
+
+
 # ------------------------------------------------------------------------------------------------
 # E-DSAM depth decomposition
 # ------------------------------------------------------------------------------------------------
