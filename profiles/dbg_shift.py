@@ -1,4 +1,6 @@
-"""Experiment: does tcgen05.mma accept a 128B-swizzled K-major A tile whose descriptor start address is advanced by
+"""[The RGBD_DBG_SHIFT / RGBD_DBG_BO measurement hook this script drives lived in csrc/conv_gemm.cu up to commit 47717bd and was
+removed afterwards; check that commit out to re-run the experiment.  Result: profiles/r01_notes.md.]
+Experiment: does tcgen05.mma accept a 128B-swizzled K-major A tile whose descriptor start address is advanced by
 whole 128-byte rows (not 1024-byte aligned)?  Needed to reuse one shared-memory tile for the 3 dx taps of a 3x3 conv."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

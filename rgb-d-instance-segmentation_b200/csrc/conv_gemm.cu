@@ -56,7 +56,6 @@ struct KParams {
     int in_h, in_w, m3_py, m3_px, m3_stride, m3_masked_segs, m3_n_seg;
     int dsam_taps;            // dsam_fwd_kernel: 9 (3x3 stride 2 on parity planes)
     int c_blocks, sa_stages, a_stage_bytes;   // conv3x3_kernel: 64-channel blocks, A-ring depth, bytes per A stage
-    int dbg_shift, dbg_bo;   // experiment: A tile loaded `dbg_shift` pixels early, descriptor start advanced by as many rows
 };
 
 struct alignas(16) SmemCtl {
@@ -445,7 +444,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 uint8_t* sb = sa + a_bytes;
                 tc::mbar_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
                 const int4 sl = s_slices[j];
-                tc::tma_load_4d(sa, &tmap_a, &ctl->full[stage], sl.x, x0 + sl.y - p.dbg_shift, y0 + sl.z, pl0 + sl.w);
+                tc::tma_load_4d(sa, &tmap_a, &ctl->full[stage], sl.x, x0 + sl.y, y0 + sl.z, pl0 + sl.w);
                 if (!p.b_resident)
                     tc::tma_load_2d(sb, &tmap_b, &ctl->full[stage], j * (p.kb_bytes >> 1), nt * p.BLOCK_N);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -469,8 +468,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 tc::tc_fence_after();
                 const uint32_t sa = tc::smem_u32(s_ring + (size_t)stage * stage_bytes);
                 const uint32_t sb = p.b_resident ? tc::smem_u32(s_bres + (size_t)j * b_bytes) : sa + a_bytes;
-                uint64_t adesc = tc::make_kmajor_desc(sa + (uint32_t)(p.dbg_shift * p.kb_bytes), p.kb_bytes);
-                if (p.dbg_bo) adesc |= (uint64_t)(p.dbg_shift & 7) << 49;
+                const uint64_t adesc = tc::make_kmajor_desc(sa, p.kb_bytes);
                 const uint64_t bdesc = tc::make_kmajor_desc(sb, p.kb_bytes);
                 for (int k = 0; k < k_per_block; ++k)
                     tc::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (j | k) != 0);
@@ -1229,7 +1227,7 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     }
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     if (d->conv3x3_reuse) {
-        p.b_resident = 0; p.b_res_bytes = 0; p.dbg_shift = 0; p.dbg_bo = 0;
+        p.b_resident = 0; p.b_res_bytes = 0;
         p.staging_bytes = d->epi_mode == 0 ? (p.BLOCK_N / 64) * kBlockM * 128 : 0;
         p.gate_bytes = 0;
         p.sa_stages = 3;
@@ -1283,7 +1281,7 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         return RGBD_OK;
     }
     if (d->dsam_masked) {
-        p.b_resident = 0; p.b_res_bytes = 0; p.dbg_shift = 0; p.dbg_bo = 0; p.staging_bytes = 0; p.gate_bytes = 0;
+        p.b_resident = 0; p.b_res_bytes = 0; p.staging_bytes = 0; p.gate_bytes = 0;
         CUtensorMap tmap_b2;
         cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->n_pad};
         cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
@@ -1320,12 +1318,6 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dsam_fwd_kernel, tmap_a, tmap_b2, p));
         return RGBD_OK;
     }
-    {   // measurement hook of profiles/dbg_shift.py (row-shifted descriptor experiment); 0 in normal operation
-        const char* e1 = getenv("RGBD_DBG_SHIFT");
-        const char* e2 = getenv("RGBD_DBG_BO");
-        p.dbg_shift = e1 ? atoi(e1) : 0;
-        p.dbg_bo = e2 ? atoi(e2) : 0;
-    }
     const int b_total = p.n_slices * p.BLOCK_N * kb_bytes;
     p.b_resident = (p.n_tiles_n == 1 && b_total <= 100 * 1024) ? 1 : 0;
     p.b_res_bytes = p.b_resident ? b_total : 0;
@@ -1343,8 +1335,7 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     if (smem_bytes < 160 * 1024) smem_bytes = 160 * 1024;
     static const bool no_pair_g = getenv("RGBD_NO_CTA_PAIR") != nullptr;
     const int total_m = p.total_tiles / p.n_tiles_n;
-    if ((d->epi_mode == 1 || d->epi_mode == 3) && !p.b_resident && !no_pair_g && total_m >= 2 && (p.BLOCK_N / 2) % 16 == 0 &&
-        p.dbg_shift == 0) {
+    if ((d->epi_mode == 1 || d->epi_mode == 3) && !p.b_resident && !no_pair_g && total_m >= 2 && (p.BLOCK_N / 2) % 16 == 0) {
         CUtensorMap tmap_b2;
         cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->n_pad};
         cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
