@@ -203,6 +203,18 @@ int rgbd_ratio_tail(const long long* pool_sums, int pool_stride, int cell_pixels
                     const float* conv_shift, const float* const* fc_w_host, const float* const* fc_b_host, float out_min,
                     float out_max, float* gap_ws, float* ratio_out, int B, rgbd_stream_t stream);
 
+/* Reference helper API on caller-supplied intermediates (the batched rgbd_depth_decompose never needs them):
+ * rgbd_depth_select_modes  = DSAModule._select_depth_distribution_modes (CM:720-752): hist (B,512) int64 + bin_edges
+ *   (B,513) fp32 -> up to num_modes peaks (scipy find_peaks with prominence >= threshold * max) ordered by (height, centre)
+ *   descending: n_modes_out (B), peak_bins_out (B,3), centres_out (B,3).
+ * rgbd_depth_region_codes  = DSAModule._generate_depth_region_masks (CM:774-798): gray (B,pixels) + windows (B,3,2) +
+ *   n_windows (B) -> one code byte per pixel, bit t = lo_t <= g <= hi_t, bit n_windows = the remaining region. */
+size_t rgbd_depth_helper_workspace_bytes(int B);
+int rgbd_depth_select_modes(const long long* hist, const float* edges, int B, int num_modes, double prominence_threshold,
+                            int* n_modes_out, int* peak_bins_out, float* centres_out, void* workspace, rgbd_stream_t stream);
+int rgbd_depth_region_codes(const float* gray, const float* windows, const int* n_windows, int B, long long pixels,
+                            uint8_t* codes_out, void* workspace, rgbd_stream_t stream);
+
 /* ---- resize half of the data mapper's front-end (map_10channel_case2, DL:405-414), bit-exact with the libraries the
  * reference calls.  rgbd_resize_pil_bilinear_u8: Pillow Image.resize((w,h), BILINEAR) for (B,H,W,C) uint8 images, C <= 4
  * (HF image processor, PIL backend, resample = 2): antialiased triangle filter, 22-bit fixed-point coefficients, horizontal

@@ -70,6 +70,11 @@ SIGNATURES = {
     "rgbd_ratio_stem_compact_width": (C.c_int, [C.c_int]),
     "rgbd_ratio_stem_pack_compact": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                C.c_void_p]),
+    "rgbd_depth_helper_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "rgbd_depth_select_modes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    "rgbd_depth_region_codes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
     "rgbd_resize_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
     "rgbd_resize_pil_bilinear_u8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
     "rgbd_resize_cv_linear_u8": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),

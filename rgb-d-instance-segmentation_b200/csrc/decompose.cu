@@ -187,9 +187,12 @@ __global__ void __launch_bounds__(256) decomp_hist_kernel(const float* __restric
 
 // One CTA (512 threads, one per bin) per image: scipy _local_maxima_1d + _peak_prominences(wlen=None),
 // keep prominence >= 0.01*max (float64), order by (height, centre) descending, first 3; then windows.
+// edges_in != nullptr (helper API, CM:720-752): bin edges (B, 513) supplied by the caller instead of the image's range;
+// ratio == nullptr: no windows (they belong to _define_depth_interval_windows)
 __global__ void __launch_bounds__(kBins) decomp_modes_kernel(const unsigned long long* __restrict__ hist,
                                                              ImgState* __restrict__ st, const float* __restrict__ ratio,
-                                                             int num_modes) {
+                                                             int num_modes, double prom_thr,
+                                                             const float* __restrict__ edges_in) {
     __shared__ long long h[kBins];
     __shared__ long long cand_h[kBins / 2];
     __shared__ int cand_bin[kBins / 2];
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(kBins) decomp_modes_kernel(const unsigned long
     __syncthreads();
     long long hmax = 0;
     for (int k = 0; k < kBins / 32; ++k) hmax = hmax_s[k] > hmax ? hmax_s[k] : hmax;
-    const double pmin = 0.01 * (double)hmax;
+    const double pmin = prom_thr * (double)hmax;
 
     // every rising edge starts at most one plateau -> independent per thread
     const int n = kBins, i_max = n - 1;
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(kBins) decomp_modes_kernel(const unsigned long
     __syncthreads();
     if (i == 0) {
         ImgState loc = s;                 // one read of the per-image state; the serial part below works on registers
-        const float rt = ratio[b];
+        const float rt = ratio ? ratio[b] : 0.f;
         const int nc = n_cand;
         int nm = 0;
         if (!(loc.status & RGBD_DECOMP_RANGE_NOT_FINITE)) {
@@ -255,7 +258,14 @@ __global__ void __launch_bounds__(kBins) decomp_modes_kernel(const unsigned long
                 }
                 int pb = cand_bin[best];
                 cand_bin[best] = -1;
-                float e0 = bin_edge(loc, pb), e1 = bin_edge(loc, pb + 1);
+                float e0, e1;
+                if (edges_in) {
+                    e0 = edges_in[(long long)b * (kBins + 1) + pb];
+                    e1 = edges_in[(long long)b * (kBins + 1) + pb + 1];
+                } else {
+                    e0 = bin_edge(loc, pb);
+                    e1 = bin_edge(loc, pb + 1);
+                }
                 float centre = e0 + (e1 - e0) / 2.0f;
                 float hw = (centre * rt) / 2.0f;
                 float lo = centre - hw;
@@ -398,7 +408,7 @@ extern "C" int rgbd_depth_decompose(const float* depth3, long long depth_batch_s
     RGBD_CHECK_LAUNCH();
     decomp_hist_kernel<<<grid, 256, 0, s>>>(gray, st, hist, HW);
     RGBD_CHECK_LAUNCH();
-    decomp_modes_kernel<<<B, kBins, 0, s>>>(hist, st, ratio, num_modes);
+    decomp_modes_kernel<<<B, kBins, 0, s>>>(hist, st, ratio, num_modes, 0.01, nullptr);
     RGBD_CHECK_LAUNCH();
     decomp_codes_kernel<<<grid, 256, 0, s>>>(gray, st, codes_out, HW);
     RGBD_CHECK_LAUNCH();
@@ -423,5 +433,62 @@ extern "C" int rgbd_depth_decompose(const float* depth3, long long depth_batch_s
         decomp_edges_kernel<<<B, 256, 0, s>>>(st, edges_out);
         RGBD_CHECK_LAUNCH();
     }
+    return RGBD_OK;
+}
+
+// ---- reference helper API on caller-supplied intermediates (DSAModule._select_depth_distribution_modes CM:720-752 and
+// ---- _generate_depth_region_masks CM:774-798); the batched path above never needs them ----------------------------------
+namespace {
+
+__global__ void helper_state_init_kernel(ImgState* st, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) st[i] = ImgState{};
+}
+
+__global__ void helper_state_windows_kernel(ImgState* st, int B, const float* __restrict__ windows, const int* __restrict__ n_windows) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    ImgState s = {};
+    s.n_modes = n_windows[b];
+    for (int k = 0; k < 3; ++k) {
+        s.lo[k] = k < s.n_modes ? windows[(b * 3 + k) * 2] : 0.f;
+        s.hi[k] = k < s.n_modes ? windows[(b * 3 + k) * 2 + 1] : 0.f;
+    }
+    st[b] = s;
+}
+
+}  // namespace
+
+extern "C" size_t rgbd_depth_helper_workspace_bytes(int B) { return sizeof(ImgState) * (size_t)(B > 0 ? B : 0) + 256; }
+
+extern "C" int rgbd_depth_select_modes(const long long* hist, const float* edges, int B, int num_modes, double prominence_threshold,
+                                       int* n_modes_out, int* peak_bins_out, float* centres_out, void* workspace,
+                                       rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(hist && edges && n_modes_out && peak_bins_out && centres_out && workspace, "depth_select_modes: null pointer");
+    RGBD_CHECK_ARG(B >= 1 && num_modes >= 1 && num_modes <= 3, "depth_select_modes: num_modes must be in [1,3]");
+    cudaStream_t s = (cudaStream_t)stream;
+    ImgState* st = (ImgState*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    helper_state_init_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B);
+    RGBD_CHECK_LAUNCH();
+    decomp_modes_kernel<<<B, kBins, 0, s>>>(reinterpret_cast<const unsigned long long*>(hist), st, nullptr, num_modes,
+                                            prominence_threshold, edges);
+    RGBD_CHECK_LAUNCH();
+    decomp_export_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B, num_modes, n_modes_out, peak_bins_out, centres_out, nullptr, nullptr,
+                                                         nullptr, nullptr);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_depth_region_codes(const float* gray, const float* windows, const int* n_windows, int B, long long pixels,
+                                       uint8_t* codes_out, void* workspace, rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(gray && windows && n_windows && codes_out && workspace, "depth_region_codes: null pointer");
+    RGBD_CHECK_ARG(B >= 1 && pixels >= 1 && pixels < (1ll << 31), "depth_region_codes: bad geometry");
+    cudaStream_t s = (cudaStream_t)stream;
+    ImgState* st = (ImgState*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    helper_state_windows_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B, windows, n_windows);
+    RGBD_CHECK_LAUNCH();
+    dim3 grid(min(ceil_div((int)pixels, 256 * 4), 296), B);
+    decomp_codes_kernel<<<grid, 256, 0, s>>>(gray, st, codes_out, (int)pixels);
+    RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }

@@ -184,6 +184,46 @@ def pack_pixel_values(rgb_u8: torch.Tensor, depth_u8: torch.Tensor, out: Optiona
     return out
 
 
+def depth_select_modes(hist: torch.Tensor, edges: torch.Tensor, num_modes: int = 3,
+                       prominence_threshold: float = 0.01) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``DSAModule._select_depth_distribution_modes`` (CM:720-752) on caller-supplied histograms: hist (B,512) int64,
+    edges (B,513) fp32 -> (n_modes (B,), peak_bins (B,3), centres (B,3)) ordered by (height, centre) descending."""
+    lib = _lib.load()
+    _req(hist, "hist", torch.int64)
+    _req(edges, "bin_edges", torch.float32)
+    B = hist.shape[0]
+    if hist.shape != (B, 512) or edges.shape != (B, 513):
+        raise RgbdB200Error("depth_select_modes: the device peak finder is built for 512 bins (hist (B,512), edges (B,513))")
+    dev = hist.device
+    n = torch.empty(B, device=dev, dtype=torch.int32)
+    bins = torch.empty(B, 3, device=dev, dtype=torch.int32)
+    centres = torch.empty(B, 3, device=dev, dtype=torch.float32)
+    ws = torch.empty(int(lib.rgbd_depth_helper_workspace_bytes(B)), device=dev, dtype=torch.uint8)
+    check(lib.rgbd_depth_select_modes(hist.data_ptr(), edges.data_ptr(), B, int(num_modes), float(prominence_threshold),
+                                      n.data_ptr(), bins.data_ptr(), centres.data_ptr(), ws.data_ptr(), _stream()),
+          "rgbd_depth_select_modes")
+    _count(3)
+    return n, bins, centres
+
+
+def depth_region_codes(gray: torch.Tensor, windows: torch.Tensor, n_windows: torch.Tensor) -> torch.Tensor:
+    """``DSAModule._generate_depth_region_masks`` (CM:774-798) as one code byte per pixel: gray (B,...) fp32, windows
+    (B,3,2) fp32, n_windows (B,) int32 -> codes (same shape as gray) uint8, bit n_windows[b] = the remaining region."""
+    lib = _lib.load()
+    _req(gray, "depth_map", torch.float32)
+    _req(windows, "interval_windows", torch.float32)
+    _req(n_windows, "n_windows", torch.int32)
+    B = gray.shape[0]
+    if windows.shape != (B, 3, 2) or n_windows.shape != (B,):
+        raise RgbdB200Error("depth_region_codes: windows must be (B,3,2) and n_windows (B,)")
+    codes = torch.empty(gray.shape, device=gray.device, dtype=torch.uint8)
+    ws = torch.empty(int(lib.rgbd_depth_helper_workspace_bytes(B)), device=gray.device, dtype=torch.uint8)
+    check(lib.rgbd_depth_region_codes(gray.data_ptr(), windows.data_ptr(), n_windows.data_ptr(), B, gray[0].numel(),
+                                      codes.data_ptr(), ws.data_ptr(), _stream()), "rgbd_depth_region_codes")
+    _count(2)
+    return codes
+
+
 def resize_pil_bilinear(img_u8: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
     """(B,H,W,C) or (B,H,W) uint8 -> (B,h,w[,C]) uint8, bit-exact with ``PIL.Image.resize((w,h), BILINEAR)`` -- the resize
     of the HF image processor (PIL backend) the reference's mapper runs on the colour image and on ``depth.convert('RGB')``."""

@@ -427,6 +427,41 @@ class DSAModule(nn.Module):
         dec = Fn.depth_decompose(torch.tensor([0.1], device=g.device), [], gray=g, debug=True)
         return dec.hist[0].cpu().numpy(), dec.edges[0].cpu().numpy()
 
+    def _select_depth_distribution_modes(self, hist, bin_edges, num_modes=3, prominence_threshold=0.01):
+        """CM:720-752: centres of the ``num_modes`` highest prominent histogram peaks (scipy ``find_peaks`` semantics),
+        highest first; ``[]`` when no peak survives."""
+        if not 1 <= num_modes <= 3:
+            raise RgbdB200Error("the device peak finder selects 1..3 modes")
+        h = torch.as_tensor(np.ascontiguousarray(hist, dtype=np.int64)).reshape(1, -1).cuda()
+        e = torch.as_tensor(np.ascontiguousarray(bin_edges, dtype=np.float32)).reshape(1, -1).cuda()
+        n, _, centres = Fn.depth_select_modes(h, e, num_modes, prominence_threshold)
+        c = centres[0].cpu().numpy()
+        return [c[k] for k in range(int(n[0]))]
+
+    def _define_depth_interval_windows(self, depth_modes, window_size_ratio=0.1):
+        """CM:754-772.  Six scalar operations on at most three numbers: the batched path does them inside the device
+        kernel (decompose.cu); this mirror of the helper keeps the reference's float32 arithmetic and return types."""
+        interval_windows = []
+        for mode_center in depth_modes:
+            window_half_width = mode_center * window_size_ratio / 2.0
+            interval_windows.append((max(0, mode_center - window_half_width), mode_center + window_half_width))
+        return interval_windows
+
+    def _generate_depth_region_masks(self, depth_map, interval_windows):
+        """CM:774-798: one boolean mask per window plus the remaining region (numpy arrays, like the reference)."""
+        if len(interval_windows) > 3:
+            raise RgbdB200Error("region codes hold at most 3 windows + the remaining region")
+        d = np.ascontiguousarray(depth_map, dtype=np.float32)
+        g = torch.from_numpy(d)[None].cuda()
+        win = torch.zeros(1, 3, 2, dtype=torch.float32)
+        for k, (lo, hi) in enumerate(interval_windows):
+            win[0, k, 0], win[0, k, 1] = float(lo), float(hi)
+        nw = torch.tensor([len(interval_windows)], dtype=torch.int32)
+        codes = Fn.depth_region_codes(g, win.cuda(), nw.cuda())[0].cpu().numpy()
+        if not interval_windows:                      # no windows: everything is "remaining"
+            return [np.ones(d.shape, dtype=bool)]
+        return [((codes >> t) & 1).astype(bool) for t in range(len(interval_windows) + 1)]
+
 
 # =====================================================================================================
 # E-DSAM ratio predictor

@@ -137,6 +137,41 @@ def test_decompose_edge_cases_bit_exact(fn):
         _check_decomposition(fn, [gray], [ratio], levels)
 
 
+def test_dsam_helper_methods_match_reference_goldens(mods, golden_dir):
+    """DSAModule._calculate_depth_histogram / _select_depth_distribution_modes / _define_depth_interval_windows /
+    _generate_depth_region_masks (CM:701-798) as methods, on the reference's own outputs (tests/golden/decompose.npz)."""
+    g = np.load(os.path.join(golden_dir, "decompose.npz"))
+    m = mods.DSAModule(8, 16, 3).cuda()
+    for name, gray, ratio in decompose_cases(synthetic):
+        if not np.isfinite(gray).any():                  # numpy raises inside the reference for this case
+            continue
+        hist, edges = m._calculate_depth_histogram(gray)
+        assert np.array_equal(hist, g[f"{name}.hist"]) and np.array_equal(edges, g[f"{name}.edges"])
+        modes = m._select_depth_distribution_modes(hist, edges, num_modes=3)
+        ref_modes = g[f"{name}.modes"]
+        assert len(modes) == len(ref_modes) and all(np.float32(a) == np.float32(b) for a, b in zip(modes, ref_modes)), name
+        wins = m._define_depth_interval_windows(modes, window_size_ratio=ratio)
+        ref_w = g[f"{name}.windows"]
+        assert len(wins) == len(ref_w)
+        for (lo, hi), (rl, rh) in zip(wins, ref_w):
+            assert np.float32(lo) == rl and np.float32(hi) == rh, name
+        if modes:
+            masks = m._generate_depth_region_masks(gray, wins)
+            ref_masks = np.unpackbits(g[f"{name}.masks"])[:(len(wins) + 1) * gray.size].reshape(len(wins) + 1, *gray.shape).astype(bool)
+            assert len(masks) == len(wins) + 1
+            for a, b in zip(masks, ref_masks):
+                assert a.dtype == bool and np.array_equal(a, b), name
+    # fewer modes on request, a stricter prominence threshold, and no windows at all
+    name, gray, ratio = decompose_cases(synthetic)[0]
+    hist, edges = g[f"{name}.hist"], g[f"{name}.edges"]
+    assert m._select_depth_distribution_modes(hist, edges, num_modes=1) == [m._select_depth_distribution_modes(hist, edges)[0]]
+    strict = m._select_depth_distribution_modes(hist, edges, num_modes=3, prominence_threshold=0.9)
+    want = O.select_depth_modes(hist, edges, 3, 0.9)[1]
+    assert [np.float32(v) for v in strict] == [np.float32(v) for v in want]
+    rest = m._generate_depth_region_masks(gray, [])
+    assert len(rest) == 1 and rest[0].all()
+
+
 def test_decompose_full_size_batch_bit_exact(fn):
     grays, ratios = [], []
     for j, kind in enumerate(["nyu", "nyu", "nyu", "uniform", "constant", "two_valued"]):
