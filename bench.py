@@ -225,11 +225,14 @@ def run_own(args):
     feats = make_features(B, 7 + rank, dev)
     feats_host = [f.cpu().pin_memory() for f in feats]
 
-    use_graph = args.graph        # measured: no gain (9.04 vs 8.99 ms/step) -- the GPU is busy end to end
+    use_graph = args.graph        # measured: 6.89 vs 7.02 ms/step -- launch gaps are ~2 % of the step now
     if use_graph:
-        graphed = modules.GraphedDepthGuidance(model, pv, feats)     # CUDA graph of the whole step (static shapes)
-        launches_per_step = None
-
+        try:
+            graphed = modules.GraphedDepthGuidance(model, pv, feats)     # CUDA graph of the whole step (static shapes)
+        except Exception as e:                                           # never lose the measurement to a capture problem
+            print(f"[bench] CUDA graph capture failed ({e!r}); launching kernel by kernel", file=sys.stderr)
+            use_graph = False
+    if use_graph:
         def step():
             return graphed()
     else:
@@ -600,7 +603,9 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-steps", type=int, default=5)
     ap.add_argument("--mode", default="infer", choices=["infer", "train"])
-    ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph instead of ~40 launches")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="launch the ~22 kernels of a step one by one instead of replaying the step as one CUDA graph")
+    ap.set_defaults(graph=True)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
