@@ -151,6 +151,13 @@ typedef struct rgbd_conv_gemm_desc {
        (tap, channel block, segment, 64 channels), segment m3_n_seg-1 = rgb_projection, m3_masked_segs = m3_n_seg-1;
        needs epi_mode 1, kb_elems 64, plane_per_img 4; slices are ignored. */
     int dsam_masked;
+    /* epi_mode 1 only: next_operand != NULL also writes the result as the NEXT stride-2 DSAM stage's operand, i.e. exactly
+       what rgbd_dsam_pack(out, next_codes, next_operand, n_img, n, next_c_pad, out_h, out_w, next_n_seg, next_masked_segs,
+       parity_split = 1, hi_lo = 0) would produce (bf16, (n_img, next_n_seg, 4, ceil(out_h/2), ceil(out_w/2), next_c_pad));
+       next_codes: pooled region codes (n_img, out_h, out_w), needed when next_masked_segs > 0. */
+    void* next_operand;
+    const void* next_codes;
+    int next_c_pad, next_n_seg, next_masked_segs;
 } rgbd_conv_gemm_desc;
 int rgbd_conv_gemm(const rgbd_conv_gemm_desc* desc_host, rgbd_stream_t stream);
 

@@ -30,6 +30,8 @@ class ConvGemmDesc(C.Structure):
         ("codes", C.c_void_p), ("in_h", C.c_int), ("in_w", C.c_int), ("m3_py", C.c_int), ("m3_px", C.c_int),
         ("m3_stride", C.c_int), ("m3_masked_segs", C.c_int), ("m3_n_seg", C.c_int),
         ("dsam_masked", C.c_int),
+        ("next_operand", C.c_void_p), ("next_codes", C.c_void_p),
+        ("next_c_pad", C.c_int), ("next_n_seg", C.c_int), ("next_masked_segs", C.c_int),
     ]
 
 

@@ -55,6 +55,11 @@ struct KParams {
     const uint8_t* codes;     // epilogue mode 3: region codes at the resolution of dX
     int in_h, in_w, m3_py, m3_px, m3_stride, m3_masked_segs, m3_n_seg;
     int dsam_taps;            // dsam_fwd_kernel: 9 (3x3 stride 2 on parity planes)
+    // epilogue mode 1: also emit the result as the NEXT DSAM stage's bf16 parity-split operand (what rgbd_dsam_pack would
+    // build from the fp32 output), so the cascade needs no pack kernel between its stages
+    __nv_bfloat16* next_op;
+    const uint8_t* next_codes;
+    int next_c_pad, next_n_seg, next_masked_segs;
     int c_blocks, sa_stages, a_stage_bytes;   // conv3x3_kernel: 64-channel blocks, A-ring depth, bytes per A stage
 };
 
@@ -313,6 +318,29 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (n0 + j < p.N) o[base + (size_t)(n0 + j) * plane] = f[j];
+                    if (p.next_op && n0 < p.next_c_pad) {
+                        uint4 v4[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            uint32_t* w = reinterpret_cast<uint32_t*>(&v4[e]);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const int j = e * 8 + t * 2;
+                                w[t] = tc::pack_bf16x2(n0 + j < p.N ? f[j] : 0.f, n0 + j + 1 < p.N ? f[j + 1] : 0.f);
+                            }
+                        }
+                        const int H2 = (p.out_h + 1) >> 1, W2 = (p.out_w + 1) >> 1;
+                        const int par = (oy & 1) * 2 + (ox & 1);
+                        const unsigned code = p.next_masked_segs ? p.next_codes[((size_t)img * p.out_h + oy) * p.out_w + ox] : 0u;
+                        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+                        for (int sg = 0; sg < p.next_n_seg; ++sg) {
+                            const bool keep = sg >= p.next_masked_segs || ((code >> sg) & 1u);
+                            const size_t pl = ((size_t)img * p.next_n_seg + sg) * 4 + par;
+                            uint4* dst = reinterpret_cast<uint4*>(p.next_op + ((pl * H2 + (oy >> 1)) * W2 + (ox >> 1)) * p.next_c_pad + n0);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) dst[e] = keep ? v4[e] : zero;
+                        }
+                    }
                 }
             } else {
                 if (uniform) {
@@ -1109,6 +1137,11 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
                            (long long)d->n_img * ceil_div(d->out_w, d->bx) * ceil_div(d->out_h, d->by) >= 2,
                        "conv_gemm: dsam_masked needs epilogue mode 1, kb=64, C %% 64 == 0, 4 parity planes, codes, "
                        "2..5 segments and at least two pixel tiles");
+    if (d->next_operand)
+        RGBD_CHECK_ARG(d->epi_mode == 1 && d->next_c_pad >= d->n && d->next_c_pad % 32 == 0 && d->next_n_seg >= 1 &&
+                           d->next_n_seg <= 8 && d->next_masked_segs >= 0 && d->next_masked_segs <= 4 &&
+                           d->next_masked_segs <= d->next_n_seg && (d->next_masked_segs == 0 || d->next_codes),
+                       "conv_gemm: next_operand needs epilogue mode 1 and the next stage's packing geometry");
     if (d->epi_mode == 3)
         RGBD_CHECK_ARG(d->codes && d->m3_n_seg >= 1 && d->m3_n_seg <= 8 && d->block_n == 32 * d->m3_n_seg && d->in_h >= 1 &&
                            d->in_w >= 1 && (d->m3_stride == 1 || d->m3_stride == 2) && !d->conv3x3_reuse,
@@ -1192,6 +1225,9 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     p.tiles_y = ceil_div(d->out_h, d->by);
     p.n_slices = (d->conv3x3_reuse || d->dsam_masked) ? 0 : d->n_slices;
     p.dsam_taps = 9;
+    p.next_op = reinterpret_cast<__nv_bfloat16*>(d->next_operand);
+    p.next_codes = reinterpret_cast<const uint8_t*>(d->next_codes);
+    p.next_c_pad = d->next_c_pad; p.next_n_seg = d->next_n_seg; p.next_masked_segs = d->next_masked_segs;
     p.kb_bytes = kb_bytes;
     p.c_blocks = d->a_c / 64;
     p.sa_stages = 0;

@@ -363,7 +363,8 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
               cells: Tuple[int, int] = (0, 0), tile_order: int = 0, block_n: Optional[int] = None,
               conv3x3_reuse: bool = False, codes: Optional[torch.Tensor] = None, in_hw: Tuple[int, int] = (0, 0),
               parity: Tuple[int, int] = (0, 0), m3_stride: int = 1, m3_masked_segs: int = 0, m3_n_seg: int = 0,
-              dsam_masked: bool = False) -> None:
+              dsam_masked: bool = False, next_operand: Optional[torch.Tensor] = None,
+              next_codes: Optional[torch.Tensor] = None, next_geom: Tuple[int, int, int] = (0, 0, 0)) -> None:
     """Launch the tcgen05 implicit-GEMM kernel.  a_dims = (planes, y, x, c) of the bf16 channels-last operand.
     ``conv3x3_reuse``: 3x3 stride-1 conv whose A tile is shared by the three dx taps (``slices`` may be None).
     ``dsam_masked``: stride-2 DSAM stage on the unmasked operand, region masking in shared memory (``slices`` None)."""
@@ -393,6 +394,9 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
     d.n_slices = n_slices; d.kb_elems = kb
     d.conv3x3_reuse = 1 if conv3x3_reuse else 0
     d.dsam_masked = 1 if dsam_masked else 0
+    d.next_operand = _req(next_operand, "next_operand", torch.bfloat16).data_ptr() if next_operand is not None else None
+    d.next_codes = _req(next_codes, "next_codes", torch.uint8).data_ptr() if next_codes is not None else None
+    d.next_c_pad, d.next_n_seg, d.next_masked_segs = next_geom
     d.n_img = n_img; d.out_h, d.out_w = out_hw; d.bx, d.by = box
     d.n = n; d.n_pad = n_pad; d.block_n = block_n or pick_block_n(n_pad)
     d.tile_order = tile_order; d.epi_mode = epi_mode; d.act = act

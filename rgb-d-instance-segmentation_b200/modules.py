@@ -21,6 +21,9 @@ from . import functional as Fn
 from ._lib import RgbdB200Error
 
 
+#: False: every DSAM stage packs its own operand (A/B switch for the epilogue-emitted operands of the inference cascade)
+FUSE_STAGE_PACKS = os.environ.get("RGBD_NO_STAGE_PACK_FUSION", "") in ("", "0")
+
 #: RGBD_DSAM_PREMASKED=1 keeps the five-fold pre-masked DSAM operand in HBM (A/B measurements against the shared-memory masking kernel)
 _PREMASKED = os.environ.get("RGBD_DSAM_PREMASKED", "") not in ("", "0")
 
@@ -354,11 +357,32 @@ class DSAModule(nn.Module):
                              block_n=32 * n_seg)
         return dx, grads
 
+    def _uses_masked_kernel(self, B: int, H: int, W: int) -> bool:
+        """Stride-2 stage handled by dsam_fwd_kernel (one unmasked operand copy, masking in shared memory)."""
+        pk = self._refresh()
+        c_pad, kb, n_pad, n_seg = self._geometry()
+        Ho, Wo = (H + 1) // 2, (W + 1) // 2
+        box = _best_box(Ho, Wo)
+        return bool(self._proj and pk["w_masked"] is not None and not pk["split"] and not _PREMASKED
+                    and n_pad // Fn.pick_block_n(n_pad) <= 2 and B * (-(-Ho // box[1])) * (-(-Wo // box[0])) >= 2)
+
+    def _emit_target(self, B: int, H: int, W: int, dev):
+        """(workspace, (c_pad, n_seg, masked_segs)) the PREVIOUS stage's epilogue can fill instead of this stage's pack
+        kernel, or None (1x1 stages and the split-precision mode pack for themselves)."""
+        pk = self._refresh()
+        if not self._proj or pk["split"]:
+            return None
+        c_pad, kb, n_pad, n_seg = self._geometry()
+        if self._uses_masked_kernel(B, H, W):
+            return self._workspace(B, H, W, dev, n_op=1), (c_pad, 1, 0)
+        return self._workspace(B, H, W, dev), (c_pad, n_seg, self.num_depth_regions + 1)
+
     def _stage_forward_impl(self, rgb_features: torch.Tensor, codes: torch.Tensor, bias_variant: torch.Tensor,
-                            residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+                            residual: Optional[torch.Tensor] = None, emit_next=None, prepacked: bool = False) -> torch.Tensor:
         """Batched tensor-core path: features (B,C_in,H,W) fp32, pooled region codes (B,H,W) uint8 and the
         per-image bias count (Decomposition.bias_variant) -> sum_t conv_t(F*p_t) + projection(F) [+ residual]
-        (fp32 result, bf16 operands)."""
+        (fp32 result, bf16 operands).  ``emit_next = (workspace, geometry, codes)`` of the next stage: the epilogue also
+        writes that stage's packed operand; ``prepacked``: this stage's operand was written that way."""
         pk = self._refresh()
         x = Fn._req(rgb_features.detach().contiguous(), "rgb_features", torch.float32)
         if residual is not None:
@@ -369,22 +393,25 @@ class DSAModule(nn.Module):
         R = self.num_depth_regions
         Ho, Wo = (H + 1) // 2, (W + 1) // 2
         box = _best_box(Ho, Wo)
-        if (self._proj and pk["w_masked"] is not None and not pk["split"] and not _PREMASKED
-                and n_pad // Fn.pick_block_n(n_pad) <= 2 and B * (-(-Ho // box[1])) * (-(-Wo // box[0])) >= 2):
+        skip_pack = prepacked or getattr(self, "_gemm_only", False)     # bench.py times the GEMM alone on packed operands
+        nxt = {}
+        if emit_next is not None:
+            nxt = dict(next_operand=emit_next[0], next_geom=emit_next[1], next_codes=emit_next[2])
+        if self._uses_masked_kernel(B, H, W):
             # one unmasked operand copy; the kernel masks the tile per region in shared memory.  The masking is
             # redone for every N tile, so wide stages (768 outputs = 3 N tiles) keep the pre-masked operand
             # (measured, B=32: 406 us vs 302 us for stage 2; 492 vs 583 and 362 vs 399 us for stages 0 and 1)
             packed = self._workspace(B, H, W, x.device, n_op=1)
-            if not getattr(self, "_gemm_only", False):
+            if not skip_pack:
                 Fn.dsam_pack(x, codes, packed, c_pad, 1, 0, True)
             out = torch.empty(B, self.out_channels, Ho, Wo, device=x.device, dtype=torch.float32)
             Fn.conv_gemm(packed, (B * 4, Ho, Wo, c_pad), 4, pk["w_masked"], None, 64, B, (Ho, Wo), box, self.out_channels,
                          pk["bias"], variant=bias_variant, epi_mode=1, out=out,
                          residual=residual.contiguous() if residual is not None else None, codes=codes, in_hw=(H, W),
-                         m3_masked_segs=R + 1, m3_n_seg=n_seg, dsam_masked=True)
+                         m3_masked_segs=R + 1, m3_n_seg=n_seg, dsam_masked=True, **nxt)
             return out
         packed = self._workspace(B, H, W, x.device)
-        if not getattr(self, "_gemm_only", False):        # bench.py times the GEMM alone on packed operands
+        if not skip_pack:
             Fn.dsam_pack(x, codes, packed, c_pad, n_seg, R + 1, self._proj, hi_lo=pk["split"])
         n_op = n_seg * (2 if pk["split"] else 1)
         if self._proj:
@@ -400,7 +427,7 @@ class DSAModule(nn.Module):
         variant = bias_variant
         Fn.conv_gemm(packed, a_dims, ppi, pk["w"], pk["slices"], kb, B, (Ho, Wo), _best_box(Ho, Wo), self.out_channels,
                      pk["bias"], variant=variant, epi_mode=1, out=out,
-                     residual=residual.contiguous() if residual is not None else None)
+                     residual=residual.contiguous() if residual is not None else None, **nxt)
         return out
 
     def forward(self, rgb_features, depth_map, window_size_ratio=0.1):
@@ -702,12 +729,24 @@ def depth_guidance_forward(ratio_predictor: EnhancedDepthImageRatioPredictor, ds
     ratios = ratios.detach()                                                # consumed through .item() in CM:339
     levels = [tuple(f.shape[2:]) for f in feats[:3]]
     dec = Fn.depth_decompose(ratios.reshape(-1).contiguous(), levels, depth3=depth)
+    training = torch.is_grad_enabled() and any(p.requires_grad for m in (*dsams, dggm) for p in m.parameters())
     cp1 = [feats[0]]
     x = feats[0]
+    prepacked = False
     for k, dsam in enumerate(dsams):                                        # CM:339-352
-        x = dsam.stage_forward(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1])
+        if training or not FUSE_STAGE_PACKS:
+            x = dsam.stage_forward(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1])
+        else:
+            # inference: stage k's epilogue also writes stage k+1's packed bf16 operand (no pack kernel in between)
+            emit = None
+            if k + 1 < len(dsams):
+                tgt = dsams[k + 1]._emit_target(x.shape[0], feats[k + 1].shape[2], feats[k + 1].shape[3], x.device)
+                if tgt is not None:
+                    emit = (tgt[0], tgt[1], dec.pooled[k + 1])
+            x = dsam._stage_forward_impl(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1], emit_next=emit,
+                                         prepacked=prepacked)
+            prepacked = emit is not None
         cp1.append(x)
-    training = torch.is_grad_enabled() and any(p.requires_grad for m in (*dsams, dggm) for p in m.parameters())
     if training:
         if out is not None:
             raise RgbdB200Error("preallocated outputs are an inference-path option")

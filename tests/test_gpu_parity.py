@@ -693,6 +693,35 @@ def test_hot_path_is_reproducible_run_to_run(mods, fn):
         assert all(torch.equal(a, b) for a, b in zip(outs, runs[0][1]))
 
 
+@pytest.mark.parametrize("chans,hw", [((96, 192, 384, 768), (192, 256)), ((32, 72, 96, 160), (72, 88)),
+                                      ((128, 256, 512, 1024), (100, 132))])
+def test_stage_operands_emitted_by_the_previous_epilogue_are_bit_identical(mods, fn, monkeypatch, chans, hw):
+    """Inference cascade: stage k's epilogue writes stage k+1's packed bf16 operand (unmasked single copy or the five-fold
+    pre-masked layout).  It must be exactly what the pack kernel builds from the fp32 result, so every output is
+    bit-identical with the fusion switched off; odd sizes exercise the parity-plane padding."""
+    H, W = hw
+    B = 3
+    m = mods.DepthGuidance(chans)
+    m.load_state_dict(OW.guidance_weights(seed=78, channels=chans))
+    m.cuda().eval()
+    rgbs, ds = zip(*[synthetic.synth_rgbd_u8(800 + j, H, W, "nyu") for j in range(B)])
+    pv = fn.pack_pixel_values(torch.from_numpy(np.stack(rgbs)).cuda(), torch.from_numpy(np.stack(ds)).cuda())
+    g = torch.Generator(device="cpu").manual_seed(4)
+    sizes = [(-(-H // s), -(-W // s)) for s in (4, 8, 16, 32)]
+    feats = [torch.randn(B, c, h, w, generator=g).cuda() for c, (h, w) in zip(chans, sizes)]
+    ratios = torch.tensor([[0.1], [0.3], [0.5]], device="cuda")
+    outs = []
+    for fused in (True, False, True):
+        monkeypatch.setattr(mods, "FUSE_STAGE_PACKS", fused)
+        n0 = fn.LAUNCHES
+        with torch.no_grad():
+            outs.append([o.clone() for o in m(pv, feats, ratios=ratios)])
+        outs[-1].append(fn.LAUNCHES - n0)
+    assert outs[0][4] < outs[1][4]                      # fewer launches with the fusion
+    for a, b, c in zip(outs[0][:4], outs[1][:4], outs[2][:4]):
+        assert torch.equal(a, b) and torch.equal(a, c)
+
+
 def test_large_frame_swin_b_cross_implementation(mods, fn, monkeypatch):
     """BASELINE configs[4]: 960x1280 frames, Swin-B channels, window ratio forced to output_max.  No oracle at this size;
     the independent kernel variants of each stage must agree: fused front end (sliding-window operand) vs stem GEMM +
