@@ -614,6 +614,13 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         B, _, H, W = depth_image.shape
         if H % 4 or W % 4:
             raise RgbdB200Error("the fused AdaptiveAvgPool2d(4) epilogue needs H and W divisible by 4")
+        if self.training and not getattr(self, "_warned_train_mode", False):
+            import warnings
+            warnings.warn("rgbd_b200.EnhancedDepthImageRatioPredictor always uses the BatchNorm running statistics and no "
+                          "Dropout (eval semantics), also under .train(): the reference would use batch statistics and "
+                          "update the running ones (CM:1444-1487).  The module receives no gradient either way (its output "
+                          "is consumed through .item(), CM:339).", RuntimeWarning, stacklevel=2)
+            self._warned_train_mode = True
         pk = self._refresh()
         ws = self._workspace(B, H, W, depth_image.device)
         d = depth_image.detach()
