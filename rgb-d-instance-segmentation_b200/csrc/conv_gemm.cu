@@ -30,6 +30,7 @@ constexpr int kMaxStages = 12;
 constexpr int kMaxSlices = 1024;
 constexpr int kThreads = 384;        // 4 control warps + 8 epilogue warps
 constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = kEpiThreads / 32;   // arrivals per CTA on tmem_empty: one per epilogue warp
 constexpr int kTmemCols = 512;
 
 struct KParams {
@@ -366,8 +367,13 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
             }
         }
         tc::tc_fence_before();
-        if (c.tmem_empty_remote[as]) tc::mbar_arrive_cluster(c.tmem_empty_remote[as]);
-        else tc::mbar_arrive(&ctl->tmem_empty[as]);
+        // one arrive per warp, CTA-scope release: the payload is tensor memory (read complete: tcgen05.wait::ld above,
+        // ordered by the tcgen05 fence); a cluster-scope release per thread costs a MEMBAR.ALL.GPU + ERRBAR each
+        __syncwarp();
+        if (lane == 0) {
+            if (c.tmem_empty_remote[as]) tc::mbar_arrive_cluster_tmem(c.tmem_empty_remote[as]);
+            else tc::mbar_arrive(&ctl->tmem_empty[as]);
+        }
         if (++as == 2) { as = 0; aphase ^= 1; }
         if (MODE == 0) {
             if (p.gate_bytes) {
@@ -427,7 +433,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&ctl->tmem_full[s], 1);
-            tc::mbar_init(&ctl->tmem_empty[s], kEpiThreads);
+            tc::mbar_init(&ctl->tmem_empty[s], kEpiWarps);
         }
         tc::mbar_init(&ctl->b_full, 1);
         tc::mbar_init(&ctl->gate_full, 1);
@@ -575,7 +581,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&ctl->tmem_full[s], 1);
-            tc::mbar_init(&ctl->tmem_empty[s], kEpiThreads);
+            tc::mbar_init(&ctl->tmem_empty[s], kEpiWarps);
         }
         tc::mbar_init(&ctl->gate_full, 1);
         tc::mbar_init(&ctl->gate_empty, kEpiThreads);
@@ -715,7 +721,7 @@ dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             tc::mbar_init(&ctl->masked_full[g], 2 * 4);        // one arrive per mask warp of BOTH CTAs (counted in the leader)
             tc::mbar_init(&ctl->masked_empty[g], 1);           // multicast commit
             tc::mbar_init(&ctl->tmem_full[g], 1);
-            tc::mbar_init(&ctl->tmem_empty[g], 2 * kEpiThreads);
+            tc::mbar_init(&ctl->tmem_empty[g], 2 * kEpiWarps);
         }
         tc::fence_barrier_init();
     }
@@ -891,7 +897,7 @@ conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&ctl->tmem_full[s], 1);
-            tc::mbar_init(&ctl->tmem_empty[s], 2 * kEpiThreads);
+            tc::mbar_init(&ctl->tmem_empty[s], 2 * kEpiWarps);
         }
         tc::fence_barrier_init();
     }
@@ -1002,7 +1008,7 @@ conv3x3_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&ctl->tmem_full[s], 1);
-            tc::mbar_init(&ctl->tmem_empty[s], 2 * kEpiThreads);       // the epilogue threads of BOTH CTAs
+            tc::mbar_init(&ctl->tmem_empty[s], 2 * kEpiWarps);     // the epilogue warps of BOTH CTAs
         }
         tc::fence_barrier_init();
     }
