@@ -777,8 +777,9 @@ dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 }
             }
         }
-    } else if (warp == 1 && lane == 0 && leader) {
-        // ================= MMA issuer (leader) =================
+    } else if (warp == 1 && leader) {
+        // ================= MMA issuer (leader): the whole warp runs the uniform control flow so the descriptors stay in
+        // uniform registers (no per-MMA ELECT/R2UR waterfall); one elected lane issues =================
         const uint32_t idesc = tc::make_idesc_bf16(2 * kBlockM, p.BLOCK_N);
         int g = 0, r = 0, sb = 0, as = 0;
         uint32_t pg = 0, pb = 0, aphase = 0;
@@ -786,7 +787,7 @@ dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
             tc::tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BLOCK_N);
-            uint32_t first = 1;
+            uint32_t first = 0;                                 // 0 until the tile's first MMA (overwrites the accumulator)
             for (int gi = 0; gi < groups_per_tile; ++gi) {
                 tc::mbar_wait(&ctl->masked_full[g], pg);       // both CTAs: raw tile landed and masked copies written
                 tc::tc_fence_after();
@@ -796,19 +797,24 @@ dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     const uint8_t* a_tile = sg < n_msk ? s_msk + (size_t)(g * n_msk + sg) * kTile : s_rawt + (size_t)r * kTile;
                     const uint64_t adesc = tc::make_kmajor_desc(tc::smem_u32(a_tile), 128);
                     const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_b + (size_t)sb * b_bytes), 128);
-                    for (int k = 0; k < 4; ++k) {
-                        tc::umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
-                        first = 0;
+                    if (tc::elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc::umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (first | k) ? 1u : 0u);
+                        tc::umma_commit_2cta(&ctl->empty[sb]);
+                        if (sg == n_seg - 1) {
+                            tc::umma_commit_2cta(&ctl->masked_empty[g]);
+                            tc::umma_commit_2cta(&ctl->a_empty[r]);
+                            if (gi == groups_per_tile - 1) tc::umma_commit_2cta(&ctl->tmem_full[as]);
+                        }
                     }
-                    tc::umma_commit_2cta(&ctl->empty[sb]);
+                    __syncwarp();
+                    first = 1;
                     if (++sb == p.stages) { sb = 0; pb ^= 1; }
                 }
-                tc::umma_commit_2cta(&ctl->masked_empty[g]);
-                tc::umma_commit_2cta(&ctl->a_empty[r]);
                 if (++g == 2) { g = 0; pg ^= 1; }
                 if (++r == kDsamRaw) r = 0;
             }
-            tc::umma_commit_2cta(&ctl->tmem_full[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 12) {
@@ -933,7 +939,8 @@ conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0 && leader) {
+    } else if (warp == 1 && leader) {
+        // whole warp in uniform control flow, one elected lane issues (descriptors stay in uniform registers)
         const uint32_t idesc = tc::make_idesc_bf16(2 * kBlockM, p.BLOCK_N);
         const int k_per_block = p.kb_bytes >> 5;
         int stage = 0, as = 0;
@@ -948,12 +955,15 @@ conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint64_t adesc = tc::make_kmajor_desc(sa, p.kb_bytes);
                 const uint64_t bdesc = tc::make_kmajor_desc(sa + a_bytes, p.kb_bytes);
-                for (int k = 0; k < k_per_block; ++k)
-                    tc::umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (j | k) != 0);
-                tc::umma_commit_2cta(&ctl->empty[stage]);
+                if (tc::elect_one()) {
+                    for (int k = 0; k < k_per_block; ++k)
+                        tc::umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (j | k) != 0);
+                    tc::umma_commit_2cta(&ctl->empty[stage]);
+                    if (j == p.n_slices - 1) tc::umma_commit_2cta(&ctl->tmem_full[as]);
+                }
+                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            tc::umma_commit_2cta(&ctl->tmem_full[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 4) {
@@ -1051,8 +1061,9 @@ conv3x3_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
         }
-    } else if (warp == 1 && lane == 0 && leader) {
-        // ================= MMA issuer (leader CTA only) =================
+    } else if (warp == 1 && leader) {
+        // ================= MMA issuer (leader CTA only): whole warp in uniform control flow, one elected lane issues (keeps the
+        // descriptors in uniform registers: no per-MMA ELECT/R2UR waterfall) =================
         const uint32_t idesc = tc::make_idesc_bf16(2 * kBlockM, p.BLOCK_N);
         int sa = 0, sb = 0, as = 0;
         uint32_t pa = 0, pb = 0, aphase = 0;
@@ -1060,7 +1071,7 @@ conv3x3_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
             tc::tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BLOCK_N);
-            uint32_t first = 1;
+            uint32_t started = 0;
             for (int dy = 0; dy < 3; ++dy) {
                 for (int cb = 0; cb < p.c_blocks; ++cb) {
                     tc::mbar_wait(&ctl->a_full[sa], pa);
@@ -1070,18 +1081,24 @@ conv3x3_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         tc::tc_fence_after();
                         const uint64_t adesc = tc::make_kmajor_desc(a_base + (uint32_t)(dx * 128), 128);
                         const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_b + (size_t)sb * b_bytes), 128);
-                        for (int k = 0; k < 4; ++k) {
-                            tc::umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
-                            first = 0;
+                        if (tc::elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc::umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                                   (started | k) ? 1u : 0u);
+                            tc::umma_commit_2cta(&ctl->empty[sb]);
+                            if (dx == 2) {
+                                tc::umma_commit_2cta(&ctl->a_empty[sa]);
+                                if (dy == 2 && cb == p.c_blocks - 1) tc::umma_commit_2cta(&ctl->tmem_full[as]);
+                            }
                         }
-                        tc::umma_commit_2cta(&ctl->empty[sb]);
+                        __syncwarp();
+                        started = 1;
                         if (++sb == p.stages) { sb = 0; pb ^= 1; }
                     }
-                    tc::umma_commit_2cta(&ctl->a_empty[sa]);
                     if (++sa == p.sa_stages) { sa = 0; pa ^= 1; }
                 }
             }
-            tc::umma_commit_2cta(&ctl->tmem_full[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 4) {
