@@ -484,8 +484,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ================= MMA issuer =================
+    } else if (warp == 1) {
+        // ================= MMA issuer: whole warp in uniform control flow, one elected lane issues =================
         const uint32_t idesc = tc::make_idesc_bf16(kBlockM, p.BLOCK_N);
         const int k_per_block = p.kb_bytes >> 5;           // UMMA_K = 16 bf16 = 32 bytes
         int stage = 0;
@@ -504,12 +504,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint32_t sb = p.b_resident ? tc::smem_u32(s_bres + (size_t)j * b_bytes) : sa + a_bytes;
                 const uint64_t adesc = tc::make_kmajor_desc(sa, p.kb_bytes);
                 const uint64_t bdesc = tc::make_kmajor_desc(sb, p.kb_bytes);
-                for (int k = 0; k < k_per_block; ++k)
-                    tc::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (j | k) != 0);
-                tc::umma_commit(&ctl->empty[stage]);
+                if (tc::elect_one()) {
+                    for (int k = 0; k < k_per_block; ++k)
+                        tc::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (j | k) != 0);
+                    tc::umma_commit(&ctl->empty[stage]);
+                    if (j == p.n_slices - 1) tc::umma_commit(&ctl->tmem_full[as]);
+                }
+                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            tc::umma_commit(&ctl->tmem_full[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 4) {
@@ -621,8 +624,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ================= MMA issuer =================
+    } else if (warp == 1) {
+        // ================= MMA issuer: whole warp in uniform control flow, one elected lane issues =================
         const uint32_t idesc = tc::make_idesc_bf16(kBlockM, p.BLOCK_N);
         int sa = 0, sb = 0, as = 0;
         uint32_t pa = 0, pb = 0, aphase = 0;
@@ -630,7 +633,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc::mbar_wait(&ctl->tmem_empty[as], aphase ^ 1);
             tc::tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BLOCK_N);
-            uint32_t first = 1;
+            uint32_t first = 0;                 // 0 until the tile's first MMA (overwrites the accumulator)
             for (int dy = 0; dy < 3; ++dy) {
                 for (int cb = 0; cb < p.c_blocks; ++cb) {
                     tc::mbar_wait(&ctl->a_full[sa], pa);
@@ -640,18 +643,23 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         tc::tc_fence_after();
                         const uint64_t adesc = tc::make_kmajor_desc(a_base + (uint32_t)(dx * 128), 128);
                         const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_b + (size_t)sb * b_bytes), 128);
-                        for (int k = 0; k < 4; ++k) {
-                            tc::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);
-                            first = 0;
+                        if (tc::elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc::umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (first | k) ? 1u : 0u);
+                            tc::umma_commit(&ctl->empty[sb]);
+                            if (dx == 2) {
+                                tc::umma_commit(&ctl->a_empty[sa]);
+                                if (dy == 2 && cb == p.c_blocks - 1) tc::umma_commit(&ctl->tmem_full[as]);
+                            }
                         }
-                        tc::umma_commit(&ctl->empty[sb]);
+                        __syncwarp();
+                        first = 1;
                         if (++sb == p.stages) { sb = 0; pb ^= 1; }
                     }
-                    tc::umma_commit(&ctl->a_empty[sa]);
                     if (++sa == p.sa_stages) { sa = 0; pa ^= 1; }
                 }
             }
-            tc::umma_commit(&ctl->tmem_full[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 4) {

@@ -95,7 +95,8 @@ dsam_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
+        // whole warp in uniform control flow, one elected lane issues (descriptors stay in uniform registers)
         const uint32_t idesc = tc::make_idesc_bf16(kBlockM, p.BLOCK_N);
         int stage = 0;
         uint32_t phase = 0, aphase = 0;
@@ -111,12 +112,17 @@ dsam_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                 tc::tc_fence_after();
                 const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint64_t adesc = tc::make_kmajor_desc(sa, 128), bdesc = tc::make_kmajor_desc(sa + a_bytes, 128);
-                for (int k = 0; k < 4; ++k)
-                    tc::umma_bf16(tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (j | k) != 0);
-                tc::umma_commit(&ctl->empty[stage]);
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::umma_bf16(tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (j | k) != 0);
+                    tc::umma_commit(&ctl->empty[stage]);
+                }
+                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            tc::umma_commit(&ctl->acc_full);
+            if (tc::elect_one()) tc::umma_commit(&ctl->acc_full);
+            __syncwarp();
             aphase ^= 1;
         }
     } else if (warp >= 3) {
