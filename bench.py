@@ -436,8 +436,8 @@ def run_own(args):
             "roofline_extra": extra,
             # E-DSAM tensor-core utilisation (BASELINE metric): sm__pipe_tensor_cycles_active from the committed
             # `ncu --set full` capture (batch 8; never measured under this run)
-            "tc_util_pct_ncu": {"source": "profiles/r01_ncu_full_b8_final.txt", "conv3x3_2cta_kernel": 82.8,
-                                "ratio_front_kernel": 56.9, "dsam_fwd_kernel": [46.9, 44.6]},
+            "tc_util_pct_ncu": {"source": "profiles/r01_ncu_full_b8_final.txt", "conv3x3_2cta_kernel": 98.7,
+                                "ratio_front_kernel": 56.9, "dsam_fwd_kernel": [58.2, 45.3], "conv_gemm_2cta_kernel": 77.4},
             "kernel_ms_per_step": {k: v * 1e3 for k, v in kt.items()},
             "cpu_baseline": cpu_base,
         }
