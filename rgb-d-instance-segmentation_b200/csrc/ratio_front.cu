@@ -302,12 +302,13 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_cluster_tmem(x_remote[0]);
+            // the stash must be free before E2 overwrites it: checked HERE, inside the wait for GEMM 2, not after it
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous TMA store has read the stash
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
 
             // ---- E2: f = relu(acc2 + sh2) -> bf16 -> TMEM P+128 (A of GEMM 3) and the shared-memory stash (gating)
             tc::mbar_wait_sleep(&ctl->acc_full[c][1], ph);
             tc::tc_fence_after();
-            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous TMA store has read the stash
-            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
 #pragma unroll 1
             for (int k = h; k < 4; k += 2) {
                 uint32_t v[32];
