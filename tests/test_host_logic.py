@@ -189,3 +189,80 @@ def test_state_dict_keys_match_the_reference_layout():
     keys = set(g.state_dict().keys())
     ref = set(OW.guidance_weights(seed=1).keys())
     assert keys == ref, keys ^ ref
+
+
+def test_masked_kernel_weight_order_matches_the_premasked_layout():
+    """dsam_fwd_kernel's K order (tap, 64-channel block, segment, channel) against the pre-masked layout's (segment, tap,
+    channel): the same convolution, emulated in numpy on the same bf16 weights (host packing logic only)."""
+    ci, co, hw = 96, 64, (6, 8)
+    m = modules.DSAModule(ci, co, 3)
+    m.load_state_dict(OW.dsam_weights(ci, co, seed=5))
+    pk = m._refresh()
+    c_pad, kb, n_pad, n_seg = m._geometry()
+    assert pk["w_masked"] is not None and pk["w_masked"].shape == (n_pad, 9 * c_pad * n_seg)
+    rs = np.random.RandomState(1)
+    feat = rs.randn(1, ci, *hw).astype(np.float32)
+    codes = rs.randint(0, 16, hw).astype(np.uint8)
+    packed = emu_dsam_pack(feat, codes[None], c_pad, n_seg, 4, True)             # (1, n_seg, 4, H2, W2, c_pad)
+    Ho, Wo = (hw[0] + 1) // 2, (hw[1] + 1) // 2
+    ref = emu_conv_gemm(packed.reshape(-1, *packed.shape[3:]), n_seg * 4, pk["w"].float().numpy(),
+                        pk["slices"].numpy().tolist(), kb, 1, (Ho, Wo))
+    # masked kernel: raw tile of (tap, cb) from the UNMASKED planes, rows masked by the code of the INPUT pixel the tap reads
+    wm = pk["w_masked"].float().numpy().astype(np.float64)
+    fpad = np.zeros((c_pad, hw[0] + 2, hw[1] + 2))
+    fpad[:ci, 1:-1, 1:-1] = feat[0]
+    cpad = np.zeros((hw[0] + 2, hw[1] + 2), np.uint8)
+    cpad[1:-1, 1:-1] = codes
+    out = np.zeros((Ho, Wo, n_pad))
+    k = 0
+    for tap in range(9):
+        dy, dx = tap // 3, tap % 3
+        for cb in range(c_pad // 64):
+            for seg in range(n_seg):
+                for oy in range(Ho):
+                    for ox in range(Wo):
+                        iy, ix = 2 * oy + dy, 2 * ox + dx                      # padded coordinates
+                        keep = seg == n_seg - 1 or (cpad[iy, ix] >> seg) & 1
+                        if keep:
+                            out[oy, ox] += wm[:, k:k + 64] @ fpad[cb * 64:(cb + 1) * 64, iy, ix]
+                k += 64
+    assert np.abs(out - ref[0]).max() < 1e-9 * max(np.abs(ref).max(), 1.0)
+
+
+def test_compact_stem_operand_equals_the_row_im2col_operand():
+    """ratio_front's sliding-window operand E (depth channels-last, two copies shifted by one pixel; K = (dy, dx, c)) against
+    the row-im2col operand R (K = (t, j, dx, c)): identical stem pre-activations on the same bf16 weights."""
+    m = modules.EnhancedDepthImageRatioPredictor(3)
+    m.load_state_dict(OW.ratio_weights(seed=7))
+    m.eval()
+    pk = m._refresh()
+    w1 = pk["w1"].float().numpy().astype(np.float64)           # (192, 256)
+    w1c = pk["w1c"].float().numpy().astype(np.float64)         # (192, 224)
+    H, W = 5, 12
+    Wp = W + 8
+    rs = np.random.RandomState(2)
+    d = rs.randn(3, H, W)
+    # E[s][r][xx][c] = d[c][r-3][xx+s-3]
+    E = np.zeros((2, H + 6, Wp, 4))
+    for s in range(2):
+        for r in range(H + 6):
+            for xx in range(Wp):
+                y, x = r - 3, xx + s - 3
+                if 0 <= y < H and 0 <= x < W:
+                    E[s, r, xx, :3] = d[:, y, x]
+    flat = E.reshape(2, H + 6, Wp * 4)
+    # R[r][x][(j*8+dx)*4+c] = d[c][r-3+j][x+dx-3]
+    R = np.zeros((H + 6, W, 64))
+    for r in range(H + 6):
+        for x in range(W):
+            for j in range(2):
+                for dx in range(7):
+                    y, xs = r - 3 + j, x + dx - 3
+                    if 0 <= y < H and 0 <= xs < W:
+                        R[r, x, (j * 8 + dx) * 4:(j * 8 + dx) * 4 + 3] = d[:, y, xs]
+    for y in range(H):
+        for x in range(W):
+            a_r = np.concatenate([R[y + 2 * t, x] for t in range(4)])                       # slice t = rows y + 2t
+            s, p = x & 1, x >> 1                                                           # copy and pixel pair
+            a_e = np.concatenate([flat[s, y + dy, p * 8:p * 8 + 32] for dy in range(7)])    # 64-byte windows, 16-byte stride
+            assert np.allclose(w1 @ a_r, w1c @ a_e, rtol=0, atol=1e-12)
