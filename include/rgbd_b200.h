@@ -217,6 +217,10 @@ int rgbd_ratio_tail(const long long* pool_sums, int pool_stride, int cell_pixels
  * rgbd_depth_region_codes  = DSAModule._generate_depth_region_masks (CM:774-798): gray (B,pixels) + windows (B,3,2) +
  *   n_windows (B) -> one code byte per pixel, bit t = lo_t <= g <= hi_t, bit n_windows = the remaining region. */
 size_t rgbd_depth_helper_workspace_bytes(int B);
+/* CustomMask2FormerPixelLevelModule.to_grayscale (CM:392-502), 3-channel float32 tensors: gray = (0.299 r + 0.587 g) + 0.114 b
+ * per pixel; rgb3 (B,3,pixels) with element strides batch_stride / channel_stride -> gray_out (B,pixels). */
+int rgbd_to_grayscale(const float* rgb3, long long batch_stride, long long channel_stride, float* gray_out, int B,
+                      long long pixels, void* workspace, rgbd_stream_t stream);
 int rgbd_depth_select_modes(const long long* hist, const float* edges, int B, int num_modes, double prominence_threshold,
                             int* n_modes_out, int* peak_bins_out, float* centres_out, void* workspace, rgbd_stream_t stream);
 int rgbd_depth_region_codes(const float* gray, const float* windows, const int* n_windows, int B, long long pixels,

@@ -73,6 +73,8 @@ SIGNATURES = {
     "rgbd_ratio_stem_pack_compact": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                C.c_void_p]),
     "rgbd_depth_helper_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "rgbd_to_grayscale": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p,
+                                    C.c_void_p]),
     "rgbd_depth_select_modes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
     "rgbd_depth_region_codes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,

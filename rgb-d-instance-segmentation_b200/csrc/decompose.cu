@@ -492,3 +492,23 @@ extern "C" int rgbd_depth_region_codes(const float* gray, const float* windows, 
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }
+
+// CustomMask2FormerPixelLevelModule.to_grayscale (CM:392-502) for 3-channel float32 tensors: gray = (0.299 r + 0.587 g) + 0.114 b
+// per pixel (no FMA contraction), B images with arbitrary batch / channel strides.  workspace: rgbd_depth_helper_workspace_bytes(B).
+extern "C" int rgbd_to_grayscale(const float* rgb3, long long batch_stride, long long channel_stride, float* gray_out, int B,
+                                 long long pixels, void* workspace, rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(rgb3 && gray_out && workspace, "to_grayscale: null pointer");
+    RGBD_CHECK_ARG(B >= 1 && pixels >= 1 && pixels < (1ll << 31), "to_grayscale: bad geometry");
+    cudaStream_t s = (cudaStream_t)stream;
+    ImgState* st = (ImgState*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    helper_state_init_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B);
+    RGBD_CHECK_LAUNCH();
+    const int HW = (int)pixels;
+    dim3 grid(min(ceil_div(HW, 256 * 4), 296), B);
+    const bool vec = HW % 4 == 0 && batch_stride % 4 == 0 && channel_stride % 4 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(rgb3) | reinterpret_cast<uintptr_t>(gray_out)) & 15) == 0;
+    if (vec) decomp_gray_kernel<true><<<grid, 256, 0, s>>>(rgb3, batch_stride, channel_stride, gray_out, st, HW);
+    else decomp_gray_kernel<false><<<grid, 256, 0, s>>>(rgb3, batch_stride, channel_stride, gray_out, st, HW);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}

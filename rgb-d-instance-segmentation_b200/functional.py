@@ -184,6 +184,21 @@ def pack_pixel_values(rgb_u8: torch.Tensor, depth_u8: torch.Tensor, out: Optiona
     return out
 
 
+def to_grayscale(rgb3: torch.Tensor) -> torch.Tensor:
+    """(B,3,H,W) float32 (any batch / channel strides, contiguous planes) -> (B,H,W): CM:466-480, bit-exact."""
+    lib = _lib.load()
+    _req(rgb3, "image", torch.float32, False)
+    if rgb3.dim() != 4 or rgb3.shape[1] != 3:
+        raise RgbdB200Error("to_grayscale: expected (B,3,H,W)")
+    B, _, H, W = rgb3.shape
+    bs, cs = _plane_strided(rgb3, "image")
+    out = torch.empty(B, H, W, device=rgb3.device, dtype=torch.float32)
+    ws = torch.empty(int(lib.rgbd_depth_helper_workspace_bytes(B)), device=rgb3.device, dtype=torch.uint8)
+    check(lib.rgbd_to_grayscale(rgb3.data_ptr(), bs, cs, out.data_ptr(), B, H * W, ws.data_ptr(), _stream()), "rgbd_to_grayscale")
+    _count(2)
+    return out
+
+
 def depth_select_modes(hist: torch.Tensor, edges: torch.Tensor, num_modes: int = 3,
                        prominence_threshold: float = 0.01) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """``DSAModule._select_depth_distribution_modes`` (CM:720-752) on caller-supplied histograms: hist (B,512) int64,

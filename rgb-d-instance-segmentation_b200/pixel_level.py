@@ -60,6 +60,58 @@ class CustomMask2FormerPixelLevelModule(Mask2FormerPixelLevelModule):
             cp[k + 1] = dsam.stage_forward(cp[k], dec.pooled[k], dec.bias_variant, residual=cp[k + 1])
         return cp
 
+    def to_grayscale(self, image_data):
+        """CM:392-502.  ndarray (H,W,3) / (3,H,W) / (H,W,1) / (1,H,W) / (H,W) -> (H,W) ndarray of the input dtype (host
+        arithmetic, as in the reference); tensor (3,H,W) / (H,W,3) / (1,H,W) / (H,W,1) -> (1,H,W), (B,C,H,W) -> (B,1,H,W);
+        float32 CUDA tensors go through the device kernel (bit-exact ``(0.299 r + 0.587 g) + 0.114 b``)."""
+        import numpy as np
+        from . import functional as Fn
+        if isinstance(image_data, np.ndarray):
+            if image_data.ndim == 3:
+                shape = image_data.shape
+                if shape[-1] == 3:
+                    gray = 0.299 * image_data[:, :, 0] + 0.587 * image_data[:, :, 1] + 0.114 * image_data[:, :, 2]
+                elif shape[0] == 3:
+                    gray = 0.299 * image_data[0] + 0.587 * image_data[1] + 0.114 * image_data[2]
+                elif shape[-1] == 1 or shape[0] == 1:
+                    gray = image_data.squeeze()
+                else:
+                    raise ValueError("Input NumPy ndarray image should be RGB (H, W, 3) or (C, H, W) with C=3, or grayscale "
+                                     "(H, W, 1), (1, H, W) or (H, W).")
+            elif image_data.ndim == 2:
+                gray = image_data
+            else:
+                raise ValueError("Input NumPy ndarray image should be 2D (H, W) or 3D (H, W, C) or (C, H, W).")
+            return gray.astype(image_data.dtype)
+        if not isinstance(image_data, torch.Tensor):
+            raise TypeError("Input image_data must be NumPy ndarray or PyTorch Tensor.")
+        t = image_data
+        if t.ndim == 4:
+            channels, batched = t.shape[1], True
+        elif t.ndim == 3:
+            batched = False
+            if t.shape[0] == 3:
+                channels = 3
+            elif t.shape[-1] == 3:
+                channels, t = 3, t.permute(2, 0, 1)
+            elif t.shape[0] == 1:
+                channels = 1
+            elif t.shape[-1] == 1:
+                channels, t = 1, t.permute(2, 0, 1)
+            else:
+                raise ValueError("Input PyTorch Tensor image with ndim=3, but cannot determine channel location.")
+        else:
+            raise ValueError("Input PyTorch Tensor image should be 3D (C, H, W) or (H, W, 3) or 4D (B, C, H, W).")
+        if channels == 1:
+            return t
+        if channels != 3:
+            raise ValueError("Input PyTorch Tensor image should be grayscale or RGB (channels 1 or 3).")
+        x = t if batched else t[None]
+        if x.dtype != torch.float32:
+            raise ValueError("rgbd_b200.to_grayscale runs on float32 tensors (the dtype of pixel_values)")
+        gray = Fn.to_grayscale(x.contiguous())
+        return gray[:, None] if batched else gray
+
     def forward(self, pixel_values: Tensor, output_hidden_states: bool = False) -> Mask2FormerPixelLevelModuleOutput:
         rgb = pixel_values[:, 0:3, :, :]
         color_feature_map = self.encoder(rgb).feature_maps                                  # CM:330

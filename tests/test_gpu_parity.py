@@ -137,6 +137,42 @@ def test_decompose_edge_cases_bit_exact(fn):
         _check_decomposition(fn, [gray], [ratio], levels)
 
 
+def test_to_grayscale_method_mirrors_the_reference(golden_dir):
+    """CustomMask2FormerPixelLevelModule.to_grayscale (CM:392-502): tensor and ndarray layouts, dtypes, errors."""
+    from rgbd_b200 import pixel_level
+    plm = pixel_level.CustomMask2FormerPixelLevelModule(pixel_level.swin_tiny_mask2former_config(num_labels=4), version="0.0.0")
+    g = np.load(os.path.join(golden_dir, "gray.npz"))
+    rs = np.random.RandomState(0)
+    x = rs.randn(3, 37, 53).astype(np.float32)
+    ref = O.to_grayscale(x)
+    t = torch.from_numpy(x).cuda()
+    assert torch.equal(plm.to_grayscale(t).cpu(), torch.from_numpy(ref)[None])                       # (3,H,W) -> (1,H,W)
+    assert torch.equal(plm.to_grayscale(t.permute(1, 2, 0)).cpu(), torch.from_numpy(ref)[None])      # (H,W,3)
+    b = torch.stack([t, t.flip(1)])
+    gb = plm.to_grayscale(b)
+    assert gb.shape == (2, 1, 37, 53) and torch.equal(gb[0, 0].cpu(), torch.from_numpy(ref))
+    pv = torch.randn(2, 10, 24, 32, device="cuda")                                                   # strided view of pixel_values
+    assert torch.equal(plm.to_grayscale(pv[:, 3:6])[1, 0].cpu(), torch.from_numpy(O.to_grayscale(pv[1, 3:6].cpu().numpy())))
+    one = torch.randn(1, 5, 7, device="cuda")
+    assert plm.to_grayscale(one) is one and plm.to_grayscale(one.permute(1, 2, 0)).shape == (1, 5, 7)
+    # ndarray branch keeps the input dtype (uint8 truncation included), like the reference
+    u8 = rs.randint(0, 256, (9, 11, 3)).astype(np.uint8)
+    want = (0.299 * u8[:, :, 0] + 0.587 * u8[:, :, 1] + 0.114 * u8[:, :, 2]).astype(np.uint8)
+    assert np.array_equal(plm.to_grayscale(u8), want) and plm.to_grayscale(u8).dtype == np.uint8
+    assert np.array_equal(plm.to_grayscale(np.ascontiguousarray(u8.transpose(2, 0, 1))), want)
+    assert plm.to_grayscale(u8[:, :, :1]).shape == (9, 11) and plm.to_grayscale(u8[:, :, 0]).shape == (9, 11)
+    if "ref0" in g.files and "in0" in g.files:
+        assert np.array_equal(plm.to_grayscale(torch.from_numpy(g["in0"]).cuda()).cpu().numpy()[0], g["ref0"])
+    with pytest.raises(TypeError):
+        plm.to_grayscale([[1.0]])
+    with pytest.raises(ValueError):
+        plm.to_grayscale(np.zeros((2, 5, 7)))
+    with pytest.raises(ValueError):
+        plm.to_grayscale(torch.zeros(2, 5, 7, device="cuda"))
+    with pytest.raises(ValueError):
+        plm.to_grayscale(torch.zeros(5, device="cuda"))
+
+
 def test_dsam_helper_methods_match_reference_goldens(mods, golden_dir):
     """DSAModule._calculate_depth_histogram / _select_depth_distribution_modes / _define_depth_interval_windows /
     _generate_depth_region_masks (CM:701-798) as methods, on the reference's own outputs (tests/golden/decompose.npz)."""
