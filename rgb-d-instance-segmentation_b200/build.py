@@ -35,6 +35,12 @@ def _digest() -> str:
         if name.endswith((".cu", ".cuh", ".h")):
             h.update(open(os.path.join(CSRC, name), "rb").read())
     h.update(open(os.path.join(INCLUDE, "rgbd_b200.h"), "rb").read())
+    # flags and toolkit are part of the identity: the bit-exact kernels depend on -fmad=false and on the compiler
+    h.update(repr((ARCH, COMMON, sorted(NO_FMAD), SOURCES)).encode())
+    try:
+        h.update(subprocess.run([_nvcc(), "--version"], capture_output=True, text=True).stdout.encode())
+    except OSError:
+        pass
     return h.hexdigest()
 
 
