@@ -33,6 +33,27 @@ void rgbd_set_error(const char* fmt, ...);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Per-device launch state.  SM count, opt-in shared memory and cudaFuncSetAttribute are properties of the CURRENT device:
+// a process that drives several GPUs (one module per device, tests touching cuda:1 after cuda:0) must see each device's own.
+#define RGBD_MAX_DEVICES 64
+struct RgbdDeviceInfo { int device; int num_sms; int max_smem; };
+int rgbd_device_info(RgbdDeviceInfo* info);      // api.cu: current device, cached per device, thread-safe
+
+#ifdef __cplusplus
+#include <mutex>
+// Runs `body` once per device (per call site), under a lock; `body` may `return` an error code.
+#define RGBD_ONCE_PER_DEVICE(dev, body)                                   \
+    do {                                                                  \
+        static std::mutex _rgbd_m;                                        \
+        static bool _rgbd_done[RGBD_MAX_DEVICES] = {};                    \
+        std::lock_guard<std::mutex> _rgbd_g(_rgbd_m);                     \
+        if (!_rgbd_done[(dev)]) {                                         \
+            body;                                                         \
+            _rgbd_done[(dev)] = true;                                     \
+        }                                                                 \
+    } while (0)
+#endif
+
 #ifdef __CUDACC__
 // Order-preserving float <-> uint32 encoding (for atomicMin/atomicMax on floats of any sign).
 __device__ __forceinline__ uint32_t f32_to_ordered(float f) {

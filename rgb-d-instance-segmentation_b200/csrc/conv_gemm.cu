@@ -1279,19 +1279,16 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     RGBD_CHECK_ARG(total < (1ll << 31), "conv_gemm: too many tiles");
     p.total_tiles = (int)total;
 
-    static int num_sms = 0;
-    static int max_smem = 0;
-    if (!num_sms) {
-        int dev = 0;
-        RGBD_CHECK_CUDA(cudaGetDevice(&dev));
-        RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    RgbdDeviceInfo di;
+    if (int rc = rgbd_device_info(&di)) return rc;
+    const int num_sms = di.num_sms, max_smem = di.max_smem;
+    RGBD_ONCE_PER_DEVICE(di.device, {
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(dsam_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    }
+    });
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     if (d->conv3x3_reuse) {
         p.b_resident = 0; p.b_res_bytes = 0;

@@ -314,14 +314,12 @@ extern "C" int rgbd_dsam_wgrad(const void* g_bf16, int g_w_pitch, const void* xt
             if (C_pad % bn == 0) { p.BLOCK_N = bn; break; }
     p.n_tiles = C_pad / p.BLOCK_N;
     p.m_tiles = ceil_div(N_out, kBlockM);
-    static int num_sms = 0, max_smem = 0;
-    if (!num_sms) {
-        int dev = 0;
-        RGBD_CHECK_CUDA(cudaGetDevice(&dev));
-        RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    RgbdDeviceInfo di;
+    if (int rc = rgbd_device_info(&di)) return rc;
+    const int num_sms = di.num_sms, max_smem = di.max_smem;
+    RGBD_ONCE_PER_DEVICE(di.device, {
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(dsam_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    }
+    });
     const int base_tiles = p.n_seg * p.taps * p.m_tiles * p.n_tiles;
     int ksplit = 1;
     while (ksplit * 2 <= B && base_tiles * ksplit < 2 * num_sms) ksplit *= 2;

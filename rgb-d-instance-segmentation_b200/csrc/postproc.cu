@@ -368,11 +368,11 @@ extern "C" int rgbd_postprocess_instances(const float* class_logits, const float
     int* slot = reinterpret_cast<int*>(ws + l.slot);
 
     const int n_sort = next_pow2(n_cand < Q ? Q : n_cand);
-    static bool attr_set = false;
-    if (!attr_set) {
+    RgbdDeviceInfo di;
+    if (int rc = rgbd_device_info(&di)) return rc;
+    RGBD_ONCE_PER_DEVICE(di.device, {
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(postproc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSort * 8));
-        attr_set = true;
-    }
+    });
     postproc_select_kernel<<<B, 256, (size_t)n_sort * 8, s>>>(class_logits, g, n_sort, sel_score, sel_query, sel_label);
     RGBD_CHECK_LAUNCH();
     RGBD_CHECK_CUDA(cudaMemsetAsync(any_target, 0, (size_t)B * Q * 4, s));

@@ -338,15 +338,14 @@ extern "C" int rgbd_ratio_chain(const void* x1_bf16, const void* w2_bf16, const 
     RGBD_CHECK_ARG(total < (1ll << 31), "ratio_chain: too many tiles");
     p.total_tiles = (int)total;
     p.sh2 = sh2; p.sh3 = sh3; p.sh4 = sh4;
-    static int num_sms = 0;
     const int smem_bytes = 1024 + kW2Bytes + kW3Bytes + kW4Bytes + kStages * kSliceBytes + kStagingBytes +
                            (int)sizeof(ChainCtl) + (128 + 128 + 64 + 128) * 4 + 64;
-    if (!num_sms) {
-        int dev = 0;
-        RGBD_CHECK_CUDA(cudaGetDevice(&dev));
-        RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    RgbdDeviceInfo di;
+    if (int rc = rgbd_device_info(&di)) return rc;
+    const int num_sms = di.num_sms;
+    RGBD_ONCE_PER_DEVICE(di.device, {
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(ratio_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    }
+    });
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     ratio_chain_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(m_x1, m_w2, m_w3, m_w4, m_out, p);
     RGBD_CHECK_LAUNCH();

@@ -482,15 +482,14 @@ int launch_front(const CUtensorMap& m_r, const CUtensorMap& m_r1, const CUtensor
                  const CUtensorMap& m_w3, const CUtensorMap& m_w4, const CUtensorMap& m_out, const CUtensorMap& m_out1,
                  const FrontParams& p, cudaStream_t stream) {
     using Cfg = StemCfg<EM>;
-    static int num_sms = 0;
     const int smem_bytes = 1024 + Cfg::kBlocks * Cfg::kW1Block + kWRest + Cfg::kStages * Cfg::kStageBytes + 2 * kStashBytes +
                            (int)sizeof(FrontCtl) + (192 + 128 + 64 + 128) * 4 + 64;
-    if (!num_sms) {
-        int dev = 0;
-        RGBD_CHECK_CUDA(cudaGetDevice(&dev));
-        RGBD_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    RgbdDeviceInfo di;
+    if (int rc = rgbd_device_info(&di)) return rc;
+    const int num_sms = di.num_sms;
+    RGBD_ONCE_PER_DEVICE(di.device, {
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(ratio_front_kernel<EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    }
+    });
     const int n_units = (p.total_tiles + 1) / 2;
     int clusters = num_sms / 2;
     if (clusters > n_units) clusters = n_units;

@@ -23,7 +23,16 @@ def _count(n: int) -> None:
     LAUNCHES += n
 
 
+_last_device = None      # device index of the tensor most recently validated by _req
+
+
 def _stream() -> int:
+    """Current stream handle.  Kernels launch on the CURRENT device: a tensor that lives on another GPU would be
+    dereferenced from the wrong device, so the mismatch raises here (wrap the call in ``torch.cuda.device(t.device)``)."""
+    cur = torch.cuda.current_device()
+    if _last_device is not None and _last_device != cur:
+        raise RgbdB200Error(f"tensors live on cuda:{_last_device} but the current device is cuda:{cur}; "
+                            f"call inside `with torch.cuda.device({_last_device}):`")
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -36,6 +45,8 @@ def _req(t: torch.Tensor, name: str, dtype=None, contiguous: bool = True) -> tor
         raise RgbdB200Error(f"{name} must be {dtype}, got {t.dtype}")
     if contiguous and not t.is_contiguous():
         raise RgbdB200Error(f"{name} must be contiguous")
+    global _last_device
+    _last_device = t.device.index
     return t
 
 

@@ -44,6 +44,15 @@ def _best_box(out_h: int, out_w: int) -> Tuple[int, int]:
     return best
 
 
+#: workspaces kept alive per module (distinct batch sizes / resolutions, e.g. a last partial batch); oldest evicted first
+MAX_CACHED_SHAPES = 4
+
+
+def _evict(cache: dict) -> None:
+    while len(cache) >= MAX_CACHED_SHAPES:
+        cache.pop(next(iter(cache)))
+
+
 class _Versioned:
     """Re-pack derived tensors only when a source parameter changed (torch bumps ``_version`` on in-place
     updates such as optimizer steps / load_state_dict)."""
@@ -260,7 +269,8 @@ class DSAModule(nn.Module):
                 shape = (B, n_op, 4, (H + 1) // 2, (W + 1) // 2, c_pad)
             else:
                 shape = (B, n_op, 1, H, W, c_pad)
-            self._ws = {key: torch.zeros(shape, device=dev, dtype=torch.bfloat16)}   # keep one shape alive
+            _evict(self._ws)
+            self._ws[key] = torch.zeros(shape, device=dev, dtype=torch.bfloat16)
         return self._ws[key]
 
     def _param_list(self):
@@ -328,9 +338,9 @@ class DSAModule(nn.Module):
         H2, W2 = ((H + 1) // 2, (W + 1) // 2) if self._proj else (H, W)
         key = (B, H, W, str(x.device))
         if key not in self._ws_t:
-            self._ws_t = {key: torch.zeros(B, n_seg, 6 if self._proj else 1, c_pad, H2,
-                                           _round_up(W2, 8),
-                                           device=x.device, dtype=torch.bfloat16)}
+            _evict(self._ws_t)
+            self._ws_t[key] = torch.zeros(B, n_seg, 6 if self._proj else 1, c_pad, H2, _round_up(W2, 8),
+                                          device=x.device, dtype=torch.bfloat16)
         xt = self._ws_t[key]
         Fn.dsam_pack_t(x, codes, xt, c_pad, xt.shape[-1], n_seg, R + 1, self._proj)
         dw = Fn.dsam_wgrad(gp, xt, c_out, c_pad, (Ho, Wo), n_seg, self._proj)       # (c_out, n_seg, taps, c_pad)
@@ -391,6 +401,19 @@ class DSAModule(nn.Module):
         assert Cc == self.in_channels, f"Expected {self.in_channels} channels, got {Cc}"
         c_pad, kb, n_pad, n_seg = self._geometry()
         R = self.num_depth_regions
+        Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if self._proj else (H, W)
+        if tuple(codes.shape) != (B, H, W) or codes.dtype != torch.uint8:
+            raise RgbdB200Error(f"region codes must be uint8 {(B, H, W)}, got {codes.dtype} {tuple(codes.shape)}")
+        if bias_variant.numel() != B:
+            raise RgbdB200Error(f"bias_variant must have {B} entries, got {bias_variant.numel()}")
+        if residual is not None and tuple(residual.shape) != (B, self.out_channels, Ho, Wo):
+            # the reference fails at `cp[k+1] += dsam_out` (CM:342) on a pyramid whose levels do not halve (ceil) exactly
+            raise RgbdB200Error(f"residual must be {(B, self.out_channels, Ho, Wo)} (the stage's output shape), "
+                                f"got {tuple(residual.shape)}")
+        if emit_next is not None:
+            nws, ngeom, ncodes = emit_next
+            if tuple(ncodes.shape) != (B, Ho, Wo) or ncodes.dtype != torch.uint8:
+                raise RgbdB200Error(f"next stage's region codes must be uint8 {(B, Ho, Wo)}, got {tuple(ncodes.shape)}")
         Ho, Wo = (H + 1) // 2, (W + 1) // 2
         box = _best_box(Ho, Wo)
         skip_pack = prepacked or getattr(self, "_gemm_only", False)     # bench.py times the GEMM alone on packed operands
@@ -591,7 +614,8 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         key = (B, H, W, str(dev), self.use_fused_chain, self.use_fused_front, compact)
         if key not in self._ws:
             bf = dict(device=dev, dtype=torch.bfloat16)
-            self._ws = {key: {
+            _evict(self._ws)
+            self._ws[key] = {
                 "stem": (torch.empty(B, 2, H + 6, Fn.ratio_stem_compact_width(W), 4, **bf) if compact
                          else torch.empty(B, H + 6, W, 64, **bf)),
                 "x1": torch.empty(B, H, W, 192, **bf) if not self.use_fused_front else None,
@@ -599,7 +623,7 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
                 "x3": torch.empty(B, H, W, 64, **bf) if not (self.use_fused_chain or self.use_fused_front) else None,
                 "x4": torch.empty(B, H, W, 128, **bf),
                 "pool": torch.empty(B, 16, 256, device=dev, dtype=torch.int64),     # fixed-point cell sums
-            }}
+            }
         return self._ws[key]
 
     def _compact(self, H: int, W: int) -> bool:
@@ -766,7 +790,12 @@ def depth_guidance_forward(ratio_predictor: EnhancedDepthImageRatioPredictor, ds
 class GraphedDepthGuidance:
     """The inference hot path captured once into a CUDA graph (static shapes, static input tensors): one graph launch
     replaces ~40 kernel launches per step.  ``inputs`` are the tensors captured; copy new data into them (or pass them
-    as views of a staging buffer) and call the object to replay.  Outputs are the same tensors on every replay."""
+    as views of a staging buffer) and call the object to replay.  Outputs are the same tensors on every replay.
+
+    The graph bakes in raw pointers to the modules' workspaces and packed bf16 weights.  The wrapper therefore (i) keeps
+    its own references to every such tensor (eager calls at other shapes may evict them from the modules' caches, but
+    cannot free them), and (ii) refuses to replay once a parameter or buffer changed (optimizer step, load_state_dict):
+    the packed weights inside the graph would be stale -- build a new ``GraphedDepthGuidance`` instead."""
 
     def __init__(self, module: DepthGuidance, pixel_values: torch.Tensor, color_feature_map: Sequence[torch.Tensor],
                  warmup: int = 2):
@@ -782,7 +811,35 @@ class GraphedDepthGuidance:
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.outputs = module(self.pixel_values, self.features)
+        self._keepalive = self._collect(module)
+        self._param_key = self._versions(module)
+
+    @staticmethod
+    def _collect(module) -> list:
+        """Every tensor reachable from the sub-modules' private caches (workspaces, packed weights, slice tables)."""
+        kept = []
+
+        def walk(o):
+            if isinstance(o, torch.Tensor):
+                kept.append(o)
+            elif isinstance(o, dict):
+                for v in o.values():
+                    walk(v)
+            elif isinstance(o, (list, tuple)):
+                for v in o:
+                    walk(v)
+        for sub in module.modules():
+            for name in ("_ws", "_ws_t", "_packed", "_packed_bwd"):
+                walk(getattr(sub, name, None))
+        return kept
+
+    @staticmethod
+    def _versions(module) -> tuple:
+        return tuple((t.data_ptr(), t._version) for t in (*module.parameters(), *module.buffers()))
 
     def __call__(self) -> List[torch.Tensor]:
+        if self._versions(self.module) != self._param_key:
+            raise RgbdB200Error("GraphedDepthGuidance: a parameter or buffer changed after capture; the graph holds the "
+                                "old packed weights -- capture a new graph")
         self.graph.replay()
         return self.outputs

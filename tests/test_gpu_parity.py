@@ -14,6 +14,7 @@ from rgbd_b200 import synthetic
 from oracle import hotpath as O
 from oracle import weights as OW
 from oracle.make_golden import decompose_cases
+from rgbd_b200 import _lib as _rgbd_lib
 
 pytestmark = pytest.mark.gpu
 
@@ -957,3 +958,62 @@ def test_depth_encoder_version_branches(mods, golden_dir, version):
     odd = [torch.randn(3, c, 5, 7, device="cuda") for c in plm.ratio_predictor.depth_channels_list]
     w_rp = {k[len("ratio_predictor."):]: v for k, v in w.items() if k.startswith("ratio_predictor.")}
     assert rel_err(plm.ratio_predictor(odd), O.ratio_from_features_forward(w_rp, [t.cpu() for t in odd])) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# robustness of the host plumbing: graph-owned buffers, shape validation, device mismatch
+# ---------------------------------------------------------------------------------------------------
+def test_graphed_guidance_survives_cache_eviction_and_rejects_stale_weights(mods, fn):
+    chans, (H, W) = (32, 64, 96, 160), (64, 96)
+    m = mods.DepthGuidance(chans)
+    m.load_state_dict(OW.guidance_weights(seed=31, channels=chans))
+    m.cuda().eval()
+
+    def inputs(B, seed):
+        rgbs, ds = zip(*[synthetic.synth_rgbd_u8(seed + j, H, W, "nyu") for j in range(B)])
+        pv = fn.pack_pixel_values(torch.from_numpy(np.stack(rgbs)).cuda(), torch.from_numpy(np.stack(ds)).cuda())
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        return pv, [torch.randn(B, c, H // s, W // s, generator=g).cuda() for c, s in zip(chans, (4, 8, 16, 32))]
+    pv, feats = inputs(2, 700)
+    with torch.no_grad():
+        want = [t.clone() for t in m(pv, feats)]
+    graphed = mods.GraphedDepthGuidance(m, pv, feats)
+    # eager calls at more shapes than the caches hold: the modules drop the captured workspaces, the graph keeps them
+    with torch.no_grad():
+        for B in range(3, 3 + mods.MAX_CACHED_SHAPES + 1):
+            m(*inputs(B, 710 + B))
+    junk = [torch.randn(64 << 20, device="cuda") for _ in range(4)]     # would reuse freed blocks
+    got = graphed()
+    torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    del junk
+    with torch.no_grad():
+        m.dsam0.conv_layers[0].weight.mul_(1.5)
+    with pytest.raises(_rgbd_lib.RgbdB200Error):
+        graphed()
+
+
+def test_stage_forward_validates_pyramid_shapes(mods, fn):
+    m = mods.DSAModule(32, 64, 3)
+    m.load_state_dict(OW.dsam_weights(32, 64, seed=5))
+    m.cuda().eval()
+    feat = torch.randn(2, 32, 15, 20, device="cuda")
+    gray = torch.from_numpy(np.stack([_gray_for(j, "nyu", (60, 80)) for j in range(2)])).cuda()
+    dec = fn.depth_decompose(torch.tensor([0.2, 0.3]).cuda(), [(15, 20)], gray=gray)
+    good = torch.zeros(2, 64, 8, 10, device="cuda")
+    m.stage_forward(feat, dec.pooled[0], dec.bias_variant, residual=good)
+    with pytest.raises(_rgbd_lib.RgbdB200Error):        # a backbone that floors odd sizes: 15 -> 7 instead of 8
+        m.stage_forward(feat, dec.pooled[0], dec.bias_variant, residual=torch.zeros(2, 64, 7, 10, device="cuda"))
+    with pytest.raises(_rgbd_lib.RgbdB200Error):
+        m.stage_forward(feat, dec.pooled[0][:, :14].contiguous(), dec.bias_variant, residual=good)
+
+
+def test_tensor_on_another_device_raises(fn):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    x = torch.zeros(1, 3, 8, 8, device="cuda:1")
+    with torch.cuda.device(0), pytest.raises(_rgbd_lib.RgbdB200Error):
+        fn.to_grayscale(x)
+    with torch.cuda.device(1):
+        fn.to_grayscale(x)                                # per-device launch state: works on the second GPU too
