@@ -10,8 +10,12 @@ synthetic NYUv2-shaped frames: workload = BASELINE.json configs[1] (batch 32 per
 feature pyramid, bf16 tensor-core operands with fp32 accumulation).  The Swin backbone / pixel decoder stay
 on stock PyTorch and are outside the step.
 
-Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same through the
-nn.Module API with HOST (pinned) inputs and the fused features read back to the host every step.
+Prints ONE JSON line (rank 0).  `value` = hot-path frames/s with inputs resident in HBM.  `e2e` = the WHOLE RGB-D
+Mask2Former (reference predictor path, mask2former/predictor.py:19-36 + :697-703) fed from pinned HOST uint8 frames:
+H2D -> device front-end -> stock Swin / pixel decoder / transformer under bf16 autocast with the CUDA hot path in
+between -> device post-processing -> instance maps back in pinned host memory.  `e2e_hot_path_host_features` = the hot
+path alone through the nn.Module API with host features (the PCIe-bound secondary of round 1).  `train` = BASELINE
+configs[3] restricted to the hot path (fwd + bwd + NCCL gradient all-reduce, batch 8 per GPU).
 """
 from __future__ import annotations
 
@@ -42,9 +46,7 @@ FLOP_DSAM = sum(5 * 2.0 * (H // (2 * s)) * (W // (2 * s)) * co * 9 * ci
                 for s, ci, co in zip(STRIDES[:3], CHANS[:3], CHANS[1:]))      # 23.89 GFLOP
 FEAT_ELEMS = sum(c * (H // s) * (W // s) for c, s in zip(CHANS, STRIDES))      # 3 456 000
 BYTES_DGGM = 3 * 4 * FEAT_ELEMS + 4 * 4 * H * W               # read colour + branch-1, write fused, read grad+mask
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE conv3x3_2cta_kernel launch at batch 32, from the ncu --set full
-# capture profiles/r01_ncu_full_b32_conv3x3_2cta.txt (the bf16 128-channel input is 2.517 GB: it is read from DRAM once)
-TRAFFIC_CONV5_B32 = 2.555123e9 + 7.578368e6
+POST_THRESHOLD = 0.0     # the reference's Evaluator(threshold=0.0) (finetuning.py:95): every candidate segment is painted
 
 
 def peaks():
@@ -72,42 +74,111 @@ def make_features(n: int, seed: int, device) -> list:
     return [torch.randn(n, c, H // s, W // s, generator=g).to(device) for c, s in zip(CHANS, STRIDES)]
 
 
+def workload_config(batch: int) -> dict:
+    """The ONE config both arms print (the reference arm runs bounded 1-frame samples of it; see cpu_baseline.sample)."""
+    return {"workload": "configs[1]: batch-32/GPU inference, 480x640 RGB-D, Swin-T pyramid, depth-guidance hot path",
+            "batch_per_gpu": batch, "frame": [H, W], "channels": list(CHANS),
+            "l2": "per-step inputs (835 MB) exceed the 126 MB L2; no flush needed"}
+
+
+def build_whole_model():
+    """RGB-D Mask2Former (Swin-T, 100 queries, 80 labels; hyper-parameters of the reference's checkpoints/standard) with
+    random-init stock weights (torch seed 0) and the deterministic depth-guidance weights."""
+    from rgbd_b200 import pixel_level, synthetic_weights as SW
+    torch.manual_seed(0)
+    model = pixel_level.build_rgbd_mask2former(pixel_level.swin_tiny_mask2former_config()).eval()
+    w = SW.guidance_weights(seed=42, channels=CHANS)
+    missing = model.model.pixel_level_module.load_state_dict(w, strict=False)
+    assert not missing.unexpected_keys
+    return model, w
+
+
 # --------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port of the reference's CPU path on the host cores
+# reference arm / cpu_baseline: the reference's CPU path on the host cores (oracle port; DESIGN.md section 2)
 # --------------------------------------------------------------------------------------------------------
-def cpu_reference(steps: int, warmup: int):
-    from oracle import hotpath as O, weights as OW
+def _cpu_inputs():
+    from oracle import hotpath as O
     from rgbd_b200 import synthetic
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    w = OW.guidance_weights(seed=42, channels=CHANS)
     rgb, depth = make_frames(1, first=0)
     pv = torch.from_numpy(synthetic.assemble_pixel_values(rgb[0], depth[0], O.gradient_features))[None]
-    feats = make_features(1, 7, "cpu")
+    return pv, make_features(1, 7, "cpu")
+
+
+def _time_cpu(fn, steps, warmup):
     with torch.no_grad():
         for _ in range(warmup):
-            O.depth_guidance_forward(w, pv, feats)
+            fn()
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.depth_guidance_forward(w, pv, feats)
-        dt = time.perf_counter() - t0
-    return {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} steps x 1 frame 480x640 (oracle port of CM:324-355, torch-CPU fp32, {cores} threads)"}, dt / steps
+            fn()
+        return (time.perf_counter() - t0) / steps
+
+
+def cpu_hot_path(steps: int, warmup: int, threads=None):
+    """BASELINE.md section 2 (ii)+(i): the whole hot path CM:324-355 on one 480x640 frame (oracle port, torch-CPU fp32)."""
+    from oracle import hotpath as O
+    from rgbd_b200 import synthetic_weights as SW
+    cores = threads or (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    w = SW.guidance_weights(seed=42, channels=CHANS)
+    pv, feats = _cpu_inputs()
+    sec = _time_cpu(lambda: O.depth_guidance_forward(w, pv, feats), steps, warmup)
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} steps x 1 frame 480x640 (oracle port of CM:324-355, torch-CPU fp32, {cores} threads)"}, sec
+
+
+def cpu_modules(steps: int, threads=None):
+    """BASELINE.md section 2 (i) DGGM alone and (ii) E-DSAM alone (ratio predictor + decomposition + 3 DSAM stages)."""
+    from oracle import hotpath as O
+    from rgbd_b200 import synthetic_weights as SW
+    cores = threads or (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    w = SW.guidance_weights(seed=42, channels=CHANS)
+    pv, feats = _cpu_inputs()
+    dggm_w = O._sub(w, "depth_gradient_injection.")
+
+    def edsam():
+        ratios = O.ratio_predictor_forward(O._sub(w, "ratio_predictor."), pv[:, 3:6])
+        gray = O.to_grayscale(pv[0, 3:6].numpy())
+        x = feats[0]
+        for k in range(3):
+            x = feats[k + 1] + O.dsam_forward(O._sub(w, f"dsam{k}."), x, gray, ratios[0].item())
+    t_dggm = _time_cpu(lambda: O.dggm_forward(dggm_w, feats, pv[:, 6:9], pv[:, 9:10]), max(steps, 3), 1)
+    t_edsam = _time_cpu(edsam, steps, 1)
+    return {"dggm_alone_frames_per_s": 1.0 / t_dggm, "edsam_alone_frames_per_s": 1.0 / t_edsam, "cores": cores}
+
+
+def cpu_whole_model(steps: int, warmup: int, threads=None):
+    """whole v0.4.0 model forward + HF post_process_instance_segmentation on one frame."""
+    from oracle import model as OM
+    cores = threads or (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    model, w = build_whole_model()
+    cpu_model = OM.cpu_oracle_model(model, w)
+    pv, _ = _cpu_inputs()
+    sec = _time_cpu(lambda: OM.predict(cpu_model, pv, threshold=POST_THRESHOLD, target_sizes=[(H, W)]), steps, warmup)
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} steps x 1 frame 480x640: stock HF Swin-T/pixel decoder/transformer on CPU fp32 + oracle hot path "
+                      f"+ HF post_process_instance_segmentation ({cores} threads)"}, sec
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, sec_per_step = cpu_reference(max(args.steps, 1), max(args.warmup, 1))
+    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
+    base, sec_per_step = cpu_hot_path(steps, warmup)
+    whole, whole_sec = cpu_whole_model(min(steps, 10), min(warmup, 2))
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] sample: depth-guidance hot path, 1 frame/step on host cores", "frame": [H, W],
-                   "channels": list(CHANS)},
+        "config": workload_config(args.batch),
         "cpu_baseline": base,
-        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # like with like: `value` is the hot path alone (compare with the own arm's `value`), `e2e` the whole model from
+        # pixel_values to instance maps (compare with the own arm's `e2e`); nothing crosses a host<->device link here
+        "e2e": {"value": whole["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "ms_per_step": whole_sec * 1e3, "sample": whole["sample"]},
         "gpu_launches": 0,
     }
     emit(line)
@@ -180,50 +251,53 @@ def bind_to_gpu_numa_node(local: int):
         return None
 
 
+def static_profile():
+    """ncu-derived numbers that cannot be measured inside a plain run (tensor-pipe utilisation, DRAM traffic): loaded from
+    the committed profiles/r02_ncu.json, which records the commit and batch size of its capture."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
+
+
 def run_own(args):
     import torch.distributed as dist
     import rgbd_b200  # noqa: F401
-    from rgbd_b200 import functional as Fn, modules
-    from oracle import weights as OW       # deterministic weights only (no oracle compute on this arm)
+    from rgbd_b200 import functional as Fn, modules, parallel, serving, synthetic, synthetic_weights as SW
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, local, world = parallel.env_rank_world()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     old_affinity = bind_to_gpu_numa_node(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        parallel.init_process_group("nccl", dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    scaling = "weak"
     B = args.batch
+    if args.frames_total:
+        # BASELINE configs[2]: a fixed set of frames split over the ranks (256 frames -> 128/64/32 per GPU at 2/4/8 GPUs)
+        b0, b1 = parallel.shard_range(args.frames_total, rank, world)
+        B = b1 - b0
+        scaling = "strong"
+    frames_per_step = sum(parallel.gather_counts(B, dev))
     model = modules.DepthGuidance(CHANS)
-    model.load_state_dict(OW.guidance_weights(seed=42, channels=CHANS))
+    model.load_state_dict(SW.guidance_weights(seed=42, channels=CHANS))
     model.to(dev).eval()
 
     # ---- synthetic inputs: a few distinct frames tiled to the batch, built with the device front-end (K0)
     n_distinct = min(B, 8)
     rgb_u8, depth_u8 = make_frames(n_distinct, first=rank * 1000)
-    from rgbd_b200 import synthetic
-    pv_host = torch.empty(B, 10, H, W, dtype=torch.float32).pin_memory()
-    for j in range(B):
-        k = j % n_distinct
-        pv_host[j, 0:3] = torch.from_numpy(synthetic.normalise_u8(rgb_u8[k]))
-        pv_host[j, 3:6] = torch.from_numpy(synthetic.normalise_u8(np.repeat(depth_u8[k][:, :, None], 3, axis=2)))
-    pv = pv_host.to(dev)
-    depth_dev = torch.from_numpy(depth_u8).to(dev)[torch.arange(B) % n_distinct].contiguous()
-    Fn.gradient_features(depth_dev, norm_out=pv[:, 6:9], vmask_out=pv[:, 9:10])
-    pv_host.copy_(pv)
     idx = np.arange(B) % n_distinct
     rgb_host = torch.from_numpy(np.ascontiguousarray(rgb_u8[idx])).pin_memory()        # (B,H,W,3) uint8
     depth_host = torch.from_numpy(np.ascontiguousarray(depth_u8[idx])).pin_memory()    # (B,H,W)   uint8
+    pv = Fn.pack_pixel_values(rgb_host.to(dev), depth_host.to(dev))
     feats = make_features(B, 7 + rank, dev)
-    feats_host = [f.cpu().pin_memory() for f in feats]
 
     use_graph = args.graph        # measured: 6.89 vs 7.02 ms/step -- launch gaps are ~2 % of the step now
     if use_graph:
@@ -258,26 +332,166 @@ def run_own(args):
     e1.record()
     barrier()
     launches = launches_per_step * args.steps          # kernels of this library executed inside the timed region
-    elapsed = e0.elapsed_time(e1) / 1e3
-    t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed = float(t.item())
-    value = world * B * args.steps / elapsed
+    elapsed = parallel.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    value = frames_per_step * args.steps / elapsed
 
-    # ---- e2e: every step copies its inputs from pinned host memory, runs the hot path through the nn.Module API and
-    # reads the fused features back to pinned host memory.  The three legs run on their own streams with two input
-    # buffers, so step i's H2D overlaps step i-1's compute and step i-2's D2H (how a serving loop would drive it).
-    # Headline e2e: the host holds what the reference's data mapper holds (DL:395-433) -- uint8 colour + depth frames --
-    # plus the encoder features; pixel_values (normalisation, Sobel gradient features, validity mask) is built on the
-    # device by rgbd_pack_pixel_values (bit-exact with the CPU mapper, tests/test_gpu_parity.py).  The variant that
-    # ships a ready-made fp32 pixel_values tensor instead (12.3 MB/frame more over PCIe) is reported as e2e_fp32_inputs.
-    d2h = sum(f.numel() * 4 for f in feats_host)
+    # ---- e2e (headline): the whole RGB-D Mask2Former from pinned host uint8 frames to instance maps in pinned host memory
+    e2e = None
+    if not args.no_whole_model:
+        whole, _ = build_whole_model()
+        whole.to(dev)
+        seg = serving.RgbdInstanceSegmenter(whole, B, (H, W), threshold=POST_THRESHOLD)
+        for b in range(2):
+            seg.in_host[b][0].copy_(rgb_host)
+            seg.in_host[b][1].copy_(depth_host)
+        Fn.LAUNCHES = 0
+        seg.submit()
+        whole_launches_per_step = Fn.LAUNCHES
+        for _ in range(max(args.warmup, 3) - 1):
+            seg.submit()
+        seg.drain()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            seg.submit()
+        seg.drain()
+        e1.record()
+        barrier()
+        whole_elapsed = parallel.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+        counts = seg.out_host[(args.steps - 1) & 1]["count"]
+        # stage breakdown of one un-pipelined step (CUDA events around the stock sub-modules; reported, not the metric)
+        marks = {}
+
+        def timed(mod, name):
+            def pre(m, a, k=None):
+                marks[name] = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+                marks[name][0].record()
+
+            def post(m, a, o):
+                marks[name][1].record()
+            return [mod.register_forward_pre_hook(pre), mod.register_forward_hook(post)]
+        plm = whole.model.pixel_level_module
+        hooks = timed(plm.encoder, "swin_encoder") + timed(plm.decoder, "pixel_decoder") + \
+            timed(whole.model.transformer_module, "transformer_decoder") + timed(plm, "pixel_level_module")
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        seg.submit()
+        seg.drain()
+        t1.record()
+        torch.cuda.synchronize()
+        for h_ in hooks:
+            h_.remove()
+        br = {k: v[0].elapsed_time(v[1]) for k, v in marks.items()}
+        br["hot_path_incl_float_casts"] = br["pixel_level_module"] - br["swin_encoder"] - br["pixel_decoder"]
+        br["step_unpipelined"] = t0.elapsed_time(t1)
+        hot_ms = elapsed / args.steps * 1e3
+        e2e = {"value": frames_per_step * args.steps / whole_elapsed, "unit": UNIT,
+               "h2d_bytes_per_step": seg.h2d_bytes_per_step, "d2h_bytes_per_step": seg.d2h_bytes_per_step,
+               "ms_per_step": whole_elapsed / args.steps * 1e3,
+               "how": "rgbd_b200.serving.RgbdInstanceSegmenter: pinned-host uint8 colour + depth frames -> H2D -> "
+                      "rgbd_pack_pixel_values -> Mask2FormerForUniversalSegmentation (stock HF Swin-T / pixel decoder / "
+                      "transformer decoder, bf16 autocast, random-init) with the CUDA depth-guidance hot path -> device "
+                      "post_process_instance_segmentation (threshold 0.0, target 480x640) -> segmentation map + labels + "
+                      "scores + counts to pinned host; H2D / compute / D2H on 3 streams, 2 buffers",
+               "own_kernel_launches_per_step": whole_launches_per_step,
+               "hot_path_ms_per_step": hot_ms, "hot_path_share_of_step": hot_ms / (whole_elapsed / args.steps * 1e3),
+               "breakdown_ms": br, "segments_last_step": int(counts.sum())}
+        launches += whole_launches_per_step * args.steps
+        del seg, whole
+        torch.cuda.empty_cache()
+
+    # ---- secondary e2e: the hot path ALONE through the nn.Module API with host-resident encoder features (what round 1
+    # reported as e2e).  Every step ships uint8 frames + fp32 features in and the fp32 fused features out, so it is bound by
+    # the host link, not by the path; in the real model those features never leave the GPU.
+    hp = hot_path_host_features(args, model, B, rgb_host, depth_host, feats, pv, dev, barrier, world, frames_per_step)
+    clocks = sampler.stop()          # sampled over the device-resident and the e2e timed regions
+
+    # ---- per-kernel timing for the roofline (separate, after the headline measurement; CUDA events on the
+    # launching stream around each stage of the same step)
+    pk = PerKernel(model, pv, feats, args.steps)
+    kt = pk.measure()
+    pkv = peaks()
+    sp = static_profile()
+    conv5_tf = FLOP_CONV5 * B / kt["ratio_conv3x3"] / 1e12
+    dggm_gbs = BYTES_DGGM * B / kt["dggm"] / 1e9
+    dsam_tf = FLOP_DSAM * B / kt["dsam_gemm"] / 1e12
+    traffic = None
+    if sp and sp.get("batch") == B:
+        traffic = sp.get("dram_bytes_per_launch", {}).get("conv3x3_2cta_kernel")
+    roof = {"kernel": "conv3x3_2cta_kernel (ratio predictor 3x3 128->256 conv + BN + ReLU + AdaptiveAvgPool2d(4), CTA pairs)", "bound": "tensor",
+            "achieved": conv5_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": conv5_tf / pkv["tf_burst"],
+            "frac_of_sustained": conv5_tf / pkv["tf_sustained"],
+            "frac_of_nominal_dense_bf16": conv5_tf / 2250.0,      # frac can pass 1.0: the peak is what cuBLAS reaches here
+            "traffic": traffic,
+            "traffic_source": (f"static: {sp['source']} @ {sp['commit']} (batch {sp['batch']})" if traffic is not None else None),
+            "peak_source": pkv["source"] + " burst bf16 cuBLAS (the kernel is timed alone, back to back)"}
+    extra = [
+        {"kernel": "dggm_fwd_kernel (DGGM + branch sum)", "bound": "hbm", "achieved": dggm_gbs, "peak": pkv["hbm_gbs"],
+         "unit": "GB/s", "frac": dggm_gbs / pkv["hbm_gbs"], "bytes_per_frame": BYTES_DGGM},
+        {"kernel": "3 DSAM stages (useful FLOPs: K padding not counted)",
+         "bound": "tensor", "achieved": dsam_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": dsam_tf / pkv["tf_burst"]},
+    ]
+    if "ratio_front" in kt:
+        compact = model.ratio_predictor._compact(H, W)
+        # stem GEMM (K = 147 useful taps of 256) + 192->128 + 128->64 + 64->128 point-wise layers
+        front_tf = 2.0 * (147 * 192 + 192 * 128 + 128 * 64 + 64 * 128) * H * W * B / kt["ratio_front"] / 1e12
+        front_gbs = ((16 if compact else 128) + 256) * H * W * B / kt["ratio_front"] / 1e9
+        extra.append({"kernel": "ratio_front_kernel (stem + feature fusion + attention, one kernel)", "bound": "tensor",
+                      "achieved": front_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": front_tf / pkv["tf_burst"],
+                      "hbm_gbs": front_gbs})
+
+    # ---- BASELINE configs[3] on the hot path: fwd + bwd + gradient all-reduce, batch 8 per GPU
+    train = None
+    if not args.no_train:
+        del model
+        if use_graph:
+            del graphed
+        torch.cuda.empty_cache()
+        train = train_record(args, dev, rank, world, barrier)
+
+    if rank == 0:
+        if old_affinity:
+            os.sched_setaffinity(0, old_affinity)          # the CPU baseline uses every host core
+        cpu_base, _ = cpu_hot_path(args.cpu_steps, 1)
+        if not args.no_cpu_detail:
+            one, _ = cpu_hot_path(1, 0, threads=1)
+            wm, _ = cpu_whole_model(max(1, min(args.cpu_steps, 3)), 1)
+            cpu_base["detail"] = {"hot_path_1_thread_frames_per_s": one["value"], **cpu_modules(max(1, min(args.cpu_steps, 3))),
+                                  "whole_model_plus_postprocess_frames_per_s": wm["value"], "whole_model_sample": wm["sample"]}
+        cfg = workload_config(B)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "launch": "CUDA graph replay of the hot-path step" if use_graph else "kernel-by-kernel launches",
+            "e2e": e2e if e2e is not None else hp,
+            "e2e_hot_path_host_features": hp,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "roofline_extra": extra,
+            # E-DSAM tensor-core utilisation (BASELINE metric): sm__pipe_tensor_cycles_active from a committed `ncu --set full`
+            # capture -- static, never measured under this run; the file records its commit and batch
+            "tc_util_pct_ncu": ({"source": f"static: {sp['source']} @ {sp['commit']} (batch {sp['batch']})", **sp["tc_util_pct"]}
+                                if sp else None),
+            "kernel_ms_per_step": {k: v * 1e3 for k, v in kt.items()},
+            "train": train,
+            "cpu_baseline": cpu_base,
+        }
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def hot_path_host_features(args, model, B, rgb_host, depth_host, feats, pv, dev, barrier, world, frames_per_step):
+    """Round 1's e2e loop, kept as a labelled secondary: pinned-host uint8 frames + fp32 encoder features in, fp32 fused
+    features out, one slab per direction, H2D / compute / D2H on 3 streams with 2 buffers."""
+    from rgbd_b200 import functional as Fn, parallel
+    feats_host = [f.cpu().pin_memory() for f in feats]
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     s_main = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    # One pinned host slab and one device slab per direction: the inputs (and the outputs) of a step are views of it, so a
-    # step costs ONE host->device and ONE device->host transfer (large DMAs use the PCIe link best).
     def carve(slab, shapes_dtypes):
         views, off = [], 0
         for shape, dt in shapes_dtypes:
@@ -294,222 +508,116 @@ def run_own(args):
         return off
 
     feat_specs = [(tuple(f.shape), torch.float32) for f in feats_host]
-    in_specs = {True: [((B, H, W, 3), torch.uint8), ((B, H, W), torch.uint8)] + feat_specs,
-                False: [(tuple(pv_host.shape), torch.float32)] + feat_specs}
-    in_host, in_dev = {}, {}
-    for mode, specs in in_specs.items():
-        hs = torch.empty(slab_bytes(specs), dtype=torch.uint8).pin_memory()
-        hv = carve(hs, specs)
-        srcs = ([rgb_host, depth_host] if mode else [pv_host]) + feats_host
-        for v, src in zip(hv, srcs):
-            v.copy_(src)
-        in_host[mode] = hs
-        in_dev[mode] = []
-        for _ in range(2):
-            ds = torch.empty(hs.numel(), dtype=torch.uint8, device=dev)
-            in_dev[mode].append((ds, carve(ds, specs)))
-    pv_buf = [pv, torch.empty_like(pv)]
-    out_dev = []
-    out_host2 = []
+    specs = [((B, H, W, 3), torch.uint8), ((B, H, W), torch.uint8)] + feat_specs
+    in_host = torch.empty(slab_bytes(specs), dtype=torch.uint8).pin_memory()
+    for v, src in zip(carve(in_host, specs), [rgb_host, depth_host] + feats_host):
+        v.copy_(src)
+    in_dev = []
+    for _ in range(2):
+        ds = torch.empty(in_host.numel(), dtype=torch.uint8, device=dev)
+        in_dev.append((ds, carve(ds, specs)))
+    pv_buf = [torch.empty_like(pv), torch.empty_like(pv)]
+    out_dev, out_host = [], []
     for _ in range(2):
         ds = torch.empty(slab_bytes(feat_specs), dtype=torch.uint8, device=dev)
         out_dev.append((ds, carve(ds, feat_specs)))
-        out_host2.append(torch.empty(ds.numel(), dtype=torch.uint8).pin_memory())
+        out_host.append(torch.empty(ds.numel(), dtype=torch.uint8).pin_memory())
 
-    def e2e_run(n_steps, from_u8):
-        ev_in = [None, None]
-        ev_free = [None, None]       # compute finished reading input buffer b (and writing output buffer b)
-        ev_d2h = [None, None]        # D2H finished reading output buffer b
+    def run(n_steps):
+        ev_in, ev_free, ev_d2h = [None, None], [None, None], [None, None]
         for i in range(n_steps):
             b = i & 1
-            slab, views = in_dev[from_u8][b]
+            slab, views = in_dev[b]
             with torch.cuda.stream(s_in):
                 if ev_free[b] is not None:
                     s_in.wait_event(ev_free[b])
-                slab.copy_(in_host[from_u8], non_blocking=True)
+                slab.copy_(in_host, non_blocking=True)
                 ev_in[b] = s_in.record_event()
             s_main.wait_event(ev_in[b])
             if ev_d2h[b] is not None:
                 s_main.wait_event(ev_d2h[b])               # output buffer b is free again
             with torch.no_grad():
-                if from_u8:
-                    Fn.pack_pixel_values(views[0], views[1], out=pv_buf[b])
-                    model(pv_buf[b], views[2:], out=out_dev[b][1])
-                else:
-                    model(views[0], views[1:], out=out_dev[b][1])
+                Fn.pack_pixel_values(views[0], views[1], out=pv_buf[b])
+                model(pv_buf[b], views[2:], out=out_dev[b][1])
             ev_free[b] = s_main.record_event()
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_free[b])
-                out_host2[b].copy_(out_dev[b][0], non_blocking=True)
+                out_host[b].copy_(out_dev[b][0], non_blocking=True)
                 ev_d2h[b] = s_out.record_event()
         for e in ev_d2h:
             if e is not None:
                 s_main.wait_event(e)
-        return None
 
-    def e2e_measure(from_u8):
-        e2e_run(4, from_u8)
-        times = []
-        for _ in range(2):                  # PCIe on these shared hosts is noisy: best of two runs of K steps each
-            barrier()
-            e0.record()
-            kept = e2e_run(args.steps, from_u8)
-            e1.record()
-            barrier()
-            del kept
-            times.append(e0.elapsed_time(e1) / 1e3)
-        tt = torch.tensor(times, device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)         # per run: the slowest rank
-        return world * B * args.steps / float(tt.min().item()), times
-
-    feat_bytes = sum(f.numel() * 4 for f in feats_host)
-    h2d = in_host[True].numel()
-    h2d_fp32 = in_host[False].numel()
-    d2h = out_host2[0].numel()
-    e2e_value, e2e_times = e2e_measure(True)
-    # the pipelined loop must have produced the real thing: its last host result equals the device-resident step's output
+    run(4)
+    times = []
+    for _ in range(2):                  # PCIe on these shared hosts is noisy: best of two runs of K steps each
+        barrier()
+        e0.record()
+        run(args.steps)
+        e1.record()
+        barrier()
+        times.append(parallel.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev))
     torch.cuda.synchronize()
     with torch.no_grad():
         want = model(pv, feats)
-    got = carve(out_host2[(args.steps - 1) & 1], feat_specs)
-    # the path is bit-reproducible (fixed summation orders, fixed-point integer atomics for the pooled sums); reported, not
-    # asserted, so a surprise cannot take the measurement down
-    e2e_check = {"bit_identical": all(torch.equal(g_, w_.cpu()) for g_, w_ in zip(got, want)),
-                 "max_rel_diff": max(float((g_ - w_.cpu()).abs().max() / w_.abs().max().clamp_min(1e-30)) for g_, w_ in zip(got, want))}
-    e2e_fp32_value, e2e_fp32_times = e2e_measure(False)
-    clocks = sampler.stop()          # sampled over the device-resident and the e2e timed regions
-
-    # ---- per-kernel timing for the roofline (separate, after the headline measurement; CUDA events on the
-    # launching stream around each stage of the same step)
-    pk = PerKernel(model, pv, feats, args.steps)
-    kt = pk.measure()
-    pkv = peaks()
-    conv5_tf = FLOP_CONV5 * B / kt["ratio_conv3x3"] / 1e12
-    dggm_gbs = BYTES_DGGM * B / kt["dggm"] / 1e9
-    dsam_tf = FLOP_DSAM * B / kt["dsam_gemm"] / 1e12
-    roof = {"kernel": "conv3x3_2cta_kernel (ratio predictor 3x3 128->256 conv + BN + ReLU + AdaptiveAvgPool2d(4), CTA pairs)", "bound": "tensor",
-            "achieved": conv5_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": conv5_tf / pkv["tf_burst"],
-            "frac_of_sustained": conv5_tf / pkv["tf_sustained"],
-            "frac_of_nominal_dense_bf16": conv5_tf / 2250.0,      # frac can pass 1.0: the peak is what cuBLAS reaches here
-            "traffic": TRAFFIC_CONV5_B32 if B == 32 else None,
-            "peak_source": pkv["source"] + " burst bf16 cuBLAS (the kernel is timed alone, back to back)"}
-    extra = [
-        {"kernel": "dggm_fwd_kernel (DGGM + branch sum)", "bound": "hbm", "achieved": dggm_gbs, "peak": pkv["hbm_gbs"],
-         "unit": "GB/s", "frac": dggm_gbs / pkv["hbm_gbs"], "bytes_per_frame": BYTES_DGGM},
-        {"kernel": "dsam_fwd_kernel x2 + conv_gemm_2cta_kernel (3 DSAM stages, useful FLOPs: K padding not counted)",
-         "bound": "tensor", "achieved": dsam_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": dsam_tf / pkv["tf_burst"]},
-    ]
-    if "ratio_front" in kt:
-        compact = model.ratio_predictor._compact(H, W)
-        # stem GEMM (K = 147 useful taps of 256) + 192->128 + 128->64 + 64->128 point-wise layers
-        front_tf = 2.0 * (147 * 192 + 192 * 128 + 128 * 64 + 64 * 128) * H * W * B / kt["ratio_front"] / 1e12
-        front_gbs = ((16 if compact else 128) + 256) * H * W * B / kt["ratio_front"] / 1e9
-        extra.append({"kernel": "ratio_front_kernel (stem + feature fusion + attention, one kernel)", "bound": "tensor",
-                      "achieved": front_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": front_tf / pkv["tf_burst"],
-                      "hbm_gbs": front_gbs, "note": "latency-bound: TMEM->register->TMEM hand-offs between the four chained GEMMs"})
-    if rank == 0:
-        if old_affinity:
-            os.sched_setaffinity(0, old_affinity)          # the CPU baseline uses every host core
-        cpu_base, _ = cpu_reference(args.cpu_steps, 1)
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[1]: batch-32/GPU inference, 480x640 RGB-D, Swin-T pyramid, depth-guidance hot path",
-                       "batch_per_gpu": B, "frame": [H, W], "channels": list(CHANS),
-                       "l2": "per-step inputs (835 MB) exceed the 126 MB L2; no flush needed",
-                       "launch": "CUDA graph replay of the step" if use_graph else "kernel-by-kernel launches"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "how": "pinned-host uint8 colour + depth frames (what the reference's mapper holds, DL:395-433) and fp32 "
-                           "encoder features -> device front-end rgbd_pack_pixel_values (bit-exact pixel_values) -> "
-                           "DepthGuidance.forward -> fused features to pinned host; one H2D and one D2H transfer per step (inputs / outputs are views "
-                           "of one slab each), H2D / compute / D2H on 3 streams, 2 buffers; best of 2 runs of K steps (max over ranks per run)",
-                    "runs_s": [float(x) for x in e2e_times]},
-            "e2e_check": e2e_check,
-            "e2e_fp32_inputs": {"value": e2e_fp32_value, "unit": UNIT, "h2d_bytes_per_step": h2d_fp32,
-                                "d2h_bytes_per_step": d2h, "how": "same loop, but the host ships a ready-made fp32 "
-                                "pixel_values (B,10,H,W) tensor instead of the uint8 frames",
-                                "runs_s": [float(x) for x in e2e_fp32_times]},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "roofline": roof,
-            "roofline_extra": extra,
-            # E-DSAM tensor-core utilisation (BASELINE metric): sm__pipe_tensor_cycles_active from the committed
-            # `ncu --set full` capture (batch 8; never measured under this run)
-            "tc_util_pct_ncu": {"source": "profiles/r01_ncu_full_b8_final.txt", "conv3x3_2cta_kernel": 98.7,
-                                "ratio_front_kernel": 56.9, "dsam_fwd_kernel": [58.2, 45.3], "conv_gemm_2cta_kernel": 77.4},
-            "kernel_ms_per_step": {k: v * 1e3 for k, v in kt.items()},
-            "cpu_baseline": cpu_base,
-        }
-        emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    got = carve(out_host[(args.steps - 1) & 1], feat_specs)
+    check = {"bit_identical_to_device_resident_step": all(torch.equal(g_, w_.cpu()) for g_, w_ in zip(got, want))}
+    return {"value": frames_per_step * args.steps / min(times), "unit": UNIT, "h2d_bytes_per_step": in_host.numel(),
+            "d2h_bytes_per_step": out_host[0].numel(), "runs_s": times, "check": check,
+            "how": "hot path only: pinned-host uint8 frames + fp32 encoder features -> rgbd_pack_pixel_values -> "
+                   "DepthGuidance.forward -> fp32 fused features to pinned host (host-link bound; secondary)"}
 
 
-def run_train(args):
-    """BASELINE configs[3] restricted to the hot path: one fine-tuning step of the depth-guidance modules (forward +
-    backward: DSAM wgrad/dgrad/dbias, DGGM dW/db) at batch 8 per GPU, gradients all-reduced over NCCL when N > 1.
-    Reported as an extra JSON line (`"mode": "train"`); the headline metric stays the inference line."""
-    import torch.distributed as dist
-    import rgbd_b200  # noqa: F401
-    from rgbd_b200 import functional as Fn, modules, synthetic
-    from oracle import weights as OW
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+def train_record(args, dev, rank, world, barrier):
+    """BASELINE configs[3] restricted to the hot path (reference: HF Trainer step under finetuning.py:98-113): one
+    fine-tuning step of the depth-guidance modules in .train() mode -- ratio predictor with batch-statistics BatchNorm and
+    Dropout (no gradient: CM:339), DSAM wgrad / dgrad / dbias, DGGM dW / db -- at batch 8 per GPU; gradients are
+    all-reduced over NCCL bucket by bucket while the backward of the earlier stages is still running."""
+    from rgbd_b200 import functional as Fn, modules, parallel, synthetic_weights as SW
     B = 8
     model = modules.DepthGuidance(CHANS)
-    model.load_state_dict(OW.guidance_weights(seed=42, channels=CHANS))
+    model.load_state_dict(SW.guidance_weights(seed=42, channels=CHANS))
     model.to(dev).train()
     rgb_u8, depth_u8 = make_frames(B, first=rank * 1000)
-    pv = torch.empty(B, 10, H, W, device=dev)
-    for j in range(B):
-        pv[j, 0:3] = torch.from_numpy(synthetic.normalise_u8(rgb_u8[j])).to(dev)
-        pv[j, 3:6] = torch.from_numpy(synthetic.normalise_u8(np.repeat(depth_u8[j][:, :, None], 3, axis=2))).to(dev)
-    Fn.gradient_features(torch.from_numpy(depth_u8).to(dev), norm_out=pv[:, 6:9], vmask_out=pv[:, 9:10])
+    pv = Fn.pack_pixel_values(torch.from_numpy(rgb_u8).to(dev), torch.from_numpy(depth_u8).to(dev))
     feats = make_features(B, 7 + rank, dev)
     douts = [torch.randn_like(f) for f in feats]
-    params = [p for n, p in model.named_parameters() if not n.startswith("ratio_predictor.")]
+    for p in model.ratio_predictor.parameters():
+        p.requires_grad_(False)                            # CM:339: consumed through .item(), never receives a gradient
+    buckets = [list(model.dsam2.parameters()), list(model.dsam1.parameters()),
+               list(model.dsam0.parameters()) + list(model.depth_gradient_injection.parameters())]
+    reducer = parallel.GradBucketReducer(buckets)
 
     def step():
-        for p in params:
-            p.grad = None
+        for b in buckets:
+            for p in b:
+                p.grad = None
         out = model(pv, feats)
         torch.autograd.backward(out, douts)
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-        return out
+        reducer.finish()
 
-    for _ in range(3):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        emit({"mode": "train", "metric": "rgbd_480x640_train_frames_per_sec_depth_guidance_hot_path",
-              "value": world * B * args.steps / float(t.item()), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-              "ms_per_step": float(t.item()) / args.steps * 1e3, "batch_per_gpu": B,
-              "grad_elements_allreduced": int(sum(p.numel() for p in params)) if world > 1 else 0,
-              "config": {"workload": "configs[3] hot-path share: fwd+bwd of DSAM x3 + DGGM, batch 8/GPU, NCCL grad all-reduce"}})
-    if world > 1:
-        dist.destroy_process_group()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(3):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    t = parallel.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    reducer.remove()
+    return {"metric": "rgbd_480x640_train_frames_per_sec_depth_guidance_hot_path", "value": world * B * args.steps / t,
+            "unit": UNIT, "ms_per_step": t / args.steps * 1e3, "batch_per_gpu": B, "n_gpus": world,
+            "grad_elements_allreduced_per_step": reducer.n_elements if world > 1 else 0,
+            "buckets": [sum(p.numel() for p in b) for b in buckets],
+            "ratio_predictor_mode": "train (batch-statistics BatchNorm, Dropout)" if getattr(
+                model.ratio_predictor, "TRAIN_MODE_SUPPORTED", False) else "eval semantics",
+            "workload": "configs[3] hot-path share: fwd+bwd of ratio predictor (fwd) + DSAM x3 + DGGM, NCCL bucketed "
+                        "gradient all-reduce overlapped with the backward"}
 
 
 class PerKernel:
@@ -603,15 +711,17 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-steps", type=int, default=5)
-    ap.add_argument("--mode", default="infer", choices=["infer", "train"])
+    ap.add_argument("--frames-total", type=int, default=0,
+                    help="BASELINE configs[2]: split this many frames over the ranks (strong scaling) instead of --batch per GPU")
+    ap.add_argument("--no-whole-model", action="store_true", help="skip the whole-model e2e leg (e2e falls back to the hot-path loop)")
+    ap.add_argument("--no-train", action="store_true", help="skip the configs[3] train sub-record")
+    ap.add_argument("--no-cpu-detail", action="store_true", help="cpu_baseline: only the all-core hot-path figure")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch the ~22 kernels of a step one by one instead of replaying the step as one CUDA graph")
     ap.set_defaults(graph=True)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.mode == "train":
-        run_train(args)
     else:
         run_own(args)
 

@@ -1,116 +1,7 @@
-"""Deterministic weights for parity tests (test infrastructure).
-
-Weights come from ``np.random.RandomState`` (frozen stream), not torch's RNG, so the
-golden fixtures generated from the reference can be replayed on any torch build.  Keys
-follow the reference's ``state_dict`` names (CM:623-645, CM:1175-1191, CM:1369-1442).
-"""
-from __future__ import annotations
-
-from typing import Dict, List
-
-import numpy as np
-import torch
-
-
-def _normal(rs, shape, std):
-    return torch.from_numpy((rs.standard_normal(size=shape) * std).astype(np.float32))
-
-
-def _uniform(rs, shape, lo, hi):
-    return torch.from_numpy(rs.uniform(lo, hi, size=shape).astype(np.float32))
-
-
-def conv_weights(rs, prefix: str, c_out: int, c_in: int, k: int, bias: bool = True) -> Dict[str, torch.Tensor]:
-    fan_in = c_in * k * k
-    out = {prefix + ".weight": _normal(rs, (c_out, c_in, k, k), 1.0 / np.sqrt(fan_in))}
-    if bias:
-        out[prefix + ".bias"] = _normal(rs, (c_out,), 0.1)
-    return out
-
-
-def bn_weights(rs, prefix: str, c: int) -> Dict[str, torch.Tensor]:
-    return {
-        prefix + ".weight": _uniform(rs, (c,), 0.5, 1.5),
-        prefix + ".bias": _normal(rs, (c,), 0.1),
-        prefix + ".running_mean": _normal(rs, (c,), 0.1),
-        prefix + ".running_var": _uniform(rs, (c,), 0.5, 1.5),
-        prefix + ".num_batches_tracked": torch.tensor(0, dtype=torch.long),
-    }
-
-
-def linear_weights(rs, prefix: str, c_out: int, c_in: int) -> Dict[str, torch.Tensor]:
-    return {prefix + ".weight": _normal(rs, (c_out, c_in), 1.0 / np.sqrt(c_in)),
-            prefix + ".bias": _normal(rs, (c_out,), 0.1)}
-
-
-def dsam_weights(c_in: int, c_out: int, seed: int, num_regions: int = 3) -> Dict[str, torch.Tensor]:
-    rs = np.random.RandomState(seed)
-    w: Dict[str, torch.Tensor] = {}
-    k = 3 if c_in != c_out else 1
-    for t in range(num_regions + 1):
-        w.update(conv_weights(rs, f"conv_layers.{t}", c_out, c_in, k))
-    if c_in != c_out:
-        w.update(conv_weights(rs, "rgb_projection", c_out, c_in, 3, bias=False))
-    return w
-
-
-def dggm_weights(channels: List[int], d: int, seed: int) -> Dict[str, torch.Tensor]:
-    rs = np.random.RandomState(seed)
-    w: Dict[str, torch.Tensor] = {}
-    for i, c in enumerate(channels):
-        w.update(conv_weights(rs, f"depth_enhancement_layers.{i}.0", c, d, 1))
-        # spread the sign of the pre-activation so ReLU both passes and clips
-        w[f"depth_enhancement_layers.{i}.0.bias"] = _normal(rs, (c,), 0.3)
-    return w
-
-
-def ratio_weights(seed: int, c_in: int = 3) -> Dict[str, torch.Tensor]:
-    rs = np.random.RandomState(seed)
-    w: Dict[str, torch.Tensor] = {}
-    for name, k in (("scale1_conv", 3), ("scale2_conv", 5), ("scale3_conv", 7)):
-        w.update(conv_weights(rs, name + ".0", 64, c_in, k))
-        w.update(bn_weights(rs, name + ".1", 64))
-    w.update(conv_weights(rs, "feature_fusion.0", 128, 192, 1))
-    w.update(bn_weights(rs, "feature_fusion.1", 128))
-    w.update(conv_weights(rs, "attention.0", 64, 128, 1))
-    w.update(conv_weights(rs, "attention.2", 128, 64, 1))
-    w.update(conv_weights(rs, "feature_extractor.0", 256, 128, 3))
-    w.update(bn_weights(rs, "feature_extractor.1", 256))
-    w.update(conv_weights(rs, "feature_extractor.4", 512, 256, 3))
-    w.update(bn_weights(rs, "feature_extractor.5", 512))
-    w.update(linear_weights(rs, "fc_layers.0", 128, 512))
-    w.update(linear_weights(rs, "fc_layers.3", 64, 128))
-    w.update(linear_weights(rs, "fc_layers.6", 32, 64))
-    w.update(linear_weights(rs, "fc_layers.8", 1, 32))
-    return w
-
-
-def ratio_feat_weights(seed: int, channels=(96, 192, 384, 768)) -> Dict[str, torch.Tensor]:
-    """``RatioPredictor`` (CM:823-858): fc_layers.{0,2,4} = Linear sum(C)->64->32->1."""
-    rs = np.random.RandomState(seed)
-    w: Dict[str, torch.Tensor] = {}
-    w.update(linear_weights(rs, "fc_layers.0", 64, int(sum(channels))))
-    w.update(linear_weights(rs, "fc_layers.2", 32, 64))
-    w.update(linear_weights(rs, "fc_layers.4", 1, 32))
-    return w
-
-
-def guidance_weights_feature_ratio(seed: int, channels=(96, 192, 384, 768)) -> Dict[str, torch.Tensor]:
-    """Parameters of the version 0.1.3 / 0.3.0 hot path: ``guidance_weights`` with the feature-based ratio predictor."""
-    w = {k: v for k, v in guidance_weights(seed, channels).items() if not k.startswith("ratio_predictor.")}
-    for k, v in ratio_feat_weights(seed + 11, channels).items():
-        w["ratio_predictor." + k] = v
-    return w
-
-
-def guidance_weights(seed: int, channels=(96, 192, 384, 768)) -> Dict[str, torch.Tensor]:
-    """All hot-path parameters with the pixel-level module's prefixes (CM:123-134)."""
-    w: Dict[str, torch.Tensor] = {}
-    for k, v in ratio_weights(seed).items():
-        w["ratio_predictor." + k] = v
-    for s in range(3):
-        for k, v in dsam_weights(channels[s], channels[s + 1], seed + 1 + s).items():
-            w[f"dsam{s}." + k] = v
-    for k, v in dggm_weights(list(channels), 3, seed + 7).items():
-        w["depth_gradient_injection." + k] = v
-    return w
+"""Test-infrastructure alias: the deterministic weight factory lives in the product package
+(``rgbd_b200.synthetic_weights``) so that ``bench.py``'s own arm never imports ``oracle``; the oracle and the golden
+generators keep using it under this name."""
+import rgbd_b200  # noqa: F401  (root shim)
+from rgbd_b200.synthetic_weights import *  # noqa: F401,F403
+from rgbd_b200.synthetic_weights import (bn_weights, conv_weights, dggm_weights, dsam_weights, guidance_weights,  # noqa: F401
+                                         guidance_weights_feature_ratio, linear_weights, ratio_feat_weights, ratio_weights)
