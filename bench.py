@@ -82,15 +82,10 @@ def workload_config(batch: int) -> dict:
 
 
 def build_whole_model():
-    """RGB-D Mask2Former (Swin-T, 100 queries, 80 labels; hyper-parameters of the reference's checkpoints/standard) with
-    random-init stock weights (torch seed 0) and the deterministic depth-guidance weights."""
-    from rgbd_b200 import pixel_level, synthetic_weights as SW
-    torch.manual_seed(0)
-    model = pixel_level.build_rgbd_mask2former(pixel_level.swin_tiny_mask2former_config()).eval()
-    w = SW.guidance_weights(seed=42, channels=CHANS)
-    missing = model.model.pixel_level_module.load_state_dict(w, strict=False)
-    assert not missing.unexpected_keys
-    return model, w
+    """RGB-D Mask2Former (Swin-T, 100 queries, 80 labels) with random-init stock weights and the deterministic
+    depth-guidance weights (rgbd_b200.synthetic_weights)."""
+    from rgbd_b200 import synthetic_weights as SW
+    return SW.build_synthetic_rgbd_mask2former(CHANS, guidance_seed=42, torch_seed=0)
 
 
 # --------------------------------------------------------------------------------------------------------

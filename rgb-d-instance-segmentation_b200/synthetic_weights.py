@@ -114,3 +114,46 @@ def guidance_weights(seed: int, channels=(96, 192, 384, 768)) -> Dict[str, torch
     for k, v in dggm_weights(list(channels), 3, seed + 7).items():
         w["depth_gradient_injection." + k] = v
     return w
+
+
+def make_decisive(model, class_gain: float = 60.0, mask_gain: float = 60.0, query_gain: float = 50.0,
+                  decoder_damp: float = 0.1) -> None:
+    """Turn a random-init ``Mask2FormerForUniversalSegmentation`` into a DECISIVE synthetic model (no training data here).
+
+    Out of the box the heads give near-uniform class scores (0.0200-0.0204 over 80 labels), mask logits with a standard
+    deviation of 0.08 and -- because the query embeddings are drawn with std 0.02 while every attention / FFN update is
+    O(1) and identical for all queries -- 100 virtually identical queries: instance selection then hinges on 1e-4 score
+    differences that no two implementations (not even two BLAS builds) reproduce, and mAP is degenerate.  This scales
+    the query embeddings up, damps the decoder's residual updates so queries stay distinct, and sharpens the class head
+    and the last mask-embedding layer: ~60 distinct predicted labels, blob-like masks covering 5-60 % of the frame, class
+    scores 0.4-1.0 (measured on the synthetic NYUv2-shaped frames).  Applied identically to every model under comparison
+    (tests/test_gpu_map_parity.py); the depth-guidance hot path is untouched."""
+    tm = model.model.transformer_module
+    with torch.no_grad():
+        tm.queries_features.weight.mul_(query_gain)
+        tm.queries_embedder.weight.mul_(query_gain)
+        for layer in tm.decoder.layers:
+            for name, p in layer.named_parameters():
+                if name.endswith("weight") and ("out_proj" in name or "linear2" in name or "fc2" in name):
+                    p.mul_(decoder_damp)
+        model.class_predictor.weight.mul_(class_gain)
+        model.class_predictor.bias.mul_(class_gain)
+        last = [m for m in tm.decoder.mask_predictor.mask_embedder.modules() if isinstance(m, torch.nn.Linear)][-1]
+        last.weight.mul_(mask_gain)
+        last.bias.mul_(mask_gain)
+
+
+def build_synthetic_rgbd_mask2former(channels=(96, 192, 384, 768), guidance_seed: int = 42, torch_seed: int = 0,
+                                     decisive: bool = False, num_labels: int = 80):
+    """RGB-D Mask2Former (Swin-T, 100 queries; hyper-parameters of the reference's checkpoints/standard/config.json) with
+    random-init stock weights (``torch.manual_seed(torch_seed)``) and the deterministic depth-guidance weights.
+    Returns (model in eval mode on the CPU, guidance state_dict)."""
+    from . import pixel_level
+    torch.manual_seed(torch_seed)
+    model = pixel_level.build_rgbd_mask2former(pixel_level.swin_tiny_mask2former_config(num_labels=num_labels)).eval()
+    w = guidance_weights(seed=guidance_seed, channels=channels)
+    missing = model.model.pixel_level_module.load_state_dict(w, strict=False)
+    assert not missing.unexpected_keys, missing.unexpected_keys
+    if decisive:
+        make_decisive(model)
+    return model, w

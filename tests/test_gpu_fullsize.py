@@ -11,7 +11,6 @@ Reference: mask2former/utils/custom_model.py:324-355 (wiring), :647-699 (DSAModu
 predictor).  Bars: integer artefacts bit-exact; bf16-operand paths within 1e-2 relative; the fp32 mode within 1e-4.
 Measured numbers are appended to $RGBD_PARITY_REPORT (JSON lines) when that variable is set.
 """
-import json
 import os
 
 import numpy as np
@@ -22,6 +21,7 @@ import rgbd_b200  # noqa: F401
 from rgbd_b200 import synthetic
 from oracle import hotpath as O
 from oracle import weights as OW
+from _parity_report import report
 
 pytestmark = pytest.mark.gpu
 
@@ -56,15 +56,6 @@ def rel_err(a, b) -> float:
 def rel_l2(a, b) -> float:
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
-
-
-def report(name: str, **values) -> None:
-    path = os.environ.get("RGBD_PARITY_REPORT")
-    line = json.dumps({"test": name, **values})
-    print("[parity]", line)
-    if path:
-        with open(path, "a") as f:
-            f.write(line + "\n")
 
 
 def frames_u8(n, first, hw=(H, W), kinds=("nyu",)):

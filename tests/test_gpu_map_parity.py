@@ -1,0 +1,145 @@
+"""End-to-end mask-mAP parity on a synthetic NYUv2-shaped set (BASELINE.json north_star).
+
+Mirrors the reference's evaluator (mask2former/utils/model_essential_part.py:56 ``MeanAveragePrecision(iou_type="segm")``,
+:80-109 ``postprocess_prediction_batch``, :114-157 the metric update / compute):
+
+    GPU arm:  RGB-D Mask2Former on cuda (stock HF parts in fp32, the CUDA depth-guidance hot path) -> this library's
+              device post-processing (``postprocess.postprocess_prediction_batch``) -> ``postprocess.MaskAP``
+    CPU arm:  the same weights on the CPU with the oracle hot path (oracle/model.py) -> HF's own
+              ``post_process_instance_segmentation`` -> the oracle AP (oracle/postproc.py)
+
+16 frames of 480x640, two label sets: (A) <= 20 random rectangles per frame over 48 classes (SURVEY 8d config 4 -- a
+random-init model scores ~0 on them in both arms), and (B) instances taken from the CPU arm's own predictions so that
+mAP is far from 0 and sensitive to mask / score / label differences.  The synthetic model is made decisive first
+(``synthetic_weights.make_decisive``: distinct queries, peaked class scores, blob masks).
+"""
+import numpy as np
+import pytest
+import torch
+
+import rgbd_b200  # noqa: F401
+from rgbd_b200 import synthetic, synthetic_weights as SW
+from oracle import hotpath as O
+from oracle import model as OM
+from oracle import postproc as OP
+from _parity_report import report
+
+pytestmark = pytest.mark.gpu
+H, W = 480, 640
+N_FRAMES = 16
+THRESHOLD = 0.5
+
+
+def rectangle_targets(n, seed):
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        k = rs.randint(3, 21)
+        masks = np.zeros((k, H, W), dtype=bool)
+        for j in range(k):
+            h, w = rs.randint(30, 240), rs.randint(30, 320)
+            y, x = rs.randint(0, H - h), rs.randint(0, W - w)
+            masks[j, y:y + h, x:x + w] = True
+        out.append({"masks": torch.from_numpy(masks), "labels": torch.from_numpy(rs.randint(0, 48, size=k))})
+    return out
+
+
+@pytest.fixture(scope="module")
+def arms():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rgbd_b200 import postprocess
+    model, w = SW.build_synthetic_rgbd_mask2former(decisive=True)
+    cpu_model = OM.cpu_oracle_model(model, w)
+    kinds = ["nyu"] * 13 + ["uniform", "two_valued", "nyu"]
+    frames = [synthetic.synth_rgbd_u8(900 + j, H, W, kinds[j]) for j in range(N_FRAMES)]
+    pv = torch.from_numpy(np.stack([synthetic.assemble_pixel_values(r, d, O.gradient_features) for r, d in frames]))
+    sizes = [(H, W)] * N_FRAMES
+    # ---- CPU arm (4 frames per forward to bound memory)
+    cpu_preds, cpu_cls, cpu_msk = [], [], []
+    for i in range(0, N_FRAMES, 4):
+        res, c, m = OM.predict(cpu_model, pv[i:i + 4], threshold=THRESHOLD, target_sizes=sizes[i:i + 4], return_binary_maps=True)
+        cpu_cls.append(c)
+        cpu_msk.append(m)
+        for r in res:       # Evaluator.postprocess_prediction_batch (model_essential_part.py:95-107)
+            if r["segments_info"]:
+                cpu_preds.append({"masks": r["segmentation"].to(torch.bool),
+                                  "labels": torch.tensor([s["label_id"] for s in r["segments_info"]]),
+                                  "scores": torch.tensor([s["score"] for s in r["segments_info"]])})
+            else:
+                cpu_preds.append({"masks": torch.zeros(0, H, W, dtype=torch.bool), "labels": torch.tensor([]),
+                                  "scores": torch.tensor([])})
+    # ---- GPU arms: bf16-operand hot path (default) and the split-precision fp32 mode
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model.cuda()
+    gpu = {}
+    for precision in ("bf16", "fp32"):
+        plm = model.model.pixel_level_module
+        for d in (plm.dsam0, plm.dsam1, plm.dsam2):
+            d.precision = precision
+        with torch.no_grad():
+            outs = [model(pixel_values=pv[i:i + 8].cuda()) for i in range(0, N_FRAMES, 8)]
+        cls = torch.cat([o.class_queries_logits for o in outs]).float()
+        msk = torch.cat([o.masks_queries_logits for o in outs]).float()
+        preds = postprocess.postprocess_prediction_batch((cls, msk), sizes, threshold=THRESHOLD)
+        gpu[precision] = {"preds": preds, "cls": cls.cpu(), "msk": msk.cpu()}
+    return {"cpu_preds": cpu_preds, "cpu_cls": torch.cat(cpu_cls), "cpu_msk": torch.cat(cpu_msk), "gpu": gpu}
+
+
+def oracle_ap(preds, targets):
+    ious = [OP.mask_iou(p["masks"].numpy(), t["masks"].numpy()) if len(p["labels"]) and len(t["labels"])
+            else np.zeros((len(p["labels"]), len(t["labels"]))) for p, t in zip(preds, targets)]
+    return OP.average_precision([{"labels": p["labels"].numpy(), "scores": p["scores"].numpy()} for p in preds],
+                                [{"labels": t["labels"].numpy()} for t in targets], ious)
+
+
+def device_ap(preds, targets):
+    from rgbd_b200 import postprocess
+    ap = postprocess.MaskAP()
+    ap.update(preds, targets)
+    return ap.compute()
+
+
+def self_targets(cpu_preds, per_image=8):
+    """Label set B: every 3rd of the CPU arm's own segments (in its score order), at most ``per_image`` per frame."""
+    out = []
+    for p in cpu_preds:
+        idx = list(range(0, len(p["labels"]), 3))[:per_image]
+        out.append({"masks": p["masks"][idx], "labels": p["labels"][idx].long()})
+    return out
+
+
+def test_logits_and_instance_counts_match(arms):
+    counts_cpu = [len(p["labels"]) for p in arms["cpu_preds"]]
+    assert sum(counts_cpu) > 10 * N_FRAMES                 # the synthetic model IS decisive: many instances pass 0.5
+    for precision, tol in (("fp32", 2e-3), ("bf16", 2e-2)):
+        g = arms["gpu"][precision]
+        e_cls = float((g["cls"] - arms["cpu_cls"]).norm() / arms["cpu_cls"].norm())
+        e_msk = float((g["msk"] - arms["cpu_msk"]).norm() / arms["cpu_msk"].norm())
+        counts = [len(p["labels"]) for p in g["preds"]]
+        diff = [a - b for a, b in zip(counts, counts_cpu)]
+        report("map_parity_logits", precision=precision, class_logits_rel_l2=e_cls, mask_logits_rel_l2=e_msk,
+               instances_cpu=counts_cpu, instances_gpu=counts)
+        assert e_cls < tol and e_msk < tol, (precision, e_cls, e_msk)
+        if precision == "fp32":
+            assert counts == counts_cpu, diff              # per-image instance counts equal
+        else:
+            assert max(abs(d) for d in diff) <= 2, diff    # bf16 operands: a score within ~1e-3 of the threshold may cross it
+
+
+@pytest.mark.parametrize("label_set", ["rectangles", "self"])
+def test_mask_map_parity(arms, label_set):
+    targets = rectangle_targets(N_FRAMES, 77) if label_set == "rectangles" else self_targets(arms["cpu_preds"])
+    ref = oracle_ap(arms["cpu_preds"], targets)
+    # the evaluator itself: device IoU + MaskAP on the CPU arm's predictions == the oracle AP
+    same = device_ap(arms["cpu_preds"], targets)
+    for k in ("map", "map_50", "map_75"):
+        assert abs(same[k] - ref[k]) < 1e-9, (k, same[k], ref[k])
+    for precision in ("fp32", "bf16"):
+        got = device_ap(arms["gpu"][precision]["preds"], targets)
+        report("map_parity", label_set=label_set, precision=precision, gpu=got, cpu=ref)
+        for k in ("map", "map_50", "map_75"):
+            assert abs(got[k] - ref[k]) <= 0.005, (label_set, precision, k, got[k], ref[k])
+    if label_set == "self":
+        assert ref["map"] > 0.2                              # label set B is not degenerate
