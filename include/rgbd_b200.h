@@ -23,7 +23,7 @@ extern "C" {
 
 typedef void* rgbd_stream_t; /* cudaStream_t */
 
-#define RGBD_ABI_VERSION 1
+#define RGBD_ABI_VERSION 2
 #define RGBD_HIST_BINS 512 /* CM:701 `bins=512` */
 
 #define RGBD_DTYPE_F32 0
@@ -128,7 +128,7 @@ typedef struct rgbd_conv_gemm_desc {
     int n_img, out_h, out_w, bx, by;
     int n, n_pad, block_n;
     int tile_order; /* 0: x fastest, 1: y fastest */
-    int epi_mode, act; /* act: 0 none, 1 relu, 2 sigmoid */
+    int epi_mode, act; /* act: 0 none, 1 relu, 2 sigmoid, 3 statistics (epi_mode 2 only: sums of y and of y*y, no activation) */
     const float* scale;   /* (n_pad) or NULL */
     const float* shift;   /* (n_variants, n_pad) */
     const int* variant;   /* (n_img) or NULL */
@@ -158,6 +158,9 @@ typedef struct rgbd_conv_gemm_desc {
     void* next_operand;
     const void* next_codes;
     int next_c_pad, next_n_seg, next_masked_segs;
+    /* epi_mode 2 with act 3: the statistics pass of a train-mode BatchNorm (CM:1380-1421 under .train()): pool receives
+       the cell sums of y = acc + shift, pool_sq (same shape, caller zeroes) the cell sums of y*y. */
+    long long* pool_sq;
 } rgbd_conv_gemm_desc;
 int rgbd_conv_gemm(const rgbd_conv_gemm_desc* desc_host, rgbd_stream_t stream);
 
@@ -209,6 +212,17 @@ int rgbd_ratio_stem_pack_compact(const float* depth3, long long batch_stride, lo
 int rgbd_ratio_tail(const long long* pool_sums, int pool_stride, int cell_pixels, const float* conv_w, const float* conv_scale,
                     const float* conv_shift, const float* const* fc_w_host, const float* const* fc_b_host, float out_min,
                     float out_max, float* gap_ws, float* ratio_out, int B, rgbd_stream_t stream);
+
+/* The same tail under .train() (CM:1418-1437 with BatchNorm2d in training mode and active Dropout): conv3x3 256->512 ->
+ * BatchNorm over the batch's (B,4,4) samples per channel (biased variance for normalisation; running_mean / running_var,
+ * when given, are updated in place: (1-momentum)*old + momentum*(batch mean incl. conv bias | unbiased variance)) -> ReLU
+ * -> GAP -> MLP, where drop0 (B,128) / drop1 (B,64) are the Dropout multipliers keep/(1-p) (NULL = no dropout).
+ * raw_ws: B*512*16 floats, gap_ws: B*512 floats. */
+int rgbd_ratio_tail_train(const long long* pool_sums, int pool_stride, int cell_pixels, const float* conv_w,
+                          const float* conv_bias, const float* bn_gamma, const float* bn_beta, float eps, float momentum,
+                          float* running_mean, float* running_var, const float* const* fc_w_host,
+                          const float* const* fc_b_host, const float* drop0, const float* drop1, float out_min, float out_max,
+                          float* raw_ws, float* gap_ws, float* ratio_out, int B, rgbd_stream_t stream);
 
 /* Reference helper API on caller-supplied intermediates (the batched rgbd_depth_decompose never needs them):
  * rgbd_depth_select_modes  = DSAModule._select_depth_distribution_modes (CM:720-752): hist (B,512) int64 + bin_edges

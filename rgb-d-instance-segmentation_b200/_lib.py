@@ -10,6 +10,8 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librgbd_b200.so")
 
+ABI_VERSION = 2          # RGBD_ABI_VERSION of include/rgbd_b200.h this binding was written against
+
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int)
 c_void_pp = C.POINTER(C.c_void_p)
@@ -32,6 +34,7 @@ class ConvGemmDesc(C.Structure):
         ("dsam_masked", C.c_int),
         ("next_operand", C.c_void_p), ("next_codes", C.c_void_p),
         ("next_c_pad", C.c_int), ("next_n_seg", C.c_int), ("next_masked_segs", C.c_int),
+        ("pool_sq", C.c_void_p),
     ]
 
 
@@ -89,6 +92,10 @@ SIGNATURES = {
     "rgbd_mask_iou": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "rgbd_ratio_tail": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_void_pp, c_void_pp,
                                   C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "rgbd_ratio_tail_train": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_float, C.c_float, C.c_void_p, C.c_void_p, c_void_pp, c_void_pp, C.c_void_p,
+                                        C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -112,7 +119,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.rgbd_abi_version() != 1:
+    if lib.rgbd_abi_version() != ABI_VERSION:
         raise RgbdB200Error(f"ABI version mismatch: library reports {lib.rgbd_abi_version()}")
     _lib = lib
     return lib

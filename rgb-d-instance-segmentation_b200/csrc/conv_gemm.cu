@@ -47,6 +47,7 @@ struct KParams {
     void* out;
     const float* residual;
     long long* pool;          // fixed-point (1/RGBD_POOL_FIXED_ONE) cell sums: order-independent integer atomics
+    long long* pool_sq;       // act 3 (statistics pass of a train-mode BatchNorm): cell sums of the SQUARED values
     int cells_y, cells_x;
     int total_tiles;
     int staging_bytes;    // epi_mode 0: swizzled bf16 output tile staged for TMA stores
@@ -116,6 +117,7 @@ __device__ __forceinline__ void pool_add(long long* dst, float v) {
     atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__double2ll_rn((double)v * RGBD_POOL_FIXED_ONE));
 }
 
+// ACT 3 = "statistics": identity here; the pooled epilogue additionally accumulates the squares into pool_sq
 template <int ACT>
 __device__ __forceinline__ float act_fn(float x) {
     if (ACT == 1) return fmaxf(x, 0.f);
@@ -138,8 +140,9 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
     int as = 0;
     uint32_t aphase = 0, gphase = 0;
     float acc[8];                              // pooled-mode running sums (lane L owns column 32*k + L)
+    float acc_sq[8];                           // ... of the squares (ACT 3 only; dead code otherwise)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int k = 0; k < 8; ++k) acc[k] = acc_sq[k] = 0.f;
     int cur_key = -1, cur_nt = 0;
     const int cell_h = p.cells_y ? p.out_h / p.cells_y : 1, cell_w = p.cells_x ? p.out_w / p.cells_x : 1;
     const int ncells = p.cells_y * p.cells_x;
@@ -183,6 +186,10 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
                         if (kk < n_chunks && (kk & 1) == half) {
                             pool_add(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
                             acc[kk] = 0.f;
+                            if (ACT == 3) {
+                                pool_add(p.pool_sq + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc_sq[kk]);
+                                acc_sq[kk] = 0.f;
+                            }
                         }
                     }
                 }
@@ -347,6 +354,11 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
                 if (uniform) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = valid ? f[j] : 0.f;
+                    float g[32];
+                    if (ACT == 3) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) g[j] = f[j] * f[j];
+                    }
 #pragma unroll
                     for (int s = 16; s >= 1; s >>= 1) {
                         const bool upper = (lane & s) != 0;
@@ -355,14 +367,25 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
                             const float send = upper ? f[i] : f[i + s];
                             const float keep = upper ? f[i + s] : f[i];
                             f[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                            if (ACT == 3) {
+                                const float send2 = upper ? g[i] : g[i + s];
+                                const float keep2 = upper ? g[i + s] : g[i];
+                                g[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, s);
+                            }
                         }
                     }
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
-                        if (kk == k) acc[kk] += f[0];
+                        if (kk == k) {
+                            acc[kk] += f[0];
+                            if (ACT == 3) acc_sq[kk] += g[0];
+                        }
                 } else if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) pool_add(p.pool + (size_t)key * p.N_pad + n0 + j, f[j]);
+                    for (int j = 0; j < 32; ++j) {
+                        pool_add(p.pool + (size_t)key * p.N_pad + n0 + j, f[j]);
+                        if (ACT == 3) pool_add(p.pool_sq + (size_t)key * p.N_pad + n0 + j, f[j] * f[j]);
+                    }
                 }
             }
         }
@@ -394,8 +417,10 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
     if (MODE == 2 && cur_key >= 0) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-            if (kk < n_chunks && (kk & 1) == half)
+            if (kk < n_chunks && (kk & 1) == half) {
                 pool_add(p.pool + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc[kk]);
+                if (ACT == 3) pool_add(p.pool_sq + (size_t)cur_key * p.N_pad + cur_nt * p.BLOCK_N + kk * 32 + lane, acc_sq[kk]);
+            }
     }
 }
 
@@ -531,7 +556,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         } else if (p.epi_mode == 3) {
             epilogue_loop<3, 0, false>(p, c, &tmap_out);
         } else {
-            if (sc) epilogue_loop<2, 1, true>(p, c, &tmap_out);
+            if (p.act == 3) epilogue_loop<2, 3, false>(p, c, &tmap_out);
+            else if (sc) epilogue_loop<2, 1, true>(p, c, &tmap_out);
             else epilogue_loop<2, 1, false>(p, c, &tmap_out);
         }
     }
@@ -671,7 +697,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         } else if (p.epi_mode == 1) {
             epilogue_loop<1, 0, false>(p, c, &tmap_out);
         } else {
-            if (sc) epilogue_loop<2, 1, true>(p, c, &tmap_out);
+            if (p.act == 3) epilogue_loop<2, 3, false>(p, c, &tmap_out);
+            else if (sc) epilogue_loop<2, 1, true>(p, c, &tmap_out);
             else epilogue_loop<2, 1, false>(p, c, &tmap_out);
         }
     }
@@ -1113,7 +1140,8 @@ conv3x3_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ================= epilogue (both CTAs, each on its own 128 TMEM lanes) =================
         EpiCtx c{smem, nullptr, nullptr, ctl, s_scale, s_shift, tmem_base, u_begin, u_end, warp, lane, (int)rank,
                  {tc::mapa(tc::smem_u32(&ctl->tmem_empty[0]), 0), tc::mapa(tc::smem_u32(&ctl->tmem_empty[1]), 0)}};
-        if (p.scale) epilogue_loop<2, 1, true>(p, c, &tmap_a);
+        if (p.act == 3) epilogue_loop<2, 3, false>(p, c, &tmap_a);
+        else if (p.scale) epilogue_loop<2, 1, true>(p, c, &tmap_a);
         else epilogue_loop<2, 1, false>(p, c, &tmap_a);
     }
 
@@ -1183,7 +1211,10 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         RGBD_CHECK_ARG(d->out_w % d->cells_x == 0 && d->out_h % d->cells_y == 0,
                        "conv_gemm: fused average pooling needs H,W divisible by the %dx%d cell grid (got %dx%d)",
                        d->cells_y, d->cells_x, d->out_h, d->out_w);
+        RGBD_CHECK_ARG(d->act == 1 || (d->act == 3 && d->pool_sq && !d->scale),
+                       "conv_gemm: the pooled epilogue takes act 1 (ReLU) or act 3 (statistics: needs pool_sq, no scale)");
     } else {
+        RGBD_CHECK_ARG(d->act != 3, "conv_gemm: act 3 (statistics) belongs to epilogue mode 2");
         RGBD_CHECK_ARG(d->out, "conv_gemm: null output");
     }
     if (d->epi_mode == 0)
@@ -1270,7 +1301,7 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     p.epi_mode = d->epi_mode; p.act = d->act;
     p.scale = d->scale; p.shift = d->shift; p.variant = d->variant;
     p.gate = reinterpret_cast<const __nv_bfloat16*>(d->gate);
-    p.out = d->out; p.residual = d->residual; p.pool = d->pool;
+    p.out = d->out; p.residual = d->residual; p.pool = d->pool; p.pool_sq = d->pool_sq;
     p.cells_y = d->cells_y; p.cells_x = d->cells_x;
     p.codes = reinterpret_cast<const uint8_t*>(d->codes);
     p.in_h = d->in_h; p.in_w = d->in_w; p.m3_py = d->m3_py; p.m3_px = d->m3_px; p.m3_stride = d->m3_stride;

@@ -16,6 +16,9 @@ constexpr int kXImgStride = kIcChunk * 36 + 8;     // +8 floats: the 4 images of
 
 // CTA = 16 output channels x 4 images: the 16 x 2304 weights (147 KB) are read once per 4 images, coalesced, through a
 // shared-memory chunk of 32 input channels; thread = (oc, image, output row) computes the 4 outputs of its row.
+// RAW (train-mode BatchNorm, CM:1418-1420 under .train()): the un-normalised conv outputs go to raw[b][oc][16]; the batch
+// statistics need every image before anything can be normalised.
+template <bool RAW>
 __global__ void __launch_bounds__(256) ratio_tail_conv_kernel(const long long* __restrict__ pool, int pool_stride,
                                                               float inv_cell, const float* __restrict__ w,
                                                               const float* __restrict__ scale,
@@ -60,6 +63,13 @@ __global__ void __launch_bounds__(256) ratio_tail_conv_kernel(const long long* _
         }
     }
     const int oc = oc0 + ol;
+    if (RAW) {
+        if (b0 + im < B) {
+            float4* dst = reinterpret_cast<float4*>(gap + ((size_t)(b0 + im) * kCout + oc) * 16 + oy * 4);
+            *dst = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+        return;
+    }
     const float sc = scale[oc], sh = shift[oc];
     float s = 0.f;
 #pragma unroll
@@ -88,13 +98,22 @@ __device__ __forceinline__ void fc_layer(const float* __restrict__ w, const floa
 __global__ void __launch_bounds__(512) ratio_tail_mlp_kernel(const float* __restrict__ gap, const float* w0, const float* b0,
                                                              const float* w1, const float* b1, const float* w2,
                                                              const float* b2, const float* w3, const float* b3,
-                                                             float out_min, float out_span, float* __restrict__ ratio) {
+                                                             float out_min, float out_span, float* __restrict__ ratio,
+                                                             const float* __restrict__ drop0, const float* __restrict__ drop1) {
     __shared__ float a[kCout], h0[128], h1[64], h2[32], raw[1];
     const int b = blockIdx.x;
     for (int i = threadIdx.x; i < kCout; i += blockDim.x) a[i] = gap[(size_t)b * kCout + i];
     __syncthreads();
     fc_layer(w0, b0, a, h0, 512, 128, true);
+    if (drop0) {        // nn.Dropout(0.3) in train mode (CM:1430): y = x * keep / (1 - p), the multiplier comes from the caller
+        for (int i = threadIdx.x; i < 128; i += blockDim.x) h0[i] *= drop0[(size_t)b * 128 + i];
+        __syncthreads();
+    }
     fc_layer(w1, b1, h0, h1, 128, 64, true);
+    if (drop1) {        // nn.Dropout(0.2) (CM:1433)
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) h1[i] *= drop1[(size_t)b * 64 + i];
+        __syncthreads();
+    }
     fc_layer(w2, b2, h1, h2, 64, 32, true);
     fc_layer(w3, b3, h2, raw, 32, 1, false);
     if (threadIdx.x == 0) {
@@ -103,7 +122,68 @@ __global__ void __launch_bounds__(512) ratio_tail_mlp_kernel(const float* __rest
     }
 }
 
+// Train-mode BatchNorm2d(512) over the (B, 4, 4) samples of every channel (CM:1419 under .train()), then ReLU + GAP.
+// One warp per channel: batch mean / biased variance of the raw conv outputs (the conv bias cancels in the normalised
+// value; it only enters the running mean), running statistics updated in place with torch's rule (momentum * unbiased).
+__global__ void __launch_bounds__(256) ratio_tail_bn_train_kernel(const float* __restrict__ raw, const float* __restrict__ conv_bias,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  float eps, float momentum, float* __restrict__ running_mean,
+                                                                  float* __restrict__ running_var, float* __restrict__ gap, int B) {
+    const int oc = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int n = B * 16;
+    double s = 0.0, q = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const float v = raw[((size_t)(i >> 4) * kCout + oc) * 16 + (i & 15)];
+        s += v;
+        q += (double)v * v;
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, k);
+        q += __shfl_xor_sync(0xffffffffu, q, k);
+    }
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const float sc = gamma[oc] * (float)(1.0 / sqrt(var + (double)eps));
+    const float sh = beta[oc] - (float)mean * sc;
+    if (lane == 0 && running_mean) {
+        running_mean[oc] = (1.f - momentum) * running_mean[oc] + momentum * ((float)mean + conv_bias[oc]);
+        running_var[oc] = (1.f - momentum) * running_var[oc] + momentum * (float)(n > 1 ? var * n / (n - 1) : var);
+    }
+    for (int b = 0; b < B; ++b) {
+        float v = lane < 16 ? fmaxf(fmaf(raw[((size_t)b * kCout + oc) * 16 + lane], sc, sh), 0.f) : 0.f;
+#pragma unroll
+        for (int k = 8; k > 0; k >>= 1) v += __shfl_xor_sync(0xffffffffu, v, k);
+        if (lane == 0) gap[(size_t)b * kCout + oc] = v * (1.0f / 16.0f);
+    }
+}
+
 }  // namespace
+
+extern "C" int rgbd_ratio_tail_train(const long long* pool_sums, int pool_stride, int cell_pixels, const float* conv_w,
+                                     const float* conv_bias, const float* bn_gamma, const float* bn_beta, float eps,
+                                     float momentum, float* running_mean, float* running_var, const float* const* fc_w,
+                                     const float* const* fc_b, const float* drop0, const float* drop1, float out_min,
+                                     float out_max, float* raw_ws, float* gap_ws, float* ratio_out, int B,
+                                     rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(pool_sums && conv_w && conv_bias && bn_gamma && bn_beta && fc_w && fc_b && raw_ws && gap_ws && ratio_out,
+                   "ratio_tail_train: null pointer");
+    RGBD_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "ratio_tail_train: pass both running statistics or neither");
+    RGBD_CHECK_ARG(B >= 1 && cell_pixels >= 1 && pool_stride >= kCin, "ratio_tail_train: bad geometry");
+    for (int i = 0; i < 4; ++i) RGBD_CHECK_ARG(fc_w[i] && fc_b[i], "ratio_tail_train: null fc layer %d", i);
+    cudaStream_t s = (cudaStream_t)stream;
+    ratio_tail_conv_kernel<true><<<dim3(kCout / kOcPerCta, ceil_div(B, kImgPerCta)), 256, 0, s>>>(
+        pool_sums, pool_stride, 1.0f / (float)cell_pixels, conv_w, nullptr, nullptr, raw_ws, B);
+    RGBD_CHECK_LAUNCH();
+    ratio_tail_bn_train_kernel<<<kCout / 8, 256, 0, s>>>(raw_ws, conv_bias, bn_gamma, bn_beta, eps, momentum, running_mean,
+                                                         running_var, gap_ws, B);
+    RGBD_CHECK_LAUNCH();
+    ratio_tail_mlp_kernel<<<B, 512, 0, s>>>(gap_ws, fc_w[0], fc_b[0], fc_w[1], fc_b[1], fc_w[2], fc_b[2], fc_w[3], fc_b[3],
+                                            out_min, out_max - out_min, ratio_out, drop0, drop1);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}
 
 extern "C" int rgbd_ratio_tail(const long long* pool_sums, int pool_stride, int cell_pixels, const float* conv_w,
                                const float* conv_scale, const float* conv_shift, const float* const* fc_w,
@@ -114,11 +194,11 @@ extern "C" int rgbd_ratio_tail(const long long* pool_sums, int pool_stride, int 
     RGBD_CHECK_ARG(B >= 1 && cell_pixels >= 1 && pool_stride >= kCin, "ratio_tail: bad geometry");
     for (int i = 0; i < 4; ++i) RGBD_CHECK_ARG(fc_w[i] && fc_b[i], "ratio_tail: null fc layer %d", i);
     cudaStream_t s = (cudaStream_t)stream;
-    ratio_tail_conv_kernel<<<dim3(kCout / kOcPerCta, ceil_div(B, kImgPerCta)), 256, 0, s>>>(
+    ratio_tail_conv_kernel<false><<<dim3(kCout / kOcPerCta, ceil_div(B, kImgPerCta)), 256, 0, s>>>(
         pool_sums, pool_stride, 1.0f / (float)cell_pixels, conv_w, conv_scale, conv_shift, gap_ws, B);
     RGBD_CHECK_LAUNCH();
     ratio_tail_mlp_kernel<<<B, 512, 0, s>>>(gap_ws, fc_w[0], fc_b[0], fc_w[1], fc_b[1], fc_w[2], fc_b[2], fc_w[3], fc_b[3],
-                                            out_min, out_max - out_min, ratio_out);
+                                            out_min, out_max - out_min, ratio_out, nullptr, nullptr);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }

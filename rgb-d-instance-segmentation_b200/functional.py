@@ -390,7 +390,8 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
               conv3x3_reuse: bool = False, codes: Optional[torch.Tensor] = None, in_hw: Tuple[int, int] = (0, 0),
               parity: Tuple[int, int] = (0, 0), m3_stride: int = 1, m3_masked_segs: int = 0, m3_n_seg: int = 0,
               dsam_masked: bool = False, next_operand: Optional[torch.Tensor] = None,
-              next_codes: Optional[torch.Tensor] = None, next_geom: Tuple[int, int, int] = (0, 0, 0)) -> None:
+              next_codes: Optional[torch.Tensor] = None, next_geom: Tuple[int, int, int] = (0, 0, 0),
+              pool_sq: Optional[torch.Tensor] = None) -> None:
     """Launch the tcgen05 implicit-GEMM kernel.  a_dims = (planes, y, x, c) of the bf16 channels-last operand.
     ``conv3x3_reuse``: 3x3 stride-1 conv whose A tile is shared by the three dx taps (``slices`` may be None).
     ``dsam_masked``: stride-2 DSAM stage on the unmasked operand, region masking in shared memory (``slices`` None)."""
@@ -437,6 +438,7 @@ def conv_gemm(a: torch.Tensor, a_dims: Tuple[int, int, int, int], plane_per_img:
     d.out = out.data_ptr() if out is not None else None
     d.residual = _req(residual, "residual", torch.float32).data_ptr() if residual is not None else None
     d.pool = _req(pool, "pool", torch.int64).data_ptr() if pool is not None else None
+    d.pool_sq = _req(pool_sq, "pool_sq", torch.int64).data_ptr() if pool_sq is not None else None
     d.cells_y, d.cells_x = cells
     check(lib.rgbd_conv_gemm(C.byref(d), _stream()), "rgbd_conv_gemm")
     _count(1)
@@ -609,6 +611,43 @@ def ratio_tail(pool: torch.Tensor, cell_pixels: int, conv_w: torch.Tensor, conv_
                               ptr_array([t.data_ptr() for t in fc_b]), out_min, out_max, gap.data_ptr(),
                               ratio.data_ptr(), B, _stream()), "rgbd_ratio_tail")
     _count(2)
+    return ratio
+
+
+def ratio_tail_train(pool: torch.Tensor, cell_pixels: int, conv_w: torch.Tensor, conv_bias: torch.Tensor,
+                     bn_gamma: torch.Tensor, bn_beta: torch.Tensor, eps: float, momentum: float,
+                     running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor],
+                     fc_w: Sequence[torch.Tensor], fc_b: Sequence[torch.Tensor], drop0: Optional[torch.Tensor],
+                     drop1: Optional[torch.Tensor], out_min: float, out_max: float) -> torch.Tensor:
+    """The predictor's tail under ``.train()`` (CM:1418-1437): batch-statistics BatchNorm2d(512) (running statistics
+    updated IN PLACE when given) and Dropout multipliers ``keep / (1 - p)`` of shape (B,128) / (B,64)."""
+    lib = _lib.load()
+    _req(pool, "pool", torch.int64)
+    B = pool.shape[0]
+    dev = pool.device
+    for t in (conv_w, conv_bias, bn_gamma, bn_beta, *fc_w, *fc_b):
+        _req(t, "ratio tail parameter", torch.float32)
+    for t, n in ((drop0, 128), (drop1, 64)):
+        if t is not None:
+            _req(t, "dropout multiplier", torch.float32)
+            if tuple(t.shape) != (B, n):
+                raise RgbdB200Error(f"dropout multiplier must be {(B, n)}, got {tuple(t.shape)}")
+    if (running_mean is None) != (running_var is None):
+        raise RgbdB200Error("pass both running statistics or neither")
+    if running_mean is not None:
+        _req(running_mean, "running_mean", torch.float32)
+        _req(running_var, "running_var", torch.float32)
+    raw = torch.empty(B, 512, 16, device=dev, dtype=torch.float32)
+    gap = torch.empty(B, 512, device=dev, dtype=torch.float32)
+    ratio = torch.empty(B, 1, device=dev, dtype=torch.float32)
+    check(lib.rgbd_ratio_tail_train(
+        pool.data_ptr(), pool.shape[-1], cell_pixels, conv_w.data_ptr(), conv_bias.data_ptr(), bn_gamma.data_ptr(),
+        bn_beta.data_ptr(), float(eps), float(momentum), running_mean.data_ptr() if running_mean is not None else None,
+        running_var.data_ptr() if running_var is not None else None, ptr_array([t.data_ptr() for t in fc_w]),
+        ptr_array([t.data_ptr() for t in fc_b]), drop0.data_ptr() if drop0 is not None else None,
+        drop1.data_ptr() if drop1 is not None else None, out_min, out_max, raw.data_ptr(), gap.data_ptr(), ratio.data_ptr(),
+        B, _stream()), "rgbd_ratio_tail_train")
+    _count(3)
     return ratio
 
 

@@ -523,9 +523,11 @@ def _fold_bn(conv_bias: torch.Tensor, bn: nn.BatchNorm2d) -> Tuple[torch.Tensor,
 
 
 class EnhancedDepthImageRatioPredictor(nn.Module):
-    """CM:1363-1487: (B,3,H,W) depth -> (B,1) window_size_ratio in [0.01, 0.5].  BatchNorm is folded
-    (eval semantics, running statistics); the module receives no gradient in the v0.4.0 model (its output
-    is consumed through ``.item()``, CM:339), so only the forward exists."""
+    """CM:1363-1487: (B,3,H,W) depth -> (B,1) window_size_ratio in [0.01, 0.5].  ``eval()``: BatchNorm folded into the
+    weights (running statistics), everything up to the 4x4 pooled map in two fused tensor-core kernels.  ``train()``:
+    batch-statistics BatchNorm (a statistics pass + a normalising pass per BatchNorm layer, running statistics updated
+    with momentum like torch) and Dropout with injectable keep-masks.  The module receives no gradient in the v0.4.0 model
+    (its output is consumed through ``.item()``, CM:339), so only the forward exists."""
 
     def __init__(self, input_channels: int = 3):
         super().__init__()
@@ -556,6 +558,8 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         self._ver = _Versioned()
         self._packed: Dict[str, torch.Tensor] = {}
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self._ver_train = _Versioned()
+        self._packed_train: Dict[str, torch.Tensor] = {}
 
     def _refresh(self):
         srcs = list(self.parameters()) + list(self.buffers())
@@ -631,20 +635,152 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         when its tile is 128 consecutive pixels of a row and the width is even."""
         return self.use_fused_front and self.use_compact_operand and _best_box(H, W) == (128, 1) and W % 2 == 0
 
-    def forward(self, depth_image: torch.Tensor) -> torch.Tensor:
+    # ---- .train(): batch-statistics BatchNorm + Dropout (CM:1380-1437 with the modules in training mode; SURVEY H6) -------
+    TRAIN_MODE_SUPPORTED = True
+
+    def _refresh_train(self):
+        """Un-folded weights for the train-mode passes: the BatchNorm scale depends on the batch, so it is folded into the
+        bf16 weights per step (after the statistics pass that ran on the plain bf16 weights)."""
+        srcs = [p for p in self.parameters()]
+        if not self._ver_train.stale(srcs) and self._packed_train:
+            return self._packed_train
+        dev = srcs[0].device
+        bf = torch.bfloat16
+        with torch.no_grad():
+            w1 = torch.zeros(192, 4, 2, 8, 4, device=dev, dtype=torch.float32)
+            for idx, (seq, k) in enumerate(((self.scale1_conv, 3), (self.scale2_conv, 5), (self.scale3_conv, 7))):
+                o = (7 - k) // 2
+                full = torch.zeros(64, 3, 8, 8, device=dev)
+                full[:, :, o:o + k, o:o + k] = seq[0].weight.float()
+                w1[idx * 64:(idx + 1) * 64, :, :, :, :3] = full.reshape(64, 3, 4, 2, 8).permute(0, 2, 3, 4, 1)
+            pk = {"w1": w1.reshape(192, 256).contiguous(),
+                  "w2": self.feature_fusion[0].weight.float().reshape(128, 192).contiguous(),
+                  "w5": self.feature_extractor[0].weight.float().permute(0, 2, 3, 1).reshape(256, 9 * 128).contiguous()}
+            for k in ("w1", "w2", "w5"):
+                pk[k + "_bf"] = pk[k].to(bf).contiguous()
+            pk["zeros"] = torch.zeros(256, device=dev, dtype=torch.float32)
+            # layers without BatchNorm + slice tables: the same operands as the eval path (kept here so that the running
+            # statistics, which change every training step, do not invalidate them)
+            pk["w3"] = self.attention[0].weight.float().reshape(64, 128).to(bf).contiguous()
+            pk["sh3"] = self.attention[0].bias.detach().float().contiguous()
+            pk["w4"] = self.attention[2].weight.float().reshape(128, 64).to(bf).contiguous()
+            pk["sh4"] = self.attention[2].bias.detach().float().contiguous()
+            pk["w6"] = self.feature_extractor[4].weight.detach().float().contiguous()
+            for j, li in enumerate((0, 3, 6, 8)):
+                pk[f"fw{j}"] = self.fc_layers[li].weight.detach().float().contiguous()
+                pk[f"fb{j}"] = self.fc_layers[li].bias.detach().float().contiguous()
+
+            def sl(entries):
+                return torch.tensor(entries, device=dev, dtype=torch.int32).contiguous()
+            pk["sl1"] = sl([(0, 0, 2 * t, 0) for t in range(4)])
+            pk["sl2"] = sl([(64 * cb, 0, 0, 0) for cb in range(3)])
+            pk["sl3"] = sl([(64 * cb, 0, 0, 0) for cb in range(2)])
+            pk["sl4"] = sl([(0, 0, 0, 0)])
+            pk["sl5"] = sl([(64 * cb, dx - 1, dy - 1, 0) for dy in range(3) for dx in range(3) for cb in range(2)])
+        self._packed_train = pk
+        return pk
+
+    @staticmethod
+    def _batch_norm_train(sum_fx: torch.Tensor, sq_fx: torch.Tensor, count: int, bn: nn.BatchNorm2d,
+                          conv_bias: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Fixed-point per-image sums of the raw conv outputs (and of their squares) -> this batch's BatchNorm as a
+        per-channel (scale, shift); ``bn``'s running statistics are updated like torch does (CM:1382 et al. in training
+        mode: momentum * batch mean / UNBIASED batch variance).  The conv bias cancels in the normalised value."""
+        c = bn.num_features
+        mean = sum_fx[:c].double() / (Fn.POOL_FIXED_ONE * count)
+        var = (sq_fx[:c].double() / (Fn.POOL_FIXED_ONE * count) - mean * mean).clamp_min(0.0)
+        scale = bn.weight.double() / torch.sqrt(var + bn.eps)
+        shift = bn.bias.double() - mean * scale
+        if bn.track_running_stats and bn.running_mean is not None:
+            bn.num_batches_tracked += 1
+            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            bn.running_mean.mul_(1 - m).add_((m * (mean + conv_bias.double())).float())
+            bn.running_var.mul_(1 - m).add_((m * var * (count / max(count - 1, 1))).float())
+        return scale.float(), shift.float()
+
+    def _forward_train(self, depth_image: torch.Tensor, dropout_masks=None) -> torch.Tensor:
+        B, _, H, W = depth_image.shape
+        dev = depth_image.device
+        pt = self._refresh_train()
+        pk = pt
+        key = (B, H, W, str(dev), "train")
+        if key not in self._ws:
+            _evict(self._ws)
+            bf = dict(device=dev, dtype=torch.bfloat16)
+            self._ws[key] = {"stem": torch.empty(B, H + 6, W, 64, **bf), "x1": torch.empty(B, H, W, 192, **bf),
+                             "x2": torch.empty(B, H, W, 128, **bf), "x3": torch.empty(B, H, W, 64, **bf),
+                             "x4": torch.empty(B, H, W, 128, **bf),
+                             "pool": torch.empty(B, 16, 256, device=dev, dtype=torch.int64),
+                             "stat": torch.empty(2, B, 1, 256, device=dev, dtype=torch.int64)}
+        ws = self._ws[key]
+        d = depth_image.detach()
+        d = d if d.dtype == torch.float32 else d.float()
+        box = _best_box(H, W)
+        n = B * H * W
+        bf = torch.bfloat16
+
+        def stats(operand, a_dims, w_bf, slices, n_out, **kw):
+            st = ws["stat"][:, :, :, :n_out].contiguous() if n_out != 256 else ws["stat"]
+            st.zero_()
+            Fn.conv_gemm(operand, a_dims, 1, w_bf, slices, 64, B, (H, W), box, n_out, pt["zeros"][:n_out], act=3, epi_mode=2,
+                         pool=st[0], pool_sq=st[1], cells=(1, 1), **kw)
+            return st[0].sum(dim=(0, 1)), st[1].sum(dim=(0, 1))
+
+        with torch.no_grad():
+            Fn.ratio_stem_pack(d, ws["stem"])
+            # multi-scale stem (CM:1458-1463): statistics pass, then conv + BN(batch) + ReLU
+            s1, q1 = stats(ws["stem"], (B, H + 6, W, 64), pt["w1_bf"], pk["sl1"], 192, tile_order=1)
+            sc, sh = zip(*[self._batch_norm_train(s1[i * 64:(i + 1) * 64], q1[i * 64:(i + 1) * 64], n, seq[1], seq[0].bias)
+                           for i, seq in enumerate((self.scale1_conv, self.scale2_conv, self.scale3_conv))])
+            sc1, sh1 = torch.cat(sc), torch.cat(sh).contiguous()
+            Fn.conv_gemm(ws["stem"], (B, H + 6, W, 64), 1, (pt["w1"] * sc1[:, None]).to(bf).contiguous(), pk["sl1"], 64, B, (H, W),
+                         box, 192, sh1, act=1, out=ws["x1"], tile_order=1)
+            # feature_fusion (CM:1466)
+            s2, q2 = stats(ws["x1"], (B, H, W, 192), pt["w2_bf"], pk["sl2"], 128)
+            sc2, sh2 = self._batch_norm_train(s2, q2, n, self.feature_fusion[1], self.feature_fusion[0].bias)
+            Fn.conv_gemm(ws["x1"], (B, H, W, 192), 1, (pt["w2"] * sc2[:, None]).to(bf).contiguous(), pk["sl2"], 64, B, (H, W), box,
+                         128, sh2.contiguous(), act=1, out=ws["x2"])
+            # attention (CM:1469-1470; no BatchNorm)
+            Fn.conv_gemm(ws["x2"], (B, H, W, 128), 1, pk["w3"], pk["sl3"], 64, B, (H, W), box, 64, pk["sh3"], act=1, out=ws["x3"])
+            Fn.conv_gemm(ws["x3"], (B, H, W, 64), 1, pk["w4"], pk["sl4"], 64, B, (H, W), box, 128, pk["sh4"], act=2,
+                         gate=ws["x2"], out=ws["x4"])
+            # feature_extractor[0:4] (CM:1412-1416)
+            reuse = dict(tile_order=1, conv3x3_reuse=(box == (128, 1)))
+            s5, q5 = stats(ws["x4"], (B, H, W, 128), pt["w5_bf"], pk["sl5"], 256, **reuse)
+            sc5, sh5 = self._batch_norm_train(s5, q5, n, self.feature_extractor[1], self.feature_extractor[0].bias)
+            ws["pool"].zero_()
+            Fn.conv_gemm(ws["x4"], (B, H, W, 128), 1, (pt["w5"] * sc5[:, None]).to(bf).contiguous(), pk["sl5"], 64, B, (H, W), box,
+                         256, sh5.contiguous(), act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), **reuse)
+            # feature_extractor[4:7] + GAP + fc_layers with Dropout (CM:1418-1437)
+            mult = []
+            for j, (p_drop, width) in enumerate(((self.fc_layers[2].p, 128), (self.fc_layers[5].p, 64))):
+                keep = dropout_masks[j] if dropout_masks is not None else torch.rand(B, width, device=dev) >= p_drop
+                keep = keep.to(device=dev)
+                if tuple(keep.shape) != (B, width):
+                    raise RgbdB200Error(f"dropout_masks[{j}] must be {(B, width)} keep-masks")
+                mult.append((keep.float() / (1.0 - p_drop)).contiguous())
+            bn6, c6 = self.feature_extractor[5], self.feature_extractor[4]
+            track = bn6.track_running_stats and bn6.running_mean is not None
+            if track:
+                bn6.num_batches_tracked += 1
+            m6 = bn6.momentum if bn6.momentum is not None else 1.0 / float(bn6.num_batches_tracked)
+            return Fn.ratio_tail_train(ws["pool"], (H // 4) * (W // 4), pk["w6"], c6.bias.detach().float().contiguous(),
+                                       bn6.weight.detach().float().contiguous(), bn6.bias.detach().float().contiguous(), bn6.eps,
+                                       m6, bn6.running_mean if track else None, bn6.running_var if track else None,
+                                       [pk[f"fw{j}"] for j in range(4)], [pk[f"fb{j}"] for j in range(4)], mult[0], mult[1],
+                                       self.output_min, self.output_max)
+
+    def forward(self, depth_image: torch.Tensor, dropout_masks=None) -> torch.Tensor:
+        """``dropout_masks`` (train mode only): optional ((B,128), (B,64)) boolean KEEP masks of the two Dropout layers
+        (CM:1430, 1433); drawn from torch's generator when omitted."""
         assert depth_image.dim() == 4, f"Expected 4D tensor, got {depth_image.dim()}D"
         assert depth_image.shape[1] == self.input_channels, \
             f"Expected {self.input_channels} channels, got {depth_image.shape[1]}"
         B, _, H, W = depth_image.shape
         if H % 4 or W % 4:
             raise RgbdB200Error("the fused AdaptiveAvgPool2d(4) epilogue needs H and W divisible by 4")
-        if self.training and not getattr(self, "_warned_train_mode", False):
-            import warnings
-            warnings.warn("rgbd_b200.EnhancedDepthImageRatioPredictor always uses the BatchNorm running statistics and no "
-                          "Dropout (eval semantics), also under .train(): the reference would use batch statistics and "
-                          "update the running ones (CM:1444-1487).  The module receives no gradient either way (its output "
-                          "is consumed through .item(), CM:339).", RuntimeWarning, stacklevel=2)
-            self._warned_train_mode = True
+        if self.training:
+            return self._forward_train(depth_image, dropout_masks)
         pk = self._refresh()
         ws = self._workspace(B, H, W, depth_image.device)
         d = depth_image.detach()

@@ -1017,3 +1017,63 @@ def test_tensor_on_another_device_raises(fn):
         fn.to_grayscale(x)
     with torch.cuda.device(1):
         fn.to_grayscale(x)                                # per-device launch state: works on the second GPU too
+
+
+# ---------------------------------------------------------------------------------------------------
+# train-mode ratio predictor: batch-statistics BatchNorm, running-stat updates, Dropout (CM:1380-1437)
+# ---------------------------------------------------------------------------------------------------
+def test_ratio_predictor_train_mode_matches_reference_golden(mods, golden_dir):
+    from oracle.make_golden_train import SEED_W, train_inputs
+    g = np.load(os.path.join(golden_dir, "ratio_train.npz"))
+    m = mods.EnhancedDepthImageRatioPredictor(3)
+    m.load_state_dict(OW.ratio_weights(seed=SEED_W))
+    m.cuda().train()
+    for step in range(2):
+        x, keep = train_inputs(synthetic, step)
+        r = m(x.cuda(), dropout_masks=keep)
+        assert not r.requires_grad
+        ref = torch.from_numpy(g[f"step{step}.ratio"])
+        assert float(((r.cpu() - ref).abs() / ref).max()) < BF16_TOL, (step, r.cpu().flatten(), ref.flatten())
+        sd = m.state_dict()
+        for k, v in sd.items():
+            if "running" in k:
+                want = torch.from_numpy(g[f"step{step}.{k}"])
+                assert rel_err(v, want) < BF16_TOL, (step, k, rel_err(v, want))
+            elif "num_batches" in k:
+                assert int(v) == step + 1, (k, int(v))
+    # eval() afterwards uses the UPDATED running statistics, like the reference
+    m.eval()
+    x, _ = train_inputs(synthetic, 0)
+    w_after = {k: v.cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        r_eval = m(x.cuda())
+    ref_eval = O.ratio_predictor_forward(w_after, x)
+    assert float(((r_eval.cpu() - ref_eval).abs() / ref_eval).max()) < BF16_TOL
+
+
+@pytest.mark.parametrize("B,hw", [(2, (96, 160)), (8, (480, 640))])
+def test_ratio_predictor_train_mode_against_oracle(mods, B, hw):
+    """Larger shapes incl. the fine-tuning batch of BASELINE configs[3] (8 frames of 480x640) against the oracle's train-mode
+    restatement (itself pinned by the reference golden above)."""
+    w = OW.ratio_weights(seed=510)
+    m = mods.EnhancedDepthImageRatioPredictor(3)
+    m.load_state_dict(w)
+    m.cuda().train()
+    kinds = ("nyu", "nyu", "uniform", "nyu", "two_valued", "nyu", "nyu", "constant")
+    frames = []
+    for j in range(B):
+        _, d = synthetic.synth_rgbd_u8(170 + j, hw[0], hw[1], kinds[j % len(kinds)])
+        frames.append(synthetic.normalise_u8(np.repeat(d[:, :, None], 3, axis=2)))
+    x = torch.from_numpy(np.stack(frames))
+    rs = np.random.RandomState(3)
+    keep = (torch.from_numpy(rs.rand(B, 128) >= 0.3), torch.from_numpy(rs.rand(B, 64) >= 0.2))
+    ref, w_ref = O.ratio_predictor_forward_train(w, x, keep)
+    r = m(x.cuda(), dropout_masks=keep)
+    err = float(((r.cpu() - ref).abs() / ref).max())
+    assert err < BF16_TOL, (err, r.cpu().flatten(), ref.flatten())
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            assert rel_err(v, w_ref[k]) < BF16_TOL, (k, rel_err(v, w_ref[k]))
+    # without injected masks the module draws its own: still a valid ratio, and it differs from the masked run
+    r2 = m(x.cuda())
+    assert bool(((r2 >= 0.01) & (r2 <= 0.5)).all())

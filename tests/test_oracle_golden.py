@@ -203,3 +203,20 @@ def test_front_end_matches_huggingface_processor_and_reference_mapper(golden_dir
     for j in range(3):
         pv = synthetic.assemble_pixel_values(g[f"f{j}.rgb"], g[f"f{j}.depth"], O.gradient_features)
         assert pv.dtype == np.float32 and np.array_equal(pv, g[f"f{j}.pixel_values"])
+
+
+def test_ratio_predictor_train_mode_matches_reference_golden(golden_dir):
+    """oracle.ratio_predictor_forward_train == the reference module in .train() (batch-statistics BatchNorm, running
+    statistics after each of two steps, injected Dropout keep-masks); golden from oracle/make_golden_train.py."""
+    from oracle.make_golden_train import SEED_W, train_inputs
+    g = np.load(os.path.join(golden_dir, "ratio_train.npz"))
+    w = OW.ratio_weights(seed=SEED_W)
+    for step in range(2):
+        x, keep = train_inputs(synthetic, step)
+        r, w = O.ratio_predictor_forward_train(w, x, keep)
+        np.testing.assert_allclose(r.numpy(), g[f"step{step}.ratio"], rtol=1e-5, atol=1e-7)
+        for k in w:
+            if "running" in k:
+                np.testing.assert_allclose(w[k].numpy(), g[f"step{step}.{k}"], rtol=2e-5, atol=1e-6, err_msg=k)
+            elif "num_batches" in k:
+                assert int(w[k]) == int(g[f"step{step}.{k}"]) == step + 1
