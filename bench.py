@@ -653,12 +653,18 @@ class PerKernel:
                     pk["sh4"], ws["x4"], box))
             out["ratio_stem_pack"] = self._time(lambda: (Fn.ratio_stem_pack_compact if compact else Fn.ratio_stem_pack)(
                 pv[:, 3:6], ws["stem"]))
-            out["ratio_tail"] = self._time(lambda: Fn.ratio_tail(
-                ws["pool"], (H // 4) * (W // 4), pk["w6"], pk["sc6"], pk["sh6"], [pk[f"fw{j}"] for j in range(4)],
-                [pk[f"fb{j}"] for j in range(4)], rp.output_min, rp.output_max))
+            fcw, fcb = [pk[f"fw{j}"] for j in range(4)], [pk[f"fb{j}"] for j in range(4)]
+            if rp.use_tensor_core_tail:
+                out["ratio_tail"] = self._time(lambda: Fn.ratio_tail_tc(
+                    ws["pool"], (H // 4) * (W // 4), ws["a6"], ws["gap_fx"], pk["w6_bf"], pk["sl6"], pk["sh6"], fcw, fcb,
+                    rp.output_min, rp.output_max))
+            else:
+                out["ratio_tail"] = self._time(lambda: Fn.ratio_tail(
+                    ws["pool"], (H // 4) * (W // 4), pk["w6"], pk["sc6"], pk["sh6"], fcw, fcb, rp.output_min, rp.output_max))
             ratios = rp(pv[:, 3:6])
             levels = [tuple(f.shape[2:]) for f in feats[:3]]
-            out["depth_decompose"] = self._time(lambda: Fn.depth_decompose(ratios.reshape(-1), levels, depth3=pv[:, 3:6]))
+            out["depth_decompose"] = self._time(lambda: Fn.depth_decompose(ratios.reshape(-1), levels, depth3=pv[:, 3:6],
+                                                                           want_codes=False))
             dec = Fn.depth_decompose(ratios.reshape(-1), levels, depth3=pv[:, 3:6])
 
             def cascade(gemm_only=False):

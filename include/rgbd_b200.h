@@ -82,10 +82,11 @@ int rgbd_pack_pixel_values(const uint8_t* rgb_hwc, const uint8_t* depth, float* 
  * Outputs (optional ones may be NULL): hist_out int64 (B,512); edges_out f32 (B,513); n_modes_out (B);
  * peak_bins_out (B,3); centres_out (B,3); windows_out (B,3,2); status_out (B); bias_variant_out (B) = how many
  * conv biases the reference adds for the image (n_modes+1, or num_modes+1 when no mode survives, CM:676-691);
- * codes_out uint8 (B,H,W) REQUIRED:
- * bit t = region mask t in the reference's list order (modes by (height, centre) descending, then the remaining
+ * codes_out uint8 (B,H,W): bit t = region mask t in the reference's list order (modes by (height, centre) descending, then the remaining
  * region at index n_modes; all zero when no mode survives, CM:676-678); pooled_out_host[l] uint8
- * (B, level_h[l], level_w[l]) = the codes OR-pooled over adaptive_max_pool2d's windows. */
+ * (B, level_h[l], level_w[l]) = the codes OR-pooled over adaptive_max_pool2d's windows.  codes_out may be NULL when the
+ * levels are exactly (H/4,W/4), (H/8,W/8), (H/16,W/16) with H, W multiples of 16 (the Swin pyramid): codes and pooled copies
+ * then come from one fused pass and the full-resolution codes need not be stored. */
 size_t rgbd_depth_decompose_workspace_bytes(int B);
 int rgbd_depth_decompose(const float* depth3, long long depth_batch_stride, long long depth_channel_stride,
                          const float* gray_in, const float* ratio, int B, int H, int W, int num_modes, float* gray_out,
@@ -212,6 +213,14 @@ int rgbd_ratio_stem_pack_compact(const float* depth3, long long batch_stride, lo
 int rgbd_ratio_tail(const long long* pool_sums, int pool_stride, int cell_pixels, const float* conv_w, const float* conv_scale,
                     const float* conv_shift, const float* const* fc_w_host, const float* const* fc_b_host, float out_min,
                     float out_max, float* gap_ws, float* ratio_out, int B, rgbd_stream_t stream);
+
+/* Tensor-core variant of the tail: rgbd_ratio_tail_prepare turns the pooled sums into the bf16 channels-last 4x4 map
+ * a (B,4,4,256) and zeroes gap_fx (B,512); rgbd_conv_gemm (3x3 taps as slices, epi_mode 2 with a 1x1 cell grid, act 1) adds
+ * ReLU(BN(conv)) summed over the 16 pixels into gap_fx as fixed point; rgbd_ratio_tail_mlp_fx = GAP/16 -> MLP -> ratio. */
+int rgbd_ratio_tail_prepare(const long long* pool_sums, int pool_stride, int cell_pixels, void* a_bf16, long long* gap_fx, int B,
+                            rgbd_stream_t stream);
+int rgbd_ratio_tail_mlp_fx(const long long* gap_fx, const float* const* fc_w_host, const float* const* fc_b_host, float out_min,
+                           float out_max, float* ratio_out, int B, rgbd_stream_t stream);
 
 /* The same tail under .train() (CM:1418-1437 with BatchNorm2d in training mode and active Dropout): conv3x3 256->512 ->
  * BatchNorm over the batch's (B,4,4) samples per channel (biased variance for normalisation; running_mean / running_var,

@@ -19,7 +19,8 @@ namespace {
 constexpr int kBins = RGBD_HIST_BINS;   // 512
 
 struct ImgState {
-    uint32_t min_enc, max_enc;      // order-preserving encodings of nanmin / nanmax
+    uint32_t min_inv, max_enc;      // order-preserving encodings of nanmax and (bitwise inverted, so that an all-zero state is
+                                    // the identity of both atomicMax reductions and a memset initialises it) of nanmin
     uint32_t n_finite, has_inf;
     float first, last, step, denom; // histogram range after the first==last widening
     int step_zero;                  // numpy's denormal special case (gh-5437)
@@ -31,15 +32,31 @@ struct ImgState {
     int peak_bin[3];
 };
 
-__global__ void decomp_init_kernel(ImgState* st, unsigned long long* hist, int B) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) {
-        ImgState z = {};
-        z.min_enc = 0xffffffffu;
-        z.max_enc = 0u;
-        st[i] = z;
+// block-wide min/max/count reduction of the per-thread partials, then ONE set of atomics per CTA
+__device__ __forceinline__ void reduce_minmax(ImgState* st, uint32_t lmin, uint32_t lmax, uint32_t nfin, uint32_t ninf) {
+    __shared__ uint32_t red[4][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        nfin += __shfl_xor_sync(0xffffffffu, nfin, o);
+        ninf |= __shfl_xor_sync(0xffffffffu, ninf, o);
     }
-    if (i < B * kBins) hist[i] = 0ull;
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[0][w] = lmin; red[1][w] = lmax; red[2][w] = nfin; red[3][w] = ninf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int k = 1; k < nw; ++k) {
+            lmin = min(lmin, red[0][k]); lmax = max(lmax, red[1][k]); nfin += red[2][k]; ninf |= red[3][k];
+        }
+        if (nfin) {
+            atomicMax(&st->min_inv, ~lmin);
+            atomicMax(&st->max_enc, lmax);
+            atomicAdd(&st->n_finite, nfin);
+            if (ninf) atomicOr(&st->has_inf, 1u);
+        }
+    }
 }
 
 // gray + per-image nanmin/nanmax; 4 pixels per thread (128-bit loads / stores when VEC)
@@ -86,19 +103,7 @@ __global__ void __launch_bounds__(256) decomp_gray_kernel(const float* __restric
             for (int e = 0; e < n; ++e) out[i4 + e] = v[e];
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-        nfin += __shfl_xor_sync(0xffffffffu, nfin, o);
-        ninf |= __shfl_xor_sync(0xffffffffu, ninf, o);
-    }
-    if ((threadIdx.x & 31) == 0 && nfin) {
-        atomicMin(&st[b].min_enc, lmin);
-        atomicMax(&st[b].max_enc, lmax);
-        atomicAdd(&st[b].n_finite, nfin);
-        if (ninf) atomicOr(&st[b].has_inf, 1u);
-    }
+    reduce_minmax(st + b, lmin, lmax, nfin, ninf);
 }
 
 // gray supplied by the caller (DSAModule.forward API): only the min/max reduction
@@ -116,30 +121,17 @@ __global__ void __launch_bounds__(256) decomp_minmax_kernel(const float* __restr
             if (isinf(v)) ninf = 1u;
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-        nfin += __shfl_xor_sync(0xffffffffu, nfin, o);
-        ninf |= __shfl_xor_sync(0xffffffffu, ninf, o);
-    }
-    if ((threadIdx.x & 31) == 0 && nfin) {
-        atomicMin(&st[b].min_enc, lmin);
-        atomicMax(&st[b].max_enc, lmax);
-        atomicAdd(&st[b].n_finite, nfin);
-        if (ninf) atomicOr(&st[b].has_inf, 1u);
-    }
+    reduce_minmax(st + b, lmin, lmax, nfin, ninf);
 }
 
-__global__ void decomp_range_kernel(ImgState* st, int B) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    ImgState& s = st[b];
+// histogram range of one image from its nanmin / nanmax (numpy _get_outer_edges + linspace step); every kernel that needs it
+// recomputes it from the reduced state (deterministic), decomp_modes_kernel stores it
+__device__ __forceinline__ void compute_range(ImgState& s) {
     if (s.n_finite == 0 || s.has_inf) {   // numpy raises "range ... is not finite"
         s.status |= RGBD_DECOMP_RANGE_NOT_FINITE;
         s.first = 0.f; s.last = 1.f;
     } else {
-        s.first = ordered_to_f32(s.min_enc);
+        s.first = ordered_to_f32(~s.min_inv);
         s.last = ordered_to_f32(s.max_enc);
         if (s.first == s.last) {            // _get_outer_edges: expand empty range
             s.first = s.first - 0.5f;
@@ -160,49 +152,64 @@ __device__ __forceinline__ float bin_edge(const ImgState& s, int i) {
 
 __global__ void __launch_bounds__(256) decomp_hist_kernel(const float* __restrict__ gray, const ImgState* __restrict__ st,
                                                           unsigned long long* __restrict__ hist, int HW) {
-    __shared__ unsigned int h[kBins];
-    __shared__ float edges[kBins + 1];
+    __shared__ unsigned int h[8][kBins];            // one sub-histogram per warp: no atomics contention between warps
     const int b = blockIdx.y;
-    const ImgState s = st[b];
-    for (int i = threadIdx.x; i < kBins; i += blockDim.x) h[i] = 0u;
-    for (int i = threadIdx.x; i <= kBins; i += blockDim.x) edges[i] = bin_edge(s, i);
+    ImgState s = st[b];
+    compute_range(s);
+    for (int i = threadIdx.x; i < 8 * kBins; i += blockDim.x) (&h[0][0])[i] = 0u;
     __syncthreads();
     if (s.status & RGBD_DECOMP_RANGE_NOT_FINITE) return;
     const float* in = gray + (long long)b * HW;
+    unsigned int* hw = h[threadIdx.x >> 5];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
         float x = in[i];
         if (x >= s.first && x <= s.last) {          // drops NaN
             float f = ((x - s.first) / s.denom) * (float)kBins;
             int idx = (int)f;                        // astype(intp): truncation
             if (idx == kBins) idx -= 1;
-            if (x < edges[idx]) idx -= 1;
-            if (x >= edges[idx + 1] && idx != kBins - 1) idx += 1;
-            atomicAdd(&h[idx], 1u);
+            if (x < bin_edge(s, idx)) idx -= 1;
+            if (x >= bin_edge(s, idx + 1) && idx != kBins - 1) idx += 1;
+            atomicAdd(&hw[idx], 1u);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kBins; i += blockDim.x)
-        if (h[i]) atomicAdd(&hist[(long long)b * kBins + i], (unsigned long long)h[i]);
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+        unsigned int t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += h[w][i];
+        if (t) atomicAdd(&hist[(long long)b * kBins + i], (unsigned long long)t);
+    }
 }
+
+struct ExportPtrs {
+    int* n_modes; int* peak_bins; float* centres; float* windows; int* status; int* bias_variant;
+};
 
 // One CTA (512 threads, one per bin) per image: scipy _local_maxima_1d + _peak_prominences(wlen=None),
 // keep prominence >= 0.01*max (float64), order by (height, centre) descending, first 3; then windows.
+// Parallel form: (1) every rising edge starts at most one plateau -> peak list; (2) one WARP per peak scans outwards 32 bins
+// at a time for the first higher bin (ballot) and the minimum on the way (shuffle-min) -- uint8 depth gives ~200 peaks whose
+// walks are hundreds of bins long, serial per thread before; (3) three block-wide arg-max rounds over (height, bin).
 // edges_in != nullptr (helper API, CM:720-752): bin edges (B, 513) supplied by the caller instead of the image's range;
-// ratio == nullptr: no windows (they belong to _define_depth_interval_windows)
+// ratio == nullptr: no windows (they belong to _define_depth_interval_windows).  range_from_minmax: the state holds only the
+// reduced nanmin / nanmax (batched path); the histogram range is derived and stored here.
 __global__ void __launch_bounds__(kBins) decomp_modes_kernel(const unsigned long long* __restrict__ hist,
                                                              ImgState* __restrict__ st, const float* __restrict__ ratio,
                                                              int num_modes, double prom_thr,
-                                                             const float* __restrict__ edges_in) {
+                                                             const float* __restrict__ edges_in, int range_from_minmax,
+                                                             ExportPtrs ex) {
     __shared__ long long h[kBins];
-    __shared__ long long cand_h[kBins / 2];
-    __shared__ int cand_bin[kBins / 2];
-    __shared__ int n_cand;
-    __shared__ long long hmax_s[kBins / 32];
+    __shared__ int peak_bin[kBins / 2];
+    __shared__ unsigned long long cand[kBins / 2];     // (height << 16) | bin of the peaks that pass the prominence filter
+    __shared__ int n_peaks, n_cand;
+    __shared__ unsigned long long red[kBins / 32];
+    __shared__ unsigned long long picked[3];
     const int b = blockIdx.x;
     const int i = threadIdx.x;
+    const int lane = i & 31, warp = i >> 5;
     ImgState& s = st[b];
     h[i] = (long long)hist[(long long)b * kBins + i];
-    if (i == 0) n_cand = 0;
+    if (i == 0) { n_peaks = 0; n_cand = 0; }
     __syncthreads();
     // block max
     long long m = h[i];
@@ -211,53 +218,89 @@ __global__ void __launch_bounds__(kBins) decomp_modes_kernel(const unsigned long
         long long other = __shfl_xor_sync(0xffffffffu, m, o);
         m = other > m ? other : m;
     }
-    if ((i & 31) == 0) hmax_s[i >> 5] = m;
+    if (lane == 0) red[warp] = (unsigned long long)m;
     __syncthreads();
     long long hmax = 0;
-    for (int k = 0; k < kBins / 32; ++k) hmax = hmax_s[k] > hmax ? hmax_s[k] : hmax;
+    for (int k = 0; k < kBins / 32; ++k) hmax = (long long)red[k] > hmax ? (long long)red[k] : hmax;
     const double pmin = prom_thr * (double)hmax;
 
-    // every rising edge starts at most one plateau -> independent per thread
+    // (1) every rising edge starts at most one plateau -> independent per thread
     const int n = kBins, i_max = n - 1;
     if (i >= 1 && i < i_max && h[i - 1] < h[i]) {
         int ahead = i + 1;
         while (ahead < i_max && h[ahead] == h[i]) ++ahead;
-        if (h[ahead] < h[i]) {
-            int peak = (i + ahead - 1) / 2;
-            long long hp = h[peak];
-            int k = peak;
-            long long lmin = hp;
-            while (k >= 0 && h[k] <= hp) { if (h[k] < lmin) lmin = h[k]; --k; }
-            k = peak;
-            long long rmin = hp;
-            while (k <= i_max && h[k] <= hp) { if (h[k] < rmin) rmin = h[k]; ++k; }
-            long long prom = hp - (lmin > rmin ? lmin : rmin);
-            if (pmin <= (double)prom) {
-                int slot = atomicAdd(&n_cand, 1);
-                cand_h[slot] = hp;
-                cand_bin[slot] = peak;
-            }
-        }
+        if (h[ahead] < h[i]) peak_bin[atomicAdd(&n_peaks, 1)] = (i + ahead - 1) / 2;
     }
     __syncthreads();
+    // (2) prominence of peak p by warp (p mod 16)
+    const int np = n_peaks;
+    for (int pi = warp; pi < np; pi += kBins / 32) {
+        const int peak = peak_bin[pi];
+        const long long hp = h[peak];
+        long long lmin = hp, rmin = hp;
+        for (int base = peak; ; base -= 32) {            // bins peak, peak-1, ...: stop at the first bin higher than the peak
+            const int k = base - lane;
+            const long long v = k >= 0 ? h[k] : 0;
+            const bool stop = k < 0 || v > hp;
+            const unsigned sm = __ballot_sync(0xffffffffu, stop);
+            const int first = sm ? __ffs(sm) - 1 : 32;
+            long long mine = lane < first ? v : hp;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const long long other = __shfl_xor_sync(0xffffffffu, mine, o);
+                mine = other < mine ? other : mine;
+            }
+            lmin = mine < lmin ? mine : lmin;
+            if (sm) break;
+        }
+        for (int base = peak; ; base += 32) {
+            const int k = base + lane;
+            const long long v = k <= i_max ? h[k] : 0;
+            const bool stop = k > i_max || v > hp;
+            const unsigned sm = __ballot_sync(0xffffffffu, stop);
+            const int first = sm ? __ffs(sm) - 1 : 32;
+            long long mine = lane < first ? v : hp;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const long long other = __shfl_xor_sync(0xffffffffu, mine, o);
+                mine = other < mine ? other : mine;
+            }
+            rmin = mine < rmin ? mine : rmin;
+            if (sm) break;
+        }
+        const long long prom = hp - (lmin > rmin ? lmin : rmin);
+        if (lane == 0 && pmin <= (double)prom) cand[atomicAdd(&n_cand, 1)] = ((unsigned long long)hp << 16) | (unsigned)peak;
+    }
+    __syncthreads();
+    // (3) selection by (height desc, centre desc); centres are non-decreasing in the bin index, so (height, bin) descending
+    // gives the same centres in the same order.  Keys are unique (one per bin); 0 never is a key (peaks sit at bins >= 1).
+    const int nc = n_cand;
+    unsigned long long key = i < nc ? cand[i] : 0ull;
+    for (int pick = 0; pick < 3; ++pick) {
+        unsigned long long best = key;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (lane == 0) red[warp] = best;
+        __syncthreads();
+        if (i == 0) {
+            unsigned long long t = 0;
+            for (int k = 0; k < kBins / 32; ++k) t = red[k] > t ? red[k] : t;
+            picked[pick] = t;
+        }
+        __syncthreads();
+        if (key == picked[pick]) key = 0ull;
+    }
     if (i == 0) {
         ImgState loc = s;                 // one read of the per-image state; the serial part below works on registers
+        if (range_from_minmax) compute_range(loc);
         const float rt = ratio ? ratio[b] : 0.f;
-        const int nc = n_cand;
         int nm = 0;
         if (!(loc.status & RGBD_DECOMP_RANGE_NOT_FINITE)) {
-            // selection by (height desc, centre desc); centres are non-decreasing in the bin index,
-            // so (height, bin) descending gives the same centres in the same order
             for (int pick = 0; pick < num_modes && pick < nc; ++pick) {
-                int best = -1;
-                for (int c = 0; c < nc; ++c) {
-                    if (cand_bin[c] < 0) continue;
-                    if (best < 0 || cand_h[c] > cand_h[best] ||
-                        (cand_h[c] == cand_h[best] && cand_bin[c] > cand_bin[best]))
-                        best = c;
-                }
-                int pb = cand_bin[best];
-                cand_bin[best] = -1;
+                const int pb = (int)(picked[pick] & 0xffffu);
                 float e0, e1;
                 if (edges_in) {
                     e0 = edges_in[(long long)b * (kBins + 1) + pb];
@@ -280,6 +323,58 @@ __global__ void __launch_bounds__(kBins) decomp_modes_kernel(const unsigned long
         loc.n_modes = nm;
         for (int k = nm; k < 3; ++k) { loc.peak_bin[k] = -1; loc.centre[k] = 0.f; loc.lo[k] = 0.f; loc.hi[k] = 0.f; }
         s = loc;
+        if (ex.n_modes) ex.n_modes[b] = nm;
+        if (ex.status) ex.status[b] = loc.status;
+        // number of conv biases the reference adds: m+1 used regions, or all R+1 when no mode survives (CM:676-691)
+        if (ex.bias_variant) ex.bias_variant[b] = nm == 0 ? num_modes + 1 : nm + 1;
+        for (int k = 0; k < 3; ++k) {
+            if (ex.peak_bins) ex.peak_bins[b * 3 + k] = loc.peak_bin[k];
+            if (ex.centres) ex.centres[b * 3 + k] = loc.centre[k];
+            if (ex.windows) { ex.windows[(b * 3 + k) * 2] = loc.lo[k]; ex.windows[(b * 3 + k) * 2 + 1] = loc.hi[k]; }
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned region_code(const ImgState& s, float g) {
+    unsigned c = 0;
+    for (int t = 0; t < s.n_modes; ++t)
+        if (g >= s.lo[t] && g <= s.hi[t]) c |= 1u << t;
+    if (s.n_modes > 0 && c == 0) c = 1u << s.n_modes;
+    return c;
+}
+
+// Region codes AND their OR-pooled copies at the three pyramid levels in one pass, for the usual geometry where the levels are
+// exactly (H/4, W/4), (H/8, W/8), (H/16, W/16) (Swin strides 4/8/16; then adaptive_max_pool2d's windows are the aligned 4x4 /
+// 8x8 / 16x16 blocks).  A warp owns a 32x16-pixel block: lane (lx 0..7, ly 0..3) reads its 4x4 cell as four float4, ORs its
+// 16 codes (level 0), and the coarser levels are butterfly ORs over the lane bits (lx bit0, ly bit0 | lx bit1, ly bit1).
+__global__ void __launch_bounds__(256) decomp_codes_pool3_kernel(const float* __restrict__ gray, const ImgState* __restrict__ st,
+                                                                 uint8_t* __restrict__ codes, uint8_t* __restrict__ p0,
+                                                                 uint8_t* __restrict__ p1, uint8_t* __restrict__ p2, int H, int W) {
+    const int b = blockIdx.y;
+    const ImgState s = st[b];
+    const int lane = threadIdx.x & 31, lx = lane & 7, ly = lane >> 3;
+    const int bw = (W + 31) >> 5, bh = H >> 4;                     // warp blocks per image
+    const float* in = gray + (long long)b * H * W;
+    for (int wb = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wb < bw * bh; wb += gridDim.x * (blockDim.x >> 5)) {
+        const int x = (wb % bw) * 32 + lx * 4, y = (wb / bw) * 16 + ly * 4;
+        const bool on = x < W;                                      // W % 16 == 0: a lane's cell is entirely in or out
+        unsigned c0 = 0;
+        if (on) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float4 g = *reinterpret_cast<const float4*>(in + (long long)(y + r) * W + x);
+                const unsigned q0 = region_code(s, g.x), q1 = region_code(s, g.y), q2 = region_code(s, g.z), q3 = region_code(s, g.w);
+                if (codes) *reinterpret_cast<unsigned*>(codes + ((long long)b * H + y + r) * W + x) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+                c0 |= q0 | q1 | q2 | q3;
+            }
+            p0[((long long)b * (H >> 2) + (y >> 2)) * (W >> 2) + (x >> 2)] = (uint8_t)c0;
+        }
+        unsigned c1 = c0 | __shfl_xor_sync(0xffffffffu, c0, 1);
+        c1 |= __shfl_xor_sync(0xffffffffu, c1, 8);
+        if (on && !(lx & 1) && !(ly & 1)) p1[((long long)b * (H >> 3) + (y >> 3)) * (W >> 3) + (x >> 3)] = (uint8_t)c1;
+        unsigned c2 = c1 | __shfl_xor_sync(0xffffffffu, c1, 2);
+        c2 |= __shfl_xor_sync(0xffffffffu, c2, 16);
+        if (on && !(lx & 3) && !(ly & 3)) p2[((long long)b * (H >> 4) + (y >> 4)) * (W >> 4) + (x >> 4)] = (uint8_t)c2;
     }
 }
 
@@ -342,24 +437,6 @@ __global__ void __launch_bounds__(256) decomp_pool_levels_kernel(const uint8_t* 
     }
 }
 
-__global__ void decomp_export_kernel(const ImgState* __restrict__ st, int B, int num_modes, int* n_modes, int* peak_bins,
-                                     float* centres, float* windows, float* edges_first_last, int* status,
-                                     int* bias_variant) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const ImgState& s = st[b];
-    if (n_modes) n_modes[b] = s.n_modes;
-    if (status) status[b] = s.status;
-    // number of conv biases the reference adds: m+1 used regions, or all R+1 when no mode survives (CM:676-691)
-    if (bias_variant) bias_variant[b] = s.n_modes == 0 ? num_modes + 1 : s.n_modes + 1;
-    for (int k = 0; k < 3; ++k) {
-        if (peak_bins) peak_bins[b * 3 + k] = s.peak_bin[k];
-        if (centres) centres[b * 3 + k] = s.centre[k];
-        if (windows) { windows[(b * 3 + k) * 2] = s.lo[k]; windows[(b * 3 + k) * 2 + 1] = s.hi[k]; }
-    }
-    if (edges_first_last) { edges_first_last[b * 2] = s.first; edges_first_last[b * 2 + 1] = s.last; }
-}
-
 __global__ void decomp_edges_kernel(const ImgState* __restrict__ st, float* __restrict__ edges) {
     const int b = blockIdx.x;
     const ImgState s = st[b];
@@ -380,7 +457,7 @@ extern "C" int rgbd_depth_decompose(const float* depth3, long long depth_batch_s
                                     int* bias_variant_out, uint8_t* codes_out, int n_levels, const int* level_h, const int* level_w,
                                     uint8_t* const* pooled_out, void* workspace, rgbd_stream_t stream) {
     RGBD_CHECK_ARG((depth3 != nullptr) != (gray_in != nullptr), "depth_decompose: pass exactly one of depth3 / gray_in");
-    RGBD_CHECK_ARG(ratio && workspace && codes_out, "depth_decompose: null ratio / workspace / codes_out");
+    RGBD_CHECK_ARG(ratio && workspace, "depth_decompose: null ratio / workspace");
     RGBD_CHECK_ARG(depth3 == nullptr || gray_out != nullptr, "depth_decompose: gray_out is required with depth3");
     RGBD_CHECK_ARG(B >= 1 && H >= 1 && W >= 1, "depth_decompose: bad geometry");
     RGBD_CHECK_ARG(num_modes >= 1 && num_modes <= 3, "depth_decompose: num_modes must be in [1,3]");
@@ -390,9 +467,11 @@ extern "C" int rgbd_depth_decompose(const float* depth3, long long depth_batch_s
     uintptr_t wp = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
     unsigned long long* hist = (unsigned long long*)wp;
     ImgState* st = (ImgState*)(hist + (size_t)B * kBins);
-    decomp_init_kernel<<<ceil_div(B * kBins, 256), 256, 0, s>>>(st, hist, B);
-    RGBD_CHECK_LAUNCH();
-    dim3 grid(min(ceil_div(HW, 256 * 4), 296), B);
+    // hist + state are one block of the workspace: an all-zero state is the identity of the min/max reductions
+    RGBD_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)B * (sizeof(unsigned long long) * kBins + sizeof(ImgState)), s));
+    // streaming kernels: ~4 CTAs per SM in total, each CTA reduces to one set of atomics
+    const int per_img = max(1, min(ceil_div(HW, 256 * 4), ceil_div(4 * 148, B)));
+    dim3 grid(per_img, B);
     const float* gray = gray_in;
     if (depth3) {
         const bool vec = HW % 4 == 0 && depth_batch_stride % 4 == 0 && depth_channel_stride % 4 == 0 &&
@@ -404,29 +483,38 @@ extern "C" int rgbd_depth_decompose(const float* depth3, long long depth_batch_s
         decomp_minmax_kernel<<<grid, 256, 0, s>>>(gray_in, st, HW);
     }
     RGBD_CHECK_LAUNCH();
-    decomp_range_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B);
-    RGBD_CHECK_LAUNCH();
     decomp_hist_kernel<<<grid, 256, 0, s>>>(gray, st, hist, HW);
     RGBD_CHECK_LAUNCH();
-    decomp_modes_kernel<<<B, kBins, 0, s>>>(hist, st, ratio, num_modes, 0.01, nullptr);
+    ExportPtrs ex = {n_modes_out, peak_bins_out, centres_out, windows_out, status_out, bias_variant_out};
+    decomp_modes_kernel<<<B, kBins, 0, s>>>(hist, st, ratio, num_modes, 0.01, nullptr, 1, ex);
     RGBD_CHECK_LAUNCH();
-    decomp_codes_kernel<<<grid, 256, 0, s>>>(gray, st, codes_out, HW);
-    RGBD_CHECK_LAUNCH();
-    if (n_levels > 0) {
-        PoolLevels lv;
-        int max_px = 1;
-        for (int l = 0; l < n_levels; ++l) {
-            RGBD_CHECK_ARG(level_h[l] >= 1 && level_w[l] >= 1 && pooled_out[l], "depth_decompose: bad level %d", l);
-            lv.out[l] = pooled_out[l]; lv.h[l] = level_h[l]; lv.w[l] = level_w[l];
-            max_px = max(max_px, level_h[l] * level_w[l]);
-        }
-        dim3 g(min(ceil_div(max_px, 256), 296), B, n_levels);
-        decomp_pool_levels_kernel<<<g, 256, 0, s>>>(codes_out, lv, H, W);
+    for (int l = 0; l < n_levels; ++l)
+        RGBD_CHECK_ARG(level_h[l] >= 1 && level_w[l] >= 1 && pooled_out[l], "depth_decompose: bad level %d", l);
+    bool pyramid = n_levels == 3 && H % 16 == 0 && W % 16 == 0 && (reinterpret_cast<uintptr_t>(gray) & 15) == 0 &&
+                   (codes_out == nullptr || (reinterpret_cast<uintptr_t>(codes_out) & 3) == 0);
+    for (int l = 0; l < 3 && pyramid; ++l) pyramid = level_h[l] == (H >> (2 + l)) && level_w[l] == (W >> (2 + l));
+    if (pyramid) {
+        // codes + the three OR-pooled levels in one pass over the gray image
+        const int blocks = ceil_div(ceil_div(W, 32) * (H / 16), 8);
+        decomp_codes_pool3_kernel<<<dim3(min(blocks, ceil_div(8 * 148, B)), B), 256, 0, s>>>(gray, st, codes_out, pooled_out[0],
+                                                                                          pooled_out[1], pooled_out[2], H, W);
         RGBD_CHECK_LAUNCH();
+    } else {
+        RGBD_CHECK_ARG(codes_out, "depth_decompose: codes_out may only be omitted for a (H/4, H/8, H/16) pyramid");
+        decomp_codes_kernel<<<grid, 256, 0, s>>>(gray, st, codes_out, HW);
+        RGBD_CHECK_LAUNCH();
+        if (n_levels > 0) {
+            PoolLevels lv;
+            int max_px = 1;
+            for (int l = 0; l < n_levels; ++l) {
+                lv.out[l] = pooled_out[l]; lv.h[l] = level_h[l]; lv.w[l] = level_w[l];
+                max_px = max(max_px, level_h[l] * level_w[l]);
+            }
+            dim3 g(min(ceil_div(max_px, 256), 296), B, n_levels);
+            decomp_pool_levels_kernel<<<g, 256, 0, s>>>(codes_out, lv, H, W);
+            RGBD_CHECK_LAUNCH();
+        }
     }
-    decomp_export_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B, num_modes, n_modes_out, peak_bins_out, centres_out,
-                                                         windows_out, nullptr, status_out, bias_variant_out);
-    RGBD_CHECK_LAUNCH();
     if (hist_out)
         RGBD_CHECK_CUDA(cudaMemcpyAsync(hist_out, hist, sizeof(long long) * (size_t)B * kBins, cudaMemcpyDeviceToDevice, s));
     if (edges_out) {
@@ -470,11 +558,9 @@ extern "C" int rgbd_depth_select_modes(const long long* hist, const float* edges
     ImgState* st = (ImgState*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     helper_state_init_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B);
     RGBD_CHECK_LAUNCH();
+    ExportPtrs ex = {n_modes_out, peak_bins_out, centres_out, nullptr, nullptr, nullptr};
     decomp_modes_kernel<<<B, kBins, 0, s>>>(reinterpret_cast<const unsigned long long*>(hist), st, nullptr, num_modes,
-                                            prominence_threshold, edges);
-    RGBD_CHECK_LAUNCH();
-    decomp_export_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, B, num_modes, n_modes_out, peak_bins_out, centres_out, nullptr, nullptr,
-                                                         nullptr, nullptr);
+                                            prominence_threshold, edges, 0, ex);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }

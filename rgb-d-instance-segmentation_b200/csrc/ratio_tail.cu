@@ -95,6 +95,21 @@ __device__ __forceinline__ void fc_layer(const float* __restrict__ w, const floa
     __syncthreads();
 }
 
+// Tensor-core variant of the tail conv (rgbd_ratio_tail_prepare + rgbd_conv_gemm + rgbd_ratio_tail_mlp_fx): the pooled 4x4 map
+// as a bf16 channels-last operand, and the zeroed fixed-point GAP accumulator the GEMM's pooled epilogue adds into.
+__global__ void __launch_bounds__(256) ratio_tail_prepare_kernel(const long long* __restrict__ pool, int pool_stride, float inv_cell,
+                                                                 __nv_bfloat16* __restrict__ a, long long* __restrict__ gap_fx, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // (b, cell, c)
+    if (i < B * 16 * kCin) {
+        const int c = i % kCin, cell = (i / kCin) % 16, b = i / (kCin * 16);
+        const float v = (float)((double)pool[((size_t)b * 16 + cell) * pool_stride + c] * (1.0 / RGBD_POOL_FIXED_ONE)) * inv_cell;
+        a[i] = __float2bfloat16(v);
+    }
+    if (i < B * kCout) gap_fx[i] = 0ll;
+}
+
+// GAP_FX: `gap` holds the fixed-point sums over the 16 pixels (conv_gemm epilogue mode 2 with a 1x1 cell grid)
+template <bool GAP_FX>
 __global__ void __launch_bounds__(512) ratio_tail_mlp_kernel(const float* __restrict__ gap, const float* w0, const float* b0,
                                                              const float* w1, const float* b1, const float* w2,
                                                              const float* b2, const float* w3, const float* b3,
@@ -102,7 +117,12 @@ __global__ void __launch_bounds__(512) ratio_tail_mlp_kernel(const float* __rest
                                                              const float* __restrict__ drop0, const float* __restrict__ drop1) {
     __shared__ float a[kCout], h0[128], h1[64], h2[32], raw[1];
     const int b = blockIdx.x;
-    for (int i = threadIdx.x; i < kCout; i += blockDim.x) a[i] = gap[(size_t)b * kCout + i];
+    for (int i = threadIdx.x; i < kCout; i += blockDim.x) {
+        if (GAP_FX)
+            a[i] = (float)((double)reinterpret_cast<const long long*>(gap)[(size_t)b * kCout + i] * (1.0 / RGBD_POOL_FIXED_ONE)) * (1.0f / 16.0f);
+        else
+            a[i] = gap[(size_t)b * kCout + i];
+    }
     __syncthreads();
     fc_layer(w0, b0, a, h0, 512, 128, true);
     if (drop0) {        // nn.Dropout(0.3) in train mode (CM:1430): y = x * keep / (1 - p), the multiplier comes from the caller
@@ -179,7 +199,7 @@ extern "C" int rgbd_ratio_tail_train(const long long* pool_sums, int pool_stride
     ratio_tail_bn_train_kernel<<<kCout / 8, 256, 0, s>>>(raw_ws, conv_bias, bn_gamma, bn_beta, eps, momentum, running_mean,
                                                          running_var, gap_ws, B);
     RGBD_CHECK_LAUNCH();
-    ratio_tail_mlp_kernel<<<B, 512, 0, s>>>(gap_ws, fc_w[0], fc_b[0], fc_w[1], fc_b[1], fc_w[2], fc_b[2], fc_w[3], fc_b[3],
+    ratio_tail_mlp_kernel<false><<<B, 512, 0, s>>>(gap_ws, fc_w[0], fc_b[0], fc_w[1], fc_b[1], fc_w[2], fc_b[2], fc_w[3], fc_b[3],
                                             out_min, out_max - out_min, ratio_out, drop0, drop1);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
@@ -197,8 +217,29 @@ extern "C" int rgbd_ratio_tail(const long long* pool_sums, int pool_stride, int 
     ratio_tail_conv_kernel<false><<<dim3(kCout / kOcPerCta, ceil_div(B, kImgPerCta)), 256, 0, s>>>(
         pool_sums, pool_stride, 1.0f / (float)cell_pixels, conv_w, conv_scale, conv_shift, gap_ws, B);
     RGBD_CHECK_LAUNCH();
-    ratio_tail_mlp_kernel<<<B, 512, 0, s>>>(gap_ws, fc_w[0], fc_b[0], fc_w[1], fc_b[1], fc_w[2], fc_b[2], fc_w[3], fc_b[3],
+    ratio_tail_mlp_kernel<false><<<B, 512, 0, s>>>(gap_ws, fc_w[0], fc_b[0], fc_w[1], fc_b[1], fc_w[2], fc_b[2], fc_w[3], fc_b[3],
                                             out_min, out_max - out_min, ratio_out, nullptr, nullptr);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_ratio_tail_prepare(const long long* pool_sums, int pool_stride, int cell_pixels, void* a_bf16, long long* gap_fx,
+                                       int B, rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(pool_sums && a_bf16 && gap_fx, "ratio_tail_prepare: null pointer");
+    RGBD_CHECK_ARG(B >= 1 && cell_pixels >= 1 && pool_stride >= kCin, "ratio_tail_prepare: bad geometry");
+    ratio_tail_prepare_kernel<<<ceil_div(B * 16 * kCin, 256), 256, 0, (cudaStream_t)stream>>>(
+        pool_sums, pool_stride, 1.0f / (float)cell_pixels, reinterpret_cast<__nv_bfloat16*>(a_bf16), gap_fx, B);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_ratio_tail_mlp_fx(const long long* gap_fx, const float* const* fc_w, const float* const* fc_b, float out_min,
+                                      float out_max, float* ratio_out, int B, rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(gap_fx && fc_w && fc_b && ratio_out && B >= 1, "ratio_tail_mlp_fx: bad arguments");
+    for (int i = 0; i < 4; ++i) RGBD_CHECK_ARG(fc_w[i] && fc_b[i], "ratio_tail_mlp_fx: null fc layer %d", i);
+    ratio_tail_mlp_kernel<true><<<B, 512, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(gap_fx), fc_w[0], fc_b[0], fc_w[1],
+                                                                     fc_b[1], fc_w[2], fc_b[2], fc_w[3], fc_b[3], out_min,
+                                                                     out_max - out_min, ratio_out, nullptr, nullptr);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }

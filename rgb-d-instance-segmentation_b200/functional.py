@@ -305,7 +305,7 @@ def map_10channel(rgb_u8: torch.Tensor, depth_u8: torch.Tensor, size: Optional[T
 @dataclass
 class Decomposition:
     gray: torch.Tensor                 # (B,H,W) f32
-    codes: torch.Tensor                # (B,H,W) u8, bit t = region mask t
+    codes: Optional[torch.Tensor]      # (B,H,W) u8, bit t = region mask t (None when not requested)
     pooled: List[torch.Tensor]         # per level (B,h,w) u8
     n_modes: torch.Tensor              # (B) i32
     centres: torch.Tensor              # (B,3) f32
@@ -318,8 +318,11 @@ class Decomposition:
 
 
 def depth_decompose(ratio: torch.Tensor, levels: Sequence[Tuple[int, int]], depth3: Optional[torch.Tensor] = None,
-                    gray: Optional[torch.Tensor] = None, num_modes: int = 3, debug: bool = False) -> Decomposition:
-    """K2.  Exactly one of depth3 (B,3,H,W) / gray (B,H,W).  ratio (B) float32."""
+                    gray: Optional[torch.Tensor] = None, num_modes: int = 3, debug: bool = False,
+                    want_codes: bool = True) -> Decomposition:
+    """K2.  Exactly one of depth3 (B,3,H,W) / gray (B,H,W).  ratio (B) float32.  ``want_codes=False`` skips the
+    full-resolution code image when the levels are the aligned (H/4, H/8, H/16) pyramid (the DSAM stages only read the
+    pooled copies)."""
     lib = _lib.load()
     if (depth3 is None) == (gray is None):
         raise RgbdB200Error("pass exactly one of depth3 / gray")
@@ -343,7 +346,9 @@ def depth_decompose(ratio: torch.Tensor, levels: Sequence[Tuple[int, int]], dept
     if ratio.numel() != B:
         raise RgbdB200Error(f"ratio must have {B} elements")
     i32 = dict(device=dev, dtype=torch.int32)
-    codes = torch.empty(B, H, W, device=dev, dtype=torch.uint8)
+    pyramid = (len(levels) == 3 and H % 16 == 0 and W % 16 == 0
+               and all(tuple(lv) == (H >> (2 + k), W >> (2 + k)) for k, lv in enumerate(levels)))
+    codes = torch.empty(B, H, W, device=dev, dtype=torch.uint8) if (want_codes or not pyramid) else None
     pooled = [torch.empty(B, h, w, device=dev, dtype=torch.uint8) for h, w in levels]
     n_modes = torch.empty(B, **i32)
     peak_bins = torch.empty(B, 3, **i32)
@@ -359,10 +364,10 @@ def depth_decompose(ratio: torch.Tensor, levels: Sequence[Tuple[int, int]], dept
         gray_out.data_ptr() if depth3 is not None else None,
         hist.data_ptr() if debug else None, edges.data_ptr() if debug else None,
         n_modes.data_ptr(), peak_bins.data_ptr(), centres.data_ptr(), windows.data_ptr(), status.data_ptr(),
-        bias_variant.data_ptr(), codes.data_ptr(), len(levels), int_array([h for h, _ in levels]), int_array([w for _, w in levels]),
+        bias_variant.data_ptr(), codes.data_ptr() if codes is not None else None, len(levels), int_array([h for h, _ in levels]), int_array([w for _, w in levels]),
         ptr_array([p.data_ptr() for p in pooled]), ws.data_ptr(), _stream())
     check(rc, "rgbd_depth_decompose")
-    _count(7 + len(levels) + (1 if debug else 0))
+    _count((4 if pyramid else 5 if levels else 4) + (1 if debug else 0))
     return Decomposition(gray_out, codes, pooled, n_modes, centres, windows, peak_bins, status, bias_variant, hist, edges)
 
 
@@ -611,6 +616,34 @@ def ratio_tail(pool: torch.Tensor, cell_pixels: int, conv_w: torch.Tensor, conv_
                               ptr_array([t.data_ptr() for t in fc_b]), out_min, out_max, gap.data_ptr(),
                               ratio.data_ptr(), B, _stream()), "rgbd_ratio_tail")
     _count(2)
+    return ratio
+
+
+def ratio_tail_tc(pool: torch.Tensor, cell_pixels: int, a6: torch.Tensor, gap_fx: torch.Tensor, w6_bf16: torch.Tensor,
+                  slices: torch.Tensor, shift6: torch.Tensor, fc_w: Sequence[torch.Tensor], fc_b: Sequence[torch.Tensor],
+                  out_min: float, out_max: float) -> torch.Tensor:
+    """CM:1473-1485 with the 3x3 256->512 conv on the tensor cores: pooled sums -> bf16 4x4 map ``a6`` (B,4,4,256) ->
+    implicit GEMM (M = 16 pixels per image, N = 512, K = 2304; BatchNorm scale folded into ``w6_bf16`` (512, 9*256), ReLU and
+    the global average pool in the epilogue) -> MLP -> ratio (B,1).  ``gap_fx`` (B,1,512) int64 is scratch."""
+    lib = _lib.load()
+    _req(pool, "pool", torch.int64)
+    _req(a6, "a6", torch.bfloat16)
+    _req(gap_fx, "gap_fx", torch.int64)
+    B = pool.shape[0]
+    if a6.shape != (B, 4, 4, 256) or gap_fx.numel() != B * 512:
+        raise RgbdB200Error("ratio_tail_tc: a6 must be (B,4,4,256) and gap_fx (B,1,512)")
+    for t in (*fc_w, *fc_b):
+        _req(t, "ratio tail parameter", torch.float32)
+    check(lib.rgbd_ratio_tail_prepare(pool.data_ptr(), pool.shape[-1], cell_pixels, a6.data_ptr(), gap_fx.data_ptr(), B, _stream()),
+          "rgbd_ratio_tail_prepare")
+    _count(1)
+    conv_gemm(a6, (B, 4, 4, 256), 1, w6_bf16, slices, 64, B, (4, 4), (4, 32), 512, shift6, act=1, epi_mode=2, pool=gap_fx,
+              cells=(1, 1))
+    ratio = torch.empty(B, 1, device=pool.device, dtype=torch.float32)
+    check(lib.rgbd_ratio_tail_mlp_fx(gap_fx.data_ptr(), ptr_array([t.data_ptr() for t in fc_w]),
+                                     ptr_array([t.data_ptr() for t in fc_b]), out_min, out_max, ratio.data_ptr(), B, _stream()),
+          "rgbd_ratio_tail_mlp_fx")
+    _count(1)
     return ratio
 
 

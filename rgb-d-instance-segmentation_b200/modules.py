@@ -555,6 +555,7 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         self.use_compact_operand = True    # fused front end reads the depth image itself (sliding-window TMA) when it can
         self.use_fused_front = True        # stem GEMM + chain in one kernel; False: stem GEMM, then ...
         self.use_fused_chain = True        # ... the fused chain, or (False) three separate GEMM launches (cross-checks)
+        self.use_tensor_core_tail = True   # 3x3 256->512 conv of the tail as a tcgen05 GEMM; False: the fp32 CUDA-core kernel
         self._ver = _Versioned()
         self._packed: Dict[str, torch.Tensor] = {}
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
@@ -599,6 +600,8 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
             c6 = self.feature_extractor[4]
             pk["w6"] = c6.weight.detach().float().contiguous()
             pk["sc6"], pk["sh6"] = _fold_bn(c6.bias, self.feature_extractor[5])
+            # tensor-core tail: K = (tap, c), BatchNorm scale folded before the bf16 rounding
+            pk["w6_bf"] = (c6.weight.float().permute(0, 2, 3, 1).reshape(512, 9 * 256) * pk["sc6"][:, None]).to(bf).contiguous()
             for j, li in enumerate((0, 3, 6, 8)):
                 pk[f"fw{j}"] = self.fc_layers[li].weight.detach().float().contiguous()
                 pk[f"fb{j}"] = self.fc_layers[li].bias.detach().float().contiguous()
@@ -610,6 +613,7 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
             pk["sl3"] = sl([(64 * cb, 0, 0, 0) for cb in range(2)])
             pk["sl4"] = sl([(0, 0, 0, 0)])
             pk["sl5"] = sl([(64 * cb, dx - 1, dy - 1, 0) for dy in range(3) for dx in range(3) for cb in range(2)])
+            pk["sl6"] = sl([(64 * cb, dx - 1, dy - 1, 0) for dy in range(3) for dx in range(3) for cb in range(4)])
         self._packed = pk
         return pk
 
@@ -627,6 +631,7 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
                 "x3": torch.empty(B, H, W, 64, **bf) if not (self.use_fused_chain or self.use_fused_front) else None,
                 "x4": torch.empty(B, H, W, 128, **bf),
                 "pool": torch.empty(B, 16, 256, device=dev, dtype=torch.int64),     # fixed-point cell sums
+                "a6": torch.empty(B, 4, 4, 256, **bf), "gap_fx": torch.empty(B, 1, 512, device=dev, dtype=torch.int64),
             }
         return self._ws[key]
 
@@ -819,8 +824,11 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         Fn.conv_gemm(ws["x4"], (B, H, W, 128), 1, pk["w5"], pk["sl5"], 64, B, (H, W), box, 256, pk["sh5"],
                      act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), tile_order=1,
                      conv3x3_reuse=(box == (128, 1)))      # one 130-pixel smem tile serves the three dx taps
-        return Fn.ratio_tail(ws["pool"], (H // 4) * (W // 4), pk["w6"], pk["sc6"], pk["sh6"],
-                             [pk[f"fw{j}"] for j in range(4)], [pk[f"fb{j}"] for j in range(4)],
+        fcw, fcb = [pk[f"fw{j}"] for j in range(4)], [pk[f"fb{j}"] for j in range(4)]
+        if self.use_tensor_core_tail:
+            return Fn.ratio_tail_tc(ws["pool"], (H // 4) * (W // 4), ws["a6"], ws["gap_fx"], pk["w6_bf"], pk["sl6"], pk["sh6"],
+                                    fcw, fcb, self.output_min, self.output_max)
+        return Fn.ratio_tail(ws["pool"], (H // 4) * (W // 4), pk["w6"], pk["sc6"], pk["sh6"], fcw, fcb,
                              self.output_min, self.output_max)
 
 
@@ -895,7 +903,7 @@ def depth_guidance_forward(ratio_predictor: EnhancedDepthImageRatioPredictor, ds
         ratios = ratio_predictor(depth)                                     # CM:336
     ratios = ratios.detach()                                                # consumed through .item() in CM:339
     levels = [tuple(f.shape[2:]) for f in feats[:3]]
-    dec = Fn.depth_decompose(ratios.reshape(-1).contiguous(), levels, depth3=depth)
+    dec = Fn.depth_decompose(ratios.reshape(-1).contiguous(), levels, depth3=depth, want_codes=False)
     training = torch.is_grad_enabled() and any(p.requires_grad for m in (*dsams, dggm) for p in m.parameters())
     cp1 = [feats[0]]
     x = feats[0]

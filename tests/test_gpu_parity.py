@@ -1077,3 +1077,46 @@ def test_ratio_predictor_train_mode_against_oracle(mods, B, hw):
     # without injected masks the module draws its own: still a valid ratio, and it differs from the masked run
     r2 = m(x.cuda())
     assert bool(((r2 >= 0.01) & (r2 <= 0.5)).all())
+
+
+# ---------------------------------------------------------------------------------------------------
+# round-2 kernel variants: fused codes + pyramid pooling, tensor-core tail
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hw", [(64, 48), (96, 128), (480, 640), (16, 16)])
+def test_decompose_fused_pyramid_path_bit_exact(fn, hw):
+    """Levels (H/4, H/8, H/16): codes and the three OR-pooled copies come from ONE kernel (a warp per 32x16 block, W % 32 != 0
+    included); bit-exact against the oracle, and identical with and without the optional full-resolution code image."""
+    H, W = hw
+    kinds = ["nyu", "uniform", "two_valued", "constant", "all_invalid"]
+    grays = [_gray_for(j, kinds[j % 5], hw) for j in range(5)]
+    ratios = [0.5, 0.1, 0.3, 0.2, 0.4]
+    levels = [(H // 4, W // 4), (H // 8, W // 8), (H // 16, W // 16)]
+    _check_decomposition(fn, grays, ratios, levels)
+    g = torch.from_numpy(np.stack(grays)).cuda()
+    r = torch.tensor(ratios, dtype=torch.float32).cuda()
+    a = fn.depth_decompose(r, levels, gray=g)
+    b = fn.depth_decompose(r, levels, gray=g, want_codes=False)
+    assert b.codes is None and a.codes is not None
+    for x, y in zip(a.pooled, b.pooled):
+        assert torch.equal(x, y)
+    assert torch.equal(a.bias_variant, b.bias_variant) and torch.equal(a.windows, b.windows)
+
+
+def test_ratio_predictor_tensor_core_tail_matches_fp32_tail(mods):
+    w = OW.ratio_weights(seed=520)
+    frames = []
+    for j in range(5):
+        _, d = synthetic.synth_rgbd_u8(260 + j, 96, 160, ["nyu", "uniform", "nyu", "two_valued", "constant"][j])
+        frames.append(synthetic.normalise_u8(np.repeat(d[:, :, None], 3, axis=2)))
+    x = torch.from_numpy(np.stack(frames))
+    ref = O.ratio_predictor_forward(w, x)
+    outs = []
+    for tc_tail in (True, False):
+        m = mods.EnhancedDepthImageRatioPredictor(3)
+        m.load_state_dict(w)
+        m.cuda().eval()
+        m.use_tensor_core_tail = tc_tail
+        with torch.no_grad():
+            outs.append(m(x.cuda()).cpu())
+        assert float(((outs[-1] - ref).abs() / ref).max()) < BF16_TOL
+    assert float(((outs[0] - outs[1]).abs() / outs[1]).max()) < 2e-3
