@@ -1120,3 +1120,30 @@ def test_ratio_predictor_tensor_core_tail_matches_fp32_tail(mods):
             outs.append(m(x.cuda()).cpu())
         assert float(((outs[-1] - ref).abs() / ref).max()) < BF16_TOL
     assert float(((outs[0] - outs[1]).abs() / outs[1]).max()) < 2e-3
+
+
+def test_torch_ops_dggm_autograd_matches_module(mods):
+    """``torch.ops.rgbd_b200.dggm_forward`` (dispatcher op + registered autograd formula) == the nn.Module path."""
+    from rgbd_b200 import ops  # noqa: F401
+    chans, hw, sizes, B = [8, 16, 24, 40], (32, 48), [(8, 12), (4, 6), (2, 3), (1, 2)], 2
+    w = OW.dggm_weights(chans, 3, seed=77)
+    m = mods.DepthGradientInjectionResidual(chans, 3)
+    m.load_state_dict(w)
+    m.cuda()
+    rs = np.random.RandomState(3)
+    feats = [torch.from_numpy(rs.randn(B, c, h, ww).astype(np.float32)).cuda().requires_grad_() for c, (h, ww) in zip(chans, sizes)]
+    grad = torch.from_numpy(rs.rand(B, 3, *hw).astype(np.float32)).cuda()
+    mask = torch.from_numpy((rs.rand(B, 1, *hw) < 0.6).astype(np.float32)).cuda()
+    ws, bs = m._params()
+    outs = torch.ops.rgbd_b200.dggm_forward(feats, grad, mask, list(ws), list(bs))
+    ref = m(feats, grad, mask)
+    for a, b in zip(outs, ref):
+        assert torch.equal(a, b)
+    douts = [torch.randn_like(o) for o in outs]
+    g_op = torch.autograd.grad(outs, [*feats, *ws, *bs], douts)
+    g_ref = torch.autograd.grad(ref, [*feats, *ws, *bs], douts)
+    for a, b in zip(g_op, g_ref):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    dec = torch.ops.rgbd_b200.depth_decompose(torch.randn(2, 3, 32, 48, device="cuda"), torch.tensor([0.2, 0.3], device="cuda"),
+                                              [8, 4, 2], [12, 6, 3])
+    assert dec[0].shape == (2, 8, 12) and dec[0].dtype == torch.uint8

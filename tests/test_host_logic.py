@@ -266,3 +266,28 @@ def test_compact_stem_operand_equals_the_row_im2col_operand():
             s, p = x & 1, x >> 1                                                           # copy and pixel pair
             a_e = np.concatenate([flat[s, y + dy, p * 8:p * 8 + 32] for dy in range(7)])    # 64-byte windows, 16-byte stride
             assert np.allclose(w1 @ a_r, w1c @ a_e, rtol=0, atol=1e-12)
+
+
+def test_torch_ops_namespace_is_registered_with_schemas_and_fake_kernels():
+    """the C-ABI entry points exist as dispatcher ops ``torch.ops.rgbd_b200.*`` (schema + fake kernel, so tracing
+    works without a device); there is no CPU kernel behind them."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from rgbd_b200 import ops, _lib as L
+    for name in ops.REGISTERED:
+        assert hasattr(torch.ops.rgbd_b200, name), name
+    assert str(torch.ops.rgbd_b200.dggm_forward.default._schema) == \
+        "rgbd_b200::dggm_forward(Tensor[] feats, Tensor grad, Tensor mask, Tensor[] weights, Tensor[] biases) -> Tensor[]"
+    with FakeTensorMode():
+        feats = [torch.empty(2, 8, 4, 6, device="cuda"), torch.empty(2, 16, 2, 3, device="cuda")]
+        outs = torch.ops.rgbd_b200.dggm_forward(feats, torch.empty(2, 3, 16, 24, device="cuda"), torch.empty(2, 1, 16, 24, device="cuda"),
+                                                [torch.empty(8, 3, 1, 1, device="cuda"), torch.empty(16, 3, 1, 1, device="cuda")],
+                                                [torch.empty(8, device="cuda"), torch.empty(16, device="cuda")])
+        assert [tuple(o.shape) for o in outs] == [(2, 8, 4, 6), (2, 16, 2, 3)]
+        dec = torch.ops.rgbd_b200.depth_decompose(torch.empty(2, 3, 32, 48, device="cuda"), torch.empty(2, device="cuda"), [8, 4, 2], [12, 6, 3])
+        assert [tuple(t.shape) for t in dec] == [(2, 8, 12), (2, 4, 6), (2, 2, 3), (2,), (2,), (2, 3, 2), (2, 3)]
+        pv = torch.ops.rgbd_b200.pack_pixel_values(torch.empty(2, 32, 48, 3, dtype=torch.uint8, device="cuda"),
+                                                   torch.empty(2, 32, 48, dtype=torch.uint8, device="cuda"))
+        assert tuple(pv.shape) == (2, 10, 32, 48) and pv.dtype == torch.float32
+    with pytest.raises(L.RgbdB200Error):
+        torch.ops.rgbd_b200.to_grayscale(torch.zeros(1, 3, 4, 4))          # CPU tensors: no fallback
