@@ -103,6 +103,13 @@ int rgbd_depth_decompose(const float* depth3, long long depth_batch_stride, long
 int rgbd_dsam_pack(const float* feat, const uint8_t* codes, void* out_bf16, int B, int C, int C_pad, int H, int W, int n_seg,
                    int masked_segs, int parity_split, int hi_lo, rgbd_stream_t stream);
 
+/* GroupNorm(groups, C) of an fp32 NCHW tensor (B,C,HW), in place, affine gamma/beta (C) -- the normalisation half of the
+ * pixel decoder's input_projections = Conv2d(C_i,256,1) + GroupNorm(32,256) (HF Mask2FormerPixelDecoder, called at
+ * CM:383); the conv half is rgbd_conv_gemm over the bf16 channels-last copy rgbd_dsam_pack(n_seg=1,
+ * masked_segs=0, parity_split=0; codes may then be NULL) makes of the fused feature map. */
+int rgbd_group_norm_inplace(float* x, const float* gamma, const float* beta, int B, int C, int HW, int groups, float eps,
+                            rgbd_stream_t stream);
+
 /* Row-im2col of the 3-channel depth image for the predictor's multi-scale stem (CM:1458-1460):
  * out[img][H+6][W][64] bf16, channel (j*8+dx)*4+c = depth[img][c][r-3+j][x+dx-3]. */
 int rgbd_ratio_stem_pack(const float* depth3, long long batch_stride, long long channel_stride, void* out_bf16, int B,

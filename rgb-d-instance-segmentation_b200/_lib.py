@@ -60,6 +60,8 @@ SIGNATURES = {
                                        c_int_p, c_void_pp, C.c_void_p, C.c_void_p]),
     "rgbd_dsam_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "rgbd_group_norm_inplace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                          C.c_void_p]),
     "rgbd_ratio_stem_pack": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p]),
     "rgbd_conv_gemm": (C.c_int, [C.POINTER(ConvGemmDesc), C.c_void_p]),

@@ -214,7 +214,7 @@ extern "C" int rgbd_ratio_stem_pack_compact(const float* depth3, long long batch
 
 extern "C" int rgbd_dsam_pack(const float* feat, const uint8_t* codes, void* out_bf16, int B, int C, int C_pad, int H, int W,
                               int n_seg, int masked_segs, int parity_split, int hi_lo, rgbd_stream_t stream) {
-    RGBD_CHECK_ARG(feat && codes && out_bf16, "dsam_pack: null pointer");
+    RGBD_CHECK_ARG(feat && out_bf16 && (codes || masked_segs == 0), "dsam_pack: null pointer");
     RGBD_CHECK_ARG(B >= 1 && C >= 1 && H >= 1 && W >= 1, "dsam_pack: bad geometry");
     RGBD_CHECK_ARG(C_pad >= C && C_pad % 32 == 0, "dsam_pack: C_pad %d must be a multiple of 32 and >= C", C_pad);
     RGBD_CHECK_ARG(n_seg >= 1 && n_seg <= 8 && masked_segs >= 0 && masked_segs <= n_seg && masked_segs <= 4,
@@ -245,6 +245,59 @@ extern "C" int rgbd_ratio_stem_pack(const float* depth3, long long batch_stride,
     dim3 grid(ceil_div(W * 8, 256), H + 6, B);
     ratio_stem_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(depth3, batch_stride, channel_stride,
                                                                    (__nv_bfloat16*)out_bf16, H, W);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}
+
+// ---- GroupNorm over an NCHW fp32 tensor, in place (the pixel decoder's input_projections are
+// Conv2d(C_i, 256, 1) + GroupNorm(32, 256), transformers Mask2FormerPixelDecoder; the conv runs as rgbd_conv_gemm) ------------
+namespace {
+
+// one CTA per (image, group): the group's cpg x HW values (a few hundred KB at most) are read three times from L2 --
+// mean, centred variance (numerically what torch's rowwise moments give), normalise + affine
+__global__ void __launch_bounds__(256) group_norm_kernel(float* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int C, int HW, int groups, float eps) {
+    __shared__ double red[8];
+    __shared__ float s_mean, s_rstd;
+    const int g = blockIdx.x % groups, b = blockIdx.x / groups;
+    const int cpg = C / groups;
+    float* base = x + ((size_t)b * C + (size_t)g * cpg) * HW;
+    const int n = cpg * HW;
+    auto block_sum = [&](double v) -> double {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        double t = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+        return t;
+    };
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += base[i];
+    const double mean = block_sum(s) / n;
+    double q = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double d = (double)base[i] - mean;
+        q += d * d;
+    }
+    const double var = block_sum(q) / n;
+    if (threadIdx.x == 0) { s_mean = (float)mean; s_rstd = (float)(1.0 / sqrt(var + (double)eps)); }
+    __syncthreads();
+    const float m = s_mean, r = s_rstd;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = g * cpg + i / HW;
+        base[i] = (base[i] - m) * r * gamma[c] + beta[c];
+    }
+}
+
+}  // namespace
+
+extern "C" int rgbd_group_norm_inplace(float* x, const float* gamma, const float* beta, int B, int C, int HW, int groups, float eps,
+                                       rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(x && gamma && beta, "group_norm: null pointer");
+    RGBD_CHECK_ARG(B >= 1 && C >= 1 && HW >= 1 && groups >= 1 && C % groups == 0, "group_norm: C must be divisible by groups");
+    group_norm_kernel<<<B * groups, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, C, HW, groups, eps);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }

@@ -463,6 +463,47 @@ def dsam_pack(feat: torch.Tensor, codes: torch.Tensor, out: torch.Tensor, c_pad:
     _count(1)
 
 
+def project_group_norm(x: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.Tensor], gn_w: torch.Tensor,
+                       gn_b: torch.Tensor, groups: int, eps: float, w_cache: Optional[dict] = None) -> torch.Tensor:
+    """``Sequential(Conv2d(C, N, 1), GroupNorm(groups, N))`` -- an ``input_projections`` / lateral ``adapter`` entry of HF's
+    ``Mask2FormerPixelDecoder`` (called at CM:383) -- on this library's kernels: fp32 NCHW (B,C,h,w) -> bf16
+    channels-last copy -> tcgen05 1x1-conv GEMM (fp32 accumulate, fp32 NCHW out) -> in-place GroupNorm.  Inference only."""
+    lib = _lib.load()
+    _req(x, "features", torch.float32)
+    B, Cc, h, w = x.shape
+    N = conv_w.shape[0]
+    if conv_w.shape[1] != Cc or N % 32 or N > 256:
+        raise RgbdB200Error("project_group_norm: conv must be (N, C, 1, 1) with N a multiple of 32, at most 256")
+    c_pad = (Cc + 63) // 64 * 64
+    key = (conv_w.data_ptr(), conv_w._version, c_pad)
+    if w_cache is not None and w_cache.get("key") == key:
+        wk, sl, bias = w_cache["w"], w_cache["sl"], w_cache["b"]
+    else:
+        wk = torch.zeros(N, c_pad, device=x.device, dtype=torch.float32)
+        wk[:, :Cc] = conv_w.detach().reshape(N, Cc).float()
+        wk = wk.to(torch.bfloat16).contiguous()
+        sl = torch.tensor([(64 * cb, 0, 0, 0) for cb in range(c_pad // 64)], device=x.device, dtype=torch.int32)
+        bias = (conv_b.detach().float() if conv_b is not None else torch.zeros(N, device=x.device)).contiguous()
+        if w_cache is not None:
+            w_cache.update(key=key, w=wk, sl=sl, b=bias)
+    a = torch.empty(B, h, w, c_pad, device=x.device, dtype=torch.bfloat16)
+    check(lib.rgbd_dsam_pack(x.data_ptr(), None, a.data_ptr(), B, Cc, c_pad, h, w, 1, 0, 0, 0, _stream()), "rgbd_dsam_pack")
+    _count(1)
+    out = torch.empty(B, N, h, w, device=x.device, dtype=torch.float32)
+    best, best_eff = (128, 1), -1.0
+    for bx in (128, 64, 32, 16, 8, 4, 2, 1):
+        by = 128 // bx
+        eff = h * w / ((-(-w // bx) * bx) * (-(-h // by) * by))
+        if eff > best_eff + 1e-9:
+            best, best_eff = (bx, by), eff
+    conv_gemm(a, (B, h, w, c_pad), 1, wk, sl, 64, B, (h, w), best, N, bias, epi_mode=1, out=out)
+    check(lib.rgbd_group_norm_inplace(out.data_ptr(), _req(gn_w.detach().float().contiguous(), "gamma", torch.float32).data_ptr(),
+                                      _req(gn_b.detach().float().contiguous(), "beta", torch.float32).data_ptr(), B, N, h * w,
+                                      int(groups), float(eps), _stream()), "rgbd_group_norm_inplace")
+    _count(1)
+    return out
+
+
 def cast_bf16_pitched(src: torch.Tensor, w_pitch: int) -> torch.Tensor:
     """(..., W) fp32 -> (..., w_pitch) bf16, zero padded (TMA row strides must be multiples of 16 bytes)."""
     lib = _lib.load()

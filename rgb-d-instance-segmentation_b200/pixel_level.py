@@ -45,6 +45,40 @@ class CustomMask2FormerPixelLevelModule(Mask2FormerPixelLevelModule):
             self.dsam2 = DSAModule(in_channels=c[2], out_channels=c[3], num_depth_regions=3)
         if version in ("0.4.0", "0.3.0") or version in self.DGGM_ONLY:
             self.depth_gradient_injection = DepthGradientInjectionResidual(c, 3)
+        #: SURVEY 8f-2 (inference only, off by default): run the pixel decoder's ``input_projections`` (Conv2d(C_i,256,1) +
+        #: GroupNorm(32,256) of the three coarse levels) and its FPN lateral ``adapter_1`` on this library's kernels and hand
+        #: the stock decoder the projected maps; everything after the projections stays stock HF code.
+        self.fuse_input_projections = False
+        self._proj_cache = {}
+
+    def _decode(self, backbone_features, output_hidden_states):
+        """``self.decoder(backbone_features)`` (CM:383), optionally with the input projections computed here."""
+        dec = self.decoder
+        if not (self.fuse_input_projections and not torch.is_grad_enabled() and backbone_features[0].is_cuda):
+            return dec(backbone_features, output_hidden_states=output_hidden_states)
+        from . import functional as Fn
+        n_lv = dec.num_feature_levels
+        feats = list(backbone_features)
+        projected = {}
+        for level, idx in enumerate(range(len(feats) - 1, len(feats) - 1 - n_lv, -1)):       # coarsest first, like HF
+            conv, gn = dec.input_projections[level][0], dec.input_projections[level][1]
+            projected[idx] = Fn.project_group_norm(feats[idx].float().contiguous(), conv.weight, conv.bias, gn.weight, gn.bias,
+                                                   gn.num_groups, gn.eps, self._proj_cache.setdefault(("in", level), {}))
+        lateral = {}
+        for k, lat in enumerate(dec.lateral_convolutions):                                  # features[:num_fpn_levels][::-1]
+            idx = dec.num_fpn_levels - 1 - k
+            lateral[idx] = Fn.project_group_norm(feats[idx].float().contiguous(), lat[0].weight, lat[0].bias, lat[1].weight,
+                                                 lat[1].bias, lat[1].num_groups, lat[1].eps, self._proj_cache.setdefault(("lat", k), {}))
+        dt = backbone_features[0].dtype
+        handed = [(projected.get(i, lateral.get(i, f))).to(dt) for i, f in enumerate(feats)]
+        # the stock forward applies input_projections[level](x) / lateral_conv(x): make those the identity for this call
+        saved_in, saved_lat = dec.input_projections, dec.lateral_convolutions
+        try:
+            dec.input_projections = torch.nn.ModuleList([torch.nn.Identity() for _ in saved_in])
+            dec.lateral_convolutions = [torch.nn.Identity() for _ in saved_lat]
+            return dec(handed, output_hidden_states=output_hidden_states)
+        finally:
+            dec.input_projections, dec.lateral_convolutions = saved_in, saved_lat
 
     def _dsam_only(self, pixel_values: Tensor, feats, ratio=None):
         """CM:234-256 (ratio 0.1) / CM:258-290 (predicted ratios) batched: cp[k+1] += dsam_k(cp[k], gray(depth), ratio)
@@ -134,7 +168,7 @@ class CustomMask2FormerPixelLevelModule(Mask2FormerPixelLevelModule):
                 self.ratio_predictor, (self.dsam0, self.dsam1, self.dsam2), self.depth_gradient_injection,
                 pixel_values.float(), color_feature_map)                                    # CM:332-355
         backbone_features = [f.to(color_feature_map[0].dtype) for f in backbone_features]
-        decoder_output = self.decoder(backbone_features, output_hidden_states=output_hidden_states)   # CM:383
+        decoder_output = self._decode(backbone_features, output_hidden_states)                      # CM:383
         return Mask2FormerPixelLevelModuleOutput(
             encoder_last_hidden_state=backbone_features[-1],
             encoder_hidden_states=tuple(backbone_features) if output_hidden_states else None,

@@ -1147,3 +1147,46 @@ def test_torch_ops_dggm_autograd_matches_module(mods):
     dec = torch.ops.rgbd_b200.depth_decompose(torch.randn(2, 3, 32, 48, device="cuda"), torch.tensor([0.2, 0.3], device="cuda"),
                                               [8, 4, 2], [12, 6, 3])
     assert dec[0].shape == (2, 8, 12) and dec[0].dtype == torch.uint8
+
+
+# ---------------------------------------------------------------------------------------------------
+# the pixel decoder's input projections (Conv1x1 + GroupNorm) on this library's kernels
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c,hw,bias", [(192, (60, 80), True), (768, (15, 20), True), (96, (24, 36), False), (100, (7, 9), True)])
+def test_project_group_norm_matches_torch_modules(fn, c, hw, bias):
+    torch.manual_seed(c)
+    seq = torch.nn.Sequential(torch.nn.Conv2d(c, 256, 1, bias=bias), torch.nn.GroupNorm(32, 256)).cuda()
+    with torch.no_grad():
+        seq[1].weight.uniform_(0.5, 1.5)
+        seq[1].bias.normal_()
+    x = torch.randn(3, c, *hw, device="cuda") * 2 + 0.3
+    with torch.no_grad():
+        ref = seq(x)
+        got = fn.project_group_norm(x, seq[0].weight, seq[0].bias, seq[1].weight, seq[1].bias, 32, seq[1].eps)
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < 5e-3 and rel_err(got, ref) < BF16_TOL, (rel_l2(got, ref), rel_err(got, ref))
+
+
+def test_pixel_level_module_with_fused_input_projections(mods):
+    """The stock HF pixel decoder fed with projections computed by this library == the stock decoder doing them itself."""
+    from rgbd_b200 import synthetic_weights as SW
+    model, _ = SW.build_synthetic_rgbd_mask2former()
+    plm = model.model.pixel_level_module.cuda()
+    rgbs, ds = zip(*[synthetic.synth_rgbd_u8(400 + j, 128, 160, "nyu") for j in range(2)])
+    from rgbd_b200 import functional as Fn
+    pv = Fn.pack_pixel_values(torch.from_numpy(np.stack(rgbs)).cuda(), torch.from_numpy(np.stack(ds)).cuda())
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        ref = plm(pv)
+        plm.fuse_input_projections = True
+        n0 = Fn.LAUNCHES
+        got = plm(pv)
+        assert Fn.LAUNCHES - n0 >= 12 + 20                 # 4 projections x 3 kernels on top of the hot path's launches
+        plm.fuse_input_projections = False
+    assert torch.equal(got.encoder_last_hidden_state, ref.encoder_last_hidden_state)
+    assert rel_l2(got.decoder_last_hidden_state, ref.decoder_last_hidden_state) < BF16_TOL
+    for a, b in zip(got.decoder_hidden_states, ref.decoder_hidden_states):
+        assert a.shape == b.shape and rel_l2(a, b) < BF16_TOL, rel_l2(a, b)
+    # the decoder's own modules are back in place
+    assert isinstance(plm.decoder.input_projections[0], torch.nn.Sequential)
