@@ -161,16 +161,26 @@ __global__ void __launch_bounds__(256) decomp_hist_kernel(const float* __restric
     if (s.status & RGBD_DECOMP_RANGE_NOT_FINITE) return;
     const float* in = gray + (long long)b * HW;
     unsigned int* hw = h[threadIdx.x >> 5];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-        float x = in[i];
-        if (x >= s.first && x <= s.last) {          // drops NaN
-            float f = ((x - s.first) / s.denom) * (float)kBins;
-            int idx = (int)f;                        // astype(intp): truncation
-            if (idx == kBins) idx -= 1;
-            if (x < bin_edge(s, idx)) idx -= 1;
-            if (x >= bin_edge(s, idx + 1) && idx != kBins - 1) idx += 1;
-            atomicAdd(&hw[idx], 1u);
+    // neighbouring pixels of a depth image mostly share a bin (8-bit depth: 256 distinct values): the lanes of a warp that hit
+    // the same bin elect one leader that adds their count -- one shared-memory atomic per distinct bin instead of a
+    // serialised 32-way conflict
+    const int stride = gridDim.x * blockDim.x;
+    const int n_iter = (HW + stride - 1) / stride;
+    for (int it = 0; it < n_iter; ++it) {
+        const int i = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        int idx = -1;
+        if (i < HW) {
+            const float x = in[i];
+            if (x >= s.first && x <= s.last) {          // drops NaN
+                float f = ((x - s.first) / s.denom) * (float)kBins;
+                idx = (int)f;                            // astype(intp): truncation
+                if (idx == kBins) idx -= 1;
+                if (x < bin_edge(s, idx)) idx -= 1;
+                if (x >= bin_edge(s, idx + 1) && idx != kBins - 1) idx += 1;
+            }
         }
+        const unsigned peers = __match_any_sync(0xffffffffu, idx);
+        if (idx >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hw[idx], (unsigned)__popc(peers));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
@@ -335,11 +345,19 @@ __global__ void __launch_bounds__(kBins) decomp_modes_kernel(const unsigned long
     }
 }
 
-__device__ __forceinline__ unsigned region_code(const ImgState& s, float g) {
+// region code of one pixel; the windows are passed in registers (indexing ImgState's arrays with a run-time t would put the
+// struct in local memory)
+struct Windows { float lo0, hi0, lo1, hi1, lo2, hi2; int n; };
+__device__ __forceinline__ Windows load_windows(const ImgState& s) {
+    Windows w = {s.lo[0], s.hi[0], s.lo[1], s.hi[1], s.lo[2], s.hi[2], s.n_modes};
+    return w;
+}
+__device__ __forceinline__ unsigned region_code(const Windows& w, float g) {
     unsigned c = 0;
-    for (int t = 0; t < s.n_modes; ++t)
-        if (g >= s.lo[t] && g <= s.hi[t]) c |= 1u << t;
-    if (s.n_modes > 0 && c == 0) c = 1u << s.n_modes;
+    if (w.n > 0 && g >= w.lo0 && g <= w.hi0) c |= 1u;
+    if (w.n > 1 && g >= w.lo1 && g <= w.hi1) c |= 2u;
+    if (w.n > 2 && g >= w.lo2 && g <= w.hi2) c |= 4u;
+    if (w.n > 0 && c == 0) c = 1u << w.n;
     return c;
 }
 
@@ -351,7 +369,7 @@ __global__ void __launch_bounds__(256) decomp_codes_pool3_kernel(const float* __
                                                                  uint8_t* __restrict__ codes, uint8_t* __restrict__ p0,
                                                                  uint8_t* __restrict__ p1, uint8_t* __restrict__ p2, int H, int W) {
     const int b = blockIdx.y;
-    const ImgState s = st[b];
+    const Windows s = load_windows(st[b]);
     const int lane = threadIdx.x & 31, lx = lane & 7, ly = lane >> 3;
     const int bw = (W + 31) >> 5, bh = H >> 4;                     // warp blocks per image
     const float* in = gray + (long long)b * H * W;
@@ -382,7 +400,7 @@ __global__ void __launch_bounds__(256) decomp_codes_pool3_kernel(const float* __
 __global__ void __launch_bounds__(256) decomp_codes_kernel(const float* __restrict__ gray, const ImgState* __restrict__ st,
                                                            uint8_t* __restrict__ codes, int HW) {
     const int b = blockIdx.y;
-    const ImgState s = st[b];
+    const Windows wn = load_windows(st[b]);
     const float* in = gray + (long long)b * HW;
     uint8_t* out = codes + (long long)b * HW;
     const bool vec = (HW & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
@@ -397,13 +415,7 @@ __global__ void __launch_bounds__(256) decomp_codes_kernel(const float* __restri
         }
         unsigned packed = 0;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            unsigned c = 0;
-            for (int t = 0; t < s.n_modes; ++t)
-                if (g[e] >= s.lo[t] && g[e] <= s.hi[t]) c |= 1u << t;
-            if (s.n_modes > 0 && c == 0) c = 1u << s.n_modes;
-            packed |= c << (8 * e);
-        }
+        for (int e = 0; e < 4; ++e) packed |= region_code(wn, g[e]) << (8 * e);
         if (vec) {
             *reinterpret_cast<unsigned*>(out + i4) = packed;
         } else {
