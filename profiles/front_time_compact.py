@@ -13,16 +13,11 @@ r = torch.empty(B, 2, H + 6, Fn.ratio_stem_compact_width(W), 4, device="cuda", d
 out = torch.empty(B, H, W, 128, device="cuda", dtype=torch.bfloat16)
 Fn.ratio_stem_pack_compact(x, r)
 args = (r, pk["w1c"], pk["w2"], pk["w3"], pk["w4"], pk["sh1"], pk["sh2"], pk["sh3"], pk["sh4"], out, (128, 1))
-ref = None
-for variant in (os.environ.get("FRONT_VARIANTS", "0,1,0,1")).split(","):
-    os.environ["RGBD_FRONT_KSPLIT"] = variant          # read by the launcher at every call
-    for _ in range(3): Fn.ratio_front(*args)
-    ts = []
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); e0.record()
-        for _ in range(10): Fn.ratio_front(*args)
-        e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / 10)
-    same = "" if ref is None else f" identical to first variant: {torch.equal(out, ref)}"
-    if ref is None: ref = out.clone()
-    print(f"ratio_front compact ksplit={variant}: best {min(ts)*1e3:.1f} us median {sorted(ts)[2]*1e3:.1f} us{same}")
+for _ in range(3): Fn.ratio_front(*args)
+ts = []
+for _ in range(5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(10): Fn.ratio_front(*args)
+    e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / 10)
+print(f"ratio_front compact: best {min(ts)*1e3:.1f} us median {sorted(ts)[2]*1e3:.1f} us")

@@ -19,7 +19,6 @@
 #include "common.cuh"
 #include "rgbd_b200.h"
 #include "tc_ptx.cuh"
-#include <stdlib.h>
 
 namespace {
 
@@ -49,8 +48,6 @@ constexpr uint32_t kColQ = 384;
 
 struct FrontParams {
     int n_img, tiles_x, tiles_y, BX, BY, total_tiles;
-    int ksplit;               // 1: E1 -> GEMM 2 and E2 -> GEMM 3 hand-offs per 64-channel K slice (the GEMM starts on the first slice
-                              //    while the epilogue still converts the rest); 0: one hand-off per GEMM
     const float* sh1;
     const float* sh2;
     const float* sh3;
@@ -63,7 +60,6 @@ struct alignas(16) FrontCtl {
     uint64_t w_full;
     uint64_t acc_full[2][4];      // [chain][GEMM 1..4]   multicast commit -> both CTAs
     uint64_t x_ready[2][3];       // [chain][after E1..E3] epilogue threads of BOTH CTAs (counted in the leader)
-    uint64_t xs_ready[2][5];      // ksplit: [chain][K slice 0..2 of GEMM 2, K slice 0..1 of GEMM 3]
     uint64_t p_free[2];           // acc4 of the chain was read: its P columns may be overwritten by the next GEMM 1
     uint32_t tmem_base;
     uint32_t pad;
@@ -138,7 +134,6 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
         for (int c = 0; c < 2; ++c) {
             for (int g = 0; g < 4; ++g) tc::mbar_init(&ctl->acc_full[c][g], 1);
             for (int g = 0; g < 3; ++g) tc::mbar_init(&ctl->x_ready[c][g], 2 * (kChainThreads / 32));   // one arrive per warp
-            for (int g = 0; g < 5; ++g) tc::mbar_init(&ctl->xs_ready[c][g], 2 * (kChainThreads / 32));
             tc::mbar_init(&ctl->p_free[c], 2 * (kChainThreads / 32));
         }
         tc::fence_barrier_init();
@@ -232,63 +227,27 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
         for (int i = 0; i < n_c; ++i) {
             const uint32_t ph = (uint32_t)(i & 1);
             // GEMM 2: acc2 = ms(bf16, TMEM Q) . W2^T   (K = 192: 12 MMAs, A advances 8 columns, B 32 bytes / 8 KB per slice)
-            if (p.ksplit) {
-#pragma unroll 1
-                for (int sl = 0; sl < 3; ++sl) {
-                    tc::mbar_wait(&ctl->xs_ready[c][sl], ph);
-                    tc::tc_fence_after();
-                    if (tc::elect_one()) {
+            tc::mbar_wait(&ctl->x_ready[c][0], ph);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const int k = sl * 4 + kk;
-                            umma_bf16_ts_2cta(d, tmem + kColQ + (uint32_t)(k * 8), w2d + (uint64_t)(sl * ((64 * 128) >> 4) + kk * 2),
-                                              idesc128, k != 0);
-                        }
-                        if (sl == 2) tc::umma_commit_2cta(&ctl->acc_full[c][1]);
-                    }
-                    __syncwarp();
-                }
-            } else {
-                tc::mbar_wait(&ctl->x_ready[c][0], ph);
-                tc::tc_fence_after();
-                if (tc::elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < 12; ++k)
-                        umma_bf16_ts_2cta(d, tmem + kColQ + (uint32_t)(k * 8), w2d + (uint64_t)((k >> 2) * ((64 * 128) >> 4) + (k & 3) * 2),
-                                          idesc128, k != 0);
-                    tc::umma_commit_2cta(&ctl->acc_full[c][1]);
-                }
-                __syncwarp();
+                for (int k = 0; k < 12; ++k)
+                    umma_bf16_ts_2cta(d, tmem + kColQ + (uint32_t)(k * 8), w2d + (uint64_t)((k >> 2) * ((64 * 128) >> 4) + (k & 3) * 2),
+                                      idesc128, k != 0);
+                tc::umma_commit_2cta(&ctl->acc_full[c][1]);
             }
+            __syncwarp();
             // GEMM 3: acc3 = f(bf16, TMEM P+128) . W3^T   (K = 128: 8 MMAs)
-            if (p.ksplit) {
-#pragma unroll 1
-                for (int sl = 0; sl < 2; ++sl) {
-                    tc::mbar_wait(&ctl->xs_ready[c][3 + sl], ph);
-                    tc::tc_fence_after();
-                    if (tc::elect_one()) {
+            tc::mbar_wait(&ctl->x_ready[c][1], ph);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const int k = sl * 4 + kk;
-                            umma_bf16_ts_2cta(d, d + 128u + (uint32_t)(k * 8), w3d + (uint64_t)(sl * ((32 * 128) >> 4) + kk * 2), idesc64,
-                                              k != 0);
-                        }
-                        if (sl == 1) tc::umma_commit_2cta(&ctl->acc_full[c][2]);
-                    }
-                    __syncwarp();
-                }
-            } else {
-                tc::mbar_wait(&ctl->x_ready[c][1], ph);
-                tc::tc_fence_after();
-                if (tc::elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_bf16_ts_2cta(d, d + 128u + (uint32_t)(k * 8), w3d + (uint64_t)((k >> 2) * ((32 * 128) >> 4) + (k & 3) * 2), idesc64,
-                                          k != 0);
-                    tc::umma_commit_2cta(&ctl->acc_full[c][2]);
-                }
-                __syncwarp();
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16_ts_2cta(d, d + 128u + (uint32_t)(k * 8), w3d + (uint64_t)((k >> 2) * ((32 * 128) >> 4) + (k & 3) * 2), idesc64,
+                                      k != 0);
+                tc::umma_commit_2cta(&ctl->acc_full[c][2]);
             }
+            __syncwarp();
             // GEMM 4: acc4 = relu(.)(bf16, TMEM P+160) . W4^T   (K = 64: 4 MMAs)
             tc::mbar_wait(&ctl->x_ready[c][2], ph);
             tc::tc_fence_after();
@@ -313,7 +272,6 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
         const int bar_id = 1 + c;
         uint32_t x_remote[3], p_free_remote;
         for (int g = 0; g < 3; ++g) x_remote[g] = tc::mapa(tc::smem_u32(&ctl->x_ready[c][g]), 0);
-        const uint32_t xs_remote0 = tc::mapa(tc::smem_u32(&ctl->xs_ready[c][0]), 0);       // + 8 * slice
         p_free_remote = tc::mapa(tc::smem_u32(&ctl->p_free[c]), 0);
         const int n_c = c == 0 ? n_a : n_b;
         for (int i = 0; i < n_c; ++i) {
@@ -339,19 +297,11 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
                     o[j4 * 2 + 1] = tc::pack_bf16x2_relu(__uint_as_float(v[j4 * 4 + 2]) + b.z, __uint_as_float(v[j4 * 4 + 3]) + b.w);
                 }
                 tc::tmem_st_32x16(Q + k * 16, o);
-                if (p.ksplit) {         // chunk k completes this warp's share of K slice k / 2 of GEMM 2
-                    tc::tmem_st_wait();
-                    tc::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive_cluster_tmem(xs_remote0 + 8u * (uint32_t)(k >> 1));
-                }
             }
-            if (!p.ksplit) {
-                tc::tmem_st_wait();
-                tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive_cluster_tmem(x_remote[0]);
-            }
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster_tmem(x_remote[0]);
             // the stash must be free before E2 overwrites it: checked HERE, inside the wait for GEMM 2, not after it
             if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous TMA store has read the stash
             asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
@@ -378,19 +328,11 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
                     const int piece = ((k & 1) * 4 + g4) ^ (row & 7);
                     *reinterpret_cast<uint4*>(rowp + piece * 16) = make_uint4(o[g4 * 4], o[g4 * 4 + 1], o[g4 * 4 + 2], o[g4 * 4 + 3]);
                 }
-                if (p.ksplit) {         // K slice k / 2 of GEMM 3
-                    tc::tmem_st_wait();
-                    tc::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive_cluster_tmem(xs_remote0 + 8u * (uint32_t)(3 + (k >> 1)));
-                }
             }
-            if (!p.ksplit) {
-                tc::tmem_st_wait();
-                tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive_cluster_tmem(x_remote[1]);
-            }
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster_tmem(x_remote[1]);
 
             // ---- E3: relu(acc3 + b3) -> bf16 -> TMEM P+160 (A of GEMM 4)
             tc::mbar_wait_sleep(&ctl->acc_full[c][2], ph);
@@ -614,10 +556,6 @@ extern "C" int rgbd_ratio_front(const void* r_bf16, const void* w1_bf16, const v
     RGBD_CHECK_ARG(total < (1ll << 30), "ratio_front: too many tiles");
     p.total_tiles = (int)total;
     p.sh1 = sh1; p.sh2 = sh2; p.sh3 = sh3; p.sh4 = sh4;
-    {
-        const char* e = getenv("RGBD_FRONT_KSPLIT");        // A/B switch for profiles/front_time_compact.py
-        p.ksplit = e ? (e[0] != '0') : 1;
-    }
     return compact_operand ? launch_front<true>(m_r, m_r1, m_w1, m_w2, m_w3, m_w4, m_out, m_out1, p, (cudaStream_t)stream)
                            : launch_front<false>(m_r, m_r1, m_w1, m_w2, m_w3, m_w4, m_out, m_out1, p, (cudaStream_t)stream);
 }
