@@ -49,6 +49,27 @@ BYTES_DGGM = 3 * 4 * FEAT_ELEMS + 4 * 4 * H * W               # read colour + br
 POST_THRESHOLD = 0.0     # the reference's Evaluator(threshold=0.0) (finetuning.py:95): every candidate segment is painted
 
 
+WORKLOAD = "configs[1]: batch-32/GPU inference, 480x640 RGB-D, Swin-T pyramid, depth-guidance hot path"
+FORCED_RATIO = None
+SWIN = "tiny"
+
+
+def set_workload(name: str) -> None:
+    """`configs1` (default, the metric's configuration) or `configs4` = BASELINE.json configs[4]: 960x1280 frames, Swin-B
+    channels, window ratio forced to output_max (a builder-run record; the driver always runs the default)."""
+    global H, W, CHANS, BATCH, FLOP_CONV5, FLOP_DSAM, FEAT_ELEMS, BYTES_DGGM, WORKLOAD, FORCED_RATIO, SWIN
+    if name == "configs1":
+        return
+    assert name == "configs4", name
+    H, W, CHANS, BATCH, SWIN = 960, 1280, (128, 256, 512, 1024), 8, "base"
+    FORCED_RATIO = 0.5
+    WORKLOAD = "configs[4]: 960x1280 RGB-D, Swin-B pyramid, E-DSAM window ratio forced to output_max (0.5), batch 8/GPU"
+    FLOP_CONV5 = 2.0 * H * W * 256 * 9 * 128
+    FLOP_DSAM = sum(5 * 2.0 * (H // (2 * s)) * (W // (2 * s)) * co * 9 * ci for s, ci, co in zip(STRIDES[:3], CHANS[:3], CHANS[1:]))
+    FEAT_ELEMS = sum(c * (H // s) * (W // s) for c, s in zip(CHANS, STRIDES))
+    BYTES_DGGM = 3 * 4 * FEAT_ELEMS + 4 * 4 * H * W
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -76,16 +97,16 @@ def make_features(n: int, seed: int, device) -> list:
 
 def workload_config(batch: int) -> dict:
     """The ONE config both arms print (the reference arm runs bounded 1-frame samples of it; see cpu_baseline.sample)."""
-    return {"workload": "configs[1]: batch-32/GPU inference, 480x640 RGB-D, Swin-T pyramid, depth-guidance hot path",
-            "batch_per_gpu": batch, "frame": [H, W], "channels": list(CHANS),
-            "l2": "per-step inputs (835 MB) exceed the 126 MB L2; no flush needed"}
+    step_mb = batch * (10 * H * W + FEAT_ELEMS) * 4 / 1e6
+    return {"workload": WORKLOAD, "batch_per_gpu": batch, "frame": [H, W], "channels": list(CHANS),
+            "l2": f"per-step inputs ({step_mb:.0f} MB) exceed the 126 MB L2; no flush needed"}
 
 
 def build_whole_model():
     """RGB-D Mask2Former (Swin-T, 100 queries, 80 labels) with random-init stock weights and the deterministic
     depth-guidance weights (rgbd_b200.synthetic_weights)."""
     from rgbd_b200 import synthetic_weights as SW
-    return SW.build_synthetic_rgbd_mask2former(CHANS, guidance_seed=42, torch_seed=0)
+    return SW.build_synthetic_rgbd_mask2former(CHANS, guidance_seed=42, torch_seed=0, swin=SWIN)
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -295,6 +316,11 @@ def run_own(args):
     feats = make_features(B, 7 + rank, dev)
 
     use_graph = args.graph        # measured: 6.89 vs 7.02 ms/step -- launch gaps are ~2 % of the step now
+    if FORCED_RATIO is not None:
+        # configs[4] "max window": the predictor still runs (its cost is part of the step), its output is replaced
+        forced = torch.full((B, 1), FORCED_RATIO, device=dev)
+        rp_forward = model.ratio_predictor.forward
+        model.ratio_predictor.forward = lambda d, *a, **k: rp_forward(d, *a, **k) * 0 + forced
     if use_graph:
         try:
             graphed = modules.GraphedDepthGuidance(model, pv, feats)     # CUDA graph of the whole step (static shapes)
@@ -335,6 +361,10 @@ def run_own(args):
     if not args.no_whole_model:
         whole, _ = build_whole_model()
         whole.to(dev)
+        if FORCED_RATIO is not None:
+            wrp = whole.model.pixel_level_module.ratio_predictor
+            wrp_forward = wrp.forward
+            wrp.forward = lambda d, *a, **k: wrp_forward(d, *a, **k) * 0 + forced
         seg = serving.RgbdInstanceSegmenter(whole, B, (H, W), threshold=POST_THRESHOLD)
         for b in range(2):
             seg.in_host[b][0].copy_(rgb_host)
@@ -710,8 +740,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU and step (default: 32, or 8 for --workload configs4)")
     ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--workload", default="configs1", choices=["configs1", "configs4"],
+                    help="configs4 = BASELINE.json configs[4] (960x1280, Swin-B, ratio forced to 0.5, batch 8/GPU): builder-run record")
     ap.add_argument("--frames-total", type=int, default=0,
                     help="BASELINE configs[2]: split this many frames over the ranks (strong scaling) instead of --batch per GPU")
     ap.add_argument("--no-whole-model", action="store_true", help="skip the whole-model e2e leg (e2e falls back to the hot-path loop)")
@@ -721,6 +753,8 @@ def main():
                     help="launch the ~22 kernels of a step one by one instead of replaying the step as one CUDA graph")
     ap.set_defaults(graph=True)
     args = ap.parse_args()
+    set_workload(args.workload)
+    args.batch = args.batch or BATCH
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -221,6 +221,11 @@ int rgbd_ratio_tail(const long long* pool_sums, int pool_stride, int cell_pixels
                     const float* conv_shift, const float* const* fc_w_host, const float* const* fc_b_host, float out_min,
                     float out_max, float* gap_ws, float* ratio_out, int B, rgbd_stream_t stream);
 
+/* AdaptiveAvgPool2d(4) (CM:1417) of a bf16 channels-last (B,H,W,256) map for H or W not divisible by 4 (torch's overlapping
+ * windows); pool_means (B,16,256) receives the window MEANS in RGBD_POOL_FIXED_ONE fixed point: pass cell_pixels = 1 to the
+ * tail.  (Divisible sizes pool inside rgbd_conv_gemm's epilogue and never write the map.) */
+int rgbd_adaptive_avg_pool4(const void* x_bf16, long long* pool_means, int B, int H, int W, rgbd_stream_t stream);
+
 /* Tensor-core variant of the tail: rgbd_ratio_tail_prepare turns the pooled sums into the bf16 channels-last 4x4 map
  * a (B,4,4,256) and zeroes gap_fx (B,512); rgbd_conv_gemm (3x3 taps as slices, epi_mode 2 with a 1x1 cell grid, act 1) adds
  * ReLU(BN(conv)) summed over the 16 pixels into gap_fx as fixed point; rgbd_ratio_tail_mlp_fx = GAP/16 -> MLP -> ratio. */

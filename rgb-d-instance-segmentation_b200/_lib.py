@@ -94,6 +94,7 @@ SIGNATURES = {
     "rgbd_mask_iou": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "rgbd_ratio_tail": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_void_pp, c_void_pp,
                                   C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "rgbd_adaptive_avg_pool4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "rgbd_ratio_tail_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "rgbd_ratio_tail_mlp_fx": (C.c_int, [C.c_void_p, c_void_pp, c_void_pp, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "rgbd_ratio_tail_train": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

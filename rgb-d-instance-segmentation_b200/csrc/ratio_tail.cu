@@ -179,7 +179,38 @@ __global__ void __launch_bounds__(256) ratio_tail_bn_train_kernel(const float* _
     }
 }
 
+// AdaptiveAvgPool2d(4) of a bf16 channels-last map (B,H,W,256) for sizes the fused pooled epilogue cannot take (H or W not
+// divisible by 4: torch's windows [floor(i*H/4), ceil((i+1)*H/4)) then overlap and differ in size).  CTA = (cell, image,
+// row chunk), thread = channel; every contribution is scaled by 1/window size so the result, read with cell_pixels = 1, is
+// the window MEAN in the same 64-bit fixed point as the fused epilogue (order-independent integer atomics).
+__global__ void __launch_bounds__(256) adaptive_pool4_kernel(const __nv_bfloat16* __restrict__ x, long long* __restrict__ pool,
+                                                             int H, int W) {
+    const int cell = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
+    const int i = cell >> 2, j = cell & 3;
+    const int y0 = (i * H) / 4, y1 = ((i + 1) * H + 3) / 4, x0 = (j * W) / 4, x1 = ((j + 1) * W + 3) / 4;
+    const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+    float s = 0.f;
+    for (int y = y0 + blockIdx.z; y < y1; y += gridDim.z) {
+        const __nv_bfloat16* row = x + (((size_t)b * H + y) * W) * kCin + c;
+        float r = 0.f;
+        for (int xx = x0; xx < x1; ++xx) r += __bfloat162float(row[(size_t)xx * kCin]);
+        s += r;
+    }
+    atomicAdd(reinterpret_cast<unsigned long long*>(pool + ((size_t)b * 16 + cell) * kCin + c),
+              (unsigned long long)__double2ll_rn((double)(s * inv) * RGBD_POOL_FIXED_ONE));
+}
+
 }  // namespace
+
+extern "C" int rgbd_adaptive_avg_pool4(const void* x_bf16, long long* pool_means, int B, int H, int W, rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(x_bf16 && pool_means && B >= 1 && H >= 1 && W >= 1, "adaptive_avg_pool4: bad arguments");
+    RGBD_CHECK_CUDA(cudaMemsetAsync(pool_means, 0, (size_t)B * 16 * kCin * sizeof(long long), (cudaStream_t)stream));
+    const int chunks = H >= 64 ? 8 : 1;
+    adaptive_pool4_kernel<<<dim3(16, B, chunks), kCin, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16),
+                                                                                pool_means, H, W);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}
 
 extern "C" int rgbd_ratio_tail_train(const long long* pool_sums, int pool_stride, int cell_pixels, const float* conv_w,
                                      const float* conv_bias, const float* bn_gamma, const float* bn_beta, float eps,

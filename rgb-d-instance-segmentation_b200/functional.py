@@ -345,17 +345,16 @@ def depth_decompose(ratio: torch.Tensor, levels: Sequence[Tuple[int, int]], dept
         d3p, gip = None, gray.data_ptr()
     if ratio.numel() != B:
         raise RgbdB200Error(f"ratio must have {B} elements")
-    i32 = dict(device=dev, dtype=torch.int32)
     pyramid = (len(levels) == 3 and H % 16 == 0 and W % 16 == 0
                and all(tuple(lv) == (H >> (2 + k), W >> (2 + k)) for k, lv in enumerate(levels)))
     codes = torch.empty(B, H, W, device=dev, dtype=torch.uint8) if (want_codes or not pyramid) else None
     pooled = [torch.empty(B, h, w, device=dev, dtype=torch.uint8) for h, w in levels]
-    n_modes = torch.empty(B, **i32)
-    peak_bins = torch.empty(B, 3, **i32)
-    status = torch.empty(B, **i32)
-    bias_variant = torch.empty(B, **i32)
-    centres = torch.empty(B, 3, device=dev, dtype=torch.float32)
-    windows = torch.empty(B, 3, 2, device=dev, dtype=torch.float32)
+    # the per-image tables share one allocation (six tiny tensors cost more host time than the kernels they feed)
+    small = torch.empty(15 * B, device=dev, dtype=torch.int32)
+    n_modes, status, bias_variant = small[0:B], small[B:2 * B], small[2 * B:3 * B]
+    peak_bins = small[3 * B:6 * B].view(B, 3)
+    centres = small[6 * B:9 * B].view(torch.float32).view(B, 3)
+    windows = small[9 * B:15 * B].view(torch.float32).view(B, 3, 2)
     hist = torch.empty(B, HIST_BINS, device=dev, dtype=torch.int64) if debug else None
     edges = torch.empty(B, HIST_BINS + 1, device=dev, dtype=torch.float32) if debug else None
     ws = torch.empty(int(lib.rgbd_depth_decompose_workspace_bytes(B)), device=dev, dtype=torch.uint8)
@@ -658,6 +657,19 @@ def ratio_tail(pool: torch.Tensor, cell_pixels: int, conv_w: torch.Tensor, conv_
                               ratio.data_ptr(), B, _stream()), "rgbd_ratio_tail")
     _count(2)
     return ratio
+
+
+def adaptive_avg_pool4(x5: torch.Tensor, pool: torch.Tensor) -> None:
+    """``AdaptiveAvgPool2d(4)`` (CM:1417) of the bf16 channels-last (B,H,W,256) map into ``pool`` (B,16,256) int64 as fixed-
+    point window means (read them with ``cell_pixels = 1``); the path for H or W not divisible by 4."""
+    lib = _lib.load()
+    _req(x5, "x5", torch.bfloat16)
+    _req(pool, "pool", torch.int64)
+    B, H, W, c = x5.shape
+    if c != 256 or pool.shape != (B, 16, 256):
+        raise RgbdB200Error("adaptive_avg_pool4: x5 must be (B,H,W,256) and pool (B,16,256)")
+    check(lib.rgbd_adaptive_avg_pool4(x5.data_ptr(), pool.data_ptr(), B, H, W, _stream()), "rgbd_adaptive_avg_pool4")
+    _count(1)
 
 
 def ratio_tail_tc(pool: torch.Tensor, cell_pixels: int, a6: torch.Tensor, gap_fx: torch.Tensor, w6_bf16: torch.Tensor,

@@ -635,6 +635,21 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
             }
         return self._ws[key]
 
+    def _conv5_pool(self, ws, w5, sl5, sh5, B, H, W, box) -> int:
+        """Conv3x3 128->256 + (folded) BN + ReLU + AdaptiveAvgPool2d(4) (CM:1412-1417) into ``ws["pool"]``; returns the divisor
+        the tail applies to the pooled sums.  H, W divisible by 4: pooled inside the GEMM epilogue, the 256-channel map is
+        never written.  Otherwise torch's windows overlap: the map goes to HBM as bf16 and a pooling kernel takes the means."""
+        reuse = dict(tile_order=1, conv3x3_reuse=(box == (128, 1)))     # one 130-pixel smem tile serves the three dx taps
+        if H % 4 == 0 and W % 4 == 0:
+            ws["pool"].zero_()
+            Fn.conv_gemm(ws["x4"], (B, H, W, 128), 1, w5, sl5, 64, B, (H, W), box, 256, sh5, act=1, epi_mode=2,
+                         pool=ws["pool"], cells=(4, 4), **reuse)
+            return (H // 4) * (W // 4)
+        x5 = torch.empty(B, H, W, 256, device=ws["x4"].device, dtype=torch.bfloat16)
+        Fn.conv_gemm(ws["x4"], (B, H, W, 128), 1, w5, sl5, 64, B, (H, W), box, 256, sh5, act=1, out=x5, **reuse)
+        Fn.adaptive_avg_pool4(x5, ws["pool"])
+        return 1
+
     def _compact(self, H: int, W: int) -> bool:
         """The fused front end can read the depth image through sliding-window tensor maps (no row-im2col tensor in HBM)
         when its tile is 128 consecutive pixels of a row and the width is even."""
@@ -753,9 +768,7 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
             reuse = dict(tile_order=1, conv3x3_reuse=(box == (128, 1)))
             s5, q5 = stats(ws["x4"], (B, H, W, 128), pt["w5_bf"], pk["sl5"], 256, **reuse)
             sc5, sh5 = self._batch_norm_train(s5, q5, n, self.feature_extractor[1], self.feature_extractor[0].bias)
-            ws["pool"].zero_()
-            Fn.conv_gemm(ws["x4"], (B, H, W, 128), 1, (pt["w5"] * sc5[:, None]).to(bf).contiguous(), pk["sl5"], 64, B, (H, W), box,
-                         256, sh5.contiguous(), act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), **reuse)
+            cell_pixels = self._conv5_pool(ws, (pt["w5"] * sc5[:, None]).to(bf).contiguous(), pk["sl5"], sh5.contiguous(), B, H, W, box)
             # feature_extractor[4:7] + GAP + fc_layers with Dropout (CM:1418-1437)
             mult = []
             for j, (p_drop, width) in enumerate(((self.fc_layers[2].p, 128), (self.fc_layers[5].p, 64))):
@@ -769,7 +782,7 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
             if track:
                 bn6.num_batches_tracked += 1
             m6 = bn6.momentum if bn6.momentum is not None else 1.0 / float(bn6.num_batches_tracked)
-            return Fn.ratio_tail_train(ws["pool"], (H // 4) * (W // 4), pk["w6"], c6.bias.detach().float().contiguous(),
+            return Fn.ratio_tail_train(ws["pool"], cell_pixels, pk["w6"], c6.bias.detach().float().contiguous(),
                                        bn6.weight.detach().float().contiguous(), bn6.bias.detach().float().contiguous(), bn6.eps,
                                        m6, bn6.running_mean if track else None, bn6.running_var if track else None,
                                        [pk[f"fw{j}"] for j in range(4)], [pk[f"fb{j}"] for j in range(4)], mult[0], mult[1],
@@ -782,8 +795,6 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
         assert depth_image.shape[1] == self.input_channels, \
             f"Expected {self.input_channels} channels, got {depth_image.shape[1]}"
         B, _, H, W = depth_image.shape
-        if H % 4 or W % 4:
-            raise RgbdB200Error("the fused AdaptiveAvgPool2d(4) epilogue needs H and W divisible by 4")
         if self.training:
             return self._forward_train(depth_image, dropout_masks)
         pk = self._refresh()
@@ -820,15 +831,12 @@ class EnhancedDepthImageRatioPredictor(nn.Module):
             Fn.conv_gemm(ws["x3"], (B, H, W, 64), 1, pk["w4"], pk["sl4"], 64, B, (H, W), box, 128, pk["sh4"], act=2,
                          gate=ws["x2"], out=ws["x4"])
         # feature_extractor[0:4] (CM:1412-1416): conv3x3 + BN + ReLU + AdaptiveAvgPool2d(4), pooled in the epilogue
-        ws["pool"].zero_()
-        Fn.conv_gemm(ws["x4"], (B, H, W, 128), 1, pk["w5"], pk["sl5"], 64, B, (H, W), box, 256, pk["sh5"],
-                     act=1, epi_mode=2, pool=ws["pool"], cells=(4, 4), tile_order=1,
-                     conv3x3_reuse=(box == (128, 1)))      # one 130-pixel smem tile serves the three dx taps
+        cell_pixels = self._conv5_pool(ws, pk["w5"], pk["sl5"], pk["sh5"], B, H, W, box)
         fcw, fcb = [pk[f"fw{j}"] for j in range(4)], [pk[f"fb{j}"] for j in range(4)]
         if self.use_tensor_core_tail:
-            return Fn.ratio_tail_tc(ws["pool"], (H // 4) * (W // 4), ws["a6"], ws["gap_fx"], pk["w6_bf"], pk["sl6"], pk["sh6"],
+            return Fn.ratio_tail_tc(ws["pool"], cell_pixels, ws["a6"], ws["gap_fx"], pk["w6_bf"], pk["sl6"], pk["sh6"],
                                     fcw, fcb, self.output_min, self.output_max)
-        return Fn.ratio_tail(ws["pool"], (H // 4) * (W // 4), pk["w6"], pk["sc6"], pk["sh6"], fcw, fcb,
+        return Fn.ratio_tail(ws["pool"], cell_pixels, pk["w6"], pk["sc6"], pk["sh6"], fcw, fcb,
                              self.output_min, self.output_max)
 
 

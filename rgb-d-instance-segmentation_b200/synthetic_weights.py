@@ -144,13 +144,18 @@ def make_decisive(model, class_gain: float = 60.0, mask_gain: float = 60.0, quer
 
 
 def build_synthetic_rgbd_mask2former(channels=(96, 192, 384, 768), guidance_seed: int = 42, torch_seed: int = 0,
-                                     decisive: bool = False, num_labels: int = 80):
+                                     decisive: bool = False, num_labels: int = 80, swin: str = "tiny"):
     """RGB-D Mask2Former (Swin-T, 100 queries; hyper-parameters of the reference's checkpoints/standard/config.json) with
     random-init stock weights (``torch.manual_seed(torch_seed)``) and the deterministic depth-guidance weights.
     Returns (model in eval mode on the CPU, guidance state_dict)."""
     from . import pixel_level
     torch.manual_seed(torch_seed)
-    model = pixel_level.build_rgbd_mask2former(pixel_level.swin_tiny_mask2former_config(num_labels=num_labels)).eval()
+    overrides = {}
+    if swin == "base":          # Swin-B: embed 128, depths [2,2,18,2] -> channels [128,256,512,1024] (BASELINE configs[4])
+        from transformers import SwinConfig
+        overrides["backbone_config"] = SwinConfig(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32], window_size=7,
+                                                  drop_path_rate=0.3, out_features=["stage1", "stage2", "stage3", "stage4"])
+    model = pixel_level.build_rgbd_mask2former(pixel_level.swin_tiny_mask2former_config(num_labels=num_labels, **overrides)).eval()
     w = guidance_weights(seed=guidance_seed, channels=channels)
     missing = model.model.pixel_level_module.load_state_dict(w, strict=False)
     assert not missing.unexpected_keys, missing.unexpected_keys

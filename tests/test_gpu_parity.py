@@ -1191,3 +1191,27 @@ def test_pixel_level_module_with_fused_input_projections(mods):
         assert a.shape == b.shape and rel_l2(a, b) < BF16_TOL, rel_l2(a, b)
     # the decoder's own modules are back in place
     assert isinstance(plm.decoder.input_projections[0], torch.nn.Sequential)
+
+
+@pytest.mark.parametrize("hw", [(50, 70), (33, 47), (62, 128)])
+def test_ratio_predictor_sizes_not_divisible_by_four(mods, hw):
+    """AdaptiveAvgPool2d(4) with overlapping windows (H or W not a multiple of 4): the map is pooled by a separate kernel."""
+    w = OW.ratio_weights(seed=530)
+    m = mods.EnhancedDepthImageRatioPredictor(3)
+    m.load_state_dict(w)
+    m.cuda().eval()
+    frames = []
+    for j in range(3):
+        _, d = synthetic.synth_rgbd_u8(280 + j, hw[0], hw[1], ["nyu", "uniform", "nyu"][j])
+        frames.append(synthetic.normalise_u8(np.repeat(d[:, :, None], 3, axis=2)))
+    x = torch.from_numpy(np.stack(frames))
+    ref = O.ratio_predictor_forward(w, x)
+    with torch.no_grad():
+        r = m(x.cuda())
+    assert float(((r.cpu() - ref).abs() / ref).max()) < BF16_TOL
+    m.train()
+    rs = np.random.RandomState(4)
+    keep = (torch.from_numpy(rs.rand(3, 128) >= 0.3), torch.from_numpy(rs.rand(3, 64) >= 0.2))
+    ref_t, _ = O.ratio_predictor_forward_train(w, x, keep)
+    r_t = m(x.cuda(), dropout_masks=keep)
+    assert float(((r_t.cpu() - ref_t).abs() / ref_t).max()) < BF16_TOL
