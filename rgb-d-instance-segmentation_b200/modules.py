@@ -55,9 +55,14 @@ def _evict(cache: dict) -> None:
 
 class _Versioned:
     """Re-pack derived tensors only when a source parameter changed (torch bumps ``_version`` on in-place
-    updates such as optimizer steps / load_state_dict)."""
+    updates such as optimizer steps / load_state_dict).  Writes through ``p.data`` (``weight.data.copy_()``, EMA swaps, fused
+    optimizers of apex / DeepSpeed) bypass the version counter: call the module's ``invalidate_packed()`` after them
+    (``module.train()`` / ``.eval()`` do it too)."""
 
     def __init__(self):
+        self._key = None
+
+    def invalidate(self) -> None:
         self._key = None
 
     def stale(self, tensors: Sequence[torch.Tensor]) -> bool:
@@ -66,6 +71,21 @@ class _Versioned:
             self._key = key
             return True
         return False
+
+
+class _PackedCacheMixin:
+    """``invalidate_packed()``: drop the bf16-packed copies of the parameters (needed only after writes that bypass torch's
+    version counter); switching between ``train()`` and ``eval()`` invalidates them as well."""
+
+    def invalidate_packed(self) -> None:
+        for name in ("_ver", "_ver_bwd", "_ver_train"):
+            v = getattr(self, name, None)
+            if v is not None:
+                v.invalidate()
+
+    def train(self, mode: bool = True):
+        self.invalidate_packed()
+        return super().train(mode)
 
 
 # =====================================================================================================
@@ -156,7 +176,7 @@ class _DsamStageFunction(torch.autograd.Function):
         return (None, dx, None, None, g if ctx.has_res else None, *grads)
 
 
-class DSAModule(nn.Module):
+class DSAModule(_PackedCacheMixin, nn.Module):
     """CM:622-799.  Depth-sensitive attention: depth histogram modes -> depth-interval region masks ->
     sum_t Conv_t(mask_t * F) + projection(F).  ``in != out``: 3x3 stride-2 convs + bias-free 3x3 stride-2
     ``rgb_projection``; ``in == out``: 1x1 convs + identity residual."""
@@ -522,7 +542,7 @@ def _fold_bn(conv_bias: torch.Tensor, bn: nn.BatchNorm2d) -> Tuple[torch.Tensor,
     return scale.contiguous(), shift.contiguous()
 
 
-class EnhancedDepthImageRatioPredictor(nn.Module):
+class EnhancedDepthImageRatioPredictor(_PackedCacheMixin, nn.Module):
     """CM:1363-1487: (B,3,H,W) depth -> (B,1) window_size_ratio in [0.01, 0.5].  ``eval()``: BatchNorm folded into the
     weights (running statistics), everything up to the 4x4 pooled map in two fused tensor-core kernels.  ``train()``:
     batch-statistics BatchNorm (a statistics pass + a normalising pass per BatchNorm layer, running statistics updated
