@@ -576,6 +576,9 @@ class EnhancedDepthImageRatioPredictor(_PackedCacheMixin, nn.Module):
         self.use_fused_front = True        # stem GEMM + chain in one kernel; False: stem GEMM, then ...
         self.use_fused_chain = True        # ... the fused chain, or (False) three separate GEMM launches (cross-checks)
         self.use_tensor_core_tail = True   # 3x3 256->512 conv of the tail as a tcgen05 GEMM; False: the fp32 CUDA-core kernel
+        #: train mode: ((B,128), (B,64)) boolean keep-masks used by the NEXT forward calls instead of fresh draws (tests;
+        #: callers that reach the module through a parent's forward and cannot pass ``dropout_masks=``)
+        self.dropout_masks_override = None
         self._ver = _Versioned()
         self._packed: Dict[str, torch.Tensor] = {}
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
@@ -816,7 +819,7 @@ class EnhancedDepthImageRatioPredictor(_PackedCacheMixin, nn.Module):
             f"Expected {self.input_channels} channels, got {depth_image.shape[1]}"
         B, _, H, W = depth_image.shape
         if self.training:
-            return self._forward_train(depth_image, dropout_masks)
+            return self._forward_train(depth_image, dropout_masks if dropout_masks is not None else self.dropout_masks_override)
         pk = self._refresh()
         ws = self._workspace(B, H, W, depth_image.device)
         d = depth_image.detach()

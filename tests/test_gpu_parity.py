@@ -1215,3 +1215,39 @@ def test_ratio_predictor_sizes_not_divisible_by_four(mods, hw):
     ref_t, _ = O.ratio_predictor_forward_train(w, x, keep)
     r_t = m(x.cuda(), dropout_masks=keep)
     assert float(((r_t.cpu() - ref_t).abs() / ref_t).max()) < BF16_TOL
+
+
+def test_depth_guidance_fine_tuning_step_with_train_mode_predictor(mods):
+    """BASELINE configs[3] semantics end to end on the hot path: ``.train()`` -> the ratio comes from the batch-statistics
+    predictor (Dropout masks injected), it steers the region masks, and DSAM / DGGM gradients follow -- all against the
+    oracle run with ITS train-mode ratio (no ratio is handed over, unlike test_depth_guidance_training_gradients)."""
+    chans, (H, W), B = (32, 64, 96, 160), (64, 96), 3
+    w = OW.guidance_weights(seed=41, channels=chans)
+    m = mods.DepthGuidance(chans)
+    m.load_state_dict(w)
+    m.cuda().train()
+    pvs = [synthetic.assemble_pixel_values(*synthetic.synth_rgbd_u8(330 + j, H, W, ["nyu", "nyu", "uniform"][j]), O.gradient_features)
+           for j in range(B)]
+    pv = torch.from_numpy(np.stack(pvs))
+    rs = np.random.RandomState(12)
+    feats = [torch.from_numpy(rs.randn(B, c, H // s, W // s).astype(np.float32)) for c, s in zip(chans, (4, 8, 16, 32))]
+    douts = [torch.from_numpy(rs.randn(*f.shape).astype(np.float32)) for f in feats]
+    keep = (torch.from_numpy(rs.rand(B, 128) >= 0.3), torch.from_numpy(rs.rand(B, 64) >= 0.2))
+    ref_ratio, w_after = O.ratio_predictor_forward_train(O._sub(w, "ratio_predictor."), pv[:, 3:6], keep)
+    wr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.startswith("ratio_predictor.") else v)
+          for k, v in w.items()}
+    ref, _ = O.depth_guidance_forward(wr, pv, feats, ratios=ref_ratio)
+    sum((o * d).sum() for o, d in zip(ref, douts)).backward()
+    m.ratio_predictor.dropout_masks_override = keep
+    out = m(pv.cuda(), [f.cuda() for f in feats])
+    sum((o * d.cuda()).sum() for o, d in zip(out, douts)).backward()
+    for i in range(4):
+        assert rel_l2(out[i], ref[i]) < 3 * BF16_TOL, (i, rel_l2(out[i], ref[i]))
+    for name, p in m.named_parameters():
+        if name.startswith("ratio_predictor."):
+            assert p.grad is None, name
+        else:
+            assert rel_l2(p.grad, wr[name].grad) < 5e-2, (name, rel_l2(p.grad, wr[name].grad))
+    for k, v in m.ratio_predictor.state_dict().items():      # the step moved the running statistics like the reference would
+        if "running" in k:
+            assert rel_err(v, w_after[k]) < BF16_TOL, k
