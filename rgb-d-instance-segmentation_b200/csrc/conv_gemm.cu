@@ -424,6 +424,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
     }
 }
 
+template <bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_gate,
@@ -556,7 +557,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         } else if (p.epi_mode == 3) {
             epilogue_loop<3, 0, false>(p, c, &tmap_out);
         } else {
-            if (p.act == 3) epilogue_loop<2, 3, false>(p, c, &tmap_out);
+            if (STATS) epilogue_loop<2, 3, false>(p, c, &tmap_out);
             else if (sc) epilogue_loop<2, 1, true>(p, c, &tmap_out);
             else epilogue_loop<2, 1, false>(p, c, &tmap_out);
         }
@@ -577,6 +578,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // through a descriptor whose start address is advanced by dx rows of 128 bytes (the 128B swizzle is a function of
 // the absolute shared-memory address, profiles/r01_notes.md).  Per output tile the SM receives 6 A tiles instead
 // of 18, i.e. 676 KB instead of 864 KB over its 64 B/clk L2 port (MMA time: 9216 cycles = 590 KB at 64 B/clk).
+template <bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_gate,
@@ -697,7 +699,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         } else if (p.epi_mode == 1) {
             epilogue_loop<1, 0, false>(p, c, &tmap_out);
         } else {
-            if (p.act == 3) epilogue_loop<2, 3, false>(p, c, &tmap_out);
+            if (STATS) epilogue_loop<2, 3, false>(p, c, &tmap_out);
             else if (sc) epilogue_loop<2, 1, true>(p, c, &tmap_out);
             else epilogue_loop<2, 1, false>(p, c, &tmap_out);
         }
@@ -1023,6 +1025,7 @@ conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 // L2 inbound drops from 676 KB to 388 KB (64 B/clk port; 9216 MMA cycles = 590 KB) and its shared-memory operand
 // reads from 96 to 64 B/clk, so the kernel becomes MMA-bound.  Leader (cluster rank 0) issues the MMAs; both CTAs
 // issue TMA loads (bytes counted on the leader's barriers) and run their own epilogue on their own TMEM half.
+template <bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ KParams p) {
@@ -1140,7 +1143,7 @@ conv3x3_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ================= epilogue (both CTAs, each on its own 128 TMEM lanes) =================
         EpiCtx c{smem, nullptr, nullptr, ctl, s_scale, s_shift, tmem_base, u_begin, u_end, warp, lane, (int)rank,
                  {tc::mapa(tc::smem_u32(&ctl->tmem_empty[0]), 0), tc::mapa(tc::smem_u32(&ctl->tmem_empty[1]), 0)}};
-        if (p.act == 3) epilogue_loop<2, 3, false>(p, c, &tmap_a);
+        if (STATS) epilogue_loop<2, 3, false>(p, c, &tmap_a);
         else if (p.scale) epilogue_loop<2, 1, true>(p, c, &tmap_a);
         else epilogue_loop<2, 1, false>(p, c, &tmap_a);
     }
@@ -1299,6 +1302,7 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     p.tile_order = d->tile_order;
     p.slices = reinterpret_cast<const int4*>(d->slices);
     p.epi_mode = d->epi_mode; p.act = d->act;
+    const bool stats = d->epi_mode == 2 && d->act == 3;
     p.scale = d->scale; p.shift = d->shift; p.variant = d->variant;
     p.gate = reinterpret_cast<const __nv_bfloat16*>(d->gate);
     p.out = d->out; p.residual = d->residual; p.pool = d->pool; p.pool_sq = d->pool_sq;
@@ -1314,9 +1318,14 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     if (int rc = rgbd_device_info(&di)) return rc;
     const int num_sms = di.num_sms, max_smem = di.max_smem;
     RGBD_ONCE_PER_DEVICE(di.device, {
-        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        // the statistics epilogue (act 3, train-mode BatchNorm) lives in its own instantiations: it needs 17 more registers,
+        // which the inference kernels should not pay for
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(dsam_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     });
@@ -1368,10 +1377,12 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
             attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_2cta_kernel, tmap_a, tmap_b2, p));
+            if (stats) RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_2cta_kernel<true>, tmap_a, tmap_b2, p));
+            else RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_2cta_kernel<false>, tmap_a, tmap_b2, p));
             return RGBD_OK;
         }
-        conv3x3_kernel<<<grid, kThreads, smem3, (cudaStream_t)stream>>>(tmap_a, tmap_b, tmap_out, tmap_gate, p);
+        if (stats) conv3x3_kernel<true><<<grid, kThreads, smem3, (cudaStream_t)stream>>>(tmap_a, tmap_b, tmap_out, tmap_gate, p);
+        else conv3x3_kernel<false><<<grid, kThreads, smem3, (cudaStream_t)stream>>>(tmap_a, tmap_b, tmap_out, tmap_gate, p);
         RGBD_CHECK_LAUNCH();
         return RGBD_OK;
     }
@@ -1466,7 +1477,8 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_2cta_kernel, tmap_a, tmap_b2, p));
         return RGBD_OK;
     }
-    conv_gemm_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmap_a, tmap_b, tmap_out, tmap_gate, p);
+    if (stats) conv_gemm_kernel<true><<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmap_a, tmap_b, tmap_out, tmap_gate, p);
+    else conv_gemm_kernel<false><<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(tmap_a, tmap_b, tmap_out, tmap_gate, p);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }
