@@ -147,3 +147,43 @@ def test_postprocess_argument_errors_and_edge_shapes(fn):
     ref = OP.post_process_image(torch.tensor([[2.0, -1.0]]), torch.full((1, 1, 1), 4.0), 0.5, (5, 7))
     assert one.count.cpu().tolist() == [1] and bool(one.masks[0, 0].all())
     assert abs(float(one.scores[0, 0]) - float(ref["scores"][0])) < 1e-6
+
+
+def test_serving_pipeline_matches_direct_calls():
+    """``serving.RgbdInstanceSegmenter`` (pinned uint8 frames -> H2D -> front-end -> model -> post-processing -> pinned host,
+    pipelined over two buffers) == the same steps called one by one (predictor.py:19-36, 697-703)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from types import SimpleNamespace
+    import numpy as np
+    from rgbd_b200 import functional as Fn, postprocess, serving, synthetic, synthetic_weights as SW
+    model, _ = SW.build_synthetic_rgbd_mask2former(decisive=True, num_labels=8)
+    model.cuda()
+    B, H, W = 2, 128, 160
+    seg = serving.RgbdInstanceSegmenter(model, B, (H, W), threshold=0.5, autocast_dtype=None)
+    batches = []
+    for k in range(3):
+        rgbs, ds = zip(*[synthetic.synth_rgbd_u8(700 + 10 * k + j, H, W, "nyu") for j in range(B)])
+        batches.append((torch.from_numpy(np.stack(rgbs)), torch.from_numpy(np.stack(ds))))
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    # pipelined: three submits in flight over two buffers, results read afterwards / in between
+    got = []
+    b0 = seg.submit(*batches[0])
+    b1 = seg.submit(*batches[1])
+    got.append(seg.result(b0))
+    b2 = seg.submit(*batches[2])
+    got.append(seg.result(b1))
+    got.append(seg.result(b2))
+    for (rgb, d), res in zip(batches, got):
+        with torch.no_grad():
+            pv = Fn.pack_pixel_values(rgb.cuda(), d.cuda())
+            out = model(pixel_values=pv)
+        ref = postprocess.post_process_instance_segmentation(
+            SimpleNamespace(class_queries_logits=out.class_queries_logits, masks_queries_logits=out.masks_queries_logits),
+            threshold=0.5, target_sizes=[(H, W)] * B)
+        for r, g in zip(ref, res):
+            assert len(r["segments_info"]) == len(g["segments_info"]) > 0
+            assert [s["label_id"] for s in r["segments_info"]] == [s["label_id"] for s in g["segments_info"]]
+            assert torch.equal(r["segmentation"].cpu().to(torch.int32), g["segmentation"])
+    assert seg.h2d_bytes_per_step == B * H * W * 4 and seg.d2h_bytes_per_step > B * H * W * 4
