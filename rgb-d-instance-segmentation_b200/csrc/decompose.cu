@@ -163,24 +163,45 @@ __global__ void __launch_bounds__(256) decomp_hist_kernel(const float* __restric
     unsigned int* hw = h[threadIdx.x >> 5];
     // neighbouring pixels of a depth image mostly share a bin (8-bit depth: 256 distinct values): the lanes of a warp that hit
     // the same bin elect one leader that adds their count -- one shared-memory atomic per distinct bin instead of a
-    // serialised 32-way conflict
-    const int stride = gridDim.x * blockDim.x;
-    const int n_iter = (HW + stride - 1) / stride;
-    for (int it = 0; it < n_iter; ++it) {
-        const int i = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    // serialised 32-way conflict.  Four pixels per thread and iteration (one 128-bit load) with the next load issued before
+    // the current one is binned: the loop is bound by the latency of its loads otherwise.
+    auto bin_of = [&](float x) -> int {
         int idx = -1;
-        if (i < HW) {
-            const float x = in[i];
-            if (x >= s.first && x <= s.last) {          // drops NaN
-                float f = ((x - s.first) / s.denom) * (float)kBins;
-                idx = (int)f;                            // astype(intp): truncation
-                if (idx == kBins) idx -= 1;
-                if (x < bin_edge(s, idx)) idx -= 1;
-                if (x >= bin_edge(s, idx + 1) && idx != kBins - 1) idx += 1;
-            }
+        if (x >= s.first && x <= s.last) {          // drops NaN
+            float f = ((x - s.first) / s.denom) * (float)kBins;
+            idx = (int)f;                            // astype(intp): truncation
+            if (idx == kBins) idx -= 1;
+            if (x < bin_edge(s, idx)) idx -= 1;
+            if (x >= bin_edge(s, idx + 1) && idx != kBins - 1) idx += 1;
         }
+        return idx;
+    };
+    auto add = [&](int idx) {
         const unsigned peers = __match_any_sync(0xffffffffu, idx);
         if (idx >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hw[idx], (unsigned)__popc(peers));
+    };
+    const float nan = __int_as_float(0x7fc00000);
+    const int stride = gridDim.x * blockDim.x;
+    const bool vec = (HW & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    if (vec) {
+        const int n4 = HW >> 2;
+        const int n_iter = (n4 + stride - 1) / stride;
+        const float4 nan4 = make_float4(nan, nan, nan, nan);
+        int i = blockIdx.x * blockDim.x + threadIdx.x;
+        float4 cur = i < n4 ? __ldg(reinterpret_cast<const float4*>(in) + i) : nan4;
+        for (int it = 0; it < n_iter; ++it) {
+            const int nx = i + stride;
+            const float4 next = (it + 1 < n_iter && nx < n4) ? __ldg(reinterpret_cast<const float4*>(in) + nx) : nan4;
+            add(bin_of(cur.x)); add(bin_of(cur.y)); add(bin_of(cur.z)); add(bin_of(cur.w));
+            cur = next;
+            i = nx;
+        }
+    } else {
+        const int n_iter = (HW + stride - 1) / stride;
+        for (int it = 0; it < n_iter; ++it) {
+            const int i = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+            add(bin_of(i < HW ? in[i] : nan));
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kBins; i += blockDim.x) {

@@ -1142,8 +1142,8 @@ def test_torch_ops_dggm_autograd_matches_module(mods):
     douts = [torch.randn_like(o) for o in outs]
     g_op = torch.autograd.grad(outs, [*feats, *ws, *bs], douts)
     g_ref = torch.autograd.grad(ref, [*feats, *ws, *bs], douts)
-    for a, b in zip(g_op, g_ref):
-        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    for a, b in zip(g_op, g_ref):            # dW / db are reduced with float atomics: equal up to the summation order
+        assert rel_l2(a, b) < 1e-4, rel_l2(a, b)
     dec = torch.ops.rgbd_b200.depth_decompose(torch.randn(2, 3, 32, 48, device="cuda"), torch.tensor([0.2, 0.3], device="cuda"),
                                               [8, 4, 2], [12, 6, 3])
     assert dec[0].shape == (2, 8, 12) and dec[0].dtype == torch.uint8
