@@ -109,7 +109,9 @@ def _(image):
 def depth_decompose(depth3: Tensor, ratio: Tensor, level_h: List[int], level_w: List[int]) -> List[Tensor]:
     """CM:701-798 + CM:687 batched: [pooled region codes per level ..., bias_variant (B), n_modes (B), windows (B,3,2), centres (B,3)]."""
     dec = Fn.depth_decompose(ratio.reshape(-1).contiguous(), list(zip(level_h, level_w)), depth3=depth3, want_codes=False)
-    return [*dec.pooled, dec.bias_variant, dec.n_modes, dec.windows, dec.centres]
+    # the per-image tables are views of one allocation inside functional.depth_decompose; dispatcher ops must not return
+    # outputs that alias each other
+    return [*dec.pooled, dec.bias_variant.clone(), dec.n_modes.clone(), dec.windows.clone(), dec.centres.clone()]
 
 
 @depth_decompose.register_fake

@@ -117,16 +117,19 @@ class RgbdInstanceSegmenter:
             if e is not None:
                 main.wait_event(e)
 
-    def result(self, b: int) -> List[Dict]:
-        """HF-shaped results of buffer ``b`` (``post_process_instance_segmentation`` return structure, PR:701-703)."""
+    def result(self, b: int, copy: bool = True) -> List[Dict]:
+        """HF-shaped results of buffer ``b`` (``post_process_instance_segmentation`` return structure, PR:701-703).  The pinned
+        staging buffer is reused by the second-next ``submit``: the maps are copied out unless ``copy=False`` (then they are
+        views that stay valid only until that submit)."""
         self._ev_d2h[b].synchronize()
         oh = self.out_host[b]
+        seg = oh["segmentation"].clone() if copy else oh["segmentation"]
         res = []
         for i in range(self.B):
             n = int(oh["count"][i])
             info = [{"id": j, "label_id": int(oh["labels"][i, j]), "was_fused": False,
                      "score": round(float(oh["scores"][i, j]), 6)} for j in range(n)]
-            res.append({"segmentation": oh["segmentation"][i], "segments_info": info})
+            res.append({"segmentation": seg[i], "segments_info": info})
         return res
 
     def __call__(self, rgb_u8: torch.Tensor, depth_u8: torch.Tensor) -> List[Dict]:
