@@ -78,7 +78,7 @@ class RgbdInstanceSegmenter:
 
     def submit(self, rgb_u8: Optional[torch.Tensor] = None, depth_u8: Optional[torch.Tensor] = None) -> int:
         """Enqueue one batch (host uint8 tensors (B,H,W,3) / (B,H,W); ``None`` re-sends what the staging buffer holds).
-        Returns the buffer index whose pinned results ``result(b)`` will expose after ``wait()``."""
+        Returns the buffer index whose results ``result(b)`` reads once the download has finished."""
         b = self._step & 1
         self._step += 1
         main = torch.cuda.current_stream(self.device)
