@@ -705,11 +705,11 @@ class PerKernel:
                                                                            want_codes=False))
             dec = Fn.depth_decompose(ratios.reshape(-1), levels, depth3=pv[:, 3:6])
 
-            def cascade(gemm_only=False):
-                x = feats[0]
-                for k, d in enumerate((m.dsam0, m.dsam1, m.dsam2)):
-                    x = d.stage_forward(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1])
-            out["dsam_cascade_total"] = self._time(cascade)
+            from rgbd_b200.modules import dsam_cascade
+            dsams = (m.dsam0, m.dsam1, m.dsam2)
+            # the cascade exactly as the step runs it: one pack kernel (stage 0), stages 1-2 get their operand from the
+            # previous stage's epilogue
+            out["dsam_cascade_total"] = self._time(lambda: dsam_cascade(dsams, feats, dec, False))
             # GEMM-only time of the three stages (operands already packed by the cascade above)
             def gemms():
                 x = feats[0]

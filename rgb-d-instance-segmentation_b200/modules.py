@@ -921,6 +921,28 @@ class DepthGuidance(nn.Module):
                                       self.depth_gradient_injection, pixel_values, color_feature_map, ratios, out)
 
 
+def dsam_cascade(dsams: Sequence[DSAModule], feats: Sequence[torch.Tensor], dec, training: bool) -> List[torch.Tensor]:
+    """CM:339-352: ``cp1[k+1] += dsam_k(cp1[k])`` with the UPDATED cp1[k]; returns cp1.  Inference: stage k's epilogue also
+    writes stage k+1's packed bf16 operand (no pack kernel in between)."""
+    cp1 = [feats[0]]
+    x = feats[0]
+    prepacked = False
+    for k, dsam in enumerate(dsams):
+        if training or not FUSE_STAGE_PACKS:
+            x = dsam.stage_forward(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1])
+        else:
+            emit = None
+            if k + 1 < len(dsams):
+                tgt = dsams[k + 1]._emit_target(x.shape[0], feats[k + 1].shape[2], feats[k + 1].shape[3], x.device)
+                if tgt is not None:
+                    emit = (tgt[0], tgt[1], dec.pooled[k + 1])
+            x = dsam._stage_forward_impl(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1], emit_next=emit,
+                                         prepacked=prepacked)
+            prepacked = emit is not None
+        cp1.append(x)
+    return cp1
+
+
 def depth_guidance_forward(ratio_predictor: EnhancedDepthImageRatioPredictor, dsams: Sequence[DSAModule],
                            dggm: DepthGradientInjectionResidual, pixel_values: torch.Tensor,
                            color_feature_map: Sequence[torch.Tensor], ratios: Optional[torch.Tensor] = None,
@@ -936,23 +958,7 @@ def depth_guidance_forward(ratio_predictor: EnhancedDepthImageRatioPredictor, ds
     levels = [tuple(f.shape[2:]) for f in feats[:3]]
     dec = Fn.depth_decompose(ratios.reshape(-1).contiguous(), levels, depth3=depth, want_codes=False)
     training = torch.is_grad_enabled() and any(p.requires_grad for m in (*dsams, dggm) for p in m.parameters())
-    cp1 = [feats[0]]
-    x = feats[0]
-    prepacked = False
-    for k, dsam in enumerate(dsams):                                        # CM:339-352
-        if training or not FUSE_STAGE_PACKS:
-            x = dsam.stage_forward(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1])
-        else:
-            # inference: stage k's epilogue also writes stage k+1's packed bf16 operand (no pack kernel in between)
-            emit = None
-            if k + 1 < len(dsams):
-                tgt = dsams[k + 1]._emit_target(x.shape[0], feats[k + 1].shape[2], feats[k + 1].shape[3], x.device)
-                if tgt is not None:
-                    emit = (tgt[0], tgt[1], dec.pooled[k + 1])
-            x = dsam._stage_forward_impl(x, dec.pooled[k], dec.bias_variant, residual=feats[k + 1], emit_next=emit,
-                                         prepacked=prepacked)
-            prepacked = emit is not None
-        cp1.append(x)
+    cp1 = dsam_cascade(dsams, feats, dec, training)                         # CM:339-352
     if training:
         if out is not None:
             raise RgbdB200Error("preallocated outputs are an inference-path option")
