@@ -196,4 +196,9 @@ def build_rgbd_mask2former(config=None, version: str = "0.4.0"):
     config = config or swin_tiny_mask2former_config()
     model = Mask2FormerForUniversalSegmentation(config)
     model.model.pixel_level_module = CustomMask2FormerPixelLevelModule(config, version=version)
+    # The reference builds its pixel-level module inside the model's __init__, i.e. BEFORE Hugging Face's post_init() walks
+    # the tree (CM:45-53); swapped in afterwards it would keep torch's default initialisers and, worse, raw
+    # ``nn.Parameter(torch.Tensor(...))`` members such as the pixel decoder's ``level_embed`` would stay UNINITIALISED memory.
+    # post_init() initialises exactly the modules that are not flagged as initialised yet.
+    model.post_init()
     return model
