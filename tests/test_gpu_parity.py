@@ -576,6 +576,12 @@ def test_whole_model_logits_match_cpu_oracle_model(mods):
     plm = model.model.pixel_level_module
     missing = plm.load_state_dict(w, strict=False)
     assert not missing.unexpected_keys
+    # every parameter is initialised (the pixel decoder's raw ``level_embed`` used to stay uninitialised memory)
+    assert float(plm.decoder.level_embed.abs().max()) < 10 and all(bool(torch.isfinite(p).all()) for p in model.parameters())
+    # a random-init head produces near-uniform class logits -- differences of almost equal numbers, whose RELATIVE error says
+    # little; the decisive synthetic model behaves like a trained one (tests/test_gpu_map_parity.py)
+    from rgbd_b200 import synthetic_weights as SW
+    SW.make_decisive(model)
     H, W = 128, 160
     pvs = []
     for j in range(2):
