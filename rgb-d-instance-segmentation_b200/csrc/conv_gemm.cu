@@ -63,6 +63,7 @@ struct KParams {
     const uint8_t* next_codes;
     int next_c_pad, next_n_seg, next_masked_segs;
     int c_blocks, sa_stages, a_stage_bytes;   // conv3x3_kernel: 64-channel blocks, A-ring depth, bytes per A stage
+    int acc_stages;           // accumulator buffers in tensor memory: 2 (epilogue of tile t overlaps the MMAs of tile t+1) or 1
 };
 
 struct alignas(16) SmemCtl {
@@ -397,7 +398,7 @@ __device__ __forceinline__ void epilogue_loop(const KParams& p, const EpiCtx& c,
             if (c.tmem_empty_remote[as]) tc::mbar_arrive_cluster_tmem(c.tmem_empty_remote[as]);
             else tc::mbar_arrive(&ctl->tmem_empty[as]);
         }
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
         if (MODE == 0) {
             if (p.gate_bytes) {
                 tc::mbar_arrive(&ctl->gate_empty);
@@ -539,7 +540,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            if (++as == 2) { as = 0; aphase ^= 1; }
+            if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
@@ -688,7 +689,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     if (++sa == p.sa_stages) { sa = 0; pa ^= 1; }
                 }
             }
-            if (++as == 2) { as = 0; aphase ^= 1; }
+            if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 4) {
         EpiCtx c{smem, s_staging, s_gate, ctl, s_scale, s_shift, tmem_base, t_begin, t_end, warp, lane, -1, {0u, 0u}};
@@ -722,6 +723,13 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // (cta_group::2): every CTA masks its own tile, the weight tiles are split between the two CTAs.
 constexpr int kDsamThreads = 512;            // 4 control warps + 8 epilogue warps + 4 mask warps
 constexpr int kDsamRaw = 3;                  // raw (unmasked) tile ring: prefetched ahead of the masking
+// TMEM_A: the masked copies live in TENSOR MEMORY instead of shared memory (tcgen05.st by the mask warps, tcgen05.mma with
+// the A operand in TMEM): the 64 KB of masked-copy writes and the 64 KB of A reads per (tap, channel block) group leave the
+// shared-memory port, which bounded the kernel at N = 192 (154 B/clk wanted of 128 B/clk, profiles/r01_notes.md).  Tensor
+// memory then holds ONE accumulator buffer [0, BLOCK_N) and two groups of four 32-column bf16 operands at [256, 512): the
+// epilogue no longer overlaps the next tile's MMAs (~3 k of ~40 k cycles per tile).
+constexpr uint32_t kDsamTmemA = 256;
+template <bool TMEM_A>
 __global__ void __launch_bounds__(kDsamThreads, 1)
 dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ KParams p) {
@@ -732,8 +740,8 @@ dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int n_msk = p.m3_masked_segs;
     const int b_bytes = (p.BLOCK_N / 2) * 128;
     uint8_t* s_rawt = smem;                                    // kDsamRaw raw tiles (TMA targets; also the projection operand)
-    uint8_t* s_msk = s_rawt + kDsamRaw * kTile;                // 2 groups x n_msk masked copies
-    uint8_t* s_b = s_msk + 2 * n_msk * kTile;
+    uint8_t* s_msk = s_rawt + kDsamRaw * kTile;                // 2 groups x n_msk masked copies (not with TMEM_A)
+    uint8_t* s_b = s_msk + (TMEM_A ? 0 : 2 * n_msk * kTile);
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(s_b + (size_t)p.stages * b_bytes);
     float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + sizeof(SmemCtl));
     float* s_shift = s_scale + p.BLOCK_N;
@@ -834,10 +842,15 @@ dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     const uint8_t* a_tile = sg < n_msk ? s_msk + (size_t)(g * n_msk + sg) * kTile : s_rawt + (size_t)r * kTile;
                     const uint64_t adesc = tc::make_kmajor_desc(tc::smem_u32(a_tile), 128);
                     const uint64_t bdesc = tc::make_kmajor_desc(tc::smem_u32(s_b + (size_t)sb * b_bytes), 128);
+                    const uint32_t a_tmem = tmem_base + kDsamTmemA + (uint32_t)((g * 4 + sg) * 32);
                     if (tc::elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tc::umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (first | k) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) {
+                            if (TMEM_A && sg < n_msk)
+                                tc::umma_bf16_ts_2cta(d_tmem, a_tmem + (uint32_t)(k * 8), bdesc + (uint64_t)(k * 2), idesc, (first | k) ? 1u : 0u);
+                            else
+                                tc::umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (first | k) ? 1u : 0u);
+                        }
                         tc::umma_commit_2cta(&ctl->empty[sb]);
                         if (sg == n_seg - 1) {
                             tc::umma_commit_2cta(&ctl->masked_empty[g]);
@@ -852,7 +865,7 @@ dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 if (++g == 2) { g = 0; pg ^= 1; }
                 if (++r == kDsamRaw) r = 0;
             }
-            if (++as == 2) { as = 0; aphase ^= 1; }
+            if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 12) {
         // ================= mask warps: masked copies of the raw tile =================
@@ -876,17 +889,39 @@ dsam_fwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     tc::mbar_wait(&ctl->a_full[r], pr);
                     const uint8_t* src = s_rawt + (size_t)r * kTile + row * 128;
                     uint4 v[8];
+                    if (TMEM_A) {
+                        // logical order (16-byte piece j of the row sits at chunk j ^ (row & 7) of the 128B-swizzled tile; the XOR
+                        // keeps the eight lanes of a quarter-warp on distinct chunks): words 4j .. 4j+3 = channels 8j .. 8j+7
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (((j + row) & 7) << 4));   // rotated: bank-conflict free
-                    tc::mbar_wait(&ctl->masked_empty[g], pg ^ 1);
-                    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-                    for (int sg = 0; sg < n_msk; ++sg) {
-                        uint8_t* dst = s_msk + (size_t)(g * n_msk + sg) * kTile + row * 128;
-                        const bool keep = (code >> sg) & 1u;
+                        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (((j ^ row) & 7) << 4));
+                        tc::mbar_wait(&ctl->masked_empty[g], pg ^ 1);
+                        tc::tc_fence_after();                  // the MMAs that read this group's columns have completed
+                        const uint32_t t0 = tmem_base + ((uint32_t)((warp - 12) * 32) << 16) + kDsamTmemA + (uint32_t)(g * 4 * 32);
+                        for (int sg = 0; sg < n_msk; ++sg) {
+                            const bool keep = (code >> sg) & 1u;
+                            uint32_t w[32];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(dst + (((j + row) & 7) << 4)) = keep ? v[j] : zero;
+                            for (int j = 0; j < 8; ++j) {
+                                w[4 * j] = keep ? v[j].x : 0u; w[4 * j + 1] = keep ? v[j].y : 0u;
+                                w[4 * j + 2] = keep ? v[j].z : 0u; w[4 * j + 3] = keep ? v[j].w : 0u;
+                            }
+                            tc::tmem_st_32x32(t0 + (uint32_t)(sg * 32), w);
+                        }
+                        tc::tmem_st_wait();
+                        tc::tc_fence_before();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (((j + row) & 7) << 4));   // rotated: bank-conflict free
+                        tc::mbar_wait(&ctl->masked_empty[g], pg ^ 1);
+                        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+                        for (int sg = 0; sg < n_msk; ++sg) {
+                            uint8_t* dst = s_msk + (size_t)(g * n_msk + sg) * kTile + row * 128;
+                            const bool keep = (code >> sg) & 1u;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(dst + (((j + row) & 7) << 4)) = keep ? v[j] : zero;
+                        }
+                        tc::fence_proxy_async();               // generic-proxy writes -> visible to the tensor core's smem reads
                     }
-                    tc::fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's smem reads
                     __syncwarp();
                     // one arrive per warp, CTA-scope release: the copies are read by THIS CTA's tensor core (async proxy,
                     // ordered by the fence above); the remote barrier only signals the leader's MMA thread
@@ -1001,7 +1036,7 @@ conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            if (++as == 2) { as = 0; aphase ^= 1; }
+            if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 4) {
         EpiCtx c{smem, nullptr, nullptr, ctl, s_scale, s_shift, tmem_base, u_begin, u_end, warp, lane, (int)rank,
@@ -1137,7 +1172,7 @@ conv3x3_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (++sa == p.sa_stages) { sa = 0; pa ^= 1; }
                 }
             }
-            if (++as == 2) { as = 0; aphase ^= 1; }
+            if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
         }
     } else if (warp >= 4) {
         // ================= epilogue (both CTAs, each on its own 128 TMEM lanes) =================
@@ -1303,6 +1338,7 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
     p.slices = reinterpret_cast<const int4*>(d->slices);
     p.epi_mode = d->epi_mode; p.act = d->act;
     const bool stats = d->epi_mode == 2 && d->act == 3;
+    p.acc_stages = 2;
     p.scale = d->scale; p.shift = d->shift; p.variant = d->variant;
     p.gate = reinterpret_cast<const __nv_bfloat16*>(d->gate);
     p.out = d->out; p.residual = d->residual; p.pool = d->pool; p.pool_sq = d->pool_sq;
@@ -1327,7 +1363,8 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         RGBD_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        RGBD_CHECK_CUDA(cudaFuncSetAttribute(dsam_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(dsam_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        RGBD_CHECK_CUDA(cudaFuncSetAttribute(dsam_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     });
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     if (d->conv3x3_reuse) {
@@ -1401,8 +1438,12 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
             return RGBD_ERR_CUDA;
         }
         const int b_half = (p.BLOCK_N / 2) * 128;
+        const char* tmem_e = getenv("RGBD_DSAM_TMEM");                  // A/B switch (read per launch)
+        const bool tmem_env = tmem_e == nullptr || tmem_e[0] != (char)48;
+        const bool tmem_a = tmem_env && p.BLOCK_N <= 256 && p.m3_masked_segs <= 4;   // masked copies in tensor memory
+        if (tmem_a) p.acc_stages = 1;
         const int fixedm = 1024 + (int)sizeof(SmemCtl) + 64 + 2 * p.BLOCK_N * (int)sizeof(float) +
-                           (kDsamRaw + 2 * p.m3_masked_segs) * kBlockM * 128;
+                           (kDsamRaw + (tmem_a ? 0 : 2 * p.m3_masked_segs)) * kBlockM * 128;
         int sbm = (max_smem - fixedm) / b_half;
         if (sbm > kMaxStages) sbm = kMaxStages;
         RGBD_CHECK_ARG(sbm >= 2, "conv_gemm: not enough shared memory for the masked DSAM pipeline");
@@ -1421,7 +1462,8 @@ extern "C" int rgbd_conv_gemm(const rgbd_conv_gemm_desc* d, rgbd_stream_t stream
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dsam_fwd_kernel, tmap_a, tmap_b2, p));
+        if (tmem_a) RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dsam_fwd_kernel<true>, tmap_a, tmap_b2, p));
+        else RGBD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dsam_fwd_kernel<false>, tmap_a, tmap_b2, p));
         return RGBD_OK;
     }
     const int b_total = p.n_slices * p.BLOCK_N * kb_bytes;

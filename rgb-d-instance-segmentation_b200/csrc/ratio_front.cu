@@ -65,15 +65,6 @@ struct alignas(16) FrontCtl {
     uint32_t pad;
 };
 
-__device__ __forceinline__ void umma_bf16_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-
 __device__ __forceinline__ void decode(const FrontParams& p, int t, int& img, int& ty, int& tx) {
     ty = t % p.tiles_y; t /= p.tiles_y;       // walk down columns: the 4 row taps of the stem re-hit L2
     tx = t % p.tiles_x;
@@ -232,7 +223,7 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
             if (tc::elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 12; ++k)
-                    umma_bf16_ts_2cta(d, tmem + kColQ + (uint32_t)(k * 8), w2d + (uint64_t)((k >> 2) * ((64 * 128) >> 4) + (k & 3) * 2),
+                    tc::umma_bf16_ts_2cta(d, tmem + kColQ + (uint32_t)(k * 8), w2d + (uint64_t)((k >> 2) * ((64 * 128) >> 4) + (k & 3) * 2),
                                       idesc128, k != 0);
                 tc::umma_commit_2cta(&ctl->acc_full[c][1]);
             }
@@ -243,7 +234,7 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
             if (tc::elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    umma_bf16_ts_2cta(d, d + 128u + (uint32_t)(k * 8), w3d + (uint64_t)((k >> 2) * ((32 * 128) >> 4) + (k & 3) * 2), idesc64,
+                    tc::umma_bf16_ts_2cta(d, d + 128u + (uint32_t)(k * 8), w3d + (uint64_t)((k >> 2) * ((32 * 128) >> 4) + (k & 3) * 2), idesc64,
                                       k != 0);
                 tc::umma_commit_2cta(&ctl->acc_full[c][2]);
             }
@@ -253,7 +244,7 @@ ratio_front_kernel(const __grid_constant__ CUtensorMap tmap_r, const __grid_cons
             tc::tc_fence_after();
             if (tc::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16_ts_2cta(d, d + 160u + (uint32_t)(k * 8), w4d + (uint64_t)(k * 2), idesc128, k != 0);
+                for (int k = 0; k < 4; ++k) tc::umma_bf16_ts_2cta(d, d + 160u + (uint32_t)(k * 8), w4d + (uint64_t)(k * 2), idesc128, k != 0);
                 tc::umma_commit_2cta(&ctl->acc_full[c][3]);
             }
             __syncwarp();
