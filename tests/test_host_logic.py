@@ -185,10 +185,30 @@ def test_ratio_predictor_packing_reproduces_the_reference_chain():
 
 
 def test_state_dict_keys_match_the_reference_layout():
+    """Keys of the mirror == keys of the synthetic weight factory.  The factory is this repo's own code: what pins it to the
+    REFERENCE is that oracle/make_golden*.py load exactly these dicts into the reference's modules with ``load_state_dict``
+    (strict for the leaf modules; ``unexpected_keys`` asserted empty for the pixel-level module), and -- where the reference
+    tree is present -- the direct comparison below."""
     g = modules.DepthGuidance((96, 192, 384, 768))
     keys = set(g.state_dict().keys())
     ref = set(OW.guidance_weights(seed=1).keys())
     assert keys == ref, keys ^ ref
+
+
+def test_state_dict_keys_match_the_live_reference_modules():
+    from oracle import make_golden as MG
+    if not os.path.isdir(os.path.join(MG.REF, "mask2former")):
+        pytest.skip("the reference tree is only present in the build container")
+    cm, _ = MG.import_reference()
+    pairs = [(cm.DepthGradientInjectionResidual([96, 192, 384, 768], 3), modules.DepthGradientInjectionResidual([96, 192, 384, 768], 3)),
+             (cm.DSAModule(96, 192, 3), modules.DSAModule(96, 192, 3)), (cm.DSAModule(64, 64, 3), modules.DSAModule(64, 64, 3)),
+             (cm.EnhancedDepthImageRatioPredictor(3), modules.EnhancedDepthImageRatioPredictor(3))]
+    for ref_m, own_m in pairs:
+        a = {k: tuple(v.shape) for k, v in ref_m.state_dict().items()}
+        b = {k: tuple(v.shape) for k, v in own_m.state_dict().items()}
+        assert a == b, (type(ref_m).__name__, set(a.items()) ^ set(b.items()))
+        own_m.load_state_dict(ref_m.state_dict())          # checkpoints move both ways
+        ref_m.load_state_dict(own_m.state_dict())
 
 
 def test_masked_kernel_weight_order_matches_the_premasked_layout():
