@@ -97,7 +97,8 @@ class CustomMask2FormerPixelLevelModule(Mask2FormerPixelLevelModule):
     def to_grayscale(self, image_data):
         """CM:392-502.  ndarray (H,W,3) / (3,H,W) / (H,W,1) / (1,H,W) / (H,W) -> (H,W) ndarray of the input dtype (host
         arithmetic, as in the reference); tensor (3,H,W) / (H,W,3) / (1,H,W) / (H,W,1) -> (1,H,W), (B,C,H,W) -> (B,1,H,W);
-        float32 CUDA tensors go through the device kernel (bit-exact ``(0.299 r + 0.587 g) + 0.114 b``)."""
+        CUDA tensors go through the device kernel (``(0.299 r + 0.587 g) + 0.114 b`` in float32, bit-exact for float32 and
+        integer inputs)."""
         import numpy as np
         from . import functional as Fn
         if isinstance(image_data, np.ndarray):
@@ -141,9 +142,10 @@ class CustomMask2FormerPixelLevelModule(Mask2FormerPixelLevelModule):
         if channels != 3:
             raise ValueError("Input PyTorch Tensor image should be grayscale or RGB (channels 1 or 3).")
         x = t if batched else t[None]
-        if x.dtype != torch.float32:
-            raise ValueError("rgbd_b200.to_grayscale runs on float32 tensors (the dtype of pixel_values)")
-        gray = Fn.to_grayscale(x.contiguous())
+        # float32 (the dtype of pixel_values) is bit-exact with the reference.  Other dtypes are computed in float32 and cast
+        # back (CM:499 ``.to(image_data.dtype)``): identical for integer tensors, whose products torch promotes to float32
+        # anyway; float16 / bfloat16 / float64 tensors differ from the reference's per-operation rounding in the last bits.
+        gray = Fn.to_grayscale(x.float().contiguous()).to(t.dtype)
         return gray[:, None] if batched else gray
 
     def forward(self, pixel_values: Tensor, output_hidden_states: bool = False) -> Mask2FormerPixelLevelModuleOutput:

@@ -164,6 +164,16 @@ def test_to_grayscale_method_mirrors_the_reference(golden_dir):
     assert plm.to_grayscale(u8[:, :, :1]).shape == (9, 11) and plm.to_grayscale(u8[:, :, 0]).shape == (9, 11)
     if "ref0" in g.files and "in0" in g.files:
         assert np.array_equal(plm.to_grayscale(torch.from_numpy(g["in0"]).cuda()).cpu().numpy()[0], g["ref0"])
+    # other tensor dtypes: float32 arithmetic, result cast back (CM:499); uint8 equals the reference's own arithmetic (torch
+    # promotes python-float x uint8 to float32 and truncates on the cast), float64 agrees to float32 precision
+    tu8 = torch.from_numpy(np.ascontiguousarray(u8.transpose(2, 0, 1)))
+    ref_u8 = (0.299 * tu8[0] + 0.587 * tu8[1] + 0.114 * tu8[2]).unsqueeze(0).to(torch.uint8)
+    got_u8 = plm.to_grayscale(tu8.cuda())
+    assert got_u8.dtype == torch.uint8 and torch.equal(got_u8.cpu(), ref_u8)
+    t64 = torch.randn(2, 3, 6, 8, dtype=torch.float64)
+    ref64 = (0.299 * t64[:, 0] + 0.587 * t64[:, 1] + 0.114 * t64[:, 2]).unsqueeze(1)
+    got64 = plm.to_grayscale(t64.cuda())
+    assert got64.dtype == torch.float64 and got64.shape == (2, 1, 6, 8) and torch.allclose(got64.cpu(), ref64, rtol=1e-6, atol=1e-6)
     with pytest.raises(TypeError):
         plm.to_grayscale([[1.0]])
     with pytest.raises(ValueError):
