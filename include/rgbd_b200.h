@@ -23,7 +23,7 @@ extern "C" {
 
 typedef void* rgbd_stream_t; /* cudaStream_t */
 
-#define RGBD_ABI_VERSION 2
+#define RGBD_ABI_VERSION 3
 #define RGBD_HIST_BINS 512 /* CM:701 `bins=512` */
 
 #define RGBD_DTYPE_F32 0
@@ -110,9 +110,9 @@ int rgbd_dsam_pack(const float* feat, const uint8_t* codes, void* out_bf16, int 
 int rgbd_group_norm_inplace(float* x, const float* gamma, const float* beta, int B, int C, int HW, int groups, float eps,
                             rgbd_stream_t stream);
 
-/* Row-im2col of the 3-channel depth image for the predictor's multi-scale stem (CM:1458-1460):
- * out[img][H+6][W][64] bf16, channel (j*8+dx)*4+c = depth[img][c][r-3+j][x+dx-3]. */
-int rgbd_ratio_stem_pack(const float* depth3, long long batch_stride, long long channel_stride, void* out_bf16, int B,
+/* Row-im2col of the C-channel depth image (C = input_channels of the predictor, 1..4; the reference default is 3) for the
+ * multi-scale stem (CM:1458-1460): out[img][H+6][W][64] bf16, channel (j*8+dx)*4+c = depth[img][c][r-3+j][x+dx-3], zero for c >= C. */
+int rgbd_ratio_stem_pack(const float* depth3, long long batch_stride, long long channel_stride, void* out_bf16, int B, int C,
                          int H, int W, rgbd_stream_t stream);
 
 /* Implicit-GEMM convolution on tcgen05/TMEM (see csrc/conv_gemm.cu).  A: bf16 channels-last tensor viewed as
@@ -213,7 +213,7 @@ int rgbd_ratio_front(const void* r_bf16, const void* w1_bf16, const void* w2_bf1
  * ordered (dy 7, dx 8, c 4); needs bx = 128, by = 1 and an even W. */
 int rgbd_ratio_stem_compact_width(int W);
 int rgbd_ratio_stem_pack_compact(const float* depth3, long long batch_stride, long long channel_stride, void* out_bf16, int B,
-                                 int H, int W, rgbd_stream_t stream);
+                                 int C, int H, int W, rgbd_stream_t stream);
 
 /* Tail of EnhancedDepthImageRatioPredictor.forward (CM:1473-1485): pooled sums -> conv3x3 256->512 + folded BN +
  * ReLU -> GAP -> MLP -> 0.01 + 0.49*sigmoid.  conv_w (512,256,3,3) fp32; fc_w_host/fc_b_host: 4 layers. */

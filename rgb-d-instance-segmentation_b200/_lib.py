@@ -10,7 +10,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librgbd_b200.so")
 
-ABI_VERSION = 2          # RGBD_ABI_VERSION of include/rgbd_b200.h this binding was written against
+ABI_VERSION = 3          # RGBD_ABI_VERSION of include/rgbd_b200.h this binding was written against
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int)
@@ -62,7 +62,7 @@ SIGNATURES = {
                                  C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "rgbd_group_norm_inplace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                           C.c_void_p]),
-    "rgbd_ratio_stem_pack": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int,
+    "rgbd_ratio_stem_pack": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p]),
     "rgbd_conv_gemm": (C.c_int, [C.POINTER(ConvGemmDesc), C.c_void_p]),
     "rgbd_cast_bf16_pitched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
@@ -76,7 +76,7 @@ SIGNATURES = {
     "rgbd_ratio_front": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 6 + [C.c_void_p]),
     "rgbd_ratio_stem_compact_width": (C.c_int, [C.c_int]),
     "rgbd_ratio_stem_pack_compact": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                               C.c_void_p]),
+                                               C.c_int, C.c_void_p]),
     "rgbd_depth_helper_workspace_bytes": (C.c_size_t, [C.c_int]),
     "rgbd_to_grayscale": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p,
                                     C.c_void_p]),

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) dsam_pack_kernel(const float* __restrict_
 }
 
 __global__ void __launch_bounds__(256) ratio_stem_pack_kernel(const float* __restrict__ depth, long long bs, long long cs,
-                                                              __nv_bfloat16* __restrict__ out, int H, int W) {
+                                                              __nv_bfloat16* __restrict__ out, int H, int W, int C) {
     // thread = (pixel, piece): piece p of 8 holds taps dx = 2*(p&3), 2*(p&3)+1 of row j = p>>2  (8 bf16 = 16 bytes);
     // the 8 lanes of a pixel write its 128-byte row contiguously, a warp writes 4 pixels = 512 contiguous bytes
     const int img = blockIdx.z;
@@ -158,8 +158,7 @@ __global__ void __launch_bounds__(256) ratio_stem_pack_kernel(const float* __res
         const int xs = x + dx - 3;
         const bool ok = yok && dx < 7 && xs >= 0 && xs < W;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[e * 4 + c] = ok ? __ldg(d + c * cs + (size_t)y * W + xs) : 0.f;
-        v[e * 4 + 3] = 0.f;
+        for (int c = 0; c < 4; ++c) v[e * 4 + c] = (ok && c < C) ? __ldg(d + c * cs + (size_t)y * W + xs) : 0.f;
     }
     uint4 w;
     __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -174,7 +173,7 @@ __global__ void __launch_bounds__(256) ratio_stem_pack_kernel(const float* __res
 // Compact stem operand E[img][s][r][xx][4] = depth[img][c][r-3][xx+s-3] (0 outside / for c == 3): the depth image itself,
 // channels-last with zero borders, in two copies shifted by one pixel (ratio_front.cu reads 64-byte sliding windows of it).
 __global__ void __launch_bounds__(256) ratio_stem_pack_compact_kernel(const float* __restrict__ depth, long long bs, long long cs,
-                                                                      __nv_bfloat16* __restrict__ out, int H, int W, int Wp) {
+                                                                      __nv_bfloat16* __restrict__ out, int H, int W, int Wp, int C) {
     const int img = blockIdx.z, r = blockIdx.y;
     const int xx = blockIdx.x * blockDim.x + threadIdx.x;
     if (xx >= Wp) return;
@@ -185,10 +184,10 @@ __global__ void __launch_bounds__(256) ratio_stem_pack_compact_kernel(const floa
     for (int s = 0; s < 2; ++s) {
         const int xs = xx + s - 3;
         const bool ok = yok && xs >= 0 && xs < W;
-        float v[3];
+        float v[4];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = ok ? __ldg(d + c * cs + (size_t)y * W + xs) : 0.f;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], 0.f);
+        for (int c = 0; c < 4; ++c) v[c] = (ok && c < C) ? __ldg(d + c * cs + (size_t)y * W + xs) : 0.f;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
         uint2 w;
         w.x = *reinterpret_cast<uint32_t*>(&h0);
         w.y = *reinterpret_cast<uint32_t*>(&h1);
@@ -201,13 +200,13 @@ __global__ void __launch_bounds__(256) ratio_stem_pack_compact_kernel(const floa
 extern "C" int rgbd_ratio_stem_compact_width(int W) { return W + 8; }
 
 extern "C" int rgbd_ratio_stem_pack_compact(const float* depth3, long long batch_stride, long long channel_stride, void* out_bf16,
-                                            int B, int H, int W, rgbd_stream_t stream) {
+                                            int B, int C, int H, int W, rgbd_stream_t stream) {
     RGBD_CHECK_ARG(depth3 && out_bf16, "ratio_stem_pack_compact: null pointer");
-    RGBD_CHECK_ARG(B >= 1 && H >= 1 && W >= 1, "ratio_stem_pack_compact: bad geometry");
+    RGBD_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && C >= 1 && C <= 4, "ratio_stem_pack_compact: bad geometry (1..4 channels)");
     const int Wp = rgbd_ratio_stem_compact_width(W);
     dim3 grid(ceil_div(Wp, 256), H + 6, B);
     ratio_stem_pack_compact_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(depth3, batch_stride, channel_stride,
-                                                                           (__nv_bfloat16*)out_bf16, H, W, Wp);
+                                                                           (__nv_bfloat16*)out_bf16, H, W, Wp, C);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }
@@ -239,12 +238,12 @@ extern "C" int rgbd_dsam_pack(const float* feat, const uint8_t* codes, void* out
 }
 
 extern "C" int rgbd_ratio_stem_pack(const float* depth3, long long batch_stride, long long channel_stride, void* out_bf16,
-                                    int B, int H, int W, rgbd_stream_t stream) {
+                                    int B, int C, int H, int W, rgbd_stream_t stream) {
     RGBD_CHECK_ARG(depth3 && out_bf16, "ratio_stem_pack: null pointer");
-    RGBD_CHECK_ARG(B >= 1 && H >= 1 && W >= 1, "ratio_stem_pack: bad geometry");
+    RGBD_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && C >= 1 && C <= 4, "ratio_stem_pack: bad geometry (1..4 channels)");
     dim3 grid(ceil_div(W * 8, 256), H + 6, B);
     ratio_stem_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(depth3, batch_stride, channel_stride,
-                                                                   (__nv_bfloat16*)out_bf16, H, W);
+                                                                   (__nv_bfloat16*)out_bf16, H, W, C);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }

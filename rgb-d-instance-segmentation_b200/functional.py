@@ -559,8 +559,10 @@ def ratio_stem_pack(depth3: torch.Tensor, out: torch.Tensor) -> None:
     _req(depth3, "depth", torch.float32, False)
     _req(out, "stem operand", torch.bfloat16)
     B, c3, H, W = depth3.shape
+    if not 1 <= c3 <= 4:
+        raise RgbdB200Error("the stem operand holds 1..4 input channels")
     bs, cs = _plane_strided(depth3, "depth")
-    check(lib.rgbd_ratio_stem_pack(depth3.data_ptr(), bs, cs, out.data_ptr(), B, H, W, _stream()), "rgbd_ratio_stem_pack")
+    check(lib.rgbd_ratio_stem_pack(depth3.data_ptr(), bs, cs, out.data_ptr(), B, c3, H, W, _stream()), "rgbd_ratio_stem_pack")
     _count(1)
 
 
@@ -576,8 +578,10 @@ def ratio_stem_pack_compact(depth3: torch.Tensor, out: torch.Tensor) -> None:
     B, c3, H, W = depth3.shape
     if out.shape != (B, 2, H + 6, ratio_stem_compact_width(W), 4):
         raise RgbdB200Error("ratio_stem_pack_compact: out must be (B,2,H+6,Wp,4)")
+    if not 1 <= c3 <= 4:
+        raise RgbdB200Error("the stem operand holds 1..4 input channels")
     bs, cs = _plane_strided(depth3, "depth")
-    check(lib.rgbd_ratio_stem_pack_compact(depth3.data_ptr(), bs, cs, out.data_ptr(), B, H, W, _stream()),
+    check(lib.rgbd_ratio_stem_pack_compact(depth3.data_ptr(), bs, cs, out.data_ptr(), B, c3, H, W, _stream()),
           "rgbd_ratio_stem_pack_compact")
     _count(1)
 

@@ -551,8 +551,8 @@ class EnhancedDepthImageRatioPredictor(_PackedCacheMixin, nn.Module):
 
     def __init__(self, input_channels: int = 3):
         super().__init__()
-        if input_channels != 3:
-            raise ValueError("rgbd_b200's fused stem is built for 3-channel depth images")
+        if not 1 <= input_channels <= 4:
+            raise ValueError("rgbd_b200's stem operand holds 1..4 input channels per pixel (the reference default is 3)")
         self.input_channels = input_channels
         self.scale1_conv = nn.Sequential(nn.Conv2d(input_channels, 64, kernel_size=3, padding=1), nn.BatchNorm2d(64), nn.ReLU(inplace=True))
         self.scale2_conv = nn.Sequential(nn.Conv2d(input_channels, 64, kernel_size=5, padding=2), nn.BatchNorm2d(64), nn.ReLU(inplace=True))
@@ -598,10 +598,10 @@ class EnhancedDepthImageRatioPredictor(_PackedCacheMixin, nn.Module):
             for idx, (seq, k) in enumerate(((self.scale1_conv, 3), (self.scale2_conv, 5), (self.scale3_conv, 7))):
                 o = (7 - k) // 2
                 wk = seq[0].weight.float()                       # (64, 3, k, k)
-                full = torch.zeros(64, 3, 8, 8, device=dev)
+                full = torch.zeros(64, self.input_channels, 8, 8, device=dev)
                 full[:, :, o:o + k, o:o + k] = wk
                 # (n, c, dy, dx) -> (n, t, j, dx, c)
-                w1[idx * 64:(idx + 1) * 64, :, :, :, :3] = full.reshape(64, 3, 4, 2, 8).permute(0, 2, 3, 4, 1)
+                w1[idx * 64:(idx + 1) * 64, :, :, :, :self.input_channels] = full.reshape(64, self.input_channels, 4, 2, 8).permute(0, 2, 3, 4, 1)
                 s, h = _fold_bn(seq[0].bias, seq[1])
                 sc1.append(s)
                 sh1.append(h)
@@ -693,9 +693,9 @@ class EnhancedDepthImageRatioPredictor(_PackedCacheMixin, nn.Module):
             w1 = torch.zeros(192, 4, 2, 8, 4, device=dev, dtype=torch.float32)
             for idx, (seq, k) in enumerate(((self.scale1_conv, 3), (self.scale2_conv, 5), (self.scale3_conv, 7))):
                 o = (7 - k) // 2
-                full = torch.zeros(64, 3, 8, 8, device=dev)
+                full = torch.zeros(64, self.input_channels, 8, 8, device=dev)
                 full[:, :, o:o + k, o:o + k] = seq[0].weight.float()
-                w1[idx * 64:(idx + 1) * 64, :, :, :, :3] = full.reshape(64, 3, 4, 2, 8).permute(0, 2, 3, 4, 1)
+                w1[idx * 64:(idx + 1) * 64, :, :, :, :self.input_channels] = full.reshape(64, self.input_channels, 4, 2, 8).permute(0, 2, 3, 4, 1)
             pk = {"w1": w1.reshape(192, 256).contiguous(),
                   "w2": self.feature_fusion[0].weight.float().reshape(128, 192).contiguous(),
                   "w5": self.feature_extractor[0].weight.float().permute(0, 2, 3, 1).reshape(256, 9 * 128).contiguous()}

@@ -1267,3 +1267,22 @@ def test_depth_guidance_fine_tuning_step_with_train_mode_predictor(mods):
     for k, v in m.ratio_predictor.state_dict().items():      # the step moved the running statistics like the reference would
         if "running" in k:
             assert rel_err(v, w_after[k]) < BF16_TOL, k
+
+
+@pytest.mark.parametrize("c_in,hw", [(1, (48, 64)), (4, (24, 40)), (2, (33, 47))])
+def test_ratio_predictor_other_input_channel_counts(mods, c_in, hw):
+    """``EnhancedDepthImageRatioPredictor(input_channels=c)`` for c = 1..4 (the reference default is 3; the stem operand pads
+    every pixel to four channels), compact and row-im2col operands."""
+    w = OW.ratio_weights(seed=540 + c_in, c_in=c_in)
+    m = mods.EnhancedDepthImageRatioPredictor(c_in)
+    m.load_state_dict(w)
+    m.cuda().eval()
+    x = torch.from_numpy(np.random.RandomState(c_in).randn(2, c_in, *hw).astype(np.float32))
+    ref = O.ratio_predictor_forward(w, x)
+    with torch.no_grad():
+        r = m(x.cuda())
+        m.use_compact_operand = False
+        r2 = m(x.cuda())
+    assert float(((r.cpu() - ref).abs() / ref).max()) < BF16_TOL and float(((r2.cpu() - ref).abs() / ref).max()) < BF16_TOL
+    with pytest.raises(ValueError):
+        mods.EnhancedDepthImageRatioPredictor(5)
