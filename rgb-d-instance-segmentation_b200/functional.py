@@ -376,6 +376,18 @@ def depth_decompose(ratio: torch.Tensor, levels: Sequence[Tuple[int, int]], dept
 POOL_FIXED_ONE = float(1 << 24)      # RGBD_POOL_FIXED_ONE: unit of the fixed-point cell sums of conv_gemm's epilogue mode 2
 
 
+def best_box(out_h: int, out_w: int) -> Tuple[int, int]:
+    """(bx, by) with bx*by == 128 covering an out_h x out_w image with the least padding (the GEMM's 128-pixel M tile)."""
+    best, best_eff = (128, 1), -1.0
+    for bx in (128, 64, 32, 16, 8, 4, 2, 1):
+        by = 128 // bx
+        cover = (-(-out_w // bx) * bx) * (-(-out_h // by) * by)
+        eff = out_h * out_w / cover
+        if eff > best_eff + 1e-9:
+            best, best_eff = (bx, by), eff
+    return best
+
+
 def pick_block_n(n_pad: int) -> int:
     if n_pad <= 256:
         return n_pad
@@ -489,13 +501,7 @@ def project_group_norm(x: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[t
     check(lib.rgbd_dsam_pack(x.data_ptr(), None, a.data_ptr(), B, Cc, c_pad, h, w, 1, 0, 0, 0, _stream()), "rgbd_dsam_pack")
     _count(1)
     out = torch.empty(B, N, h, w, device=x.device, dtype=torch.float32)
-    best, best_eff = (128, 1), -1.0
-    for bx in (128, 64, 32, 16, 8, 4, 2, 1):
-        by = 128 // bx
-        eff = h * w / ((-(-w // bx) * bx) * (-(-h // by) * by))
-        if eff > best_eff + 1e-9:
-            best, best_eff = (bx, by), eff
-    conv_gemm(a, (B, h, w, c_pad), 1, wk, sl, 64, B, (h, w), best, N, bias, epi_mode=1, out=out)
+    conv_gemm(a, (B, h, w, c_pad), 1, wk, sl, 64, B, (h, w), best_box(h, w), N, bias, epi_mode=1, out=out)
     check(lib.rgbd_group_norm_inplace(out.data_ptr(), _req(gn_w.detach().float().contiguous(), "gamma", torch.float32).data_ptr(),
                                       _req(gn_b.detach().float().contiguous(), "beta", torch.float32).data_ptr(), B, N, h * w,
                                       int(groups), float(eps), _stream()), "rgbd_group_norm_inplace")

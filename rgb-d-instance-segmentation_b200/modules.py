@@ -32,16 +32,7 @@ def _round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
-def _best_box(out_h: int, out_w: int) -> Tuple[int, int]:
-    """(bx, by) with bx*by == 128 covering an out_h x out_w image with the least padding."""
-    best, best_eff = (128, 1), -1.0
-    for bx in (128, 64, 32, 16, 8, 4, 2, 1):
-        by = 128 // bx
-        cover = (-(-out_w // bx) * bx) * (-(-out_h // by) * by)
-        eff = out_h * out_w / cover
-        if eff > best_eff + 1e-9:
-            best, best_eff = (bx, by), eff
-    return best
+_best_box = Fn.best_box
 
 
 #: workspaces kept alive per module (distinct batch sizes / resolutions, e.g. a last partial batch); oldest evicted first
