@@ -150,32 +150,30 @@ __device__ __forceinline__ float bin_edge(const ImgState& s, int i) {
     return y + s.first;
 }
 
-__global__ void __launch_bounds__(256) decomp_hist_kernel(const float* __restrict__ gray, const ImgState* __restrict__ st,
-                                                          unsigned long long* __restrict__ hist, int HW) {
-    __shared__ unsigned int h[8][kBins];            // one sub-histogram per warp: no atomics contention between warps
-    const int b = blockIdx.y;
-    ImgState s = st[b];
-    compute_range(s);
-    for (int i = threadIdx.x; i < 8 * kBins; i += blockDim.x) (&h[0][0])[i] = 0u;
-    __syncthreads();
-    if (s.status & RGBD_DECOMP_RANGE_NOT_FINITE) return;
-    const float* in = gray + (long long)b * HW;
-    unsigned int* hw = h[threadIdx.x >> 5];
-    // neighbouring pixels of a depth image mostly share a bin (8-bit depth: 256 distinct values): the lanes of a warp that hit
-    // the same bin elect one leader that adds their count -- one shared-memory atomic per distinct bin instead of a
-    // serialised 32-way conflict.  Four pixels per thread and iteration (one 128-bit load) with the next load issued before
-    // the current one is binned: the loop is bound by the latency of its loads otherwise.
+// the binning loop of one CTA.  STEP_ZERO (numpy's denormal-range special case, uniform per image) is a template parameter:
+// as a run-time select inside bin_edge it costs two extra IEEE divisions per pixel (the kernel is issue-bound: ncu).
+template <bool STEP_ZERO>
+__device__ __forceinline__ void hist_accumulate(const float* __restrict__ in, int HW, const ImgState& s, unsigned int* hw) {
+    auto edge = [&](int i) -> float {
+        if (i == kBins) return s.last;
+        const float y = STEP_ZERO ? ((float)i / (float)kBins) * s.denom : (float)i * s.step;
+        return y + s.first;
+    };
     auto bin_of = [&](float x) -> int {
         int idx = -1;
         if (x >= s.first && x <= s.last) {          // drops NaN
             float f = ((x - s.first) / s.denom) * (float)kBins;
             idx = (int)f;                            // astype(intp): truncation
             if (idx == kBins) idx -= 1;
-            if (x < bin_edge(s, idx)) idx -= 1;
-            if (x >= bin_edge(s, idx + 1) && idx != kBins - 1) idx += 1;
+            if (x < edge(idx)) idx -= 1;
+            if (x >= edge(idx + 1) && idx != kBins - 1) idx += 1;
         }
         return idx;
     };
+    // neighbouring pixels of a depth image mostly share a bin (8-bit depth: 256 distinct values): the lanes of a warp that hit
+    // the same bin elect one leader that adds their count -- one shared-memory atomic per distinct bin instead of a
+    // serialised 32-way conflict.  Four pixels per thread and iteration (one 128-bit load) with the next load issued before
+    // the current one is binned.
     auto add = [&](int idx) {
         const unsigned peers = __match_any_sync(0xffffffffu, idx);
         if (idx >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hw[idx], (unsigned)__popc(peers));
@@ -203,6 +201,21 @@ __global__ void __launch_bounds__(256) decomp_hist_kernel(const float* __restric
             add(bin_of(i < HW ? in[i] : nan));
         }
     }
+}
+
+__global__ void __launch_bounds__(256) decomp_hist_kernel(const float* __restrict__ gray, const ImgState* __restrict__ st,
+                                                          unsigned long long* __restrict__ hist, int HW) {
+    __shared__ unsigned int h[8][kBins];            // one sub-histogram per warp: no atomics contention between warps
+    const int b = blockIdx.y;
+    ImgState s = st[b];
+    compute_range(s);
+    for (int i = threadIdx.x; i < 8 * kBins; i += blockDim.x) (&h[0][0])[i] = 0u;
+    __syncthreads();
+    if (s.status & RGBD_DECOMP_RANGE_NOT_FINITE) return;
+    const float* in = gray + (long long)b * HW;
+    unsigned int* hw = h[threadIdx.x >> 5];
+    if (s.step_zero) hist_accumulate<true>(in, HW, s, hw);
+    else hist_accumulate<false>(in, HW, s, hw);
     __syncthreads();
     for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
         unsigned int t = 0;
