@@ -155,20 +155,23 @@ __device__ __forceinline__ float bin_edge(const ImgState& s, int i) {
 template <bool STEP_ZERO>
 __device__ __forceinline__ void hist_accumulate(const float* __restrict__ in, int HW, const ImgState& s, unsigned int* hw) {
     auto edge = [&](int i) -> float {
-        if (i == kBins) return s.last;
         const float y = STEP_ZERO ? ((float)i / (float)kBins) * s.denom : (float)i * s.step;
-        return y + s.first;
+        return i == kBins ? s.last : y + s.first;
     };
+    // numpy's uniform-bin fast path, branch-free (the kernel is issue-bound and five divergent regions per pixel cost more than
+    // the arithmetic): candidate bin by truncation, then the +-1 corrections against the float32 edges.  Equivalent to
+    //   if (idx == 512) --idx;  if (x < edge(idx)) --idx;  if (x >= edge(idx + 1) && idx != 511) ++idx;
+    // because after a decrement the third test compares x with the very edge it was just found to lie below.
     auto bin_of = [&](float x) -> int {
-        int idx = -1;
-        if (x >= s.first && x <= s.last) {          // drops NaN
-            float f = ((x - s.first) / s.denom) * (float)kBins;
-            idx = (int)f;                            // astype(intp): truncation
-            if (idx == kBins) idx -= 1;
-            if (x < edge(idx)) idx -= 1;
-            if (x >= edge(idx + 1) && idx != kBins - 1) idx += 1;
-        }
-        return idx;
+        const bool ok = x >= s.first && x <= s.last;          // drops NaN
+        const float f = ((x - s.first) / s.denom) * (float)kBins;
+        int idx = (int)f;                                      // astype(intp): truncation (garbage when !ok: clamped, discarded)
+        idx = min(max(idx, 0), kBins - 1);
+        const float e0 = edge(idx), e1 = edge(idx + 1);
+        const bool below = x < e0;
+        idx -= below ? 1 : 0;
+        idx += (!below && x >= e1 && idx != kBins - 1) ? 1 : 0;
+        return ok ? idx : -1;
     };
     // neighbouring pixels of a depth image mostly share a bin (8-bit depth: 256 distinct values): the lanes of a warp that hit
     // the same bin elect one leader that adds their count -- one shared-memory atomic per distinct bin instead of a
