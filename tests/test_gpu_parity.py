@@ -1286,3 +1286,26 @@ def test_ratio_predictor_other_input_channel_counts(mods, c_in, hw):
     assert float(((r.cpu() - ref).abs() / ref).max()) < BF16_TOL and float(((r2.cpu() - ref).abs() / ref).max()) < BF16_TOL
     with pytest.raises(ValueError):
         mods.EnhancedDepthImageRatioPredictor(5)
+
+
+def test_invalidate_packed_after_writes_that_bypass_the_version_counter(mods, fn):
+    """``weight.data.mul_()`` (EMA swaps, fused optimizers) does not bump ``_version``: the bf16-packed copies stay stale until
+    ``invalidate_packed()`` -- or a ``train()`` / ``eval()`` switch -- drops them."""
+    m = mods.DSAModule(32, 64, 3)
+    m.load_state_dict(OW.dsam_weights(32, 64, seed=9))
+    m.cuda().eval()
+    feat = torch.randn(2, 32, 16, 24, device="cuda")
+    gray = torch.from_numpy(np.stack([_gray_for(j, "nyu", (64, 96)) for j in range(2)])).cuda()
+    dec = fn.depth_decompose(torch.tensor([0.2, 0.3]).cuda(), [(16, 24)], gray=gray)
+    with torch.no_grad():
+        y0 = m.stage_forward(feat, dec.pooled[0], dec.bias_variant).clone()
+        v = m.rgb_projection.weight._version
+        m.rgb_projection.weight.data.mul_(3.0)
+        assert m.rgb_projection.weight._version == v                      # the write was invisible to the cache key
+        y_stale = m.stage_forward(feat, dec.pooled[0], dec.bias_variant).clone()
+        m.invalidate_packed()
+        y_new = m.stage_forward(feat, dec.pooled[0], dec.bias_variant).clone()
+        m.rgb_projection.weight.mul_(1.0 / 3.0)                            # a versioned write is picked up by itself
+        y_back = m.stage_forward(feat, dec.pooled[0], dec.bias_variant)
+    assert torch.equal(y_stale, y0) and not torch.equal(y_new, y0)
+    assert rel_err(y_back, y0) < 1e-2
