@@ -170,7 +170,12 @@ class _DsamStageFunction(torch.autograd.Function):
 class DSAModule(_PackedCacheMixin, nn.Module):
     """CM:622-799.  Depth-sensitive attention: depth histogram modes -> depth-interval region masks ->
     sum_t Conv_t(mask_t * F) + projection(F).  ``in != out``: 3x3 stride-2 convs + bias-free 3x3 stride-2
-    ``rgb_projection``; ``in == out``: 1x1 convs + identity residual."""
+    ``rgb_projection``; ``in == out``: 1x1 convs + identity residual.
+
+    One difference from the reference under autograd: a region conv that no image of the batch used (fewer than three depth
+    modes, CM:683-691) receives a ZERO gradient here, where the reference leaves ``.grad`` as ``None``; optimizers with weight
+    decay or momentum therefore still touch it.  (A fixed gradient layout is what lets the all-reduce buckets of
+    ``parallel.GradBucketReducer`` be static.)"""
 
     #: "bf16": bf16 operands, fp32 accumulate (what torch.autocast gives the reference; ~1e-3 relative).
     #: "fp32": split precision -- activations and weights as bf16 hi + lo parts, three tensor-core products per term
