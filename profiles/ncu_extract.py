@@ -23,7 +23,8 @@ KEEP = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__pipe_tensor_cyc
 
 def short(name: str) -> str:
     name = re.sub(r"<unnamed>::|\(anonymous namespace\)::|^void ", "", name)
-    return re.sub(r"\(.*", "", name)
+    name = re.sub(r"\(.*", "", name)
+    return re.sub(r"<[^>]*>$", "", name)          # template arguments: conv3x3_2cta_kernel<0> -> conv3x3_2cta_kernel
 
 
 def to_bytes(value: str, unit: str) -> float:
