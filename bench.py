@@ -356,6 +356,24 @@ def run_own(args):
     elapsed = parallel.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
     value = frames_per_step * args.steps / elapsed
 
+    # ---- single-frame latency of the hot path (BASELINE configs[0] shape on the GPU): batch 1, CUDA-graph replay
+    latency = None
+    try:
+        pv1, feats1 = pv[:1].clone(), [f[:1].clone() for f in feats]
+        g1 = modules.GraphedDepthGuidance(model, pv1, feats1)
+        for _ in range(3):
+            g1()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            g1()
+        e1.record()
+        torch.cuda.synchronize()
+        latency = {"batch": 1, "ms_per_frame": e0.elapsed_time(e1) / 20, "launch": "CUDA graph replay"}
+        del g1
+    except Exception as e:                                   # reported, never fatal
+        latency = {"error": repr(e)}
+
     # ---- e2e (headline): the whole RGB-D Mask2Former from pinned host uint8 frames to instance maps in pinned host memory
     e2e = None
     if not args.no_whole_model:
@@ -508,6 +526,7 @@ def run_own(args):
             "tc_util_pct_ncu": ({"source": f"static: {sp['source']} @ {sp['commit']} (batch {sp['batch']})", **sp["tc_util_pct"]}
                                 if sp else None),
             "kernel_ms_per_step": {k: v * 1e3 for k, v in kt.items()},
+            "latency_batch1": latency,
             "train": train,
             "cpu_baseline": cpu_base,
         }
