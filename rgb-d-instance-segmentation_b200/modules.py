@@ -976,6 +976,9 @@ class GraphedDepthGuidance:
 
     def __init__(self, module: DepthGuidance, pixel_values: torch.Tensor, color_feature_map: Sequence[torch.Tensor],
                  warmup: int = 2):
+        if module.training:
+            raise RgbdB200Error("GraphedDepthGuidance captures the INFERENCE path: call module.eval() first (in train mode the "
+                                "ratio predictor would update its BatchNorm statistics on every replay)")
         self.module = module
         self.pixel_values = pixel_values
         self.features = list(color_feature_map)
