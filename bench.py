@@ -13,7 +13,8 @@ on stock PyTorch and are outside the step.
 Prints ONE JSON line (rank 0).  `value` = hot-path frames/s with inputs resident in HBM.  `e2e` = the WHOLE RGB-D
 Mask2Former (reference predictor path, mask2former/predictor.py:19-36 + :697-703) fed from pinned HOST uint8 frames:
 H2D -> device front-end -> stock Swin / pixel decoder / transformer under bf16 autocast with the CUDA hot path in
-between -> device post-processing -> instance maps back in pinned host memory.  `e2e_hot_path_host_features` = the hot
+between (plus, by default, the two decoder_ops kernels inside the stock decoders; `e2e_stock_decoders` = the same loop
+without them) -> device post-processing -> instance maps back in pinned host memory.  `e2e_hot_path_host_features` = the hot
 path alone through the nn.Module API with host features (the PCIe-bound secondary of round 1).  `train` = BASELINE
 configs[3] restricted to the hot path (fwd + bwd + NCCL gradient all-reduce, batch 8 per GPU).
 """
@@ -376,14 +377,17 @@ def run_own(args):
 
     # ---- e2e (headline): the whole RGB-D Mask2Former from pinned host uint8 frames to instance maps in pinned host memory
     e2e = None
-    if not args.no_whole_model:
+    e2e_stock = None
+
+    def whole_model_e2e(fast_decoder_ops: bool):
+        nonlocal launches
         whole, _ = build_whole_model()
         whole.to(dev)
         if FORCED_RATIO is not None:
             wrp = whole.model.pixel_level_module.ratio_predictor
             wrp_forward = wrp.forward
             wrp.forward = lambda d, *a, **k: wrp_forward(d, *a, **k) * 0 + forced
-        seg = serving.RgbdInstanceSegmenter(whole, B, (H, W), threshold=POST_THRESHOLD)
+        seg = serving.RgbdInstanceSegmenter(whole, B, (H, W), threshold=POST_THRESHOLD, fast_decoder_ops=fast_decoder_ops)
         for b in range(2):
             seg.in_host[b][0].copy_(rgb_host)
             seg.in_host[b][1].copy_(depth_host)
@@ -441,15 +445,27 @@ def run_own(args):
                "ms_per_step": whole_elapsed / args.steps * 1e3,
                "how": "rgbd_b200.serving.RgbdInstanceSegmenter: pinned-host uint8 colour + depth frames -> H2D -> "
                       "rgbd_pack_pixel_values -> Mask2FormerForUniversalSegmentation (stock HF Swin-T / pixel decoder / "
-                      "transformer decoder, bf16 autocast, random-init) with the CUDA depth-guidance hot path -> device "
+                      "transformer decoder modules and weights, bf16 autocast, random-init) with the CUDA depth-guidance hot "
+                      "path" + (" and the decoder_ops kernels (rgbd_msda_fwd in the pixel decoder's 6 deformable-attention "
+                                "layers, rgbd_attention_mask in the 10 mask-predictor calls)" if fast_decoder_ops else "") +
+                      " -> device "
                       "post_process_instance_segmentation (threshold 0.0, target 480x640) -> segmentation map + labels + "
                       "scores + counts to pinned host; H2D / compute / D2H on 3 streams, 2 buffers",
                "own_kernel_launches_per_step": whole_launches_per_step,
                "hot_path_ms_per_step": hot_ms, "hot_path_share_of_step": hot_ms / (whole_elapsed / args.steps * 1e3),
                "breakdown_ms": br, "segments_last_step": int(counts.sum()), "check": e2e_check}
-        launches += whole_launches_per_step * args.steps
+        if fast_decoder_ops:
+            launches += whole_launches_per_step * args.steps
         del seg, whole
         torch.cuda.empty_cache()
+        return e2e
+
+    if not args.no_whole_model:
+        e2e = whole_model_e2e(True)
+        # the same loop with the stock decoders untouched (HF grid_sample-based deformable attention, ATen attention masks)
+        e2e_stock = whole_model_e2e(False)
+        e2e_stock = {k: e2e_stock[k] for k in ("value", "unit", "ms_per_step", "own_kernel_launches_per_step", "breakdown_ms")}
+        e2e_stock["how"] = "same pipeline with decoder_ops disabled: every kernel outside the depth-guidance hot path is stock PyTorch/cuDNN"
 
     # ---- secondary e2e: the hot path ALONE through the nn.Module API with host-resident encoder features (what round 1
     # reported as e2e).  Every step ships uint8 frames + fp32 features in and the fp32 fused features out, so it is bound by
@@ -516,6 +532,7 @@ def run_own(args):
             "dtype": "bf16", "data": "synthetic", "config": cfg,
             "launch": "CUDA graph replay of the hot-path step" if use_graph else "kernel-by-kernel launches",
             "e2e": e2e if e2e is not None else hp,
+            "e2e_stock_decoders": e2e_stock,
             "e2e_hot_path_host_features": hp,
             "gpu_launches": launches,
             "clocks": clocks,

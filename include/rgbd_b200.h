@@ -23,7 +23,7 @@ extern "C" {
 
 typedef void* rgbd_stream_t; /* cudaStream_t */
 
-#define RGBD_ABI_VERSION 3
+#define RGBD_ABI_VERSION 4
 #define RGBD_HIST_BINS 512 /* CM:701 `bins=512` */
 
 #define RGBD_DTYPE_F32 0
@@ -300,6 +300,27 @@ int rgbd_postprocess_instances(const float* class_logits, const float* mask_logi
  * torchmetrics): pred (P,pixels) and gt (G,pixels) bytes 0/1 -> iou (P,G) fp32 (0 where the union is empty). */
 int rgbd_mask_iou(const uint8_t* pred_masks, const uint8_t* gt_masks, int P, int G, long long pixels, float* iou,
                   rgbd_stream_t stream);
+
+/* ---- consumers of the fused pyramid: two inference kernels for the STOCK Hugging Face pixel decoder / transformer decoder the
+ * reference hands the hot path's output to (mask2former/utils/custom_model.py:383 `self.decoder(backbone_features)`, then
+ * Mask2FormerModel.forward -> transformer_module).  Opt-in (`pixel_level.install_fast_decoder_ops`); weights, module tree and
+ * state_dict stay Hugging Face's.
+ *
+ * rgbd_msda_fwd: `multi_scale_deformable_attention(value, spatial_shapes, sampling_locations, attention_weights)` of
+ * transformers' modeling_mask2former.py (grid_sample(bilinear, zeros, align_corners=False) per level, stack, weight, sum) in one
+ * pass.  value (B,S,H,D) f32|bf16, S = sum of level_hw_host[l] = (h_l, w_l) products (HOST array, n_levels pairs);
+ * out (B,Q,H*D) f32|bf16.  reference_points == NULL: `offsets` (B,Q,H,L,P,2) ARE the sampling locations in [0,1] and `attn`
+ * (B,Q,H,L*P) the attention weights (softmax = 0) -- the function's own signature.  reference_points (B,Q,L,2) f32 given:
+ * `offsets` are the raw sampling offsets (locations = reference + offsets / (w_l, h_l), the quotient rounded to bf16 when the
+ * offsets are bf16, as torch does under autocast) and, with softmax = 1, `attn` holds logits softmaxed over L*P here.
+ * D must be a multiple of 8. */
+int rgbd_msda_fwd(const void* value, int value_dtype, const int* level_hw_host, int n_levels, const void* offsets,
+                  int offsets_dtype, const float* reference_points, const void* attn, int attn_dtype, int softmax, void* out,
+                  int out_dtype, int B, int S, int Q, int H, int D, int P, rgbd_stream_t stream);
+/* rgbd_attention_mask: Mask2FormerMaskPredictor's masked-attention mask: mask_logits (B,Q,h,w) f32|bf16 ->
+ * out (B*heads,Q,th*tw) bytes 0/1 = sigmoid(bilinear(mask_logits -> (th,tw), align_corners=False)) < 0.5, repeated per head. */
+int rgbd_attention_mask(const void* mask_logits, int dtype, int B, int Q, int h, int w, int th, int tw, int heads, uint8_t* out,
+                        rgbd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librgbd_b200.so")
 
-ABI_VERSION = 3          # RGBD_ABI_VERSION of include/rgbd_b200.h this binding was written against
+ABI_VERSION = 4          # RGBD_ABI_VERSION of include/rgbd_b200.h this binding was written against
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int)
@@ -101,6 +101,9 @@ SIGNATURES = {
                                         C.c_float, C.c_float, C.c_void_p, C.c_void_p, c_void_pp, c_void_pp, C.c_void_p,
                                         C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_void_p]),
+    "rgbd_msda_fwd": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 6 + [C.c_void_p]),
+    "rgbd_attention_mask": (C.c_int, [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -1,0 +1,86 @@
+"""Opt-in inference kernels for the two stock Hugging Face modules that CONSUME the hot path's fused pyramid (reference
+call site mask2former/utils/custom_model.py:383 ``self.decoder(backbone_features)`` and the transformer module behind it).
+The module tree, parameter names and state_dict stay Hugging Face's: ``install_fast_decoder_ops`` only rebinds the
+``forward`` of
+
+* ``Mask2FormerPixelDecoderEncoderMultiscaleDeformableAttention`` (six encoder layers): the linear layers stay
+  ``nn.Linear`` (cuBLAS); softmax + sampling locations + ``multi_scale_deformable_attention`` (per level grid_sample, stack,
+  multiply, sum: ~80 ms per 32 frames of 480x640) run as ONE kernel, ``rgbd_msda_fwd``;
+* ``Mask2FormerMaskPredictor`` (ten calls per forward): the attention mask (bilinear resize of the (B,Q,120,160) logits, sigmoid,
+  threshold, repeat per head: ~2 ms per call in ATen's plane-serial upsample kernel) is ``rgbd_attention_mask``.
+
+Both fall back to the stock forward when autograd is recording (no backward kernels here) or the tensors are not on CUDA.
+"""
+from __future__ import annotations
+
+import types
+
+import torch
+from torch import nn
+
+from . import functional as Fn
+
+
+def _msda_attention_forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
+                            position_embeddings=None, reference_points=None, spatial_shapes_list=None, level_start_index=None,
+                            output_attentions: bool = False):
+    if (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())) or not hidden_states.is_cuda \
+            or output_attentions or reference_points is None or reference_points.shape[-1] != 2:
+        return self._rgbd_stock_forward(hidden_states, attention_mask=attention_mask, encoder_hidden_states=encoder_hidden_states,
+                                        encoder_attention_mask=encoder_attention_mask, position_embeddings=position_embeddings,
+                                        reference_points=reference_points, spatial_shapes_list=spatial_shapes_list,
+                                        level_start_index=level_start_index, output_attentions=output_attentions)
+    if position_embeddings is not None:
+        hidden_states = hidden_states + position_embeddings
+    batch_size, num_queries, _ = hidden_states.shape
+    _, sequence_length, _ = encoder_hidden_states.shape
+    if sum(h * w for h, w in spatial_shapes_list) != sequence_length:
+        raise ValueError("Make sure to align the spatial shapes with the sequence length of the encoder hidden states")
+    value = self.value_proj(encoder_hidden_states)
+    if attention_mask is not None:
+        value = value.masked_fill(attention_mask[..., None], float(0))
+    value = value.view(batch_size, sequence_length, self.n_heads, self.d_model // self.n_heads)
+    offsets = self.sampling_offsets(hidden_states).view(batch_size, num_queries, self.n_heads, self.n_levels, self.n_points, 2)
+    logits = self.attention_weights(hidden_states).view(batch_size, num_queries, self.n_heads, self.n_levels * self.n_points)
+    # the kernel emits what output_proj would read: under autocast nn.Linear casts its input to the autocast dtype anyway
+    out_dtype = value.dtype if value.dtype == torch.bfloat16 else torch.float32
+    if value.dtype not in (torch.float32, torch.bfloat16):
+        value, offsets, logits = value.float(), offsets.float(), logits.float()
+    output = Fn.msda_forward(value.contiguous(), [tuple(s) for s in spatial_shapes_list], offsets.contiguous(), logits.contiguous(),
+                             reference_points=reference_points.float().contiguous(), softmax=True, out_dtype=out_dtype)
+    return self.output_proj(output), None
+
+
+def _mask_predictor_forward(self, outputs, pixel_embeddings, attention_mask_target_size=None):
+    if torch.is_grad_enabled() or not outputs.is_cuda or attention_mask_target_size is None:
+        return self._rgbd_stock_forward(outputs, pixel_embeddings, attention_mask_target_size)
+    mask_embeddings = self.mask_embedder(outputs.transpose(0, 1))
+    outputs_mask = torch.einsum("bqc, bchw -> bqhw", mask_embeddings, pixel_embeddings)
+    logits = outputs_mask if outputs_mask.dtype in (torch.float32, torch.bfloat16) else outputs_mask.float()
+    size = attention_mask_target_size
+    size = (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
+    return outputs_mask, Fn.attention_mask(logits.contiguous(), size, self.num_heads)
+
+
+def install_fast_decoder_ops(model: nn.Module, deformable_attention: bool = True, attention_mask: bool = True) -> nn.Module:
+    """Rebind the forwards described in the module docstring on every matching submodule of ``model`` (idempotent).
+    ``uninstall_fast_decoder_ops`` restores the stock forwards."""
+    from transformers.models.mask2former import modeling_mask2former as m2f
+    for mod in model.modules():
+        if hasattr(mod, "_rgbd_stock_forward"):
+            continue
+        if deformable_attention and isinstance(mod, m2f.Mask2FormerPixelDecoderEncoderMultiscaleDeformableAttention):
+            mod._rgbd_stock_forward = mod.forward
+            mod.forward = types.MethodType(_msda_attention_forward, mod)
+        elif attention_mask and isinstance(mod, m2f.Mask2FormerMaskPredictor):
+            mod._rgbd_stock_forward = mod.forward
+            mod.forward = types.MethodType(_mask_predictor_forward, mod)
+    return model
+
+
+def uninstall_fast_decoder_ops(model: nn.Module) -> nn.Module:
+    for mod in model.modules():
+        if "_rgbd_stock_forward" in mod.__dict__:
+            del mod.__dict__["forward"]
+            del mod.__dict__["_rgbd_stock_forward"]
+    return model

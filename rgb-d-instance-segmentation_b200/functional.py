@@ -831,3 +831,67 @@ def mask_iou(pred_masks: torch.Tensor, gt_masks: torch.Tensor) -> torch.Tensor:
                                 iou.data_ptr(), _stream()), "rgbd_mask_iou")
         _count(1)
     return iou
+
+
+# ------------------------------------------------------------------------------------------------
+# consumers of the fused pyramid (stock HF pixel decoder / transformer decoder): two inference kernels
+# ------------------------------------------------------------------------------------------------
+def _dt(t: torch.Tensor, name: str) -> int:
+    if t.dtype == torch.float32:
+        return 0                                     # RGBD_DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return 1                                     # RGBD_DTYPE_BF16
+    raise RgbdB200Error(f"{name} must be float32 or bfloat16, got {t.dtype}")
+
+
+def msda_forward(value: torch.Tensor, spatial_shapes: Sequence[Tuple[int, int]], offsets_or_locations: torch.Tensor,
+                 attention: torch.Tensor, reference_points: Optional[torch.Tensor] = None, softmax: bool = False,
+                 out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """Multi-scale deformable attention sampling (``rgbd_msda_fwd``; HF ``multi_scale_deformable_attention``).
+    value (B,S,H,D); offsets_or_locations (B,Q,H,L,P,2); attention (B,Q,H,L,P) or (B,Q,H,L*P); -> (B,Q,H*D).
+    Without ``reference_points`` the second argument holds sampling locations in [0,1] and ``attention`` the weights;
+    with ``reference_points`` (B,Q,L,2) it holds raw offsets (location = reference + offset / (w_l, h_l)) and
+    ``softmax=True`` softmaxes ``attention`` over L*P inside the kernel."""
+    lib = _lib.load()
+    _req(value, "value")
+    _req(offsets_or_locations, "sampling offsets / locations")
+    _req(attention, "attention weights")
+    if value.dim() != 4 or offsets_or_locations.dim() != 6 or offsets_or_locations.shape[-1] != 2:
+        raise RgbdB200Error("msda_forward: value must be (B,S,H,D) and offsets / locations (B,Q,H,L,P,2)")
+    B, S, H, D = value.shape
+    _, Q, H2, L, P, _ = offsets_or_locations.shape
+    if offsets_or_locations.shape[0] != B or H2 != H or L != len(spatial_shapes):
+        raise RgbdB200Error("msda_forward: batch / heads / levels of value, offsets and spatial_shapes disagree")
+    if attention.numel() != B * Q * H * L * P:
+        raise RgbdB200Error(f"msda_forward: attention must hold {B * Q * H * L * P} elements, got {attention.numel()}")
+    ref = None
+    if reference_points is not None:
+        ref = _req(reference_points, "reference_points", torch.float32)
+        if tuple(ref.shape) != (B, Q, L, 2):
+            raise RgbdB200Error(f"reference_points must be {(B, Q, L, 2)}, got {tuple(ref.shape)}")
+    elif softmax:
+        raise RgbdB200Error("msda_forward: softmax=True belongs to the fused mode (reference_points given)")
+    hw = int_array([v for s in spatial_shapes for v in (int(s[0]), int(s[1]))])
+    out = torch.empty(B, Q, H * D, device=value.device, dtype=out_dtype)
+    check(lib.rgbd_msda_fwd(value.data_ptr(), _dt(value, "value"), hw, L, offsets_or_locations.data_ptr(),
+                            _dt(offsets_or_locations, "offsets"), ref.data_ptr() if ref is not None else None,
+                            attention.data_ptr(), _dt(attention, "attention"), int(bool(softmax)), out.data_ptr(),
+                            _dt(out, "out"), B, S, Q, H, D, P, _stream()), "rgbd_msda_fwd")
+    _count(1)
+    return out
+
+
+def attention_mask(mask_logits: torch.Tensor, target_size: Tuple[int, int], num_heads: int) -> torch.Tensor:
+    """``rgbd_attention_mask``: (B,Q,h,w) mask logits -> (B*heads, Q, th*tw) bool, True where
+    sigmoid(bilinear(mask_logits -> target_size, align_corners=False)) < 0.5 (HF ``Mask2FormerMaskPredictor``)."""
+    lib = _lib.load()
+    _req(mask_logits, "mask_logits")
+    if mask_logits.dim() != 4:
+        raise RgbdB200Error("attention_mask: mask_logits must be (B,Q,h,w)")
+    B, Q, h, w = mask_logits.shape
+    th, tw = int(target_size[0]), int(target_size[1])
+    out = torch.empty(B * num_heads, Q, th * tw, device=mask_logits.device, dtype=torch.bool)
+    check(lib.rgbd_attention_mask(mask_logits.data_ptr(), _dt(mask_logits, "mask_logits"), B, Q, h, w, th, tw, int(num_heads),
+                                  out.data_ptr(), _stream()), "rgbd_attention_mask")
+    _count(1)
+    return out

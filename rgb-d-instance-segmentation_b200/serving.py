@@ -5,7 +5,8 @@ What ``predictor.predictor`` / ``process_prediction`` do per image in the refere
 
     pinned uint8 colour + depth  --H2D-->  rgbd_pack_pixel_values (K0: normalise + Sobel features, DL:386-425)
         -> RGB-D Mask2Former (stock Swin / pixel decoder / transformer decoder under bf16 autocast; the depth-guidance
-           hot path CM:324-355 on this library's kernels)
+           hot path CM:324-355 on this library's kernels; by default also the two decoder_ops kernels inside the stock
+           decoders: deformable-attention sampling and the masked-attention mask)
         -> device post-processing (K5)  --D2H-->  pinned segmentation map + per-segment labels / scores / counts
 
 Only ~1.2 MB per 480x640 frame crosses the host link on the way in and the painted instance map on the way out; encoder
@@ -28,10 +29,17 @@ class RgbdInstanceSegmenter:
     (``pixel_level.build_rgbd_mask2former``), already on ``device`` and in eval mode."""
 
     def __init__(self, model, batch: int, frame_hw: Tuple[int, int], threshold: float = 0.5,
-                 target_size: Optional[Tuple[int, int]] = None, autocast_dtype: Optional[torch.dtype] = torch.bfloat16):
+                 target_size: Optional[Tuple[int, int]] = None, autocast_dtype: Optional[torch.dtype] = torch.bfloat16,
+                 fast_decoder_ops: bool = True):
         p = next(model.parameters())
         if not p.is_cuda:
             raise RgbdB200Error("RgbdInstanceSegmenter: the model must live on a CUDA device (no CPU path)")
+        from . import decoder_ops
+        if fast_decoder_ops:     # rgbd_msda_fwd / rgbd_attention_mask inside the stock pixel decoder / transformer decoder
+            decoder_ops.install_fast_decoder_ops(model)
+        else:
+            decoder_ops.uninstall_fast_decoder_ops(model)
+        self.fast_decoder_ops = bool(fast_decoder_ops)
         self.model = model
         self.device = p.device
         self.B = int(batch)

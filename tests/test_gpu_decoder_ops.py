@@ -1,0 +1,184 @@
+"""GPU parity of the two opt-in kernels on the CONSUMER side of the hot path (csrc/msda.cu, csrc/maskattn.cu; reference
+call site mask2former/utils/custom_model.py:383 and the transformer module behind it).  The checker is Hugging Face's own
+pure-PyTorch code (transformers/models/mask2former/modeling_mask2former.py: `multi_scale_deformable_attention`, the
+deformable-attention module, `Mask2FormerMaskPredictor`) run in float32 on the CPU or, for the module-level checks, the
+stock forward of the same module object on the GPU.  Tolerances: float32 1e-5 (summation order only), bf16 1e-2."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fn():
+    import rgbd_b200  # noqa: F401
+    from rgbd_b200 import functional
+    functional._lib.load()
+    return functional
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def hf():
+    from transformers.models.mask2former import modeling_mask2former as m
+    return m
+
+
+SHAPES = {
+    "swin_t_480x640": [(15, 20), (30, 40), (60, 80)],
+    "odd": [(7, 5), (13, 9), (3, 11)],
+    "one_level": [(16, 16)],
+}
+
+
+@pytest.mark.parametrize("shapes", list(SHAPES), ids=list(SHAPES))
+@pytest.mark.parametrize("P", [4, 3])
+@pytest.mark.parametrize("vdtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_msda_function_matches_hf(fn, shapes, P, vdtype):
+    """`multi_scale_deformable_attention` signature: locations + weights given.  Locations reach outside [0,1] (zeros
+    padding), sit exactly on pixel centres and on the border."""
+    sp = SHAPES[shapes]
+    g = torch.Generator().manual_seed(11 + P)
+    B, H, D, L = 2, 8, 32, len(sp)
+    S = sum(h * w for h, w in sp)
+    Q = S
+    value = torch.randn(B, S, H, D, generator=g)
+    if vdtype == torch.bfloat16:
+        value = value.bfloat16().float()                   # exactly representable: the bf16 kernel path sees the same numbers
+    loc = torch.rand(B, Q, H, L, P, 2, generator=g) * 1.3 - 0.15
+    loc[0, 0] = 0.0
+    loc[0, 1] = 1.0
+    loc[0, 2] = 0.5
+    for l, (h, w) in enumerate(sp):                        # exact pixel centres of each level
+        loc[1, 3, :, l, :, 0] = (torch.randint(0, w, (H, P), generator=g) + 0.5) / w
+        loc[1, 3, :, l, :, 1] = (torch.randint(0, h, (H, P), generator=g) + 0.5) / h
+    loc[1, 4] = 5.0                                        # far outside: samples nothing (zeros padding)
+    attw = torch.softmax(torch.randn(B, Q, H, L * P, generator=g), -1).view(B, Q, H, L, P)
+    ref = hf().multi_scale_deformable_attention(value, sp, loc, attw)
+    got = fn.msda_forward(value.cuda().to(vdtype), sp, loc.cuda(), attw.cuda())
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    assert rel_l2(got.cpu(), ref) < 1e-5
+    assert float((got.cpu() - ref).abs().max()) < 2e-5
+    assert float(got[1, 4].abs().max()) == 0.0
+
+
+def test_msda_fused_softmax_and_locations(fn):
+    """Fused mode: raw offsets + reference points + logits, against the module's own arithmetic in float32."""
+    sp = SHAPES["swin_t_480x640"]
+    g = torch.Generator().manual_seed(5)
+    B, H, D, L, P = 2, 8, 32, 3, 4
+    S = sum(h * w for h, w in sp)
+    value = torch.randn(B, S, H, D, generator=g)
+    off = torch.randn(B, S, H, L, P, 2, generator=g) * 3.0
+    logit = torch.randn(B, S, H, L * P, generator=g) * 2.0
+    ref_pts = torch.rand(B, S, L, 2, generator=g)
+    norm = torch.tensor([[w, h] for h, w in sp], dtype=torch.long)
+    loc = ref_pts[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    attw = torch.softmax(logit, -1).view(B, S, H, L, P)
+    ref = hf().multi_scale_deformable_attention(value, sp, loc, attw)
+    got = fn.msda_forward(value.cuda(), sp, off.cuda(), logit.cuda(), reference_points=ref_pts.cuda(), softmax=True)
+    assert rel_l2(got.cpu(), ref) < 1e-5
+    got16 = fn.msda_forward(value.cuda(), sp, off.cuda(), logit.cuda(), reference_points=ref_pts.cuda(), softmax=True,
+                            out_dtype=torch.bfloat16)
+    assert got16.dtype == torch.bfloat16 and torch.equal(got16, got.bfloat16())
+
+
+def test_msda_argument_errors(fn):
+    from rgbd_b200._lib import RgbdB200Error
+    v = torch.zeros(1, 10, 2, 32, device="cuda")
+    loc = torch.zeros(1, 10, 2, 1, 4, 2, device="cuda")
+    w = torch.zeros(1, 10, 2, 1, 4, device="cuda")
+    with pytest.raises(RgbdB200Error):
+        fn.msda_forward(v, [(3, 3)], loc, w)                           # 9 != 10 rows
+    with pytest.raises(RgbdB200Error):
+        fn.msda_forward(v.cpu(), [(2, 5)], loc, w)                     # no CPU path
+    with pytest.raises(RgbdB200Error):
+        fn.msda_forward(torch.zeros(1, 10, 2, 12, device="cuda"), [(2, 5)], loc, w)   # head dim not a multiple of 8
+    with pytest.raises(RgbdB200Error):
+        fn.msda_forward(v.half(), [(2, 5)], loc, w)
+
+
+@pytest.mark.parametrize("autocast", [False, True], ids=["fp32", "bf16_autocast"])
+def test_deformable_attention_module_matches_stock_forward(fn, autocast):
+    """The rebound forward of HF's deformable-attention module against its stock forward, same module object and weights, at
+    the benchmarked geometry (480x640 Swin-T levels, 8 heads x 32 channels)."""
+    from rgbd_b200 import decoder_ops
+    m = hf()
+    torch.manual_seed(3)
+    mod = m.Mask2FormerPixelDecoderEncoderMultiscaleDeformableAttention(256, 8, 3, 4).cuda().eval()
+    for p in mod.parameters():
+        torch.nn.init.normal_(p, std=0.08)
+    sp = SHAPES["swin_t_480x640"]
+    B, S = 2, sum(h * w for h, w in sp)
+    x = torch.randn(B, S, 256, device="cuda")
+    pos = torch.randn(B, S, 256, device="cuda") * 0.3
+    ref_pts = torch.rand(B, S, 3, 2, device="cuda")
+    mask = torch.zeros(B, S, dtype=torch.bool, device="cuda")
+    mask[1, -50:] = True
+    kw = dict(attention_mask=mask, encoder_hidden_states=x, position_embeddings=pos, reference_points=ref_pts,
+              spatial_shapes_list=sp)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        stock, _ = mod(x, **kw)
+        decoder_ops.install_fast_decoder_ops(mod)
+        before = fn.LAUNCHES
+        fast, _ = mod(x, **kw)
+        assert fn.LAUNCHES == before + 1
+        decoder_ops.uninstall_fast_decoder_ops(mod)
+        again, _ = mod(x, **kw)
+    assert torch.equal(again, stock)
+    assert fast.dtype == stock.dtype
+    assert rel_l2(fast.float(), stock.float()) < (1e-2 if autocast else 1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("target", [(15, 20), (30, 40), (60, 80), (17, 23)], ids=lambda t: "%dx%d" % t)
+def test_attention_mask_matches_hf_mask_predictor(fn, dtype, target):
+    """`Mask2FormerMaskPredictor`'s attention mask (ATen bilinear resize + sigmoid + threshold + repeat), float32 /
+    bfloat16 ATen (CUDA) arithmetic as the checker."""
+    g = torch.Generator().manual_seed(target[0])
+    B, Q, h, w, heads = 2, 100, 120, 160, 8
+    logits = (torch.randn(B, Q, h, w, generator=g) * 4.0).to(dtype)
+    logits[0, 0] = 0.0                                               # sigmoid(0) = 0.5 is NOT < 0.5
+    logits[0, 1] = -1e-9 if dtype == torch.float32 else -1e-3        # rounds to 0.5 after the sigmoid
+    logits = logits.cuda()                                           # the checker is ATen's CUDA path, the one being replaced
+    a = torch.nn.functional.interpolate(logits, size=target, mode="bilinear", align_corners=False)
+    a = a.sigmoid().flatten(2).unsqueeze(1).repeat(1, heads, 1, 1)
+    ref = (a.flatten(0, 1) < 0.5).bool()
+    got = fn.attention_mask(logits, target, heads)
+    assert got.dtype == torch.bool and got.shape == ref.shape
+    diff = int((got != ref).sum())
+    assert diff == 0, f"{diff} of {ref.numel()} mask bits differ"
+    assert not bool(got[0:heads, 0].any()) and not bool(got[0:heads, 1].any())
+
+
+def test_whole_model_with_fast_decoder_ops(fn):
+    """RGB-D Mask2Former with and without the rebound forwards: same logits (float32), same attention-mask driven path."""
+    import numpy as np
+    from rgbd_b200 import decoder_ops, synthetic, synthetic_weights
+    model = synthetic_weights.build_synthetic_rgbd_mask2former()[0].eval().cuda()
+    frames = [synthetic.synth_rgbd_u8(40 + j, 128, 160) for j in range(2)]
+    rgb = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
+    depth = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+    pv = fn.pack_pixel_values(rgb, depth)
+    with torch.no_grad():
+        stock = model(pixel_values=pv)
+        decoder_ops.install_fast_decoder_ops(model)
+        before = fn.LAUNCHES
+        fast = model(pixel_values=pv)
+        used = fn.LAUNCHES - before
+        decoder_ops.uninstall_fast_decoder_ops(model)
+        used_stock_before = fn.LAUNCHES
+        model(pixel_values=pv)
+        hot_path_launches = fn.LAUNCHES - used_stock_before
+    assert used - hot_path_launches == 6 + 10                        # six encoder layers + ten mask-predictor calls
+    assert rel_l2(fast.masks_queries_logits, stock.masks_queries_logits) < 1e-3
+    assert rel_l2(fast.class_queries_logits, stock.class_queries_logits) < 1e-3

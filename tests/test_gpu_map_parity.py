@@ -74,16 +74,21 @@ def arms():
     torch.backends.cuda.matmul.allow_tf32 = False
     model.cuda()
     gpu = {}
-    for precision in ("bf16", "fp32"):
+    # third arm: fp32 hot path + the opt-in decoder kernels (decoder_ops: rgbd_msda_fwd, rgbd_attention_mask)
+    from rgbd_b200 import decoder_ops
+    for precision in ("bf16", "fp32", "fp32_fast_decoder_ops"):
         plm = model.model.pixel_level_module
         for d in (plm.dsam0, plm.dsam1, plm.dsam2):
-            d.precision = precision
+            d.precision = precision[:4]
+        if precision.endswith("fast_decoder_ops"):
+            decoder_ops.install_fast_decoder_ops(model)
         with torch.no_grad():
             outs = [model(pixel_values=pv[i:i + 8].cuda()) for i in range(0, N_FRAMES, 8)]
         cls = torch.cat([o.class_queries_logits for o in outs]).float()
         msk = torch.cat([o.masks_queries_logits for o in outs]).float()
         preds = postprocess.postprocess_prediction_batch((cls, msk), sizes, threshold=THRESHOLD)
         gpu[precision] = {"preds": preds, "cls": cls.cpu(), "msk": msk.cpu()}
+    decoder_ops.uninstall_fast_decoder_ops(model)
     return {"cpu_preds": cpu_preds, "cpu_cls": torch.cat(cpu_cls), "cpu_msk": torch.cat(cpu_msk), "gpu": gpu}
 
 
@@ -113,7 +118,7 @@ def self_targets(cpu_preds, per_image=8):
 def test_logits_and_instance_counts_match(arms):
     counts_cpu = [len(p["labels"]) for p in arms["cpu_preds"]]
     assert sum(counts_cpu) > 10 * N_FRAMES                 # the synthetic model IS decisive: many instances pass 0.5
-    for precision, tol in (("fp32", 2e-3), ("bf16", 2e-2)):
+    for precision, tol in (("fp32", 2e-3), ("fp32_fast_decoder_ops", 2e-3), ("bf16", 2e-2)):
         g = arms["gpu"][precision]
         e_cls = float((g["cls"] - arms["cpu_cls"]).norm() / arms["cpu_cls"].norm())
         e_msk = float((g["msk"] - arms["cpu_msk"]).norm() / arms["cpu_msk"].norm())
@@ -122,7 +127,7 @@ def test_logits_and_instance_counts_match(arms):
         report("map_parity_logits", precision=precision, class_logits_rel_l2=e_cls, mask_logits_rel_l2=e_msk,
                instances_cpu=counts_cpu, instances_gpu=counts)
         assert e_cls < tol and e_msk < tol, (precision, e_cls, e_msk)
-        if precision == "fp32":
+        if precision.startswith("fp32"):
             assert counts == counts_cpu, diff              # per-image instance counts equal
         else:
             assert max(abs(d) for d in diff) <= 4, diff    # bf16 operands: scores within ~1e-3 of the threshold may cross it
@@ -137,7 +142,7 @@ def test_mask_map_parity(arms, label_set):
     same = device_ap(arms["cpu_preds"], targets)
     for k in ("map", "map_50", "map_75"):
         assert abs(same[k] - ref[k]) < 1e-9, (k, same[k], ref[k])
-    for precision in ("fp32", "bf16"):
+    for precision in ("fp32", "fp32_fast_decoder_ops", "bf16"):
         got = device_ap(arms["gpu"][precision]["preds"], targets)
         report("map_parity", label_set=label_set, precision=precision, gpu=got, cpu=ref)
         for k in ("map", "map_50", "map_75"):

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rgbd_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.rgbd_abi_version() == _lib.ABI_VERSION == 4
     assert lib.rgbd_last_error() is not None
 
 
