@@ -1,0 +1,51 @@
+"""Timing driver for the two decoder_ops kernels at the benchmarked geometry (batch 32, 480x640 Swin-T: levels 15x20 / 30x40 /
+60x80, 8 heads x 32 channels, 4 points; mask logits (32,100,120,160)).  CUDA events, best / median of 5 x 10 launches.
+Usage: python profiles/msda_time.py [batch]          (ncu: add `-k regex:msda_fwd|attention_mask -c 4`)"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import rgbd_b200  # noqa: F401
+from rgbd_b200 import functional as Fn
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+sp = [(15, 20), (30, 40), (60, 80)]
+S = sum(h * w for h, w in sp)
+H, D, L, P = 8, 32, 3, 4
+g = torch.Generator(device="cuda").manual_seed(0)
+value = torch.randn(B, S, H, D, device="cuda", generator=g).bfloat16()
+offs = (torch.randn(B, S, H, L, P, 2, device="cuda", generator=g) * 2.0).bfloat16()
+logit = torch.randn(B, S, H, L * P, device="cuda", generator=g).bfloat16()
+ref = torch.rand(B, S, L, 2, device="cuda", generator=g)
+
+
+def timeit(fn, reps=5, n=10):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / n)
+    ts.sort()
+    return ts[0], ts[len(ts) // 2]
+
+
+best, med = timeit(lambda: Fn.msda_forward(value, sp, offs, logit, reference_points=ref, softmax=True, out_dtype=torch.bfloat16))
+alg = value.numel() * 2 + offs.numel() * 2 + logit.numel() * 2 + ref.numel() * 4 + B * S * H * D * 2
+gather = B * S * H * L * P * 4 * D * 2
+print("msda_fwd bf16 batch %d: best %.1f us median %.1f us; algorithmic HBM bytes %.1f MB -> %.0f GB/s; L2 gather bytes %.2f GB -> %.2f TB/s"
+      % (B, best * 1e3, med * 1e3, alg / 1e6, alg / best / 1e6, gather / 1e9, gather / best / 1e9))
+vf = value.float(); of = offs.float(); lf = logit.float()
+best, med = timeit(lambda: Fn.msda_forward(vf, sp, of, lf, reference_points=ref, softmax=True))
+print("msda_fwd f32  batch %d: best %.1f us median %.1f us" % (B, best * 1e3, med * 1e3))
+for dt in (torch.bfloat16, torch.float32):
+    ml = torch.randn(B, 100, 120, 160, device="cuda", generator=g).to(dt)
+    for tgt in sp:
+        best, med = timeit(lambda: Fn.attention_mask(ml, tgt, 8))
+        a = torch.nn.functional.interpolate(ml, size=tgt, mode="bilinear", align_corners=False)
+        stock = lambda: (torch.nn.functional.interpolate(ml, size=tgt, mode="bilinear", align_corners=False).sigmoid()
+                         .flatten(2).unsqueeze(1).repeat(1, 8, 1, 1).flatten(0, 1) < 0.5).bool()
+        sb, sm = timeit(stock, reps=3, n=3)
+        print("attention_mask %s -> %dx%d: best %.1f us median %.1f us (stock ATen chain: %.1f us)" % (str(dt)[6:], tgt[0], tgt[1], best * 1e3, med * 1e3, sb * 1e3))
