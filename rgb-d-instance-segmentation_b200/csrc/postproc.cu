@@ -4,14 +4,17 @@
 // 701-703), for a batch of same-sized images and without a host round trip per query:
 //   1. postproc_select_kernel   softmax over the classes, top-Q of the Q*C (query, label) scores (bitonic sort in
 //                               shared memory; defined order: score descending, flat index ascending on ties)
-//   2. postproc_stats_kernel    per candidate: bilinear 384x384 upsample of its mask logits evaluated on the fly
-//                               (torch's align_corners=False source-index arithmetic), pixel count of (logit > 0) and sum
-//                               of sigmoid over those pixels (deterministic two-level sum); non-emptiness of the
-//                               nearest-resized target mask
+//   2. postproc_grid_kernel     per candidate: bilinear 384x384 upsample of its mask logits evaluated on the fly in
+//                               separable form (torch's align_corners=False source-index arithmetic, operation for
+//                               operation), pixel count of (logit > 0), sum of sigmoid over those pixels (deterministic
+//                               two-level sum) and the SIGN BITMAP of the grid (18 KB per candidate);
+//      postproc_stats_kernel    point-wise fallback for very tall logit planes, and the non-emptiness of the
+//                               nearest-resized target mask when the target is smaller than the grid
 //   3. postproc_finalize_kernel mask score = sum / (count + 1e-6), score = class score * mask score, keep rule
 //                               (non-empty and score >= threshold), compact slots in candidate order
-//   4. postproc_masks_kernel    binary masks of the kept segments at the target size (nearest sample of the 384 grid),
-//                               and the painted segmentation map (id of the last kept segment covering a pixel)
+//   4. postproc_paint_kernel    binary masks of the kept segments at the target size (nearest sample of the 384 grid's sign
+//                               bitmap written by pass 2), and the painted segmentation map (id of the last kept segment
+//                               covering a pixel)
 // The 384x384 upsampled logits (59 MB per image for 100 queries) are never materialised.
 // rgbd_mask_iou: pairwise mask IoU (the evaluator's torchmetrics `iou_type="segm"` core) with 16-byte loads + popcount.
 // Compiled with -fmad=false: the interpolation is written as separate multiplies and adds like ATen's kernel.
@@ -22,6 +25,7 @@ namespace {
 
 constexpr int kGrid = 384;          // HF: "Scale back to preprocessed image size - (384, 384) for all models"
 constexpr int kChunk = 4096;        // grid points per CTA in the stats pass
+static_assert((kGrid * kGrid) % kChunk == 0 && kChunk % 256 == 0, "whole chunks, whole warps");
 constexpr int kMaxSort = 8192;      // Q*C candidates sorted in shared memory
 
 struct PostGeom {
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(256) postproc_select_kernel(const float* __res
 __global__ void __launch_bounds__(256) postproc_stats_kernel(const float* __restrict__ masks, PostGeom g,
                                                              const int* __restrict__ sel_query, int n_chunk_grid,
                                                              unsigned* __restrict__ part_cnt, float* __restrict__ part_sum,
-                                                             unsigned* __restrict__ any_target) {
+                                                             unsigned* __restrict__ any_target, unsigned* __restrict__ bitmap) {
     const int j = blockIdx.y, b = blockIdx.z;
     const int q = sel_query[(size_t)b * g.Q + j];
     const float* plane = masks + ((size_t)b * g.Q + q) * g.h * g.w;
@@ -121,12 +125,15 @@ __global__ void __launch_bounds__(256) postproc_stats_kernel(const float* __rest
         float sum = 0.f;
         const int base = blockIdx.x * kChunk;
         for (int i = threadIdx.x; i < kChunk; i += blockDim.x) {
-            const int pt = base + i;
-            if (pt >= kGrid * kGrid) break;
+            const int pt = base + i;                        // kGrid^2 is a multiple of kChunk: no partial chunk, warps stay whole
             const float v = grid_logit(plane, g, pt / kGrid, pt % kGrid);
             if (v > 0.f) {
                 ++cnt;
                 sum += 1.0f / (1.0f + expf(-v));
+            }
+            if (bitmap) {                                   // 32 consecutive grid points per warp -> one word of the sign bitmap
+                const unsigned word = __ballot_sync(0xffffffffu, v > 0.f);
+                if (lane == 0) bitmap[((size_t)b * g.Q + j) * (kGrid * (kGrid / 32)) + (pt >> 5)] = word;
             }
         }
 #pragma unroll
@@ -164,6 +171,104 @@ __global__ void __launch_bounds__(256) postproc_stats_kernel(const float* __rest
     }
 }
 
+// Grid pass, separable form (used when a band's source rows fit in shared memory).  ATen's bilinear value is
+//   ly0 * (lx0 * v[y0][x0] + lx1 * v[y0][x1]) + ly1 * (lx0 * v[y1][x0] + lx1 * v[y1][x1]):
+// the bracketed horizontal interpolations depend on (source row, grid column) only, so a CTA computes them ONCE for the source
+// rows its band of 32 grid rows touches (12 rows for 120 -> 384) and every grid point costs two multiplies and an add -- the same
+// operations in the same order as `grid_logit`, hence bit-identical.  Besides the (count, sigmoid sum) partials it writes the
+// SIGN BITMAP of the grid (384 x 12 words per candidate), which the mask pass reads instead of re-evaluating the bilinear.
+constexpr int kBand = 32;
+constexpr int kBands = kGrid / kBand;
+constexpr int kWordsPerRow = kGrid / 32;
+__global__ void __launch_bounds__(256) postproc_grid_kernel(const float* __restrict__ masks, PostGeom g,
+                                                            const int* __restrict__ sel_query, int rows_cap,
+                                                            unsigned* __restrict__ part_cnt, float* __restrict__ part_sum,
+                                                            unsigned* __restrict__ bitmap) {
+    extern __shared__ float s_t[];                          // rows_cap x kGrid horizontal interpolations
+    __shared__ int s_x0[kGrid], s_x1[kGrid];
+    __shared__ float s_lx0[kGrid], s_lx1[kGrid];
+    __shared__ unsigned s_cnt[8];
+    __shared__ float s_sum[8];
+    const int band = blockIdx.x, j = blockIdx.y, b = blockIdx.z;
+    const int q = sel_query[(size_t)b * g.Q + j];
+    const float* plane = masks + ((size_t)b * g.Q + q) * g.h * g.w;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int gx = threadIdx.x; gx < kGrid; gx += blockDim.x) {
+        float fx = __fsub_rn(__fmul_rn(g.rw, __fadd_rn((float)gx, 0.5f)), 0.5f);
+        fx = fx < 0.f ? 0.f : fx;
+        const int x0 = (int)fx;
+        s_x0[gx] = x0;
+        s_x1[gx] = x0 + (x0 < g.w - 1 ? 1 : 0);
+        const float lx1 = __fsub_rn(fx, (float)x0);
+        s_lx1[gx] = lx1;
+        s_lx0[gx] = __fsub_rn(1.f, lx1);
+    }
+    auto src_row = [&](int gy, int& y0, int& y1, float& ly0, float& ly1) {
+        float fy = __fsub_rn(__fmul_rn(g.rh, __fadd_rn((float)gy, 0.5f)), 0.5f);
+        fy = fy < 0.f ? 0.f : fy;
+        y0 = (int)fy;
+        y1 = y0 + (y0 < g.h - 1 ? 1 : 0);
+        ly1 = __fsub_rn(fy, (float)y0);
+        ly0 = __fsub_rn(1.f, ly1);
+    };
+    int y_lo, y_hi, t0, t1;
+    float f0, f1;
+    src_row(band * kBand, y_lo, t1, f0, f1);
+    src_row(band * kBand + kBand - 1, t0, y_hi, f0, f1);
+    const int rows = y_hi - y_lo + 1;                       // <= rows_cap (checked on the host)
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * kGrid; i += blockDim.x) {
+        const int r = i / kGrid, gx = i - r * kGrid;
+        const float* row = plane + (size_t)(y_lo + r) * g.w;
+        s_t[i] = __fadd_rn(__fmul_rn(s_lx0[gx], __ldg(row + s_x0[gx])), __fmul_rn(s_lx1[gx], __ldg(row + s_x1[gx])));
+    }
+    __syncthreads();
+    unsigned cnt = 0;
+    float sum = 0.f;
+    unsigned* bm = bitmap + ((size_t)b * g.Q + j) * (kGrid * kWordsPerRow);
+    for (int gl = warp; gl < kBand; gl += 8) {
+        const int gy = band * kBand + gl;
+        int y0, y1;
+        float ly0, ly1;
+        src_row(gy, y0, y1, ly0, ly1);
+        const float* top = s_t + (y0 - y_lo) * kGrid;
+        const float* bot = s_t + (y1 - y_lo) * kGrid;
+#pragma unroll 4
+        for (int k = 0; k < kWordsPerRow; ++k) {
+            const int gx = k * 32 + lane;
+            const float v = __fadd_rn(__fmul_rn(ly0, top[gx]), __fmul_rn(ly1, bot[gx]));
+            const bool pos = v > 0.f;
+            if (pos) {
+                ++cnt;
+                sum += 1.0f / (1.0f + expf(-v));
+            }
+            const unsigned word = __ballot_sync(0xffffffffu, pos);
+            if (lane == 0) bm[gy * kWordsPerRow + k] = word;
+        }
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, k);
+        sum += __shfl_xor_sync(0xffffffffu, sum, k);
+    }
+    if (lane == 0) {
+        s_cnt[warp] = cnt;
+        s_sum[warp] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned c = 0;
+        float sm = 0.f;
+        for (int k = 0; k < 8; ++k) {
+            c += s_cnt[k];
+            sm += s_sum[k];
+        }
+        const size_t o = ((size_t)b * g.Q + j) * kBands + band;
+        part_cnt[o] = c;
+        part_sum[o] = sm;
+    }
+}
+
 __global__ void __launch_bounds__(256) postproc_finalize_kernel(PostGeom g, float threshold, int n_chunk_grid,
                                                                 const float* __restrict__ sel_score,
                                                                 const int* __restrict__ sel_query,
@@ -171,7 +276,7 @@ __global__ void __launch_bounds__(256) postproc_finalize_kernel(PostGeom g, floa
                                                                 const unsigned* __restrict__ part_cnt,
                                                                 const float* __restrict__ part_sum,
                                                                 const unsigned* __restrict__ any_target, int* __restrict__ slot,
-                                                                int* __restrict__ out_labels, float* __restrict__ out_scores,
+                                                                int* __restrict__ inv_slot, int* __restrict__ out_labels, float* __restrict__ out_scores,
                                                                 int* __restrict__ out_query, int* __restrict__ out_count) {
     extern __shared__ float s_pred[];           // Q predicted scores, then Q keep flags
     int* s_keep = reinterpret_cast<int*>(s_pred + g.Q);
@@ -197,6 +302,7 @@ __global__ void __launch_bounds__(256) postproc_finalize_kernel(PostGeom g, floa
         for (int j = 0; j < g.Q; ++j) {
             if (s_keep[j]) {
                 slot[(size_t)b * g.Q + j] = n;
+                inv_slot[(size_t)b * g.Q + n] = j;
                 out_labels[(size_t)b * g.Q + n] = sel_label[(size_t)b * g.Q + j];
                 out_scores[(size_t)b * g.Q + n] = s_pred[j];
                 out_query[(size_t)b * g.Q + n] = sel_query[(size_t)b * g.Q + j];
@@ -214,39 +320,53 @@ __global__ void __launch_bounds__(256) postproc_finalize_kernel(PostGeom g, floa
     }
 }
 
-__global__ void __launch_bounds__(256) postproc_masks_kernel(const float* __restrict__ masks, PostGeom g,
-                                                             const int* __restrict__ sel_query, const int* __restrict__ slot,
-                                                             uint8_t* __restrict__ out_masks, int* __restrict__ seg) {
-    const int j = blockIdx.y, b = blockIdx.z;
-    const int s = slot[(size_t)b * g.Q + j];
-    if (s < 0) return;
-    const int q = sel_query[(size_t)b * g.Q + j];
-    const float* plane = masks + ((size_t)b * g.Q + q) * g.h * g.w;
+// One thread = four consecutive target pixels of one image, for ALL kept segments: the pixel -> grid-point mapping is computed
+// once, every segment costs a few bit extractions from its sign bitmap (L1/L2-resident: 18 KB per candidate) and one 4-byte
+// store; the painted map keeps the highest slot whose bit is set ("last kept segment wins") in a register -- no atomics, no
+// fill pass.  (Per-segment CTAs with an atomicMax per positive pixel took 3/4 of the post-processing time.)
+__global__ void __launch_bounds__(256) postproc_paint_kernel(PostGeom g, const int* __restrict__ inv_slot,
+                                                             const int* __restrict__ out_count,
+                                                             const unsigned* __restrict__ bitmap, uint8_t* __restrict__ out_masks,
+                                                             int* __restrict__ seg) {
+    const int b = blockIdx.y;
     const int n_t = g.Ht * g.Wt;
-    uint8_t* dst = out_masks + ((size_t)b * g.Q + s) * n_t;
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (p0 >= n_t) return;
-    unsigned packed = 0;
     const int n = n_t - p0 < 4 ? n_t - p0 : 4;
-    int last_gy = -1, last_gx = -1;
-    float v = 0.f;
-    for (int e = 0; e < n; ++e) {
-        const int pt = p0 + e;
+    int wi[4], sh[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int pt = p0 + (e < n ? e : 0);
         const int gy = nearest_src(pt / g.Wt, g.sy), gx = nearest_src(pt % g.Wt, g.sx);
-        if (gy != last_gy || gx != last_gx) {
-            v = grid_logit(plane, g, gy, gx);
-            last_gy = gy;
-            last_gx = gx;
+        wi[e] = gy * (kGrid / 32) + (gx >> 5);
+        sh[e] = gx & 31;
+    }
+    int painted[4] = {-1, -1, -1, -1};
+    const int count = out_count[b];
+    const bool vec = n == 4 && (n_t & 3) == 0;
+    for (int sl = 0; sl < count; ++sl) {
+        const unsigned* bm = bitmap + ((size_t)b * g.Q + inv_slot[(size_t)b * g.Q + sl]) * (kGrid * (kGrid / 32));
+        unsigned packed = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const unsigned bit = (__ldg(bm + wi[e]) >> sh[e]) & 1u;
+            packed |= bit << (8 * e);
+            if (bit) painted[e] = sl;
         }
-        if (v > 0.f) {
-            packed |= 1u << (8 * e);
-            if (seg) atomicMax(seg + (size_t)b * n_t + pt, s);
+        uint8_t* dst = out_masks + ((size_t)b * g.Q + sl) * n_t + p0;
+        if (vec) {
+            *reinterpret_cast<unsigned*>(dst) = packed;
+        } else {
+            for (int e = 0; e < n; ++e) dst[e] = (uint8_t)((packed >> (8 * e)) & 1u);
         }
     }
-    if (n == 4 && (n_t & 3) == 0) {
-        *reinterpret_cast<unsigned*>(dst + p0) = packed;
-    } else {
-        for (int e = 0; e < n; ++e) dst[p0 + e] = (uint8_t)((packed >> (8 * e)) & 1u);
+    if (seg) {
+        int* sp = seg + (size_t)b * n_t + p0;
+        if (vec) {
+            *reinterpret_cast<int4*>(sp) = make_int4(painted[0], painted[1], painted[2], painted[3]);
+        } else {
+            for (int e = 0; e < n; ++e) sp[e] = painted[e];
+        }
     }
 }
 
@@ -312,7 +432,7 @@ int next_pow2(int v) {
 }
 
 struct WsLayout {
-    size_t sel_score, sel_query, sel_label, part_cnt, part_sum, any_target, slot, total;
+    size_t sel_score, sel_query, sel_label, part_cnt, part_sum, any_target, slot, inv_slot, bitmap, total;
 };
 
 WsLayout ws_layout(int B, int Q) {
@@ -331,6 +451,8 @@ WsLayout ws_layout(int B, int Q) {
     l.part_sum = take((size_t)B * Q * n_chunk * 4);
     l.any_target = take((size_t)B * Q * 4);
     l.slot = take((size_t)B * Q * 4);
+    l.inv_slot = take((size_t)B * Q * 4);
+    l.bitmap = take((size_t)B * Q * kGrid * (kGrid / 32) * 4);
     l.total = o;
     return l;
 }
@@ -366,6 +488,8 @@ extern "C" int rgbd_postprocess_instances(const float* class_logits, const float
     float* part_sum = reinterpret_cast<float*>(ws + l.part_sum);
     unsigned* any_target = reinterpret_cast<unsigned*>(ws + l.any_target);
     int* slot = reinterpret_cast<int*>(ws + l.slot);
+    int* inv_slot = reinterpret_cast<int*>(ws + l.inv_slot);
+    unsigned* bitmap = reinterpret_cast<unsigned*>(ws + l.bitmap);
 
     const int n_sort = next_pow2(n_cand < Q ? Q : n_cand);
     RgbdDeviceInfo di;
@@ -376,21 +500,34 @@ extern "C" int rgbd_postprocess_instances(const float* class_logits, const float
     postproc_select_kernel<<<B, 256, (size_t)n_sort * 8, s>>>(class_logits, g, n_sort, sel_score, sel_query, sel_label);
     RGBD_CHECK_LAUNCH();
     RGBD_CHECK_CUDA(cudaMemsetAsync(any_target, 0, (size_t)B * Q * 4, s));
-    const int n_chunk_grid = ceil_div(kGrid * kGrid, kChunk);
+    int n_chunk_grid = ceil_div(kGrid * kGrid, kChunk);
     const int n_chunk_t = (Ht >= kGrid && Wt >= kGrid) ? 0 : ceil_div(Ht * Wt, kChunk);
-    postproc_stats_kernel<<<dim3(n_chunk_grid + n_chunk_t, Q, B), 256, 0, s>>>(mask_logits, g, sel_query, n_chunk_grid, part_cnt,
-                                                                               part_sum, any_target);
-    RGBD_CHECK_LAUNCH();
-    postproc_finalize_kernel<<<B, 256, (size_t)Q * 8, s>>>(g, threshold, n_chunk_grid, sel_score, sel_query, sel_label, part_cnt,
-                                                           part_sum, any_target, slot, out_labels, out_scores, out_query,
-                                                           out_count);
-    RGBD_CHECK_LAUNCH();
-    if (out_segmentation) {
-        fill_int_kernel<<<ceil_div(B * Ht * Wt, 256 * 8), 256, 0, s>>>(out_segmentation, (size_t)B * Ht * Wt, -1);
+    // source rows one band of grid rows can touch: floor(rh * 31) + 3 bounds y1(last) - y0(first) + 1
+    const int rows_cap = (int)((double)g.rh * (kBand - 1)) + 3;
+    const size_t band_smem = (size_t)rows_cap * kGrid * sizeof(float);
+    if (band_smem <= 64 * 1024) {
+        RGBD_ONCE_PER_DEVICE(di.device, {
+            RGBD_CHECK_CUDA(cudaFuncSetAttribute(postproc_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        });
+        postproc_grid_kernel<<<dim3(kBands, Q, B), 256, band_smem, s>>>(mask_logits, g, sel_query, rows_cap, part_cnt, part_sum, bitmap);
+        RGBD_CHECK_LAUNCH();
+        if (n_chunk_t) {          // downsampled targets: any(mask) over the target pixels (the grid chunks of this launch are empty)
+            postproc_stats_kernel<<<dim3(n_chunk_t, Q, B), 256, 0, s>>>(mask_logits, g, sel_query, 0, part_cnt, part_sum, any_target,
+                                                                       nullptr);
+            RGBD_CHECK_LAUNCH();
+        }
+        n_chunk_grid = kBands;
+    } else {                      // very tall logit planes: point-wise evaluation
+        postproc_stats_kernel<<<dim3(n_chunk_grid + n_chunk_t, Q, B), 256, 0, s>>>(mask_logits, g, sel_query, n_chunk_grid, part_cnt,
+                                                                                   part_sum, any_target, bitmap);
         RGBD_CHECK_LAUNCH();
     }
-    postproc_masks_kernel<<<dim3(ceil_div(Ht * Wt, 256 * 4), Q, B), 256, 0, s>>>(mask_logits, g, sel_query, slot, out_masks,
-                                                                                out_segmentation);
+    postproc_finalize_kernel<<<B, 256, (size_t)Q * 8, s>>>(g, threshold, n_chunk_grid, sel_score, sel_query, sel_label, part_cnt,
+                                                           part_sum, any_target, slot, inv_slot, out_labels, out_scores, out_query,
+                                                           out_count);
+    RGBD_CHECK_LAUNCH();
+    RGBD_CHECK_ARG(B <= 65535, "postprocess: at most 65535 images per call");
+    postproc_paint_kernel<<<dim3(ceil_div(Ht * Wt, 256 * 4), B), 256, 0, s>>>(g, inv_slot, out_count, bitmap, out_masks, out_segmentation);
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }

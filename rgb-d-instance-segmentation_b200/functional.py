@@ -809,7 +809,7 @@ def post_process_instances(class_logits: torch.Tensor, mask_logits: torch.Tensor
                                          scores.data_ptr(), query.data_ptr(), count.data_ptr(),
                                          seg.data_ptr() if seg is not None else None, _stream()),
           "rgbd_postprocess_instances")
-    _count(5 if want_segmentation else 4)
+    _count(4 if (Ht >= 384 and Wt >= 384) else 5)      # select, grid, [target any], finalize, paint
     return InstanceBatch(masks, labels, scores, query, count, seg)
 
 
