@@ -515,6 +515,11 @@ def run_own(args):
             del graphed
         torch.cuda.empty_cache()
         train = train_record(args, dev, rank, world, barrier)
+        if not args.no_whole_model:
+            try:
+                train["whole_model"] = train_whole_model_record(args, dev, rank, world, barrier)
+            except Exception as e:                           # reported, never fatal for the headline line
+                train["whole_model"] = {"error": repr(e)}
 
     if rank == 0:
         if old_affinity:
@@ -687,6 +692,92 @@ def train_record(args, dev, rank, world, barrier):
                 model.ratio_predictor, "TRAIN_MODE_SUPPORTED", False) else "eval semantics",
             "workload": "configs[3] hot-path share: fwd+bwd of ratio predictor (fwd) + DSAM x3 + DGGM, NCCL bucketed "
                         "gradient all-reduce overlapped with the backward"}
+
+
+def train_whole_model_record(args, dev, rank, world, barrier):
+    """BASELINE configs[3] as finetuning.py runs it (mask2former/finetuning.py:98-113, HF Trainer step): the WHOLE RGB-D
+    Mask2Former in .train() mode under bf16 autocast, batch 8 per GPU, synthetic rectangle labels (<= 20 per frame, 48 classes)
+    -> transformers' Mask2FormerLoss (Hungarian matching on the host, as in the reference) -> backward (stock autograd + this
+    library's DSAM / DGGM backward kernels; the encoder and the ratio predictor receive no gradient, CM:332-339) -> bucketed NCCL
+    all-reduce overlapped with the backward -> AdamW.  The stock modules run their stock forward / backward here (decoder_ops
+    are inference kernels)."""
+    import numpy as np
+    from rgbd_b200 import functional as Fn, parallel
+    B = 8
+    model, _ = build_whole_model()
+    model.to(dev).train()
+    plm = model.model.pixel_level_module
+    for p in (*plm.encoder.parameters(), *plm.ratio_predictor.parameters()):
+        p.requires_grad_(False)
+    rgb_u8, depth_u8 = make_frames(B, first=rank * 1000)
+    pv = Fn.pack_pixel_values(torch.from_numpy(rgb_u8).to(dev), torch.from_numpy(depth_u8).to(dev))
+    rs = np.random.RandomState(100 + rank)
+    mask_labels, class_labels = [], []
+    for _ in range(B):
+        k = rs.randint(3, 21)
+        m = torch.zeros(k, H, W)
+        for j in range(k):
+            h, w = rs.randint(H // 16, H // 2), rs.randint(W // 16, W // 2)
+            y, x = rs.randint(0, H - h), rs.randint(0, W - w)
+            m[j, y:y + h, x:x + w] = 1
+        mask_labels.append(m.to(dev))
+        class_labels.append(torch.from_numpy(rs.randint(0, 48, size=k)).to(dev))
+    hot = set(id(p) for m_ in (plm.dsam0, plm.dsam1, plm.dsam2, plm.depth_gradient_injection) for p in m_.parameters())
+    dec = [p for p in plm.decoder.parameters() if p.requires_grad]
+    rest = [p for p in model.parameters() if p.requires_grad and id(p) not in hot and id(p) not in set(id(q) for q in dec)]
+    buckets = [rest, dec, list(plm.dsam2.parameters()), list(plm.dsam1.parameters()),
+               list(plm.dsam0.parameters()) + list(plm.depth_gradient_injection.parameters())]       # backward order
+    reducer = parallel.GradBucketReducer(buckets)
+    opt = torch.optim.AdamW([p for b in buckets for p in b], lr=1e-5)
+    phases = []
+
+    def step(timed=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+        if timed:
+            ev[0].record()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model(pixel_values=pv, mask_labels=mask_labels, class_labels=class_labels)
+        if timed:
+            ev[1].record()
+        out.loss.backward()
+        reducer.finish()
+        if timed:
+            ev[2].record()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        if timed:
+            ev[3].record()
+            phases.append(ev)
+        return out.loss
+
+    import warnings
+    steps = max(3, min(args.steps, 5))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(2):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step(timed=True)
+        e1.record()
+        barrier()
+    t = parallel.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    ph = [[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in phases]
+    med = [sorted(c)[len(c) // 2] for c in zip(*ph)]
+    reducer.remove()
+    grads = {"encoder_params_trainable": 0, "ratio_predictor_params_trainable": 0,
+             "trainable_elements": reducer.n_elements}
+    del model, opt
+    torch.cuda.empty_cache()
+    return {"metric": "rgbd_480x640_train_frames_per_sec_whole_model", "value": world * B * steps / t, "unit": UNIT,
+            "ms_per_step": t / steps * 1e3, "steps": steps, "batch_per_gpu": B, "n_gpus": world,
+            "phase_ms_median": {"forward_and_loss": med[0], "backward_and_allreduce": med[1], "adamw": med[2]},
+            "grad_elements_allreduced_per_step": reducer.n_elements if world > 1 else 0, "final_loss": float(loss.detach()),
+            **grads,
+            "workload": "configs[3]: whole RGB-D Mask2Former fine-tuning step, bf16 autocast, batch 8 per GPU, synthetic rectangle "
+                        "labels, HF Mask2FormerLoss, bucketed NCCL gradient all-reduce overlapped with the backward, AdamW"}
 
 
 class PerKernel:
