@@ -15,8 +15,20 @@ model.cuda()
 rgb, depth = bench.make_frames(B)
 seg = serving.RgbdInstanceSegmenter(model, B, (bench.H, bench.W), threshold=bench.POST_THRESHOLD)
 rgb, depth = torch.from_numpy(rgb), torch.from_numpy(depth)
+if os.environ.get("FUSE_PROJ"):          # SURVEY 8f-2 path: input projections + GroupNorm on this library's kernels
+    model.model.pixel_level_module.fuse_input_projections = True
 for _ in range(1 + steps):
     b = seg.submit(rgb, depth)
 seg.drain()
 torch.cuda.synchronize()
 print("ok", int(seg.out_host[b]["count"].sum()))
+if os.environ.get("TIME"):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = int(os.environ["TIME"])
+    e0.record()
+    for _ in range(n):
+        seg.submit()
+    seg.drain()
+    e1.record()
+    torch.cuda.synchronize()
+    print("fuse_input_projections=%s: %.2f ms per step of %d frames" % (bool(os.environ.get("FUSE_PROJ")), e0.elapsed_time(e1) / n, B))
