@@ -301,10 +301,11 @@ int rgbd_postprocess_instances(const float* class_logits, const float* mask_logi
 int rgbd_mask_iou(const uint8_t* pred_masks, const uint8_t* gt_masks, int P, int G, long long pixels, float* iou,
                   rgbd_stream_t stream);
 
-/* ---- consumers of the fused pyramid: two inference kernels for the STOCK Hugging Face pixel decoder / transformer decoder the
- * reference hands the hot path's output to (mask2former/utils/custom_model.py:383 `self.decoder(backbone_features)`, then
- * Mask2FormerModel.forward -> transformer_module).  Opt-in (`pixel_level.install_fast_decoder_ops`); weights, module tree and
- * state_dict stay Hugging Face's.
+/* ---- neighbours of the path inside the STOCK Hugging Face modules: three opt-in inference kernels
+ * (`decoder_ops.install_fast_decoder_ops`) for the pixel decoder / transformer decoder the reference hands the hot path's output
+ * to (mask2former/utils/custom_model.py:383 `self.decoder(backbone_features)`, then Mask2FormerModel.forward ->
+ * transformer_module) and for the Swin encoder that produces its input (CM:330).  Weights, module tree and state_dict stay
+ * Hugging Face's.
  *
  * rgbd_msda_fwd: `multi_scale_deformable_attention(value, spatial_shapes, sampling_locations, attention_weights)` of
  * transformers' modeling_mask2former.py (grid_sample(bilinear, zeros, align_corners=False) per level, stack, weight, sum) in one
@@ -321,6 +322,13 @@ int rgbd_msda_fwd(const void* value, int value_dtype, const int* level_hw_host, 
  * out (B*heads,Q,th*tw) bytes 0/1 = sigmoid(bilinear(mask_logits -> (th,tw), align_corners=False)) < 0.5, repeated per head. */
 int rgbd_attention_mask(const void* mask_logits, int dtype, int B, int Q, int h, int w, int th, int tw, int heads, uint8_t* out,
                         rgbd_stream_t stream);
+/* rgbd_window_attention: the inner op of transformers' SwinSelfAttention.forward (the stock backbone that produces the path's
+ * input pyramid, CM:330): out = softmax(q k^T / sqrt(d) + bias[head] + mask[window % n_mask_windows]) v per (window, head).
+ * q / k / v / out (n_windows, N, heads*d) f32|bf16 (the three nn.Linear outputs, untransposed); bias (heads, N, N) f32 =
+ * relative_position_bias_table gathered by relative_position_index; mask (n_mask_windows, N, N) f32 (0 / -100 of the shifted
+ * blocks) or NULL.  d must be 32, N <= 64.  Inference only. */
+int rgbd_window_attention(const void* q, const void* k, const void* v, int dtype, const float* bias, const float* mask, void* out,
+                          long long n_windows, int N, int heads, int head_dim, int n_mask_windows, rgbd_stream_t stream);
 
 #ifdef __cplusplus
 }

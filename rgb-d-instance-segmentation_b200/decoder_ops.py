@@ -1,13 +1,17 @@
-"""Opt-in inference kernels for the two stock Hugging Face modules that CONSUME the hot path's fused pyramid (reference
-call site mask2former/utils/custom_model.py:383 ``self.decoder(backbone_features)`` and the transformer module behind it).
-The module tree, parameter names and state_dict stay Hugging Face's: ``install_fast_decoder_ops`` only rebinds the
+"""Opt-in inference kernels inside the stock Hugging Face modules on either side of the hot path: the pixel decoder and the
+transformer decoder that CONSUME the fused pyramid (reference call site mask2former/utils/custom_model.py:383
+``self.decoder(backbone_features)`` and the transformer module behind it) and the Swin encoder that PRODUCES its input
+(CM:330).  The module tree, parameter names and state_dict stay Hugging Face's: ``install_fast_decoder_ops`` only rebinds the
 ``forward`` of
 
 * ``Mask2FormerPixelDecoderEncoderMultiscaleDeformableAttention`` (six encoder layers): the linear layers stay
   ``nn.Linear`` (cuBLAS); softmax + sampling locations + ``multi_scale_deformable_attention`` (per level grid_sample, stack,
   multiply, sum: ~80 ms per 32 frames of 480x640) run as ONE kernel, ``rgbd_msda_fwd``;
 * ``Mask2FormerMaskPredictor`` (ten calls per forward): the attention mask (bilinear resize of the (B,Q,120,160) logits, sigmoid,
-  threshold, repeat per head: ~2 ms per call in ATen's plane-serial upsample kernel) is ``rgbd_attention_mask``.
+  threshold, repeat per head: ~2 ms per call in ATen's plane-serial upsample kernel) is ``rgbd_attention_mask``;
+* ``SwinSelfAttention`` (12 blocks of Swin-T): the three ``nn.Linear`` projections stay; bmm -> div -> + relative position bias ->
+  + shift mask -> softmax -> cast -> bmm -> permute-copy over a (windows*heads, 49, 49) score tensor is ``rgbd_window_attention``
+  (one warp per (window, head), online softmax in registers).
 
 Both fall back to the stock forward when autograd is recording (no backward kernels here) or the tensors are not on CUDA.
 """
@@ -62,10 +66,31 @@ def _mask_predictor_forward(self, outputs, pixel_embeddings, attention_mask_targ
     return outputs_mask, Fn.attention_mask(logits.contiguous(), size, self.num_heads)
 
 
-def install_fast_decoder_ops(model: nn.Module, deformable_attention: bool = True, attention_mask: bool = True) -> nn.Module:
+def _swin_self_attention_forward(self, hidden_states, attention_mask=None, output_attentions=False):
+    n_tok = hidden_states.shape[1]
+    if torch.is_grad_enabled() or not hidden_states.is_cuda or output_attentions or self.attention_head_size != 32 or n_tok > 64 \
+            or (self.training and self.dropout.p > 0):
+        return self._rgbd_stock_forward(hidden_states, attention_mask, output_attentions)
+    q, k, v = self.query(hidden_states), self.key(hidden_states), self.value(hidden_states)
+    if q.dtype not in (torch.float32, torch.bfloat16):
+        q, k, v = q.float(), k.float(), v.float()
+    table = self.relative_position_bias_table
+    key = (table.data_ptr(), table._version, table.device)
+    cache = self.__dict__.get("_rgbd_bias_cache")
+    if cache is None or cache[0] != key:          # (heads, N, N) float32, as the stock forward gathers it on every call
+        bias = table.detach()[self.relative_position_index.view(-1)].view(n_tok, n_tok, -1).permute(2, 0, 1).float().contiguous()
+        cache = self.__dict__["_rgbd_bias_cache"] = (key, bias)
+    mask = attention_mask.float().contiguous() if attention_mask is not None else None
+    ctx = Fn.window_attention(q.contiguous(), k.contiguous(), v.contiguous(), cache[1], mask, self.num_attention_heads)
+    return (ctx,)
+
+
+def install_fast_decoder_ops(model: nn.Module, deformable_attention: bool = True, attention_mask: bool = True,
+                             window_attention: bool = True) -> nn.Module:
     """Rebind the forwards described in the module docstring on every matching submodule of ``model`` (idempotent).
     ``uninstall_fast_decoder_ops`` restores the stock forwards."""
     from transformers.models.mask2former import modeling_mask2former as m2f
+    from transformers.models.swin.modeling_swin import SwinSelfAttention
     for mod in model.modules():
         if hasattr(mod, "_rgbd_stock_forward"):
             continue
@@ -75,6 +100,9 @@ def install_fast_decoder_ops(model: nn.Module, deformable_attention: bool = True
         elif attention_mask and isinstance(mod, m2f.Mask2FormerMaskPredictor):
             mod._rgbd_stock_forward = mod.forward
             mod.forward = types.MethodType(_mask_predictor_forward, mod)
+        elif window_attention and isinstance(mod, SwinSelfAttention):
+            mod._rgbd_stock_forward = mod.forward
+            mod.forward = types.MethodType(_swin_self_attention_forward, mod)
     return model
 
 
@@ -83,4 +111,5 @@ def uninstall_fast_decoder_ops(model: nn.Module) -> nn.Module:
         if "_rgbd_stock_forward" in mod.__dict__:
             del mod.__dict__["forward"]
             del mod.__dict__["_rgbd_stock_forward"]
+            mod.__dict__.pop("_rgbd_bias_cache", None)
     return model

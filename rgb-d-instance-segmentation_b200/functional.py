@@ -895,3 +895,33 @@ def attention_mask(mask_logits: torch.Tensor, target_size: Tuple[int, int], num_
                                   out.data_ptr(), _stream()), "rgbd_attention_mask")
     _count(1)
     return out
+
+
+def window_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias: torch.Tensor, mask: Optional[torch.Tensor],
+                     num_heads: int) -> torch.Tensor:
+    """``rgbd_window_attention`` (transformers ``SwinSelfAttention``'s inner op): q / k / v (windows, N, heads*32) float32 or
+    bfloat16, bias (heads, N, N) float32, mask (nW, N, N) float32 or None (window w uses mask[w % nW]) -> (windows, N, heads*32)
+    of the inputs' dtype = softmax(q k^T / sqrt(32) + bias + mask) v."""
+    lib = _lib.load()
+    for t, name in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, name, q.dtype)
+    _req(bias, "bias", torch.float32)
+    if q.dim() != 3 or k.shape != q.shape or v.shape != q.shape:
+        raise RgbdB200Error("window_attention: q, k, v must share the shape (windows, N, C)")
+    n_win, N, Cc = q.shape
+    if Cc != num_heads * 32:
+        raise RgbdB200Error(f"window_attention: C = {Cc} is not heads * 32 = {num_heads * 32}")
+    if tuple(bias.shape) != (num_heads, N, N):
+        raise RgbdB200Error(f"window_attention: bias must be {(num_heads, N, N)}, got {tuple(bias.shape)}")
+    nw = 1
+    if mask is not None:
+        _req(mask, "mask", torch.float32)
+        if mask.dim() != 3 or tuple(mask.shape[1:]) != (N, N):
+            raise RgbdB200Error(f"window_attention: mask must be (nW, {N}, {N}), got {tuple(mask.shape)}")
+        nw = mask.shape[0]
+    out = torch.empty_like(q)
+    check(lib.rgbd_window_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), _dt(q, "q"), bias.data_ptr(),
+                                    mask.data_ptr() if mask is not None else None, out.data_ptr(), n_win, N, int(num_heads), 32, nw,
+                                    _stream()), "rgbd_window_attention")
+    _count(1)
+    return out

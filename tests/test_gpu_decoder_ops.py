@@ -1,5 +1,6 @@
-"""GPU parity of the two opt-in kernels on the CONSUMER side of the hot path (csrc/msda.cu, csrc/maskattn.cu; reference
-call site mask2former/utils/custom_model.py:383 and the transformer module behind it).  The checker is Hugging Face's own
+"""GPU parity of the opt-in kernels inside the stock modules on either side of the hot path (csrc/msda.cu, csrc/maskattn.cu:
+reference call site mask2former/utils/custom_model.py:383 and the transformer module behind it; csrc/winattn.cu: the Swin
+encoder called at CM:330).  The checker is Hugging Face's own
 pure-PyTorch code (transformers/models/mask2former/modeling_mask2former.py: `multi_scale_deformable_attention`, the
 deformable-attention module, `Mask2FormerMaskPredictor`) run in float32 on the CPU or, for the module-level checks, the
 stock forward of the same module object on the GPU.  Tolerances: float32 1e-5 (summation order only), bf16 1e-2."""
@@ -161,10 +162,13 @@ def test_attention_mask_matches_hf_mask_predictor(fn, dtype, target):
 
 
 def test_whole_model_with_fast_decoder_ops(fn):
-    """RGB-D Mask2Former with and without the rebound forwards: same logits (float32), same attention-mask driven path."""
+    """RGB-D Mask2Former with and without the rebound forwards: same logits (float32).  The model is made decisive first
+    (synthetic_weights.make_decisive): out of the box a random-init Mask2Former has near-zero mask logits, so the 1e-7 differences
+    between two float32 implementations flip attention-mask bits and the outputs of BOTH drift apart chaotically (measured: Swin
+    feature maps equal to 1e-6, mask logits 2.6e-2 apart)."""
     import numpy as np
     from rgbd_b200 import decoder_ops, synthetic, synthetic_weights
-    model = synthetic_weights.build_synthetic_rgbd_mask2former()[0].eval().cuda()
+    model = synthetic_weights.build_synthetic_rgbd_mask2former(decisive=True)[0].eval().cuda()
     frames = [synthetic.synth_rgbd_u8(40 + j, 128, 160) for j in range(2)]
     rgb = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
     depth = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
@@ -179,6 +183,85 @@ def test_whole_model_with_fast_decoder_ops(fn):
         used_stock_before = fn.LAUNCHES
         model(pixel_values=pv)
         hot_path_launches = fn.LAUNCHES - used_stock_before
-    assert used - hot_path_launches == 6 + 10                        # six encoder layers + ten mask-predictor calls
-    assert rel_l2(fast.masks_queries_logits, stock.masks_queries_logits) < 1e-3
-    assert rel_l2(fast.class_queries_logits, stock.class_queries_logits) < 1e-3
+    assert used - hot_path_launches == 6 + 10 + 12                   # six encoder layers, ten mask-predictor calls, twelve Swin blocks
+    assert rel_l2(fast.masks_queries_logits, stock.masks_queries_logits) < 2e-3
+    assert rel_l2(fast.class_queries_logits, stock.class_queries_logits) < 2e-3
+
+
+def _window_attention_reference(q, k, v, bias, mask, heads):
+    """transformers SwinSelfAttention.forward's inner arithmetic in float32."""
+    n_win, N, C = q.shape
+    sh = (n_win, N, heads, 32)
+    ql, kl, vl = (t.float().view(sh).transpose(1, 2) for t in (q, k, v))
+    s = torch.matmul(ql, kl.transpose(-1, -2)) / (32 ** 0.5) + bias.unsqueeze(0)
+    if mask is not None:
+        nw = mask.shape[0]
+        s = (s.view(n_win // nw, nw, heads, N, N) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, N, N)
+    ctx = torch.matmul(torch.softmax(s, -1), vl)
+    return ctx.permute(0, 2, 1, 3).contiguous().view(n_win, N, C)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("N,heads,masked", [(49, 3, True), (49, 6, False), (64, 4, True), (16, 1, True), (33, 24, False)])
+def test_window_attention_matches_torch(fn, dtype, N, heads, masked):
+    g = torch.Generator(device="cuda").manual_seed(N + heads)
+    nw = 6
+    n_win = nw * 5 + (0 if masked else 1)
+    q, k, v = (torch.randn(n_win, N, heads * 32, device="cuda", generator=g).to(dtype) * 1.5 for _ in range(3))
+    bias = torch.randn(heads, N, N, device="cuda", generator=g)
+    mask = None
+    if masked:
+        mask = torch.where(torch.rand(nw, N, N, device="cuda", generator=g) < 0.3, -100.0, 0.0)
+        mask[:, torch.arange(N), torch.arange(N)] = 0.0           # a token always sees itself (as in Swin's shift masks)
+    want = _window_attention_reference(q, k, v, bias, mask, heads)
+    got = fn.window_attention(q, k, v, bias, mask, heads)
+    assert got.dtype == dtype and got.shape == want.shape
+    assert rel_l2(got.float(), want) < (1e-5 if dtype == torch.float32 else 3e-3)   # bf16: output rounding only
+
+
+def test_window_attention_argument_errors(fn):
+    from rgbd_b200._lib import RgbdB200Error
+    q = torch.zeros(4, 49, 96, device="cuda")
+    bias = torch.zeros(3, 49, 49, device="cuda")
+    with pytest.raises(RgbdB200Error):
+        fn.window_attention(q, q, q, bias, None, 4)                                  # 96 != 4 * 32
+    with pytest.raises(RgbdB200Error):
+        fn.window_attention(q, q, q, bias, torch.zeros(3, 49, 49, device="cuda"), 3)  # 4 windows, 3 mask windows
+    with pytest.raises(RgbdB200Error):
+        fn.window_attention(q.cpu(), q.cpu(), q.cpu(), bias.cpu(), None, 3)
+    with pytest.raises(RgbdB200Error):
+        fn.window_attention(torch.zeros(4, 81, 96, device="cuda"), q, q, bias, None, 3)
+
+
+@pytest.mark.parametrize("autocast", [False, True], ids=["fp32", "bf16_autocast"])
+def test_swin_self_attention_module_matches_stock_forward(fn, autocast):
+    """HF's SwinSelfAttention with its rebound forward against its stock forward (same module object and weights), shifted-window
+    mask included.  Under autocast both are compared with the float32 stock result: the kernel keeps the scores in float32 where
+    the stock path rounds them to bfloat16, so it must not be further away than the stock path itself."""
+    from transformers import SwinConfig
+    from transformers.models.swin.modeling_swin import SwinSelfAttention
+    from rgbd_b200 import decoder_ops
+    torch.manual_seed(1)
+    mod = SwinSelfAttention(SwinConfig(), dim=192, num_heads=6, window_size=7).cuda().eval()
+    torch.nn.init.normal_(mod.relative_position_bias_table, std=0.5)
+    nw, batch = 12, 3
+    x = torch.randn(batch * nw, 49, 192, device="cuda")
+    mask = torch.where(torch.rand(nw, 49, 49, device="cuda") < 0.25, -100.0, 0.0)
+    mask[:, torch.arange(49), torch.arange(49)] = 0.0
+    with torch.no_grad():
+        exact = mod(x, mask)[0]
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            stock = mod(x, mask)[0]
+            decoder_ops.install_fast_decoder_ops(mod)
+            before = fn.LAUNCHES
+            fast = mod(x, mask)[0]
+            fast_nomask = mod(x, None)[0]
+            assert fn.LAUNCHES == before + 2
+            decoder_ops.uninstall_fast_decoder_ops(mod)
+            stock_nomask = mod(x, None)[0]
+    assert fast.dtype == stock.dtype and fast.shape == stock.shape
+    if autocast:
+        assert rel_l2(fast.float(), exact) <= max(rel_l2(stock.float(), exact), 4e-3) * 1.05
+        assert rel_l2(fast_nomask.float(), stock_nomask.float()) < 1e-2
+    else:
+        assert rel_l2(fast, stock) < 1e-5 and rel_l2(fast_nomask, stock_nomask) < 1e-5
