@@ -49,3 +49,26 @@ for dt in (torch.bfloat16, torch.float32):
                          .flatten(2).unsqueeze(1).repeat(1, 8, 1, 1).flatten(0, 1) < 0.5).bool()
         sb, sm = timeit(stock, reps=3, n=3)
         print("attention_mask %s -> %dx%d: best %.1f us median %.1f us (stock ATen chain: %.1f us)" % (str(dt)[6:], tgt[0], tgt[1], best * 1e3, med * 1e3, sb * 1e3))
+
+# Swin window attention at the four stage geometries of Swin-T on 480x640 (padded to 126x161 -> 18x23 windows at stage 1)
+import math
+for (hw, heads) in (((126, 161), 3), ((63, 84), 6), ((35, 42), 12), ((21, 21), 24)):
+    nw = (hw[0] // 7) * (hw[1] // 7)
+    n_win = B * nw
+    C = heads * 32
+    q, k, v = (torch.randn(n_win, 49, C, device="cuda", generator=g).bfloat16() for _ in range(3))
+    bias = torch.randn(heads, 49, 49, device="cuda", generator=g)
+    mask = torch.where(torch.rand(nw, 49, 49, device="cuda", generator=g) < 0.2, -100.0, 0.0)
+    best, med = timeit(lambda: Fn.window_attention(q, k, v, bias, mask, heads))
+
+    def stock():
+        sh = (n_win, 49, heads, 32)
+        ql, kl, vl = (t.view(sh).transpose(1, 2) for t in (q, k, v))
+        s = torch.matmul(ql, kl.transpose(-1, -2)) / math.sqrt(32) + bias.unsqueeze(0)
+        s = (s.view(n_win // nw, nw, heads, 49, 49) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, 49, 49)
+        p = torch.softmax(s, -1).to(vl.dtype)
+        return torch.matmul(p, vl).permute(0, 2, 1, 3).contiguous()
+    sb, _ = timeit(stock, reps=3, n=3)
+    flop = n_win * heads * 2 * 2 * 49 * 49 * 32
+    print("window_attention bf16 %d windows x %d heads: best %.1f us median %.1f us = %.1f TFLOP/s fp32 FMA (stock op chain: %.1f us)"
+          % (n_win, heads, best * 1e3, med * 1e3, flop / best / 1e9, sb * 1e3))
