@@ -326,9 +326,12 @@ int rgbd_attention_mask(const void* mask_logits, int dtype, int B, int Q, int h,
  * input pyramid, CM:330): out = softmax(q k^T / sqrt(d) + bias[head] + mask[window % n_mask_windows]) v per (window, head).
  * q / k / v / out (n_windows, N, heads*d) f32|bf16 (the three nn.Linear outputs, untransposed); bias (heads, N, N) f32 =
  * relative_position_bias_table gathered by relative_position_index; mask (n_mask_windows, N, N) f32 (0 / -100 of the shifted
- * blocks) or NULL.  d must be 32, N <= 64.  Inference only. */
+ * blocks) or NULL.  d must be 32, N <= 64.  workspace: rgbd_window_attention_workspace_bytes(N, heads, n_mask_windows) bytes (the
+ * additive term bias + mask as one padded table, built by the first of the two launches).  Inference only. */
+size_t rgbd_window_attention_workspace_bytes(int N, int heads, int n_mask_windows);
 int rgbd_window_attention(const void* q, const void* k, const void* v, int dtype, const float* bias, const float* mask, void* out,
-                          long long n_windows, int N, int heads, int head_dim, int n_mask_windows, rgbd_stream_t stream);
+                          long long n_windows, int N, int heads, int head_dim, int n_mask_windows, void* workspace,
+                          rgbd_stream_t stream);
 
 #ifdef __cplusplus
 }

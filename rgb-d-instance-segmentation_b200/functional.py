@@ -920,8 +920,9 @@ def window_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias: to
             raise RgbdB200Error(f"window_attention: mask must be (nW, {N}, {N}), got {tuple(mask.shape)}")
         nw = mask.shape[0]
     out = torch.empty_like(q)
+    ws = torch.empty(lib.rgbd_window_attention_workspace_bytes(N, int(num_heads), nw), device=q.device, dtype=torch.uint8)
     check(lib.rgbd_window_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), _dt(q, "q"), bias.data_ptr(),
                                     mask.data_ptr() if mask is not None else None, out.data_ptr(), n_win, N, int(num_heads), 32, nw,
-                                    _stream()), "rgbd_window_attention")
-    _count(1)
+                                    ws.data_ptr(), _stream()), "rgbd_window_attention")
+    _count(2)
     return out
