@@ -301,7 +301,7 @@ int rgbd_postprocess_instances(const float* class_logits, const float* mask_logi
 int rgbd_mask_iou(const uint8_t* pred_masks, const uint8_t* gt_masks, int P, int G, long long pixels, float* iou,
                   rgbd_stream_t stream);
 
-/* ---- neighbours of the path inside the STOCK Hugging Face modules: three opt-in inference kernels
+/* ---- neighbours of the path inside the STOCK Hugging Face modules: four opt-in inference kernels
  * (`decoder_ops.install_fast_decoder_ops`) for the pixel decoder / transformer decoder the reference hands the hot path's output
  * to (mask2former/utils/custom_model.py:383 `self.decoder(backbone_features)`, then Mask2FormerModel.forward ->
  * transformer_module) and for the Swin encoder that produces its input (CM:330).  Weights, module tree and state_dict stay
@@ -332,6 +332,12 @@ size_t rgbd_window_attention_workspace_bytes(int N, int heads, int n_mask_window
 int rgbd_window_attention(const void* q, const void* k, const void* v, int dtype, const float* bias, const float* mask, void* out,
                           long long n_windows, int N, int heads, int head_dim, int n_mask_windows, void* workspace,
                           rgbd_stream_t stream);
+/* rgbd_layer_norm: LayerNorm over the last dimension, x (rows, C) f32|bf16 -> out (rows, C) f32|bf16, float32 arithmetic
+ * (mean, biased variance, rsqrt(var + eps), * gamma + beta).  C % 4 == 0, C <= 1024.  With out_dtype = bf16 it emits exactly what
+ * the nn.Linear consumers of a pre-norm LayerNorm cast its float32 result to under bf16 autocast (SwinLayer.layernorm_before /
+ * layernorm_after).  Inference only. */
+int rgbd_layer_norm(const void* x, int x_dtype, const float* gamma, const float* beta, void* out, int out_dtype, long long rows,
+                    int C, float eps, rgbd_stream_t stream);
 
 #ifdef __cplusplus
 }

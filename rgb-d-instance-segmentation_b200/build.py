@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "librgbd_b200.so")
 
-SOURCES = ["api.cu", "dggm.cu", "gradfeat.cu", "decompose.cu", "pack.cu", "conv_gemm.cu", "ratio_chain.cu", "ratio_front.cu", "ratio_tail.cu", "ratio_feat.cu", "dsam_bwd.cu", "postproc.cu", "resize.cu", "msda.cu", "maskattn.cu", "winattn.cu"]
+SOURCES = ["api.cu", "dggm.cu", "gradfeat.cu", "decompose.cu", "pack.cu", "conv_gemm.cu", "ratio_chain.cu", "ratio_front.cu", "ratio_tail.cu", "ratio_feat.cu", "dsam_bwd.cu", "postproc.cu", "resize.cu", "msda.cu", "maskattn.cu", "winattn.cu", "layernorm.cu"]
 NO_FMAD = {"gradfeat.cu", "decompose.cu", "postproc.cu", "resize.cu", "maskattn.cu"}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]

@@ -11,7 +11,10 @@ transformer decoder that CONSUME the fused pyramid (reference call site mask2for
   threshold, repeat per head: ~2 ms per call in ATen's plane-serial upsample kernel) is ``rgbd_attention_mask``;
 * ``SwinSelfAttention`` (12 blocks of Swin-T): the three ``nn.Linear`` projections stay; bmm -> div -> + relative position bias ->
   + shift mask -> softmax -> cast -> bmm -> permute-copy over a (windows*heads, 49, 49) score tensor is ``rgbd_window_attention``
-  (one warp per (window, head), online softmax in registers).
+  (one warp per (window, head), softmax in registers);
+* ``SwinLayer.layernorm_before`` / ``layernorm_after`` under bf16 autocast: ``rgbd_layer_norm`` writes the bf16 tensor the
+  following ``nn.Linear`` layers would have cast the float32 result to (same values, 6 instead of 14+ bytes per element, and the
+  pad / roll / window-partition copies in between move half the bytes).
 
 Both fall back to the stock forward when autograd is recording (no backward kernels here) or the tensors are not on CUDA.
 """
@@ -85,12 +88,32 @@ def _swin_self_attention_forward(self, hidden_states, attention_mask=None, outpu
     return (ctx,)
 
 
+def _swin_prenorm_forward(self, x):
+    """SwinLayer.layernorm_before / layernorm_after under bf16 autocast: the float32 LayerNorm result is only ever moved (pad,
+    roll, window partition) and then cast to bf16 by nn.Linear -- emit that bf16 tensor directly.  (The residual stream is float32
+    in the first stage and bf16 afterwards -- SwinPatchMerging ends in an nn.Linear -- so both input dtypes occur.)"""
+    c = x.shape[-1]
+    if torch.is_grad_enabled() or not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16) or c % 4 or c > 1024 \
+            or len(self.normalized_shape) != 1 \
+            or self.weight is None or self.bias is None \
+            or not (torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+        return self._rgbd_stock_forward(x)
+    return Fn.layer_norm(x.contiguous(), self.weight.detach(), self.bias.detach(), self.eps, out_dtype=torch.bfloat16)
+
+
 def install_fast_decoder_ops(model: nn.Module, deformable_attention: bool = True, attention_mask: bool = True,
-                             window_attention: bool = True) -> nn.Module:
+                             window_attention: bool = True, swin_prenorm_bf16: bool = True) -> nn.Module:
     """Rebind the forwards described in the module docstring on every matching submodule of ``model`` (idempotent).
     ``uninstall_fast_decoder_ops`` restores the stock forwards."""
     from transformers.models.mask2former import modeling_mask2former as m2f
-    from transformers.models.swin.modeling_swin import SwinSelfAttention
+    from transformers.models.swin.modeling_swin import SwinLayer, SwinSelfAttention
+    if swin_prenorm_bf16:
+        for layer in model.modules():
+            if isinstance(layer, SwinLayer):
+                for ln in (layer.layernorm_before, layer.layernorm_after):
+                    if isinstance(ln, nn.LayerNorm) and not hasattr(ln, "_rgbd_stock_forward"):
+                        ln._rgbd_stock_forward = ln.forward
+                        ln.forward = types.MethodType(_swin_prenorm_forward, ln)
     for mod in model.modules():
         if hasattr(mod, "_rgbd_stock_forward"):
             continue

@@ -926,3 +926,21 @@ def window_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias: to
                                     ws.data_ptr(), _stream()), "rgbd_window_attention")
     _count(2)
     return out
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float,
+               out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """``rgbd_layer_norm``: LayerNorm over the last dimension of a float32 or bfloat16 tensor, float32 arithmetic, float32 or
+    bfloat16 output."""
+    lib = _lib.load()
+    _req(x, "x")
+    _req(weight, "weight", torch.float32)
+    _req(bias, "bias", torch.float32)
+    Cc = x.shape[-1]
+    if weight.numel() != Cc or bias.numel() != Cc:
+        raise RgbdB200Error(f"layer_norm: weight / bias must have {Cc} elements")
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    check(lib.rgbd_layer_norm(x.data_ptr(), _dt(x, "x"), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), _dt(out, "out"),
+                              x.numel() // Cc, Cc, float(eps), _stream()), "rgbd_layer_norm")
+    _count(1)
+    return out

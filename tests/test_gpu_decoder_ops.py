@@ -265,3 +265,49 @@ def test_swin_self_attention_module_matches_stock_forward(fn, autocast):
         assert rel_l2(fast_nomask.float(), stock_nomask.float()) < 1e-2
     else:
         assert rel_l2(fast, stock) < 1e-5 and rel_l2(fast_nomask, stock_nomask) < 1e-5
+
+
+@pytest.mark.parametrize("C", [96, 192, 384, 768, 1024, 4, 100])
+def test_layer_norm_matches_torch(fn, C):
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = torch.randn(3, 1001, C, device="cuda", generator=g) * 2.0 + 0.5
+    w = torch.randn(C, device="cuda", generator=g)
+    b = torch.randn(C, device="cuda", generator=g)
+    want = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5)
+    got = fn.layer_norm(x, w, b, 1e-5)
+    assert got.dtype == torch.float32 and rel_l2(got, want) < 1e-6
+    got16 = fn.layer_norm(x, w, b, 1e-5, out_dtype=torch.bfloat16)
+    assert got16.dtype == torch.bfloat16
+    # what nn.Linear would see under autocast: the float32 result rounded to bf16 -- equal up to last-bit ties of the fp32 arithmetic
+    same = float((got16 == want.bfloat16()).float().mean())
+    assert same > 0.999 and rel_l2(got16.float(), want) < 4e-3, same
+    xb = x.bfloat16()                                          # bf16 residual stream (Swin stages 2-4): widened exactly, like autocast
+    want_b = torch.nn.functional.layer_norm(xb.float(), (C,), w, b, 1e-5)
+    got_b = fn.layer_norm(xb, w, b, 1e-5, out_dtype=torch.bfloat16)
+    assert float((got_b == want_b.bfloat16()).float().mean()) > 0.999 and rel_l2(got_b.float(), want_b) < 4e-3
+
+
+def test_swin_encoder_with_bf16_prenorms_and_window_attention(fn):
+    """The stock Swin-T encoder under bf16 autocast with the rebound pre-norm LayerNorms (bf16 output) and window attention against
+    the untouched encoder, both measured against the float32 forward: the rebound version must not be further away."""
+    from rgbd_b200 import decoder_ops, synthetic_weights
+    enc = synthetic_weights.build_synthetic_rgbd_mask2former()[0].model.pixel_level_module.encoder.eval().cuda()
+    x = torch.randn(2, 3, 224, 288, device="cuda")
+    with torch.no_grad():
+        exact = enc(x).feature_maps
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            stock = enc(x).feature_maps
+            decoder_ops.install_fast_decoder_ops(enc, window_attention=False)
+            before = fn.LAUNCHES
+            ln_only = enc(x).feature_maps
+            assert fn.LAUNCHES == before + 24                      # 12 blocks x (layernorm_before, layernorm_after)
+            decoder_ops.uninstall_fast_decoder_ops(enc)
+            decoder_ops.install_fast_decoder_ops(enc)
+            both = enc(x).feature_maps
+            decoder_ops.uninstall_fast_decoder_ops(enc)
+    for i in range(4):
+        e_stock = rel_l2(stock[i].float(), exact[i])
+        assert stock[i].dtype == ln_only[i].dtype == both[i].dtype
+        # bf16 pre-norm outputs are what autocast hands the Linear layers anyway: same error level as the stock autocast run
+        assert rel_l2(ln_only[i].float(), exact[i]) <= max(e_stock * 1.25, 1e-3), (i, e_stock)
+        assert rel_l2(both[i].float(), exact[i]) <= max(e_stock * 1.25, 1e-3), (i, e_stock)
