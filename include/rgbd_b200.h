@@ -301,7 +301,7 @@ int rgbd_postprocess_instances(const float* class_logits, const float* mask_logi
 int rgbd_mask_iou(const uint8_t* pred_masks, const uint8_t* gt_masks, int P, int G, long long pixels, float* iou,
                   rgbd_stream_t stream);
 
-/* ---- neighbours of the path inside the STOCK Hugging Face modules: four opt-in inference kernels
+/* ---- neighbours of the path inside the STOCK Hugging Face modules: five opt-in inference kernels
  * (`decoder_ops.install_fast_decoder_ops`) for the pixel decoder / transformer decoder the reference hands the hot path's output
  * to (mask2former/utils/custom_model.py:383 `self.decoder(backbone_features)`, then Mask2FormerModel.forward ->
  * transformer_module) and for the Swin encoder that produces its input (CM:330).  Weights, module tree and state_dict stay
@@ -338,6 +338,13 @@ int rgbd_window_attention(const void* q, const void* k, const void* v, int dtype
  * layernorm_after).  Inference only. */
 int rgbd_layer_norm(const void* x, int x_dtype, const float* gamma, const float* beta, void* out, int out_dtype, long long rows,
                     int C, float eps, rgbd_stream_t stream);
+/* rgbd_masked_cross_attention: the attention core of nn.MultiheadAttention.forward as transformers'
+ * Mask2FormerMaskedAttentionDecoderLayer calls it (batch_first = False, boolean attn_mask): q (L, B, heads*d), k / v (S, B, heads*d)
+ * bf16 = the three input projections, mask (B*heads, L, S) bytes (non-zero = may NOT attend), out (L, B, heads*d) bf16 =
+ * softmax(q k^T / sqrt(d), masked) v per (image, head); rows whose keys are all masked give zeros.  d must be 32, S even.
+ * Inference only. */
+int rgbd_masked_cross_attention(const void* q_bf16, const void* k_bf16, const void* v_bf16, const uint8_t* mask, void* out_bf16, int B,
+                                int heads, int L, int S, int head_dim, rgbd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -104,6 +104,7 @@ SIGNATURES = {
     "rgbd_msda_fwd": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 6 + [C.c_void_p]),
     "rgbd_attention_mask": (C.c_int, [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_void_p]),
+    "rgbd_masked_cross_attention": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 5 + [C.c_void_p]),
     "rgbd_layer_norm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_float,
                                   C.c_void_p]),
     "rgbd_window_attention_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -331,6 +331,174 @@ __global__ void __launch_bounds__(kWarps * 32) window_attention_mma_kernel(const
     }
 }
 
+// ---- masked cross-attention of the Mask2Former transformer decoder (inference, bf16) -----------------------------------------
+// nn.MultiheadAttention.forward as transformers' Mask2FormerMaskedAttentionDecoderLayer calls it (the consumer of the pixel
+// decoder's multi-scale features behind CM:383): 100 queries attend to the S = 300 / 1 200 / 4 800 pixels of one feature level
+// under a BOOLEAN mask (True = may not attend; the mask rgbd_attention_mask writes).  The stock path materialises an additive
+// -inf mask, the (batch*heads, 100, S) score tensor in float32 (0.5 GB at S = 4 800), its softmax and a bf16 copy: ~1.7 ms per
+// layer at the finest level.  Here one CTA owns one (image, head): four warps x 32 query rows, the keys stream through shared
+// memory in tiles of 64 (register prefetch of the next tile), FlashAttention-2 online softmax with the mask bytes read in the
+// score fragments' own layout (two adjacent keys = one 2-byte load).
+constexpr int kKeyTile = 64;
+
+__global__ void __launch_bounds__(128) masked_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                                    const __nv_bfloat16* __restrict__ v, const uint8_t* __restrict__ mask,
+                                                                    __nv_bfloat16* __restrict__ out, int B, int H, int L, int S,
+                                                                    float scale) {
+    __shared__ __align__(16) __nv_bfloat16 s_k[kKeyTile * kPitch];
+    __shared__ __align__(16) __nv_bfloat16 s_v[kKeyTile * kPitch];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.x, b = bh / H, h = bh % H;
+    const int E = H * kHd;
+    const int row_base = blockIdx.y * 128 + warp * 32;        // this warp's 32 query rows (two 16-row tiles)
+    const int g = lane >> 2, t = lane & 3;
+    const size_t tok = (size_t)B * E;                          // elements between consecutive tokens of (len, batch, embed) tensors
+    const size_t col0 = (size_t)b * E + h * kHd;
+
+    uint32_t qa[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = row_base + mt * 16 + g, r1 = r0 + 8;
+        const uint32_t* p0 = reinterpret_cast<const uint32_t*>(q + (size_t)r0 * tok + col0) + t;
+        const uint32_t* p1 = reinterpret_cast<const uint32_t*>(q + (size_t)r1 * tok + col0) + t;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            qa[mt][ks][0] = r0 < L ? __ldg(p0 + ks * 8) : 0u;
+            qa[mt][ks][1] = r1 < L ? __ldg(p1 + ks * 8) : 0u;
+            qa[mt][ks][2] = r0 < L ? __ldg(p0 + ks * 8 + 4) : 0u;
+            qa[mt][ks][3] = r1 < L ? __ldg(p1 + ks * 8 + 4) : 0u;
+        }
+    }
+    float oc[2][4][4];
+    float m_run[2][2], l_run[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        m_run[mt][0] = m_run[mt][1] = -INFINITY;
+        l_run[mt][0] = l_run[mt][1] = 0.f;
+#pragma unroll
+        for (int dt = 0; dt < 4; ++dt) oc[mt][dt][0] = oc[mt][dt][1] = oc[mt][dt][2] = oc[mt][dt][3] = 0.f;
+    }
+    // staging: 64 keys x four 16-byte pieces per tensor = 256 pieces, two per thread and tensor
+    const int st_row = threadIdx.x >> 1, st_piece = (threadIdx.x & 1) * 2;
+    uint4 pk[2], pv[2];
+    auto fetch = [&](int key0) {
+        const int key = key0 + st_row;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            pk[i] = make_uint4(0u, 0u, 0u, 0u);
+            pv[i] = pk[i];
+            if (key < S) {
+                const size_t o = (size_t)key * tok + col0 + (st_piece + i) * 8;
+                pk[i] = __ldg(reinterpret_cast<const uint4*>(k + o));
+                pv[i] = __ldg(reinterpret_cast<const uint4*>(v + o));
+            }
+        }
+    };
+    const int kb_row = lane & 7, kb_col = (lane >> 3) * 8;
+    const int vb_row = (lane & 7) + ((lane >> 3) & 1) * 8, vb_col = (lane >> 4) * 8;
+    const uint8_t* mask_bh = mask + (size_t)bh * L * S;
+    const int n_tiles = (S + kKeyTile - 1) / kKeyTile;
+    fetch(0);
+    for (int kt = 0; kt < n_tiles; ++kt) {
+        __syncthreads();                                       // everyone is done reading the previous tile
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            *reinterpret_cast<uint4*>(s_k + st_row * kPitch + (st_piece + i) * 8) = pk[i];
+            *reinterpret_cast<uint4*>(s_v + st_row * kPitch + (st_piece + i) * 8) = pv[i];
+        }
+        __syncthreads();
+        if (kt + 1 < n_tiles) fetch((kt + 1) * kKeyTile);      // in flight while this tile is computed
+        const int key0 = kt * kKeyTile;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int r0 = row_base + mt * 16 + g, r1 = r0 + 8;
+            // mask bytes of this lane's score elements: (row, keys key0 + 8 nt + 2 t + {0, 1}) = one 2-byte load
+            uint32_t mk[8];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int c = key0 + nt * 8 + 2 * t;
+                uint32_t m0 = 0x0101u, m1 = 0x0101u;          // out of range = masked
+                if (c < S) {                                   // S is even (checked on the host): c + 1 < S as well
+                    if (r0 < L) m0 = __ldg(reinterpret_cast<const unsigned short*>(mask_bh + (size_t)r0 * S + c));
+                    if (r1 < L) m1 = __ldg(reinterpret_cast<const unsigned short*>(mask_bh + (size_t)r1 * S + c));
+                }
+                mk[nt] = m0 | (m1 << 16);
+            }
+            float sc[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+                uint32_t kb[4];
+                ldsm_x4(kb, s_k + (nt * 8 + kb_row) * kPitch + kb_col);
+                mma_bf16(sc[nt], qa[mt][0], kb[0], kb[1]);
+                mma_bf16(sc[nt], qa[mt][1], kb[2], kb[3]);
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                sc[nt][0] = (mk[nt] & 0x000000ffu) ? -INFINITY : sc[nt][0] * scale;
+                sc[nt][1] = (mk[nt] & 0x0000ff00u) ? -INFINITY : sc[nt][1] * scale;
+                sc[nt][2] = (mk[nt] & 0x00ff0000u) ? -INFINITY : sc[nt][2] * scale;
+                sc[nt][3] = (mk[nt] & 0xff000000u) ? -INFINITY : sc[nt][3] * scale;
+                mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float mn0 = fmaxf(m_run[mt][0], mx0), mn1 = fmaxf(m_run[mt][1], mx1);
+            const float ms0 = mn0 == -INFINITY ? 0.f : mn0, ms1 = mn1 == -INFINITY ? 0.f : mn1;   // all keys masked so far
+            const float c0 = __expf(m_run[mt][0] - ms0), c1 = __expf(m_run[mt][1] - ms1);
+            m_run[mt][0] = mn0;
+            m_run[mt][1] = mn1;
+            float l0 = 0.f, l1 = 0.f;
+            uint32_t pa[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float p00 = __expf(sc[nt][0] - ms0), p01 = __expf(sc[nt][1] - ms0);
+                const float p10 = __expf(sc[nt][2] - ms1), p11 = __expf(sc[nt][3] - ms1);
+                l0 += p00 + p01;
+                l1 += p10 + p11;
+                pa[nt >> 1][(nt & 1) * 2] = pack2(p00, p01);
+                pa[nt >> 1][(nt & 1) * 2 + 1] = pack2(p10, p11);
+            }
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+            l_run[mt][0] = l_run[mt][0] * c0 + l0;
+            l_run[mt][1] = l_run[mt][1] * c1 + l1;
+#pragma unroll
+            for (int dt = 0; dt < 4; ++dt) {
+                oc[mt][dt][0] *= c0; oc[mt][dt][1] *= c0;
+                oc[mt][dt][2] *= c1; oc[mt][dt][3] *= c1;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                for (int dp = 0; dp < 2; ++dp) {
+                    uint32_t vb[4];
+                    ldsm_x4_trans(vb, s_v + (kk * 16 + vb_row) * kPitch + dp * 16 + vb_col);
+                    mma_bf16(oc[mt][2 * dp], pa[kk], vb[0], vb[1]);
+                    mma_bf16(oc[mt][2 * dp + 1], pa[kk], vb[2], vb[3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = row_base + mt * 16 + g, r1 = r0 + 8;
+        const float i0 = l_run[mt][0] > 0.f ? 1.0f / l_run[mt][0] : 0.f, i1 = l_run[mt][1] > 0.f ? 1.0f / l_run[mt][1] : 0.f;
+#pragma unroll
+        for (int dt = 0; dt < 4; ++dt) {
+            const int c = dt * 8 + 2 * t;
+            if (r0 < L) *reinterpret_cast<uint32_t*>(out + (size_t)r0 * tok + col0 + c) = pack2(oc[mt][dt][0] * i0, oc[mt][dt][1] * i0);
+            if (r1 < L) *reinterpret_cast<uint32_t*>(out + (size_t)r1 * tok + col0 + c) = pack2(oc[mt][dt][2] * i1, oc[mt][dt][3] * i1);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" size_t rgbd_window_attention_workspace_bytes(int N, int heads, int n_mask_windows) {
@@ -376,6 +544,19 @@ extern "C" int rgbd_window_attention(const void* q, const void* k, const void* v
     else
         window_attention_kernel<float><<<(unsigned)blocks, kWarps * 32, smem, s>>>((const float*)q, (const float*)k, (const float*)v, add,
                                                                                   (float*)out, n_units, heads, N, nW, sqrt_d);
+    RGBD_CHECK_LAUNCH();
+    return RGBD_OK;
+}
+
+extern "C" int rgbd_masked_cross_attention(const void* q_bf16, const void* k_bf16, const void* v_bf16, const uint8_t* mask, void* out_bf16,
+                                           int B, int heads, int L, int S, int head_dim, rgbd_stream_t stream) {
+    RGBD_CHECK_ARG(q_bf16 && k_bf16 && v_bf16 && mask && out_bf16, "masked_cross_attention: null pointer");
+    RGBD_CHECK_ARG(head_dim == kHd, "masked_cross_attention: head dimension must be %d (got %d)", kHd, head_dim);
+    RGBD_CHECK_ARG(B >= 1 && heads >= 1 && L >= 1 && S >= 2 && S % 2 == 0, "masked_cross_attention: S must be even, sizes positive");
+    RGBD_CHECK_ARG((long long)B * heads <= 0x7fffffffLL && (L + 127) / 128 <= 65535, "masked_cross_attention: too many CTAs");
+    masked_cross_attention_kernel<<<dim3((unsigned)(B * heads), (unsigned)((L + 127) / 128)), 128, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)q_bf16, (const __nv_bfloat16*)k_bf16, (const __nv_bfloat16*)v_bf16, mask, (__nv_bfloat16*)out_bf16, B, heads, L, S,
+        1.0f / sqrtf((float)head_dim));
     RGBD_CHECK_LAUNCH();
     return RGBD_OK;
 }

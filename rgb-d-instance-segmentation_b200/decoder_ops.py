@@ -9,6 +9,9 @@ transformer decoder that CONSUME the fused pyramid (reference call site mask2for
   multiply, sum: ~80 ms per 32 frames of 480x640) run as ONE kernel, ``rgbd_msda_fwd``;
 * ``Mask2FormerMaskPredictor`` (ten calls per forward): the attention mask (bilinear resize of the (B,Q,120,160) logits, sigmoid,
   threshold, repeat per head: ~2 ms per call in ATen's plane-serial upsample kernel) is ``rgbd_attention_mask``;
+* ``Mask2FormerMaskedAttentionDecoderLayer.cross_attn`` (``nn.MultiheadAttention`` with a boolean mask, nine layers) under bf16
+  autocast: the additive -inf mask, the (batch*heads, 100, S) float32 score tensor, softmax, cast and second bmm are
+  ``rgbd_masked_cross_attention`` (FlashAttention-2 style, the boolean mask read directly);
 * ``SwinSelfAttention`` (12 blocks of Swin-T): the three ``nn.Linear`` projections stay; bmm -> div -> + relative position bias ->
   + shift mask -> softmax -> cast -> bmm -> permute-copy over a (windows*heads, 49, 49) score tensor is ``rgbd_window_attention``
   (one warp per (window, head), softmax in registers);
@@ -88,6 +91,31 @@ def _swin_self_attention_forward(self, hidden_states, attention_mask=None, outpu
     return (ctx,)
 
 
+def _mha_cross_attention_forward(self, query, key, value, key_padding_mask=None, need_weights=True, attn_mask=None,
+                                 average_attn_weights=True, is_causal=False):
+    """nn.MultiheadAttention.forward for the decoder's masked cross-attention (boolean attn_mask, batch_first=False) under bf16
+    autocast: the three input projections and out_proj stay F.linear / nn.Linear, the attention core is one kernel.  The attention
+    weights are not computed (the decoder layer only forwards them when output_attentions is set -- then the stock path runs)."""
+    ok = (not torch.is_grad_enabled() and query.is_cuda and attn_mask is not None and attn_mask.dtype == torch.bool
+          and attn_mask.dim() == 3 and key_padding_mask is None and not is_causal and not self.batch_first
+          and self._qkv_same_embed_dim and self.in_proj_bias is not None and self.bias_k is None and not self.add_zero_attn
+          and self.head_dim == 32 and not (self.training and self.dropout > 0) and query.dim() == 3 and key.shape[0] % 2 == 0
+          and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16)
+    if not ok:
+        return self._rgbd_stock_forward(query, key, value, key_padding_mask=key_padding_mask, need_weights=need_weights,
+                                        attn_mask=attn_mask, average_attn_weights=average_attn_weights, is_causal=is_causal)
+    e = self.embed_dim
+    w, b = self.in_proj_weight, self.in_proj_bias
+    q = nn.functional.linear(query, w[:e], b[:e])
+    k = nn.functional.linear(key, w[e:2 * e], b[e:2 * e])
+    v = nn.functional.linear(value, w[2 * e:], b[2 * e:])
+    if q.dtype != torch.bfloat16:
+        return self._rgbd_stock_forward(query, key, value, key_padding_mask=key_padding_mask, need_weights=need_weights,
+                                        attn_mask=attn_mask, average_attn_weights=average_attn_weights, is_causal=is_causal)
+    ctx = Fn.masked_cross_attention(q.contiguous(), k.contiguous(), v.contiguous(), attn_mask.contiguous(), self.num_heads)
+    return self.out_proj(ctx), None
+
+
 def _swin_prenorm_forward(self, x):
     """SwinLayer.layernorm_before / layernorm_after under bf16 autocast: the float32 LayerNorm result is only ever moved (pad,
     roll, window partition) and then cast to bf16 by nn.Linear -- emit that bf16 tensor directly.  (The residual stream is float32
@@ -102,7 +130,8 @@ def _swin_prenorm_forward(self, x):
 
 
 def install_fast_decoder_ops(model: nn.Module, deformable_attention: bool = True, attention_mask: bool = True,
-                             window_attention: bool = True, swin_prenorm_bf16: bool = True) -> nn.Module:
+                             window_attention: bool = True, swin_prenorm_bf16: bool = True,
+                             masked_cross_attention: bool = True) -> nn.Module:
     """Rebind the forwards described in the module docstring on every matching submodule of ``model`` (idempotent).
     ``uninstall_fast_decoder_ops`` restores the stock forwards."""
     from transformers.models.mask2former import modeling_mask2former as m2f
@@ -114,6 +143,12 @@ def install_fast_decoder_ops(model: nn.Module, deformable_attention: bool = True
                     if isinstance(ln, nn.LayerNorm) and not hasattr(ln, "_rgbd_stock_forward"):
                         ln._rgbd_stock_forward = ln.forward
                         ln.forward = types.MethodType(_swin_prenorm_forward, ln)
+    if masked_cross_attention:
+        for layer in model.modules():
+            if isinstance(layer, m2f.Mask2FormerMaskedAttentionDecoderLayer) and isinstance(layer.cross_attn, nn.MultiheadAttention) \
+                    and not hasattr(layer.cross_attn, "_rgbd_stock_forward"):
+                layer.cross_attn._rgbd_stock_forward = layer.cross_attn.forward
+                layer.cross_attn.forward = types.MethodType(_mha_cross_attention_forward, layer.cross_attn)
     for mod in model.modules():
         if hasattr(mod, "_rgbd_stock_forward"):
             continue

@@ -944,3 +944,25 @@ def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: f
                               x.numel() // Cc, Cc, float(eps), _stream()), "rgbd_layer_norm")
     _count(1)
     return out
+
+
+def masked_cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, attn_mask: torch.Tensor, num_heads: int) -> torch.Tensor:
+    """``rgbd_masked_cross_attention``: q (L, B, heads*32), k / v (S, B, heads*32) bfloat16 (``batch_first=False`` projections of
+    ``nn.MultiheadAttention``), attn_mask (B*heads, L, S) bool, True = may not attend -> (L, B, heads*32) bfloat16."""
+    lib = _lib.load()
+    for t_, name in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t_, name, torch.bfloat16)
+    _req(attn_mask, "attn_mask", torch.bool)
+    if q.dim() != 3 or k.dim() != 3 or v.shape != k.shape or k.shape[1:] != q.shape[1:]:
+        raise RgbdB200Error("masked_cross_attention: q (L,B,E), k / v (S,B,E)")
+    L, B, E = q.shape
+    S = k.shape[0]
+    if E != num_heads * 32:
+        raise RgbdB200Error(f"masked_cross_attention: E = {E} is not heads * 32 = {num_heads * 32}")
+    if tuple(attn_mask.shape) != (B * num_heads, L, S):
+        raise RgbdB200Error(f"masked_cross_attention: attn_mask must be {(B * num_heads, L, S)}, got {tuple(attn_mask.shape)}")
+    out = torch.empty_like(q)
+    check(lib.rgbd_masked_cross_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), attn_mask.data_ptr(), out.data_ptr(), B,
+                                          int(num_heads), L, S, 32, _stream()), "rgbd_masked_cross_attention")
+    _count(1)
+    return out

@@ -183,7 +183,7 @@ def test_whole_model_with_fast_decoder_ops(fn):
         used_stock_before = fn.LAUNCHES
         model(pixel_values=pv)
         hot_path_launches = fn.LAUNCHES - used_stock_before
-    assert used - hot_path_launches == 6 + 10 + 2 * 12               # six encoder layers, ten mask-predictor calls, twelve Swin blocks (table + attention)
+    assert used - hot_path_launches == 6 + 10 + 2 * 12               # six encoder layers, ten mask-predictor calls, twelve Swin blocks (table + attention); float32: the decoder cross-attention and the pre-norms stay stock
     assert rel_l2(fast.masks_queries_logits, stock.masks_queries_logits) < 2e-3
     assert rel_l2(fast.class_queries_logits, stock.class_queries_logits) < 2e-3
 
@@ -311,3 +311,55 @@ def test_swin_encoder_with_bf16_prenorms_and_window_attention(fn):
         # bf16 pre-norm outputs are what autocast hands the Linear layers anyway: same error level as the stock autocast run
         assert rel_l2(ln_only[i].float(), exact[i]) <= max(e_stock * 1.25, 1e-3), (i, e_stock)
         assert rel_l2(both[i].float(), exact[i]) <= max(e_stock * 1.25, 1e-3), (i, e_stock)
+
+
+@pytest.mark.parametrize("S", [300, 1200, 4800, 70])
+def test_masked_cross_attention_module_matches_stock_forward(fn, S):
+    """nn.MultiheadAttention as the Mask2Former decoder layer calls it (boolean mask, batch_first=False) with its rebound forward
+    under bf16 autocast, against the stock forward and the float32 result."""
+    from rgbd_b200 import decoder_ops
+    torch.manual_seed(S)
+    mha = torch.nn.MultiheadAttention(256, 8, 0.0).cuda().eval()
+    torch.nn.init.normal_(mha.in_proj_bias, std=0.2)
+    B, L = 3, 100
+    query = torch.randn(L, B, 256, device="cuda")
+    key = torch.randn(S, B, 256, device="cuda")
+    value = torch.randn(S, B, 256, device="cuda")
+    mask = torch.rand(B * 8, L, S, device="cuda") < 0.6
+    mask[:, :, 5] = False                                      # no fully masked row (the decoder's `where` fix guarantees it)
+    mask[:, 7, :] = True
+    mask[:, 7, S - 1] = False                                  # a row with a single visible key, in the last tile
+
+    class Holder(torch.nn.Module):                             # install() looks for decoder layers; rebind by hand here
+        pass
+    with torch.no_grad():
+        exact = mha(query, key, value, attn_mask=mask)[0]
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            stock = mha(query, key, value, attn_mask=mask)[0]
+            import types
+            mha._rgbd_stock_forward = mha.forward
+            mha.forward = types.MethodType(decoder_ops._mha_cross_attention_forward, mha)
+            before = fn.LAUNCHES
+            fast, w = mha(query, key, value, attn_mask=mask)
+            assert fn.LAUNCHES == before + 1 and w is None
+        fp32_call = mha(query, key, value, attn_mask=mask)[0]     # no autocast: stock path
+    assert fast.dtype == stock.dtype and fast.shape == stock.shape
+    assert torch.equal(fp32_call, exact)
+    e_stock, e_fast = rel_l2(stock.float(), exact), rel_l2(fast.float(), exact)
+    assert e_fast <= max(e_stock * 1.1, 4e-3), (e_fast, e_stock)
+    assert rel_l2(fast.float(), stock.float()) < 1e-2
+
+
+def test_masked_cross_attention_fully_masked_rows_give_zeros(fn):
+    q = torch.randn(100, 2, 256, device="cuda").bfloat16()
+    k = torch.randn(300, 2, 256, device="cuda").bfloat16()
+    v = torch.randn(300, 2, 256, device="cuda").bfloat16()
+    mask = torch.zeros(16, 100, 300, dtype=torch.bool, device="cuda")
+    mask[:, 3] = True
+    out = fn.masked_cross_attention(q, k, v, mask, 8)
+    assert bool((out[3] == 0).all()) and bool(torch.isfinite(out.float()).all())
+    want = torch.nn.functional.scaled_dot_product_attention(q.float().view(100, 16, 32).transpose(0, 1), k.float().view(300, 16, 32).transpose(0, 1),
+                                                            v.float().view(300, 16, 32).transpose(0, 1))
+    want = want.transpose(0, 1).reshape(100, 2, 256)
+    keep = [i for i in range(100) if i != 3]
+    assert rel_l2(out[keep].float(), want[keep]) < 4e-3
