@@ -363,3 +363,41 @@ def test_masked_cross_attention_fully_masked_rows_give_zeros(fn):
     want = want.transpose(0, 1).reshape(100, 2, 256)
     keep = [i for i in range(100) if i != 3]
     assert rel_l2(out[keep].float(), want[keep]) < 4e-3
+
+
+def test_whole_model_under_autocast_with_all_fast_ops(fn):
+    """The serving configuration: bf16 autocast with every decoder_ops kernel active (bf16 pre-norms, window attention, deformable
+    attention, attention masks, masked cross-attention) against the untouched model under the same autocast, both measured against
+    the float32 forward of the stock model: the rebound model must not be further from float32 than the stock autocast run."""
+    import numpy as np
+    from rgbd_b200 import decoder_ops, synthetic, synthetic_weights
+    model = synthetic_weights.build_synthetic_rgbd_mask2former(decisive=True)[0].eval().cuda()
+    frames = [synthetic.synth_rgbd_u8(60 + j, 192, 256) for j in range(2)]
+    rgb = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
+    depth = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+    pv = fn.pack_pixel_values(rgb, depth)
+    with torch.no_grad():
+        exact = model(pixel_values=pv)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            stock = model(pixel_values=pv)
+            decoder_ops.install_fast_decoder_ops(model)
+            before = fn.LAUNCHES
+            fast = model(pixel_values=pv)
+            used = fn.LAUNCHES - before
+            decoder_ops.uninstall_fast_decoder_ops(model)
+            before = fn.LAUNCHES
+            model(pixel_values=pv)
+            hot = fn.LAUNCHES - before
+    assert used - hot == 6 + 10 + 2 * 12 + 24 + 9            # + 24 pre-norm LayerNorms + 9 masked cross-attentions
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _parity_report import report
+    for name in ("masks_queries_logits", "class_queries_logits"):
+        e_stock = rel_l2(getattr(stock, name).float(), getattr(exact, name))
+        e_fast = rel_l2(getattr(fast, name).float(), getattr(exact, name))
+        report("decoder_ops_autocast_whole_model", tensor=name, stock_autocast_vs_fp32=e_stock, decoder_ops_autocast_vs_fp32=e_fast)
+        assert e_fast <= max(1.5 * e_stock, 1e-2), (name, e_fast, e_stock)
+    # per-pixel winner among the queries: the decision the post-processing takes
+    agree_stock = float((stock.masks_queries_logits.argmax(1) == exact.masks_queries_logits.argmax(1)).float().mean())
+    agree_fast = float((fast.masks_queries_logits.argmax(1) == exact.masks_queries_logits.argmax(1)).float().mean())
+    report("decoder_ops_autocast_whole_model", pixel_winner_agreement_with_fp32_stock=agree_stock, decoder_ops=agree_fast)
+    assert agree_fast >= agree_stock - 0.02, (agree_fast, agree_stock)
