@@ -42,6 +42,9 @@ def _msda_attention_forward(self, hidden_states, attention_mask=None, encoder_hi
                                         level_start_index=level_start_index, output_attentions=output_attentions)
     if position_embeddings is not None:
         hidden_states = hidden_states + position_embeddings
+    if hidden_states.dtype == torch.float32 and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        # the two nn.Linear below would each cast this tensor to bf16 (autocast caches weight casts only): cast it once
+        hidden_states = hidden_states.to(torch.bfloat16)
     batch_size, num_queries, _ = hidden_states.shape
     _, sequence_length, _ = encoder_hidden_states.shape
     if sum(h * w for h, w in spatial_shapes_list) != sequence_length:
