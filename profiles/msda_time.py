@@ -89,3 +89,12 @@ for S in (4800, 1200, 300):
         return torch.bmm(w, vl).transpose(0, 1).contiguous().view(100, B, 256)
     sb, _ = timeit(stock, reps=3, n=3)
     print("masked_cross_attention bf16 S=%d: best %.1f us median %.1f us (stock op chain of nn.MultiheadAttention: %.1f us)" % (S, best * 1e3, med * 1e3, sb * 1e3))
+
+# LayerNorm: this library's one-pass kernel vs ATen at the shapes of the whole model (float32 in / out = autocast semantics)
+for rows, C in ((B * 19200, 96), (B * 6300, 256), (B * 4800, 192), (B * 1200, 384), (B * 300, 768)):
+    x = torch.randn(rows, C, device="cuda", generator=g)
+    w = torch.randn(C, device="cuda", generator=g); bb = torch.randn(C, device="cuda", generator=g)
+    mine, _ = timeit(lambda: Fn.layer_norm(x, w, bb, 1e-5))
+    mine16, _ = timeit(lambda: Fn.layer_norm(x, w, bb, 1e-5, out_dtype=torch.bfloat16))
+    aten, _ = timeit(lambda: torch.nn.functional.layer_norm(x, (C,), w, bb, 1e-5))
+    print("layer_norm (%d, %d) f32->f32: %.1f us = %.0f GB/s; f32->bf16: %.1f us; ATen f32->f32: %.1f us" % (rows, C, mine * 1e3, rows * C * 8 / mine / 1e6, mine16 * 1e3, aten * 1e3))

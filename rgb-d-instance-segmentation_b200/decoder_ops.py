@@ -17,7 +17,9 @@ transformer decoder that CONSUME the fused pyramid (reference call site mask2for
   (one warp per (window, head), softmax in registers);
 * ``SwinLayer.layernorm_before`` / ``layernorm_after`` under bf16 autocast: ``rgbd_layer_norm`` writes the bf16 tensor the
   following ``nn.Linear`` layers would have cast the float32 result to (same values, 6 instead of 14+ bytes per element, and the
-  pad / roll / window-partition copies in between move half the bytes).
+  pad / roll / window-partition copies in between move half the bytes);
+* every other ``nn.LayerNorm`` (same output dtype as torch): the one-pass ``rgbd_layer_norm`` is 3-8x faster than ATen's kernel
+  at these shapes (many rows, 96-256 channels).
 
 Both fall back to the stock forward when autograd is recording (no backward kernels here) or the tensors are not on CUDA.
 """
@@ -132,9 +134,21 @@ def _swin_prenorm_forward(self, x):
     return Fn.layer_norm(x.contiguous(), self.weight.detach(), self.bias.detach(), self.eps, out_dtype=torch.bfloat16)
 
 
+def _layer_norm_forward(self, x):
+    """Any other nn.LayerNorm of the model (post-norms of the decoders, Swin's embedding / patch-merging / stage-output norms):
+    same semantics as torch (float32 result for float32 input, and for bf16 input under autocast), one-pass kernel.  ATen's kernel
+    needs 335 us for a (201 600, 256) float32 tensor and 935 us for (614 400, 96); this one 87 / 117 us."""
+    c = x.shape[-1]
+    auto = torch.is_autocast_enabled("cuda")
+    if torch.is_grad_enabled() or not x.is_cuda or c % 4 or c > 1024 or len(self.normalized_shape) != 1 or self.weight is None \
+            or self.bias is None or not (x.dtype == torch.float32 or (x.dtype == torch.bfloat16 and auto)):
+        return self._rgbd_stock_forward(x)
+    return Fn.layer_norm(x.contiguous(), self.weight.detach().float(), self.bias.detach().float(), self.eps, out_dtype=torch.float32)
+
+
 def install_fast_decoder_ops(model: nn.Module, deformable_attention: bool = True, attention_mask: bool = True,
                              window_attention: bool = True, swin_prenorm_bf16: bool = True,
-                             masked_cross_attention: bool = True) -> nn.Module:
+                             masked_cross_attention: bool = True, layer_norm: bool = True) -> nn.Module:
     """Rebind the forwards described in the module docstring on every matching submodule of ``model`` (idempotent).
     ``uninstall_fast_decoder_ops`` restores the stock forwards."""
     from transformers.models.mask2former import modeling_mask2former as m2f
@@ -164,6 +178,9 @@ def install_fast_decoder_ops(model: nn.Module, deformable_attention: bool = True
         elif window_attention and isinstance(mod, SwinSelfAttention):
             mod._rgbd_stock_forward = mod.forward
             mod.forward = types.MethodType(_swin_self_attention_forward, mod)
+        elif layer_norm and isinstance(mod, nn.LayerNorm):
+            mod._rgbd_stock_forward = mod.forward
+            mod.forward = types.MethodType(_layer_norm_forward, mod)
     return model
 
 
