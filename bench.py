@@ -420,6 +420,7 @@ def run_own(args):
                 marks[name][1].record()
             return [mod.register_forward_pre_hook(pre), mod.register_forward_hook(post)]
         plm = whole.model.pixel_level_module
+        graph_was, seg.cuda_graph = seg.cuda_graph, False      # the breakdown needs the modules' Python forwards (hooks): eager step
         hooks = timed(plm.encoder, "swin_encoder") + timed(plm.decoder, "pixel_decoder") + \
             timed(whole.model.transformer_module, "transformer_decoder") + timed(plm, "pixel_level_module")
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -430,6 +431,7 @@ def run_own(args):
         torch.cuda.synchronize()
         for h_ in hooks:
             h_.remove()
+        seg.cuda_graph = graph_was
         br = {k: v[0].elapsed_time(v[1]) for k, v in marks.items()}
         br["hot_path_incl_float_casts"] = br["pixel_level_module"] - br["swin_encoder"] - br["pixel_decoder"]
         br["step_unpipelined"] = t0.elapsed_time(t1)
@@ -446,12 +448,16 @@ def run_own(args):
                "how": "rgbd_b200.serving.RgbdInstanceSegmenter: pinned-host uint8 colour + depth frames -> H2D -> "
                       "rgbd_pack_pixel_values -> Mask2FormerForUniversalSegmentation (stock HF Swin-T / pixel decoder / "
                       "transformer decoder modules and weights, bf16 autocast, random-init) with the CUDA depth-guidance hot "
-                      "path" + (" and the decoder_ops kernels (rgbd_msda_fwd in the pixel decoder's 6 deformable-attention "
-                                "layers, rgbd_attention_mask in the 10 mask-predictor calls)" if fast_decoder_ops else "") +
+                      "path" + (" and the decoder_ops kernels inside the stock modules (rgbd_window_attention + bf16 pre-norm rgbd_layer_norm "
+                                "in Swin, rgbd_msda_fwd in the pixel decoder's 6 deformable-attention layers, rgbd_attention_mask in "
+                                "the 10 mask-predictor calls, rgbd_masked_cross_attention in the 9 decoder layers, rgbd_layer_norm for "
+                                "every other LayerNorm)" if fast_decoder_ops else "") +
+                      + ("; the device part of a step is replayed as one CUDA graph" if seg.cuda_graph else "") +
                       " -> device "
                       "post_process_instance_segmentation (threshold 0.0, target 480x640) -> segmentation map + labels + "
                       "scores + counts to pinned host; H2D / compute / D2H on 3 streams, 2 buffers",
                "own_kernel_launches_per_step": whole_launches_per_step,
+               "launch": "one CUDA graph replay per batch (front-end + model + post-processing)" if seg.cuda_graph else "eager",
                "hot_path_ms_per_step": hot_ms, "hot_path_share_of_step": hot_ms / (whole_elapsed / args.steps * 1e3),
                "breakdown_ms": br, "segments_last_step": int(counts.sum()), "check": e2e_check}
         if fast_decoder_ops:

@@ -9,12 +9,14 @@ What ``predictor.predictor`` / ``process_prediction`` do per image in the refere
            decoders: deformable-attention sampling and the masked-attention mask)
         -> device post-processing (K5)  --D2H-->  pinned segmentation map + per-segment labels / scores / counts
 
-Only ~1.2 MB per 480x640 frame crosses the host link on the way in and the painted instance map on the way out; encoder
+The device part of a step is replayed as one CUDA graph per staging buffer (``cuda_graph``), so the host only issues two copies
+and a graph launch per batch.  Only ~1.2 MB per 480x640 frame crosses the host link on the way in and the painted instance map on the way out; encoder
 features never leave the GPU.  H2D, compute and D2H run on three streams over two buffers, so step i's upload overlaps
 step i-1's compute and step i-2's download.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -24,13 +26,35 @@ from . import functional as Fn
 from ._lib import RgbdB200Error
 
 
+@contextlib.contextmanager
+def _cached_host_tensors():
+    """Stock Hugging Face code builds a few tiny device tensors from Python lists inside ``forward`` (``torch.as_tensor(
+    spatial_shapes_list, device=...)`` in the pixel decoder): pageable host-to-device copies, which a stream capture rejects.
+    Inside this context such calls are served from a cache keyed by the list's contents (filled by an eager run first)."""
+    cache: Dict = {}
+    orig = torch.as_tensor
+
+    def as_tensor(data, dtype=None, device=None):
+        if isinstance(data, (list, tuple)) and device is not None and torch.device(device).type == "cuda":
+            key = (repr(data), dtype, str(device))
+            if key not in cache:
+                cache[key] = orig(data, dtype=dtype, device=device)
+            return cache[key]
+        return orig(data, dtype=dtype, device=device)
+    torch.as_tensor = as_tensor
+    try:
+        yield cache
+    finally:
+        torch.as_tensor = orig
+
+
 class RgbdInstanceSegmenter:
     """``model``: a ``Mask2FormerForUniversalSegmentation`` whose pixel-level module is the RGB-D one
     (``pixel_level.build_rgbd_mask2former``), already on ``device`` and in eval mode."""
 
     def __init__(self, model, batch: int, frame_hw: Tuple[int, int], threshold: float = 0.5,
                  target_size: Optional[Tuple[int, int]] = None, autocast_dtype: Optional[torch.dtype] = torch.bfloat16,
-                 fast_decoder_ops: bool = True):
+                 fast_decoder_ops: bool = True, cuda_graph: Optional[bool] = None):
         p = next(model.parameters())
         if not p.is_cuda:
             raise RgbdB200Error("RgbdInstanceSegmenter: the model must live on a CUDA device (no CPU path)")
@@ -40,6 +64,18 @@ class RgbdInstanceSegmenter:
         else:
             decoder_ops.uninstall_fast_decoder_ops(model)
         self.fast_decoder_ops = bool(fast_decoder_ops)
+        #: replay the whole device step (front-end, model, post-processing) as ONE CUDA graph per staging buffer: the step is
+        #: ~1 800 kernel launches and, with decoder_ops on, its kernels (55 ms per 32 frames) finish before the host has launched
+        #: them (60+ ms).  Needs the decoder_ops forwards (the stock deformable attention builds a device tensor from a Python
+        #: list in every layer) and static shapes; the first call on each buffer runs eagerly, the second captures.  Parameters
+        #: must not change afterwards (the hot path's packed weights are baked in): call ``invalidate_graphs()`` if they do.
+        self.cuda_graph = bool(fast_decoder_ops) if cuda_graph is None else bool(cuda_graph)
+        if self.cuda_graph and not fast_decoder_ops:
+            raise RgbdB200Error("RgbdInstanceSegmenter: cuda_graph=True needs fast_decoder_ops=True")
+        self._graphs = [None, None]
+        self._calls = [0, 0]
+        self._pool = None
+        self._keep = []
         self.model = model
         self.device = p.device
         self.B = int(batch)
@@ -71,7 +107,29 @@ class RgbdInstanceSegmenter:
         self._step = 0
 
     # ---- one device step ---------------------------------------------------------------------------
+    def invalidate_graphs(self) -> None:
+        """Drop the captured graphs (after ``load_state_dict`` / any parameter change); the next calls capture again."""
+        self._graphs, self._calls, self._keep = [None, None], [0, 0], []
+
     def _compute(self, b: int) -> None:
+        if not self.cuda_graph:
+            return self._step_eager(b)
+        if self._graphs[b] is None:
+            self._calls[b] += 1
+            if self._calls[b] < 2:        # first call on this buffer: eager (allocates workspaces, packs weights, warms cuBLAS)
+                return self._step_eager(b)
+            with _cached_host_tensors() as cache:
+                self._step_eager(b)       # fills the host-tensor cache
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self._pool):
+                    self._step_eager(b)
+                if self._pool is None:
+                    self._pool = g.pool()
+                self._keep.append(cache)
+            self._graphs[b] = g
+        self._graphs[b].replay()
+
+    def _step_eager(self, b: int) -> None:
         rgb, depth = self.in_dev[b]
         with torch.no_grad():
             Fn.pack_pixel_values(rgb, depth, out=self.pv[b])

@@ -187,3 +187,28 @@ def test_serving_pipeline_matches_direct_calls():
             assert [s["label_id"] for s in r["segments_info"]] == [s["label_id"] for s in g["segments_info"]]
             assert torch.equal(r["segmentation"].cpu().to(torch.int32), g["segmentation"])
     assert seg.h2d_bytes_per_step == B * H * W * 4 and seg.d2h_bytes_per_step > B * H * W * 4
+
+
+def test_serving_with_cuda_graph_matches_eager_serving():
+    """The serving configuration (bf16 autocast, decoder_ops, one CUDA graph per staging buffer) against the same segmenter without
+    graphs, over six different batches (buffers alternate; graph replays from the third submit on)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import numpy as np
+    from rgbd_b200 import serving, synthetic, synthetic_weights as SW
+    model, _ = SW.build_synthetic_rgbd_mask2former(decisive=True, num_labels=8)
+    model.cuda()
+    B, H, W = 2, 128, 160
+    graphed = serving.RgbdInstanceSegmenter(model, B, (H, W), threshold=0.5)
+    eager = serving.RgbdInstanceSegmenter(model, B, (H, W), threshold=0.5, cuda_graph=False)
+    assert graphed.cuda_graph and not eager.cuda_graph
+    for k in range(6):
+        rgbs, ds = zip(*[synthetic.synth_rgbd_u8(800 + 10 * k + j, H, W, "nyu") for j in range(B)])
+        rgb, d = torch.from_numpy(np.stack(rgbs)), torch.from_numpy(np.stack(ds))
+        a, b = graphed(rgb, d), eager(rgb, d)
+        for x, y in zip(a, b):
+            assert [s["label_id"] for s in x["segments_info"]] == [s["label_id"] for s in y["segments_info"]]
+            assert len(x["segments_info"]) > 0 and torch.equal(x["segmentation"], y["segmentation"])
+    assert graphed._graphs[0] is not None and graphed._graphs[1] is not None
+    graphed.invalidate_graphs()
+    assert graphed._graphs == [None, None]
