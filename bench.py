@@ -452,7 +452,7 @@ def run_own(args):
                                 "in Swin, rgbd_msda_fwd in the pixel decoder's 6 deformable-attention layers, rgbd_attention_mask in "
                                 "the 10 mask-predictor calls, rgbd_masked_cross_attention in the 9 decoder layers, rgbd_layer_norm for "
                                 "every other LayerNorm)" if fast_decoder_ops else "") +
-                      + ("; the device part of a step is replayed as one CUDA graph" if seg.cuda_graph else "") +
+                      ("; the device part of a step is replayed as one CUDA graph" if seg.cuda_graph else "") +
                       " -> device "
                       "post_process_instance_segmentation (threshold 0.0, target 480x640) -> segmentation map + labels + "
                       "scores + counts to pinned host; H2D / compute / D2H on 3 streams, 2 buffers",
