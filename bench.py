@@ -396,6 +396,7 @@ def run_own(args):
         whole_launches_per_step = Fn.LAUNCHES
         for _ in range(max(args.warmup, 3) - 1):
             seg.submit()
+        seg.warmup()                                          # graph capture (one per staging buffer) belongs to the warm-up
         seg.drain()
         barrier()
         e0.record()

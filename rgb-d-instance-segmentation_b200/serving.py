@@ -107,6 +107,17 @@ class RgbdInstanceSegmenter:
         self._step = 0
 
     # ---- one device step ---------------------------------------------------------------------------
+    @property
+    def ready(self) -> bool:
+        """True once nothing one-off is left for the next ``submit`` (workspaces allocated, graphs captured)."""
+        return all(g is not None for g in self._graphs) if self.cuda_graph else self._step >= 2
+
+    def warmup(self) -> None:
+        """Re-submit what the staging buffers hold until ``ready`` (the first two steps run eagerly, the next two capture)."""
+        while not self.ready:
+            self.submit()
+        self.drain()
+
     def invalidate_graphs(self) -> None:
         """Drop the captured graphs (after ``load_state_dict`` / any parameter change); the next calls capture again."""
         self._graphs, self._calls, self._keep = [None, None], [0, 0], []
