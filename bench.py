@@ -436,6 +436,7 @@ def run_own(args):
         br = {k: v[0].elapsed_time(v[1]) for k, v in marks.items()}
         br["hot_path_incl_float_casts"] = br["pixel_level_module"] - br["swin_encoder"] - br["pixel_decoder"]
         br["step_unpipelined"] = t0.elapsed_time(t1)
+        br["note"] = "one EAGER step (module hooks need the Python forwards); the timed loop replays CUDA graphs" if graph_was else "eager"
         # the pipelined loop produced the real thing: its last result equals a synchronous call on the same frames (reported,
         # not asserted; the stock model's kernels are not guaranteed to be bit-reproducible)
         sync_res = seg.out_host[(seg._step - 1) & 1]

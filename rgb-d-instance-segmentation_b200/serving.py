@@ -132,7 +132,8 @@ class RgbdInstanceSegmenter:
             with _cached_host_tensors() as cache:
                 self._step_eager(b)       # fills the host-tensor cache
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=self._pool):
+                # thread_local: CUDA calls of other threads (NCCL watchdog, samplers) must not invalidate this capture
+                with torch.cuda.graph(g, pool=self._pool, capture_error_mode="thread_local"):
                     self._step_eager(b)
                 if self._pool is None:
                     self._pool = g.pool()
