@@ -152,5 +152,66 @@ def _(pred_masks, gt_masks):
     return pred_masks.new_empty((pred_masks.shape[0], gt_masks.shape[0]), dtype=torch.float32)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# decoder_ops kernels: inference-only neighbours of the path inside the stock Hugging Face modules (no autograd)
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op(f"{NAMESPACE}::msda_forward", mutates_args=())
+def msda_forward(value: Tensor, level_h: List[int], level_w: List[int], sampling_locations: Tensor, attention_weights: Tensor) -> Tensor:
+    """transformers ``multi_scale_deformable_attention(value, spatial_shapes, sampling_locations, attention_weights)``."""
+    return Fn.msda_forward(value, list(zip(level_h, level_w)), sampling_locations, attention_weights)
+
+
+@msda_forward.register_fake
+def _(value, level_h, level_w, sampling_locations, attention_weights):
+    B, _, H, D = value.shape
+    return value.new_empty((B, sampling_locations.shape[1], H * D), dtype=torch.float32)
+
+
+@torch.library.custom_op(f"{NAMESPACE}::attention_mask", mutates_args=())
+def attention_mask(mask_logits: Tensor, target_h: int, target_w: int, num_heads: int) -> Tensor:
+    """The attention-mask half of transformers ``Mask2FormerMaskPredictor.forward``: (B,Q,h,w) -> (B*heads, Q, th*tw) bool."""
+    return Fn.attention_mask(mask_logits, (target_h, target_w), num_heads)
+
+
+@attention_mask.register_fake
+def _(mask_logits, target_h, target_w, num_heads):
+    B, Q = mask_logits.shape[:2]
+    return mask_logits.new_empty((B * num_heads, Q, target_h * target_w), dtype=torch.bool)
+
+
+@torch.library.custom_op(f"{NAMESPACE}::window_attention", mutates_args=())
+def window_attention(q: Tensor, k: Tensor, v: Tensor, bias: Tensor, mask: Tensor, num_heads: int) -> Tensor:
+    """The inner op of transformers ``SwinSelfAttention.forward``; ``mask`` with zero windows (shape (0, N, N)) = no shift mask."""
+    return Fn.window_attention(q, k, v, bias, mask if mask.shape[0] else None, num_heads)
+
+
+@window_attention.register_fake
+def _(q, k, v, bias, mask, num_heads):
+    return torch.empty_like(q)
+
+
+@torch.library.custom_op(f"{NAMESPACE}::masked_cross_attention", mutates_args=())
+def masked_cross_attention(q: Tensor, k: Tensor, v: Tensor, attn_mask: Tensor, num_heads: int) -> Tensor:
+    """The attention core of ``nn.MultiheadAttention`` with a boolean mask (Mask2Former decoder layers), bfloat16."""
+    return Fn.masked_cross_attention(q, k, v, attn_mask, num_heads)
+
+
+@masked_cross_attention.register_fake
+def _(q, k, v, attn_mask, num_heads):
+    return torch.empty_like(q)
+
+
+@torch.library.custom_op(f"{NAMESPACE}::layer_norm", mutates_args=())
+def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float, bf16_out: bool = False) -> Tensor:
+    """LayerNorm over the last dimension, float32 arithmetic, float32 or bfloat16 output."""
+    return Fn.layer_norm(x, weight, bias, eps, out_dtype=torch.bfloat16 if bf16_out else torch.float32)
+
+
+@layer_norm.register_fake
+def _(x, weight, bias, eps, bf16_out=False):
+    return x.new_empty(x.shape, dtype=torch.bfloat16 if bf16_out else torch.float32)
+
+
 REGISTERED = ("dggm_forward", "dggm_backward_params", "gradient_features", "pack_pixel_values", "to_grayscale",
-              "depth_decompose", "post_process_instances", "mask_iou")
+              "depth_decompose", "post_process_instances", "mask_iou", "msda_forward", "attention_mask", "window_attention",
+              "masked_cross_attention", "layer_norm")

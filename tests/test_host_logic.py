@@ -309,5 +309,19 @@ def test_torch_ops_namespace_is_registered_with_schemas_and_fake_kernels():
         pv = torch.ops.rgbd_b200.pack_pixel_values(torch.empty(2, 32, 48, 3, dtype=torch.uint8, device="cuda"),
                                                    torch.empty(2, 32, 48, dtype=torch.uint8, device="cuda"))
         assert tuple(pv.shape) == (2, 10, 32, 48) and pv.dtype == torch.float32
+        # decoder_ops kernels
+        o = torch.ops.rgbd_b200.msda_forward(torch.empty(2, 126, 8, 32, device="cuda"), [2, 4, 8], [3, 6, 12],
+                                             torch.empty(2, 50, 8, 3, 4, 2, device="cuda"), torch.empty(2, 50, 8, 3, 4, device="cuda"))
+        assert tuple(o.shape) == (2, 50, 256)
+        m = torch.ops.rgbd_b200.attention_mask(torch.empty(2, 100, 24, 32, device="cuda"), 6, 8, 8)
+        assert tuple(m.shape) == (16, 100, 48) and m.dtype == torch.bool
+        q = torch.empty(12, 49, 96, device="cuda", dtype=torch.bfloat16)
+        assert torch.ops.rgbd_b200.window_attention(q, q, q, torch.empty(3, 49, 49, device="cuda"),
+                                                    torch.empty(0, 49, 49, device="cuda"), 3).shape == q.shape
+        qq = torch.empty(100, 2, 256, device="cuda", dtype=torch.bfloat16)
+        kk = torch.empty(300, 2, 256, device="cuda", dtype=torch.bfloat16)
+        assert torch.ops.rgbd_b200.masked_cross_attention(qq, kk, kk, torch.empty(16, 100, 300, device="cuda", dtype=torch.bool), 8).shape == qq.shape
+        y = torch.ops.rgbd_b200.layer_norm(torch.empty(5, 96, device="cuda"), torch.empty(96, device="cuda"), torch.empty(96, device="cuda"), 1e-5, True)
+        assert y.dtype == torch.bfloat16 and tuple(y.shape) == (5, 96)
     with pytest.raises(L.RgbdB200Error):
         torch.ops.rgbd_b200.to_grayscale(torch.zeros(1, 3, 4, 4))          # CPU tensors: no fallback
