@@ -21,7 +21,8 @@ transformer decoder that CONSUME the fused pyramid (reference call site mask2for
 * every other ``nn.LayerNorm`` (same output dtype as torch): the one-pass ``rgbd_layer_norm`` is 3-8x faster than ATen's kernel
   at these shapes (many rows, 96-256 channels).
 
-Both fall back to the stock forward when autograd is recording (no backward kernels here) or the tensors are not on CUDA.
+All of them fall back to the stock forward when autograd is recording (these are inference kernels: run under
+``torch.no_grad()``), when the tensors are not on CUDA, or when a shape / dtype is outside what the kernel covers.
 """
 from __future__ import annotations
 
@@ -36,7 +37,7 @@ from . import functional as Fn
 def _msda_attention_forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
                             position_embeddings=None, reference_points=None, spatial_shapes_list=None, level_start_index=None,
                             output_attentions: bool = False):
-    if (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())) or not hidden_states.is_cuda \
+    if torch.is_grad_enabled() or not hidden_states.is_cuda \
             or output_attentions or reference_points is None or reference_points.shape[-1] != 2:
         return self._rgbd_stock_forward(hidden_states, attention_mask=attention_mask, encoder_hidden_states=encoder_hidden_states,
                                         encoder_attention_mask=encoder_attention_mask, position_embeddings=position_embeddings,

@@ -325,3 +325,42 @@ def test_torch_ops_namespace_is_registered_with_schemas_and_fake_kernels():
         assert y.dtype == torch.bfloat16 and tuple(y.shape) == (5, 96)
     with pytest.raises(L.RgbdB200Error):
         torch.ops.rgbd_b200.to_grayscale(torch.zeros(1, 3, 4, 4))          # CPU tensors: no fallback
+
+
+def test_decoder_ops_install_uninstall_and_stock_fallback_on_cpu():
+    """decoder_ops rebinds forwards of stock Hugging Face modules; without CUDA tensors (or with autograd recording) every rebound
+    forward must fall back to the stock one, and uninstall must restore the class forwards."""
+    import torch
+    from torch import nn
+    from transformers import Mask2FormerConfig, SwinConfig
+    from transformers.models.mask2former import modeling_mask2former as m2f
+    from transformers.models.swin.modeling_swin import SwinLayer, SwinSelfAttention
+    from rgbd_b200 import decoder_ops
+    torch.manual_seed(0)
+    backbone = SwinConfig(embed_dim=32, depths=[1, 1, 1, 1], num_heads=[1, 2, 4, 8], window_size=7, image_size=64,
+                          out_features=["stage1", "stage2", "stage3", "stage4"])
+    cfg = Mask2FormerConfig(backbone_config=backbone, num_labels=4, num_queries=8, feature_size=32, mask_feature_size=32, hidden_dim=32,
+                            encoder_layers=1, decoder_layers=3, num_attention_heads=1, dim_feedforward=64, encoder_feedforward_dim=64)
+    model = m2f.Mask2FormerForUniversalSegmentation(cfg).eval()
+    x = torch.randn(1, 3, 64, 64)
+    with torch.no_grad():
+        want = model(pixel_values=x)
+    decoder_ops.install_fast_decoder_ops(model)
+    kinds = {nn.LayerNorm: 0, SwinSelfAttention: 0, nn.MultiheadAttention: 0, m2f.Mask2FormerMaskPredictor: 0,
+             m2f.Mask2FormerPixelDecoderEncoderMultiscaleDeformableAttention: 0}
+    for mod in model.modules():
+        if "_rgbd_stock_forward" in mod.__dict__:
+            for k in kinds:
+                if isinstance(mod, k):
+                    kinds[k] += 1
+    assert kinds[SwinSelfAttention] == 4 and kinds[nn.MultiheadAttention] == 2 and kinds[m2f.Mask2FormerMaskPredictor] == 1
+    assert kinds[m2f.Mask2FormerPixelDecoderEncoderMultiscaleDeformableAttention] == 1 and kinds[nn.LayerNorm] >= 8
+    pre = [layer.layernorm_before.forward.__func__ for layer in model.modules() if isinstance(layer, SwinLayer)]
+    assert all(f is decoder_ops._swin_prenorm_forward for f in pre)
+    decoder_ops.install_fast_decoder_ops(model)                      # idempotent
+    with torch.no_grad():
+        got = model(pixel_values=x)                                  # CPU tensors: every rebound forward runs the stock code
+    assert torch.equal(got.masks_queries_logits, want.masks_queries_logits)
+    assert torch.equal(got.class_queries_logits, want.class_queries_logits)
+    decoder_ops.uninstall_fast_decoder_ops(model)
+    assert not any("_rgbd_stock_forward" in m.__dict__ or "forward" in m.__dict__ for m in model.modules())
