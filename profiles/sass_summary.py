@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "rgb-d-instance-segmentation_b200", "csrc", "librgbd_b200.so")
-MNEMONICS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCCP", "SYNCS", "HMMA", "MUFU", "ATOMS", "RED", "ATOMG"]
+MNEMONICS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCCP", "SYNCS", "HMMA", "LDSM", "MUFU", "ATOMS", "RED", "ATOMG"]
 
 
 def main():
@@ -38,7 +38,7 @@ def main():
             for mn in MNEMONICS:
                 if op.startswith(mn):
                     counts[cur][mn + (".2CTA" if ".2CTA" in op and mn == "UTCHMMA" else "")] += 1
-    cols = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "SYNCS", "HMMA", "MUFU"]
+    cols = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "SYNCS", "HMMA", "LDSM", "MUFU"]
     print(f"cuobjdump -sass {os.path.relpath(LIB, ROOT)}  (sm_100a; one row per kernel; instruction counts)")
     print(f"{'kernel':58s} {'instr':>6s} " + " ".join(f"{c:>12s}" for c in cols))
     tot = collections.Counter()
