@@ -50,7 +50,9 @@ def _cached_host_tensors():
 
 class RgbdInstanceSegmenter:
     """``model``: a ``Mask2FormerForUniversalSegmentation`` whose pixel-level module is the RGB-D one
-    (``pixel_level.build_rgbd_mask2former``), already on ``device`` and in eval mode."""
+    (``pixel_level.build_rgbd_mask2former``), already on ``device`` and in eval mode.  ``fast_decoder_ops`` (default) rebinds
+    forwards of the MODEL's stock submodules (``decoder_ops.install_fast_decoder_ops``: a side effect on the caller's model that
+    stays until ``decoder_ops.uninstall_fast_decoder_ops(model)``; training and autograd keep using the stock forwards)."""
 
     def __init__(self, model, batch: int, frame_hw: Tuple[int, int], threshold: float = 0.5,
                  target_size: Optional[Tuple[int, int]] = None, autocast_dtype: Optional[torch.dtype] = torch.bfloat16,

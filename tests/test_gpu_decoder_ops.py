@@ -329,10 +329,7 @@ def test_masked_cross_attention_module_matches_stock_forward(fn, S):
     mask[:, :, 5] = False                                      # no fully masked row (the decoder's `where` fix guarantees it)
     mask[:, 7, :] = True
     mask[:, 7, S - 1] = False                                  # a row with a single visible key, in the last tile
-
-    class Holder(torch.nn.Module):                             # install() looks for decoder layers; rebind by hand here
-        pass
-    with torch.no_grad():
+    with torch.no_grad():                                      # install() looks for decoder layers; rebind by hand here
         exact = mha(query, key, value, attn_mask=mask)[0]
         with torch.autocast("cuda", dtype=torch.bfloat16):
             stock = mha(query, key, value, attn_mask=mask)[0]
