@@ -364,3 +364,27 @@ def test_decoder_ops_install_uninstall_and_stock_fallback_on_cpu():
     assert torch.equal(got.class_queries_logits, want.class_queries_logits)
     decoder_ops.uninstall_fast_decoder_ops(model)
     assert not any("_rgbd_stock_forward" in m.__dict__ or "forward" in m.__dict__ for m in model.modules())
+
+
+def test_serving_host_tensor_cache_patches_and_restores_torch_as_tensor():
+    """serving._cached_host_tensors: inside the context, list -> CUDA-device conversions are served from a cache (a stream
+    capture rejects the pageable host-to-device copy); everything else, and everything afterwards, is torch's own function."""
+    import torch
+    from rgbd_b200 import serving
+    orig = torch.as_tensor
+    calls = []
+
+    def fake(data, dtype=None, device=None):                 # stands in for the real function (no CUDA device here)
+        calls.append((repr(data), dtype, str(device)))
+        return ("tensor", len(calls))
+    torch.as_tensor = fake
+    try:
+        with serving._cached_host_tensors() as cache:
+            a = torch.as_tensor([(1, 2), (3, 4)], dtype=torch.long, device="cuda:0")
+            b = torch.as_tensor([(1, 2), (3, 4)], dtype=torch.long, device="cuda:0")       # served from the cache
+            c = torch.as_tensor([(1, 2), (3, 5)], dtype=torch.long, device="cuda:0")       # other contents: new entry
+            d = torch.as_tensor([1, 2], dtype=torch.long, device="cpu")                    # not a CUDA target: passed through
+            assert a is b and a is not c and len(cache) == 2 and len(calls) == 4 - 1 and d == ("tensor", 3)
+        assert torch.as_tensor is fake                           # restored to what it was on entry
+    finally:
+        torch.as_tensor = orig
