@@ -515,6 +515,13 @@ def run_own(args):
                       "achieved": front_tf, "peak": pkv["tf_burst"], "unit": "TFLOP/s", "frac": front_tf / pkv["tf_burst"],
                       "hbm_gbs": front_gbs})
 
+    # ---- the decoder_ops kernels at this workload's shapes (live CUDA-event timings; reported, never part of `value`)
+    if not args.no_whole_model:
+        try:
+            extra.extend(decoder_ops_rooflines(B, pkv, dev))
+        except Exception as e:                               # reported, never fatal for the headline line
+            extra.append({"kernel": "decoder_ops kernels", "error": repr(e)})
+
     # ---- BASELINE configs[3] on the hot path: fwd + bwd + gradient all-reduce, batch 8 per GPU
     train = None
     if not args.no_train:
@@ -786,6 +793,45 @@ def train_whole_model_record(args, dev, rank, world, barrier):
             **grads,
             "workload": "configs[3]: whole RGB-D Mask2Former fine-tuning step, bf16 autocast, batch 8 per GPU, synthetic rectangle "
                         "labels, HF Mask2FormerLoss, bucketed NCCL gradient all-reduce overlapped with the backward, AdamW"}
+
+
+def decoder_ops_rooflines(B, pkv, dev):
+    """Live timings of the decoder_ops kernels that carry most bytes, at the shapes the whole model gives them for this workload
+    (deformable attention of the pixel decoder's three coarse levels; LayerNorm of the pixel decoder's token stream)."""
+    from rgbd_b200 import functional as Fn
+    g = torch.Generator(device=dev).manual_seed(3)
+    sp = [(H // 32, W // 32), (H // 16, W // 16), (H // 8, W // 8)]
+    S = sum(a * b for a, b in sp)
+    value = torch.randn(B, S, 8, 32, device=dev, generator=g).bfloat16()
+    offs = (torch.randn(B, S, 8, 3, 4, 2, device=dev, generator=g) * 2.0).bfloat16()
+    logit = torch.randn(B, S, 8, 12, device=dev, generator=g).bfloat16()
+    ref = torch.rand(B, S, 3, 2, device=dev, generator=g)
+    x = torch.randn(B * S, 256, device=dev, generator=g)
+    w, b = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+
+    def timed(fn, n=10):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n / 1e3
+    t_msda = timed(lambda: Fn.msda_forward(value, sp, offs, logit, reference_points=ref, softmax=True, out_dtype=torch.bfloat16))
+    t_ln = timed(lambda: Fn.layer_norm(x, w, b, 1e-5))
+    gathered = B * S * 8 * 12 * 4 * 64                       # bytes: (query, head, level x point, corner) x 32 bf16 channels
+    hbm_msda = (value.numel() + offs.numel() + logit.numel() + B * S * 256) * 2 + ref.numel() * 4
+    l2_peak = 43.0 * 148 * 1.965                              # GB/s: ~43 B/clk/SM delivered from L2 (profiles/r02_mma_rate.txt)
+    return [
+        {"kernel": "msda_fwd_quad_kernel (pixel decoder deformable attention: softmax + locations + bilinear gather)",
+         "bound": "l2-gather", "achieved": gathered / t_msda / 1e9, "peak": l2_peak, "unit": "GB/s",
+         "frac": gathered / t_msda / 1e9 / l2_peak, "us": t_msda * 1e6, "algorithmic_hbm_gbs": hbm_msda / t_msda / 1e9,
+         "peak_source": "L2 -> SM delivery measured with bulk copies (43 B/clk/SM x 148 SMs x 1.965 GHz)"},
+        {"kernel": "layer_norm_kernel (float32 in / out, (batch x 6300, 256))", "bound": "hbm", "achieved": x.numel() * 8 / t_ln / 1e9,
+         "peak": pkv["hbm_gbs"], "unit": "GB/s", "frac": x.numel() * 8 / t_ln / 1e9 / pkv["hbm_gbs"], "us": t_ln * 1e6},
+    ]
 
 
 class PerKernel:
